@@ -1,0 +1,213 @@
+/* sdde_b200.h -- C ABI of libsdde_b200.so: B200-native ensemble integrator for constant-lag SDDEs.
+ *
+ * This is the drop-in boundary for ONE path of SciML/StochasticDelayDiffEq.jl (v1.12.0):
+ *
+ *     solve(EnsembleProblem(SDDEProblem(f, g, u0, h, tspan, p; constant_lags)), EM()/RKMil(), ensemblealg;
+ *           dt, saveat, trajectories, adaptive=false)
+ *
+ * i.e. what the reference executes, once per trajectory, through
+ *     DiffEqBase.__solve        /root/reference/src/solve.jl:1-9
+ *     DiffEqBase.__init         /root/reference/src/solve.jl:11-572
+ *     DiffEqBase.solve!         /root/reference/src/solve.jl:574-610
+ * driven by [EXT] SciMLBase.__solve(::AbstractEnsembleProblem, alg, ensemblealg; trajectories).
+ * The Julia side binds these entry points with `ccall` from a new ensemble algorithm type
+ * (`EnsembleB200`, see INTEGRATION.md and julia/EnsembleB200.jl); in this repository the same ABI is
+ * driven by Python ctypes (stochasticdelaydiffeq.jl_b200/_capi.py).
+ *
+ * All entry points are extern "C", take plain pointers and sizes, never throw and never call back
+ * into the host language.  Return value 0 = success; negative = error, message via
+ * sdde_b200_last_error().  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with SDDE_ERR_CUDA.
+ */
+#ifndef SDDE_B200_H
+#define SDDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDDE_B200_VERSION 100      /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define SDDE_API __attribute__((visibility("default")))
+#else
+#define SDDE_API
+#endif
+
+#define SDDE_MAX_STATE 8
+#define SDDE_MAX_LAG 4
+#define SDDE_MAX_NOISE 8
+#define SDDE_MAX_PARAM 128
+
+/* ---- error codes (SURVEY.md section 8(b) "Errors") ---- */
+#define SDDE_OK 0
+#define SDDE_ERR_BAD_DESC (-1)     /* malformed descriptor (sizes, NULL pointers, tf <= t0, dt == 0 with no tstops ...)
+                                      mirrors error() guards of src/solve.jl:121-123 */
+#define SDDE_ERR_UNSUPPORTED (-2)  /* valid SciML request outside this path: RKMil with non-diagonal noise,
+                                      dt > min(lag) with a non-EM algorithm (src/solve.jl:581-585), unknown model */
+#define SDDE_ERR_NOMEM (-3)
+#define SDDE_ERR_COMPILE (-4)      /* NVRTC compilation of a user model failed (log in last_error) */
+#define SDDE_ERR_CUDA (-100)       /* -100 - cudaError_t */
+#define SDDE_ERR_NCCL (-200)       /* -200 - ncclResult_t */
+
+/* ---- algorithms: the reference's alg argument ([EXT] StochasticDiffEq EM{split}, RKMil{interpretation};
+ *      dispatch site src/solve.jl:586) ---- */
+enum { SDDE_ALG_EM_SPLIT = 0,      /* EM() == EM(true) */
+       SDDE_ALG_EM_NOSPLIT = 1,    /* EM(false) */
+       SDDE_ALG_RKMIL_ITO = 2,     /* RKMil(), adaptive=false */
+       SDDE_ALG_RKMIL_STRAT = 3 }; /* RKMil(interpretation=:Stratonovich), adaptive=false */
+
+/* ---- built-in model zoo: the device-side replacement of the closures that
+ *      src/functionwrapper.jl:8-9,35-36 builds around the user's f(u,h,p,t), g(u,h,p,t).
+ *      Ids >= SDDE_MODEL_USER_BASE are returned by sdde_b200_compile_model (NVRTC). ---- */
+enum { SDDE_MODEL_LINEAR1 = 0,       /* du=(a u + b u(t-tau))dt + s u dW            p=(a,b,s)                 */
+       SDDE_MODEL_HAYES = 1,         /* test/test_prob_sol.jl:6-13                   p=(tau,a,b,c,alpha,beta,gamma) */
+       SDDE_MODEL_MACKEY_GLASS = 2,  /* du=(beta x/(1+x^n) - gamma u)dt + s u dW     p=(beta,gamma,n,s), x=u(t-tau) */
+       SDDE_MODEL_LINSYS = 3,        /* n-state linear delay system, n x m noise     p=(A,B_1..B_L,c,M,N) row-major */
+       SDDE_MODEL_SIR = 4,           /* test/nondiagonal_sparse_noise.jl:5-43        p=(beta,c,tau)            */
+       SDDE_MODEL_SCALAR_ADD = 5,    /* test/events.jl:4-5  du=a u(t-tau)dt + b dW   p=(a,b)                   */
+       SDDE_MODEL_USER_BASE = 1000 };
+
+/* ---- noise source: src/solve.jl:304-353 (WienerProcess vs prob.noise) ---- */
+enum { SDDE_NOISE_PHILOX = 0,        /* in-kernel Philox4x32-10 + float64 Box-Muller, dW = sqrt|dt_n| * xi          */
+       SDDE_NOISE_SUPPLIED_DW = 1,   /* noise[n][c][traj] = increment of step n (already scaled)                    */
+       SDDE_NOISE_SUPPLIED_GRID = 2  /* noise[n][c][traj] = W(t_n) on the schedule's own nodes n=0..N (NoiseGrid):  */
+};                                   /*   dW_n = W(t_{n+1}) - curW, curW += dW_n  ([EXT] DiffEqNoiseProcess)        */
+
+/* ---- delayed-state source.  Only DENSE exists on the GPU: the reference's saveat aliasing
+ *      (src/solve.jl:465-482) is reproduced by the oracle only, as a documented hazard. ---- */
+enum { SDDE_HISTORY_DENSE = 0 };
+
+/* ---- where a caller buffer lives ---- */
+enum { SDDE_MEM_HOST = 0, SDDE_MEM_DEVICE = 1 };
+
+/* Problem + solve-keyword descriptor.  POD; the caller owns every pointer for the duration of the call.
+ * Field <-> reference map:
+ *   model_id,params,u0,hist_c0,hist_c1,lags  SDDEProblem fields f,g,p,u0,h,constant_lags      src/solve.jl:128
+ *   t0,tf                           prob.tspan                                       src/solve.jl:116-119
+ *   dt, saveat, save_*, tstops      __init keyword arguments                         src/solve.jl:18-40
+ *   order_discontinuity_t0          prob.order_discontinuity_t0                      src/solve.jl:100-105
+ *   seed                            seed kw / prob.seed                              src/solve.jl:302
+ *   noise_mode/noise                prob.noise                                       src/solve.jl:304-353
+ *   n_traj                          `trajectories` of the ensemble solve ([EXT] SciMLBase)
+ *   params+param_stride / u0+stride what EnsembleProblem.prob_func would vary per trajectory            */
+typedef struct sdde_desc {
+    int32_t struct_size;              /* = sizeof(sdde_desc); ABI guard */
+    int32_t model_id;
+    int32_t alg;
+    int32_t n_state, n_noise, n_lag, n_param;
+    int32_t order_discontinuity_t0;   /* default 0 */
+    int32_t constant_lags_declared;   /* 1: lags were given as constant_lags (propagated-discontinuity tstops) */
+    int32_t save_start, save_end, save_everystep;
+    int32_t noise_mode;
+    int32_t noise_mem;                /* SDDE_MEM_* of `noise` */
+    int32_t out_mem;                  /* SDDE_MEM_* of `out` passed to sdde_b200_solve */
+    int32_t history_mode;
+    int32_t want_paths, want_moments;
+    int32_t lanes_per_traj;           /* 0 = auto; 1 = thread per trajectory; 4,8 = cooperative lanes (n_state >= 4) */
+    int32_t n_saveat, n_tstops;
+    int32_t reserved0;
+    double t0, tf, dt;
+    double lags[SDDE_MAX_LAG];
+    double hist_c0[SDDE_MAX_STATE];   /* h(p,t)[j] = hist_c0[j] + hist_c1[j]*t  for t < t0 */
+    double hist_c1[SDDE_MAX_STATE];
+    const double *params;             /* [n_param] if param_stride == 0 else params[k*param_stride + traj] */
+    int64_t param_stride;
+    const double *u0;                 /* [n_state] if u0_stride == 0 else u0[j*u0_stride + traj] */
+    int64_t u0_stride;
+    const double *saveat;             /* explicit save times (already expanded; src/solve.jl:659-677) */
+    const double *tstops;             /* extra user tstops */
+    const double *noise;              /* supplied noise, layout [n][channel][traj], row pitch = n_traj */
+    int64_t n_traj;                   /* trajectories solved by THIS call */
+    int64_t traj_offset;              /* global id of the first one (partition-invariant RNG streams) */
+    uint64_t seed;
+} sdde_desc;
+
+/* Host-side schedule (trajectory independent): the replay of src/solve.jl:574-610 time stepping with
+ * tstops / discontinuity propagation (src/integrators/utils.jl) and the saveat logic of
+ * src/integrators/interface.jl:357-430.  Arrays are owned by the library, freed by sdde_b200_schedule_free. */
+typedef struct sdde_schedule {
+    int64_t n_steps;
+    int64_t n_save;
+    int32_t n_lag;
+    int32_t ring_slots;        /* history ring capacity the kernels use */
+    int32_t min_gap;           /* min over steps of (n - newest node a lookup touches) */
+    int32_t n_tstops_hit;
+    double *t;                 /* [n_steps+1] */
+    double *dt;                /* [n_steps]   */
+    double *sqdt;              /* [n_steps]   */
+    int32_t *lk_mode;          /* [n_steps*n_lag] 0 prehistory, 1 exact node, 2 interpolate */
+    int64_t *lk_idx;           /* [n_steps*n_lag] node index (upper node when interpolating), -1 prehistory */
+    double *lk_theta;          /* [n_steps*n_lag] theta, or the lookup time for prehistory */
+    double *save_t;            /* [n_save] */
+    int64_t *save_step;        /* [n_save] step whose end produced the save, -1 = initial condition */
+    double *save_theta;        /* [n_save] */
+    int32_t *save_exact;       /* [n_save] */
+    double *tstops_hit;        /* [n_tstops_hit] */
+} sdde_schedule;
+
+typedef struct sdde_timing {
+    double kernel_ms;          /* CUDA-event time of the step kernels (+ moments kernels) on the compute stream */
+    double total_ms;           /* host wall time of the call */
+    double h2d_ms, d2h_ms;     /* CUDA-event time on the copy streams */
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t n_steps, n_save;
+    int32_t launches;          /* kernels launched by this call */
+    int32_t waves;             /* trajectory waves */
+    int32_t ring_slots;
+    int32_t regs_per_thread;
+    int32_t block_threads;
+    int32_t traj_per_thread;
+    int64_t ring_bytes;
+    char kernel_name[128];
+} sdde_timing;
+
+typedef struct sdde_ctx sdde_ctx;
+
+SDDE_API int sdde_b200_version(void);
+SDDE_API int sdde_b200_device_count(void);                       /* number of CUDA devices visible, <0 on error */
+SDDE_API const char *sdde_b200_last_error(void);                 /* thread-local message of the last failing call */
+
+/* One context drives one GPU (one process per GPU under torchrun; several contexts per process are fine). */
+SDDE_API sdde_ctx *sdde_b200_create(int device);
+SDDE_API void sdde_b200_destroy(sdde_ctx *ctx);
+SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value);  /* "wave_traj", "block", "batch", "chunk_steps" */
+
+/* Host only: builds the step/lookup/save schedule for a descriptor (no GPU needed). */
+SDDE_API int sdde_b200_schedule(const sdde_desc *d, sdde_schedule *out);
+SDDE_API void sdde_b200_schedule_free(sdde_schedule *s);
+
+/* Integrate d->n_traj trajectories.
+ *   out      [n_save][n_state][n_traj] float64, time-major, trajectory-contiguous (may be NULL if !want_paths);
+ *            host or device memory according to d->out_mem.
+ *   moments  [n_save][n_state][3] = (count, mean, M2) over this call's trajectories, host memory (NULL if !want_moments)
+ *   status   [n_traj] bytes, host memory, 0 = ok, 1 = non-finite state seen (-> ReturnCode.Unstable), may be NULL
+ *   tm       optional timing/launch report                                                          */
+SDDE_API int sdde_b200_solve(sdde_ctx *ctx, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm);
+
+/* Merge two (count, mean, M2) arrays of n triples: a <- merge(a, b)  (Chan et al.); host only. */
+SDDE_API int sdde_b200_merge_moments(double *a, const double *b, int64_t n);
+
+/* Register a user model from CUDA C++ source (NVRTC, sm_100a).  The source must define
+ *   struct UserModel { static constexpr int NS, NL, NW, NP; static constexpr bool DIAG;
+ *                      template<class P> __device__ static void f(double*du,const double*u,const double(*ul)[NS],const P&p,double t);
+ *                      template<class P> __device__ static void g(double*gv,const double*u,const double(*ul)[NS],const P&p,double t); };
+ * Returns a model id >= SDDE_MODEL_USER_BASE in *model_id. */
+SDDE_API int sdde_b200_compile_model(sdde_ctx *ctx, const char *source, int32_t *model_id);
+
+/* Test hooks / micro-benchmarks. */
+SDDE_API int sdde_b200_philox_normals(sdde_ctx *ctx, uint64_t seed, int64_t traj_offset, int64_t n_traj,
+                             int64_t n_steps, int32_t n_noise, double *out_host /* [n_steps][n_noise][n_traj] */);
+SDDE_API int sdde_b200_dfma_peak(sdde_ctx *ctx, double *tflops);       /* measured FP64 FMA throughput of this GPU */
+SDDE_API int sdde_b200_hbm_peak(sdde_ctx *ctx, double *gbs);           /* measured device copy bandwidth (read+write) */
+
+/* Pinned host memory helpers for the end-to-end path (Julia: unsafe_wrap the pointer). */
+SDDE_API void *sdde_b200_alloc_pinned(int64_t bytes);
+SDDE_API void sdde_b200_free_pinned(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDDE_B200_H */

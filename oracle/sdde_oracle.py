@@ -1,0 +1,657 @@
+"""CPU oracle for the fixed-step constant-lag ensemble SDDE path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a float64 restatement of what StochasticDelayDiffEq.jl v1.12.0 (``/root/reference``)
+does for ``solve(prob::SDDEProblem, EM()/RKMil(); dt, adaptive=false, ...)``, one trajectory at a
+time, vectorised here over trajectories with numpy (all arithmetic is element-wise, so every
+trajectory sees exactly the scalar IEEE-754 operation sequence written below; numpy never fuses
+multiply-add).
+
+PARITY UNPINNED: the reference ships no golden vectors for this path and Julia
+is not available in this environment, so this restatement is checked against hand-derived
+known-answer values (K1..K7 in SURVEY.md section 8(c)), not against outputs of the reference itself.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg may import this module.  The product (``stochasticdelaydiffeq.jl_b200``) never does.
+
+Reference lines followed (relative to /root/reference):
+  * queues            src/solve.jl:613-713  (tstop_saveat_disc_handling)
+  * first dt / sqdt   src/solve.jl:561-569
+  * loop order        src/solve.jl:574-610  (loopheader! -> perform_step! -> loopfooter! -> handle_tstop!)
+  * accept / next dt  src/integrators/interface.jl:1-30 + [EXT] StochasticDiffEq.apply_step!/modify_dt_for_tstops!
+  * time update+snap  src/integrators/interface.jl:70-85
+  * saving            src/integrators/interface.jl:357-430 (+ postamble! :100-117)
+  * tstop / disc      src/integrators/utils.jl:1-22, 42-79, 91-118
+  * history lookup    src/utils.jl:143-247 + src/solve.jl:407  ([EXT] DelayDiffEq.HistoryFunction,
+                      StochasticDiffEq.LinearInterpolationData / sde_interpolation)
+  * where h enters    src/functionwrapper.jl:8-9,35-36
+  * EM / RKMil update [EXT] StochasticDiffEq perform_step! (call site src/solve.jl:586), SURVEY.md section 3.3
+"""
+from __future__ import annotations
+
+import bisect
+import heapq
+import math
+from dataclasses import dataclass, field
+from fractions import Fraction
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------
+# algorithm ids (shared vocabulary with include/sdde_b200.h)
+# ----------------------------------------------------------------------------------------------
+ALG_EM_SPLIT = 0      # EM()  == EM(true)   [EXT] default split-step
+ALG_EM_NOSPLIT = 1    # EM(false)
+ALG_RKMIL_ITO = 2     # RKMil()  (interpretation = :Ito)
+ALG_RKMIL_STRAT = 3   # RKMil(interpretation = :Stratonovich)
+
+# [EXT] StochasticDiffEq.alg_order: EM 1//2, RKMil 1//1  (call site src/solve.jl:248)
+ALG_ORDER = {
+    ALG_EM_SPLIT: Fraction(1, 2),
+    ALG_EM_NOSPLIT: Fraction(1, 2),
+    ALG_RKMIL_ITO: Fraction(1, 1),
+    ALG_RKMIL_STRAT: Fraction(1, 1),
+}
+
+# lookup modes in the schedule tables
+LK_PRE = 0      # t < t0            -> user history h(p, t)
+LK_EXACT = 1    # t == sol.t[i]     -> sol.u[i]
+LK_INTERP = 2   # t in (t[i-1],t[i]) -> (1-theta) u[i-1] + theta u[i]
+
+
+def _eps(x: float) -> float:
+    """Julia ``eps(x::Float64)`` (spacing of floats at |x|)."""
+    return math.ulp(abs(x))
+
+
+# ----------------------------------------------------------------------------------------------
+# S -- step schedule (trajectory independent)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Schedule:
+    t: np.ndarray            # [N+1] node times, t[0] = t0
+    dt: np.ndarray           # [N]   dt_n used by step n (after modify_dt_for_tstops!)
+    sqdt: np.ndarray         # [N]   sqrt(|dt_n|)
+    lk_mode: np.ndarray      # [N, L] LK_*
+    lk_idx: np.ndarray       # [N, L] node index i (upper node for INTERP), -1 for PRE
+    lk_theta: np.ndarray     # [N, L] theta for INTERP; lookup time for PRE
+    lk_time: np.ndarray      # [N, L] t_n - lag (as computed in float64)
+    save_t: np.ndarray       # [n_save] saved times in output order
+    save_step: np.ndarray    # [n_save] step n whose end produced the save (-1 = initial condition)
+    save_theta: np.ndarray   # [n_save] theta (nan-free): value=(1-th)*u_n + th*u_{n+1}
+    save_exact: np.ndarray   # [n_save] 1 -> take u_{n+1} verbatim (or u0 for step -1)
+    tstops_hit: list = field(default_factory=list)
+
+    @property
+    def n_steps(self) -> int:
+        return len(self.dt)
+
+
+def expand_saveat(saveat, t0: float, tf: float):
+    """Return (interior+end save times, save_start, save_end) following src/solve.jl:32-34, 411-415, 659-677.
+
+    ``saveat`` may be ``None``/empty (=> no saveat; caller decides save_everystep), a number or a sequence.
+    For a number ``s`` the reference pushes ``(t0+s):s:tf`` when ``(t0:s:tf)[end] == tf`` else
+    ``(t0+s):s:(tf-s)``.  Julia's float ranges are computed in twice precision from a rational lift of
+    (start, step); here the k-th element is ``t0 + k*s`` evaluated as ``(n0 + k*ns)/d`` when t0 and s are
+    both exactly representable multiples of 1/d for a power-of-ten d <= 1e6, else ``t0 + k*s`` in float64.
+    For the configs of BASELINE.json (s = 1.0, 0.5, 0.1 with t0 = 0) both agree with Julia.
+    """
+    if saveat is None:
+        return np.zeros(0), True, True
+    if np.isscalar(saveat):
+        s = float(saveat)
+        if s <= 0:
+            raise ValueError("saveat must be positive")
+        pts = _float_range(t0, s, tf)          # t0:s:tf
+        if pts[-1] == tf:
+            sv = pts[1:]                        # (t0+s):s:tf
+        else:
+            sv = np.array([x for x in pts[1:] if x <= tf - s])
+        return np.asarray(sv, dtype=np.float64), True, True
+    arr = np.asarray(list(saveat), dtype=np.float64)
+    if arr.size == 0:
+        return np.zeros(0), True, True
+    save_start = bool(np.any(arr == t0))
+    save_end = bool(np.any(arr == tf))
+    interior = np.sort(arr[(arr > t0) & (arr < tf)])
+    return interior, save_start, save_end
+
+
+def _float_range(a: float, s: float, b: float) -> np.ndarray:
+    """Elements of the Julia range ``a:s:b`` (see expand_saveat docstring)."""
+    for d in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
+        na, ns, nb = round(a * d), round(s * d), b * d
+        if na / d == a and ns / d == s and ns > 0:
+            n = int(math.floor((nb - na) / ns + 1e-9))
+            return np.array([(na + k * ns) / d for k in range(n + 1)], dtype=np.float64)
+    n = int(math.floor((b - a) / s + 1e-9))
+    return np.array([a + k * s for k in range(n + 1)], dtype=np.float64)
+
+
+def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_lags_declared=True,
+                   saveat_times=(), save_start=True, save_end=True, save_everystep=False,
+                   tstops=(), neutral=False, maxsteps=50_000_000) -> Schedule:
+    """Replay the reference's (trajectory-independent) time stepping in float64.
+
+    Follows the queue construction of src/solve.jl:613-713 and the loop of src/solve.jl:574-610 with
+    the non-adaptive branch of loopfooter! (src/integrators/interface.jl:70-85), handle_tstop! /
+    handle_discontinuities! / add_next_discontinuities! (src/integrators/utils.jl).
+    """
+    t0 = float(t0); tf = float(tf); dt = float(dt)
+    if not tf > t0:
+        raise ValueError("only forward integration (tdir=+1) is supported on this path")
+    lags = [float(x) for x in lags]
+    alg_order = ALG_ORDER[alg]
+    order0 = Fraction(order_discontinuity_t0)
+    if dt == 0.0 and len(tstops) == 0:
+        # src/solve.jl:121-123
+        raise ValueError("Fixed timestep methods require a choice of dt or choosing the tstops")
+
+    # ---- src/solve.jl:625-658 : tstops heap -------------------------------------------------
+    add_prop = (order0 <= alg_order) and constant_lags_declared and len(lags) > 0
+    tst: list[float] = []
+    disc: list[tuple[float, Fraction]] = []
+    if add_prop:
+        maxlag = tf - t0
+        next_order = order0 if neutral else order0 + Fraction(1, 2)
+    if not add_prop and len(tstops) == 0:
+        heapq.heappush(tst, tf)
+    else:
+        for x in tstops:
+            x = float(x)
+            if t0 < x <= tf:
+                heapq.heappush(tst, x)
+        if add_prop:
+            for lag in lags:
+                if lag < maxlag:
+                    heapq.heappush(tst, t0 + lag)
+        heapq.heappush(tst, tf)
+    # ---- src/solve.jl:701-710 : discontinuity heap ------------------------------------------
+    if add_prop:
+        for lag in lags:
+            if lag < maxlag:
+                heapq.heappush(disc, (t0 + lag, next_order))
+    # ---- saveat heap (already expanded by the caller: src/solve.jl:659-677) -------------------
+    sv = [float(x) for x in saveat_times]
+    heapq.heapify(sv)
+
+    ts = [t0]
+    dts: list[float] = []
+    save_t: list[float] = []
+    save_step: list[int] = []
+    save_theta: list[float] = []
+    save_exact: list[int] = []
+    hits: list[float] = []
+    if save_start:
+        save_t.append(t0); save_step.append(-1); save_theta.append(1.0); save_exact.append(1)
+
+    t = t0
+    n = 0
+    while tst:
+        while t < tst[0]:
+            # modify_dt_for_tstops! [EXT] (called src/solve.jl:564 and from apply_step!):
+            top = tst[0]
+            dtn = min(dt, top - t) if dt != 0.0 else top - t
+            # loopfooter! non-adaptive (src/integrators/interface.jl:70-80)
+            ttmp = t + dtn
+            tprev = t
+            if abs(ttmp - top) < 10.0 * _eps(max(t, top)):
+                t = top
+            else:
+                t = ttmp
+            dts.append(dtn)
+            ts.append(t)
+            # savevalues! (src/integrators/interface.jl:357-430)
+            while sv and sv[0] <= t:
+                curt = heapq.heappop(sv)
+                save_t.append(curt); save_step.append(n)
+                if curt != t:
+                    save_theta.append((curt - tprev) / dtn); save_exact.append(0)
+                else:
+                    save_theta.append(1.0); save_exact.append(1)
+            if save_everystep:
+                save_t.append(t); save_step.append(n); save_theta.append(1.0); save_exact.append(1)
+            n += 1
+            if n > maxsteps:
+                raise RuntimeError("schedule exceeds maxsteps")
+            if not tst:
+                break
+        # handle_tstop! (src/integrators/utils.jl:1-22)
+        if tst:
+            top = tst[0]
+            if t == top:
+                heapq.heappop(tst)
+                hits.append(t)
+            elif t > top:
+                raise RuntimeError("stepped past a tstop (dtchangeable algorithm) -- reference errors here")
+            if disc:
+                # handle_discontinuities! (src/integrators/utils.jl:42-79)
+                d = heapq.heappop(disc)
+                order = d[1]
+                while disc and disc[0][0] == t:
+                    order = min(order, heapq.heappop(disc)[1])
+                maxdt = 10.0 * _eps(t)
+                while disc and abs(disc[0][0] - t) < maxdt:
+                    order = min(order, heapq.heappop(disc)[1])
+                while tst and abs(tst[0] - t) < maxdt:
+                    heapq.heappop(tst)
+                # add_next_discontinuities! (src/integrators/utils.jl:91-118)
+                nxt = order if neutral else order + Fraction(1, 2)
+                if nxt <= alg_order + Fraction(1, 2) and constant_lags_declared:
+                    maxlag = tf - t
+                    for lag in lags:
+                        if lag < maxlag:
+                            heapq.heappush(disc, (t + lag, nxt))
+                            heapq.heappush(tst, t + lag)
+    # postamble! -> solution_endpoint_match_cur_integrator! (src/integrators/interface.jl:100-117)
+    if save_end and (len(save_t) == 0 or save_t[-1] != t):
+        save_t.append(t); save_step.append(n - 1); save_theta.append(1.0); save_exact.append(1)
+
+    N = len(dts)
+    L = len(lags)
+    tarr = np.array(ts, dtype=np.float64)
+    lk_mode = np.zeros((N, L), dtype=np.int32)
+    lk_idx = np.full((N, L), -1, dtype=np.int64)
+    lk_theta = np.zeros((N, L), dtype=np.float64)
+    lk_time = np.zeros((N, L), dtype=np.float64)
+    for k in range(N):
+        tn = ts[k]
+        for l, lag in enumerate(lags):
+            tl = tn - lag
+            lk_time[k, l] = tl
+            if tl < t0:
+                lk_mode[k, l] = LK_PRE; lk_theta[k, l] = tl
+                continue
+            # sde_interpolation on sol.t[1..k+1] (dense history: sol.t[end] == t_n)
+            i = bisect.bisect_left(ts, tl, 0, k + 1)         # searchsortedfirst
+            if ts[i] == tl:
+                lk_mode[k, l] = LK_EXACT; lk_idx[k, l] = i; lk_theta[k, l] = 1.0
+            else:
+                h_ = ts[i] - ts[i - 1]
+                lk_mode[k, l] = LK_INTERP; lk_idx[k, l] = i
+                lk_theta[k, l] = (tl - ts[i - 1]) / h_
+    dta = np.array(dts, dtype=np.float64)
+    return Schedule(t=tarr, dt=dta, sqdt=np.sqrt(np.abs(dta)), lk_mode=lk_mode, lk_idx=lk_idx,
+                    lk_theta=lk_theta, lk_time=lk_time,
+                    save_t=np.array(save_t, dtype=np.float64), save_step=np.array(save_step, dtype=np.int64),
+                    save_theta=np.array(save_theta, dtype=np.float64),
+                    save_exact=np.array(save_exact, dtype=np.int32), tstops_hit=hits)
+
+
+# ----------------------------------------------------------------------------------------------
+# model zoo: f(u, ulag, p, t), g(u, ulag, p, t), shapes u [ns, nt], ulag [nl, ns, nt]
+# p is a sequence of scalars or of [nt] arrays (per-trajectory parameters)
+# ----------------------------------------------------------------------------------------------
+MODEL_LINEAR1 = 0
+MODEL_HAYES = 1
+MODEL_MACKEY_GLASS = 2
+MODEL_LINSYS = 3
+MODEL_SIR = 4
+MODEL_SCALAR_ADD = 5
+
+
+def ipow(x, n: int):
+    """x**n by right-to-left binary exponentiation; the SAME multiplication order is used by the
+    C oracle and by the CUDA model (so all three agree bit-for-bit when FMA contraction is off)."""
+    n = int(n)
+    result = None
+    base = x
+    while n > 0:
+        if n & 1:
+            result = base if result is None else result * base
+        n >>= 1
+        if n:
+            base = base * base
+    return np.ones_like(x) if result is None else result
+
+
+@dataclass
+class Model:
+    mid: int
+    n_state: int
+    n_lag: int
+    n_noise: int
+    diagonal: bool
+    n_param: int
+    f: callable
+    g: callable          # diagonal: returns [ns, nt]; non-diagonal: returns [ns, m, nt]
+
+
+def _linear1_f(u, ul, p, t):
+    a, b, s = p
+    return a * u + b * ul[0]
+
+
+def _linear1_g(u, ul, p, t):
+    a, b, s = p
+    return s * u
+
+
+def _hayes_f(u, ul, p, t):
+    # test/test_prob_sol.jl:6-9  du = a*u + b*h(p,t-tau) + c
+    tau, a, b, c, al, be, ga = p
+    return (a * u + b * ul[0]) + c
+
+
+def _hayes_g(u, ul, p, t):
+    # test/test_prob_sol.jl:10-13 du = alpha*u + beta*h(p,t-tau) + gamma  (beta=0 gives the convergence-test g)
+    tau, a, b, c, al, be, ga = p
+    return (al * u + be * ul[0]) + ga
+
+
+def _mg_f(u, ul, p, t):
+    beta, gamma, nexp, sigma = p
+    x = ul[0]
+    xn = ipow(x, int(np.asarray(nexp).reshape(-1)[0]))
+    return (beta * x) / (1.0 + xn) - gamma * u
+
+
+def _mg_g(u, ul, p, t):
+    beta, gamma, nexp, sigma = p
+    return sigma * u
+
+
+def make_linsys(ns: int, nl: int, m: int) -> Model:
+    """du = (A u + sum_l B_l u(t-tau_l) + c) dt + G(u) dW,  G_ij = M_ij*u_i + N_ij.
+    params (row-major): A[ns*ns], B_0..B_{nl-1}[ns*ns each], c[ns], M[ns*m], N[ns*m]."""
+    npar = ns * ns * (1 + nl) + ns + 2 * ns * m
+
+    def f(u, ul, p, t):
+        out = []
+        for i in range(ns):
+            acc = p[i * ns + 0] * u[0]
+            for j in range(1, ns):
+                acc = acc + p[i * ns + j] * u[j]
+            for l in range(nl):
+                off = ns * ns * (1 + l)
+                for j in range(ns):
+                    acc = acc + p[off + i * ns + j] * ul[l][j]
+            acc = acc + p[ns * ns * (1 + nl) + i]
+            out.append(acc)
+        return np.stack(out)
+
+    def g(u, ul, p, t):
+        offM = ns * ns * (1 + nl) + ns
+        offN = offM + ns * m
+        rows = []
+        for i in range(ns):
+            rows.append(np.stack([p[offM + i * m + j] * u[i] + p[offN + i * m + j] for j in range(m)]))
+        return np.stack(rows)            # [ns, m, nt]
+
+    return Model(MODEL_LINSYS, ns, nl, m, False, npar, f, g)
+
+
+def _sir_f(u, ul, p, t):
+    # test/nondiagonal_sparse_noise.jl:5-19
+    beta, c, tau = p
+    S, I, R = u
+    N = (S + I) + R
+    infection = ((beta * c) * I) / N * S
+    Sd, Id, Rd = ul[0]
+    Nd = (Sd + Id) + Rd
+    recovery = ((beta * c) * Id) / Nd * Sd
+    return np.stack([-infection, infection - recovery, recovery])
+
+
+def _sir_g(u, ul, p, t):
+    # test/nondiagonal_sparse_noise.jl:31-43, 3x2 pattern rows [1,0],[1,1],[0,1]
+    beta, c, tau = p
+    S, I, R = u
+    N = (S + I) + R
+    infection = ((beta * c) * I) / N * S
+    Sd, Id, Rd = ul[0]
+    Nd = (Sd + Id) + Rd
+    recovery = ((beta * c) * Id) / Nd * Sd
+    si = np.sqrt(np.maximum(0.0, infection))
+    sr = np.sqrt(np.maximum(0.0, recovery))
+    z = np.zeros_like(si)
+    return np.stack([np.stack([-si, z]), np.stack([si, -sr]), np.stack([z, sr])])
+
+
+def _sadd_f(u, ul, p, t):
+    # test/events.jl:4  f = 0.3*h(p,t-p)
+    a, b = p
+    return a * ul[0]
+
+
+def _sadd_g(u, ul, p, t):
+    a, b = p
+    return b + 0.0 * u
+
+
+MODELS = {
+    MODEL_LINEAR1: Model(MODEL_LINEAR1, 1, 1, 1, True, 3, _linear1_f, _linear1_g),
+    MODEL_HAYES: Model(MODEL_HAYES, 1, 1, 1, True, 7, _hayes_f, _hayes_g),
+    MODEL_MACKEY_GLASS: Model(MODEL_MACKEY_GLASS, 1, 1, 1, True, 4, _mg_f, _mg_g),
+    MODEL_SIR: Model(MODEL_SIR, 3, 1, 2, False, 3, _sir_f, _sir_g),
+    MODEL_SCALAR_ADD: Model(MODEL_SCALAR_ADD, 1, 1, 1, True, 2, _sadd_f, _sadd_g),
+}
+
+
+def get_model(mid: int, n_state=None, n_lag=None, n_noise=None) -> Model:
+    if mid == MODEL_LINSYS:
+        return make_linsys(int(n_state), int(n_lag), int(n_noise))
+    return MODELS[mid]
+
+
+# ----------------------------------------------------------------------------------------------
+# N -- noise: Philox4x32-10 (Salmon et al. 2011, Random123) + Box-Muller in float64
+# ----------------------------------------------------------------------------------------------
+PHILOX_M0 = np.uint64(0xD2511F53)
+PHILOX_M1 = np.uint64(0xCD9E8D57)
+PHILOX_W0 = 0x9E3779B9
+PHILOX_W1 = 0xBB67AE85
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10.  Inputs are uint32-valued arrays (any broadcastable shapes)."""
+    c0 = np.asarray(c0, dtype=np.uint64) & _MASK32
+    c1 = np.asarray(c1, dtype=np.uint64) & _MASK32
+    c2 = np.asarray(c2, dtype=np.uint64) & _MASK32
+    c3 = np.asarray(c3, dtype=np.uint64) & _MASK32
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = PHILOX_M0 * c0
+        p1 = PHILOX_M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK32
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + PHILOX_W0) & 0xFFFFFFFF
+        k1 = (k1 + PHILOX_W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def philox_normal_pair(traj_id, call, seed):
+    """Two N(0,1) float64 variates for (global trajectory id, call index):
+    counter = (traj_lo, traj_hi, call_lo, call_hi), key = (seed_lo, seed_hi);
+    m1 = (w1 & 0xFFFFF)<<32 | w0 (52 bits), u1 = (m1 + 0.5) * 2^-52 in (0,1); u2 likewise from (w2,w3);
+    z0 = sqrt(-2 ln u1) cos(2 pi u2), z1 = sqrt(-2 ln u1) sin(2 pi u2)."""
+    traj_id = np.asarray(traj_id, dtype=np.uint64)
+    call = np.asarray(call, dtype=np.uint64)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    w0, w1, w2, w3 = philox4x32_10(traj_id & _MASK32, traj_id >> np.uint64(32),
+                                   call & _MASK32, call >> np.uint64(32),
+                                   seed & 0xFFFFFFFF, seed >> 32)
+    m1 = ((w1 & np.uint64(0xFFFFF)) << np.uint64(32)) | w0
+    m2 = ((w3 & np.uint64(0xFFFFF)) << np.uint64(32)) | w2
+    u1 = (m1.astype(np.float64) + 0.5) * 2.0 ** -52
+    u2 = (m2.astype(np.float64) + 0.5) * 2.0 ** -52
+    r = np.sqrt(-2.0 * np.log(u1))
+    ang = 2.0 * np.pi * u2
+    return r * np.cos(ang), r * np.sin(ang)
+
+
+def philox_normals(traj_ids, n_steps: int, n_noise: int, seed) -> np.ndarray:
+    """xi[n, c, traj]: normal number q = n*n_noise + c comes from call q>>1, half q&1."""
+    traj_ids = np.asarray(traj_ids, dtype=np.uint64)
+    nq = n_steps * n_noise
+    ncall = (nq + 1) // 2
+    calls = np.arange(ncall, dtype=np.uint64)[:, None]
+    z0, z1 = philox_normal_pair(traj_ids[None, :], calls, seed)
+    z = np.empty((ncall * 2, traj_ids.size), dtype=np.float64)
+    z[0::2] = z0
+    z[1::2] = z1
+    return z[:nq].reshape(n_steps, n_noise, traj_ids.size)
+
+
+# ----------------------------------------------------------------------------------------------
+# H + one-step algebra + V : the trajectory loop
+# ----------------------------------------------------------------------------------------------
+def _as_params(params, n_traj):
+    """-> list of np arrays each shape [] or [nt]."""
+    p = np.asarray(params, dtype=np.float64)
+    if p.ndim == 1:
+        return [np.float64(x) for x in p]
+    assert p.shape[1] == n_traj
+    return [p[i] for i in range(p.shape[0])]
+
+
+def _history_affine(h0, h1, t, nt):
+    """h(p,t)[j] = h0[j] + h1[j]*t ; returns [ns, nt]."""
+    h0 = np.asarray(h0, dtype=np.float64)
+    h1 = np.asarray(h1, dtype=np.float64)
+    v = h0 + h1 * t
+    return np.repeat(v[:, None], nt, axis=1)
+
+
+def solve_ensemble(model: Model, params, u0, h0, h1, lags, sched: Schedule, alg, dW, *,
+                   history_mode="dense", history_fn=None, return_dense=False):
+    """Integrate ``n_traj`` trajectories with the supplied increments ``dW[n, c, traj]``.
+
+    u0: [ns] or [ns, nt].  Returns (out[n_save, ns, nt], status[nt]) (+ dense [N+1, ns, nt]).
+    history_mode:
+      'dense'                  -- delayed state from the full step history (what save_everystep=true does;
+                                   the semantics BASELINE.json's north_star describes)
+      'reference_saveat_alias' -- delayed state from the SAVED points only, constant u0 past the last saved
+                                   point (src/solve.jl:465-482 aliasing)
+    """
+    dW = np.asarray(dW, dtype=np.float64)
+    N = sched.n_steps
+    nt = dW.shape[2]
+    ns, nl, m = model.n_state, model.n_lag, model.n_noise
+    assert dW.shape[0] >= N and dW.shape[1] == (ns if model.diagonal else m)
+    p = _as_params(params, nt)
+    u0a = np.asarray(u0, dtype=np.float64)
+    u = np.repeat(u0a[:, None], nt, axis=1).copy() if u0a.ndim == 1 else u0a.copy()
+    u0full = u.copy()
+    t0 = float(sched.t[0])
+    if history_fn is None:
+        def history_fn(pp, t):
+            return _history_affine(h0, h1, t, nt)
+
+    hist_t = [t0]
+    hist_u = [u.copy()]
+    out = np.empty((len(sched.save_t), ns, nt), dtype=np.float64)
+    # saved-solution arrays (used as history in alias mode)
+    sol_t: list[float] = []
+    sol_u: list[np.ndarray] = []
+    ks = 0
+    while ks < len(sched.save_t) and sched.save_step[ks] == -1:
+        out[ks] = u; sol_t.append(t0); sol_u.append(u.copy()); ks += 1
+    if history_mode == "reference_saveat_alias" and not sol_t:
+        sol_t.append(t0); sol_u.append(u.copy())
+
+    def lookup(tl):
+        if history_mode == "dense":
+            ht, hu = hist_t, hist_u
+        else:
+            ht, hu = sol_t, sol_u
+        if tl < ht[0]:
+            return history_fn(p, tl)                                  # prehistory
+        if tl <= ht[-1]:
+            i = bisect.bisect_left(ht, tl)                            # searchsortedfirst
+            if ht[i] == tl:
+                return hu[i]
+            th = (tl - ht[i - 1]) / (ht[i] - ht[i - 1])
+            return (1.0 - th) * hu[i - 1] + th * hu[i]                # [EXT] linear sde_interpolant
+        return u0full                                                 # never-advanced stub integrator: u0
+
+    for n in range(N):
+        t = float(sched.t[n]); dt = float(sched.dt[n]); sq = float(sched.sqdt[n])
+        ul = [lookup(t - float(lag)) for lag in lags]
+        dw = dW[n]
+        fu = model.f(u, ul, p, t)
+        K = u + dt * fu
+        if alg in (ALG_EM_SPLIT, ALG_EM_NOSPLIT):
+            uc = K if alg == ALG_EM_SPLIT else u
+            gv = model.g(uc, ul, p, t)
+            if model.diagonal:
+                unew = K + gv * dw
+            else:
+                noise = gv[:, 0, :] * dw[0]
+                for j in range(1, m):
+                    noise = noise + gv[:, j, :] * dw[j]
+                unew = K + noise
+        else:
+            if not model.diagonal:
+                raise ValueError("RKMil requires diagonal noise")
+            Lg = model.g(u, ul, p, t)
+            if alg == ALG_RKMIL_ITO:
+                ut = K + Lg * sq
+                ggp = (model.g(ut, ul, p, t) - Lg) / sq
+                mil = ggp * (dw * dw - abs(dt)) / 2.0
+            else:
+                ut = u + Lg * sq
+                ggp = (model.g(ut, ul, p, t) - Lg) / sq
+                mil = ggp * (dw * dw) / 2.0
+            unew = (K + Lg * dw) + mil
+        # savevalues!
+        while ks < len(sched.save_t) and sched.save_step[ks] == n:
+            if sched.save_exact[ks]:
+                val = unew
+            else:
+                th = float(sched.save_theta[ks])
+                val = (1.0 - th) * u + th * unew
+            out[ks] = val
+            sol_t.append(float(sched.save_t[ks])); sol_u.append(np.array(val, copy=True))
+            ks += 1
+        u = unew
+        hist_t.append(float(sched.t[n + 1])); hist_u.append(u)
+    status = (~np.all(np.isfinite(out), axis=(0, 1)) | ~np.all(np.isfinite(u), axis=0)).astype(np.uint8)
+    if return_dense:
+        return out, status, np.stack(hist_u)
+    return out, status
+
+
+def moments(out: np.ndarray) -> np.ndarray:
+    """(count, mean, M2) per (save, state) over trajectories -- [n_save, ns, 3]
+    ([EXT] SciMLBase.EnsembleAnalysis.timeseries_steps_meanvar; var = M2/(count-1))."""
+    cnt = np.full(out.shape[:2], out.shape[2], dtype=np.float64)
+    mean = out.mean(axis=2)
+    m2 = ((out - mean[:, :, None]) ** 2).sum(axis=2)
+    return np.stack([cnt, mean, m2], axis=2)
+
+
+def merge_moments(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Chan et al. pairwise merge of (count, mean, M2) triples."""
+    na, ma, sa = a[..., 0], a[..., 1], a[..., 2]
+    nb, mb, sb = b[..., 0], b[..., 1], b[..., 2]
+    n = na + nb
+    with np.errstate(invalid="ignore", divide="ignore"):
+        d = mb - ma
+        mean = np.where(n > 0, ma + d * (nb / np.where(n > 0, n, 1)), 0.0)
+        m2 = sa + sb + d * d * (na * nb / np.where(n > 0, n, 1))
+    return np.stack([n, mean, m2], axis=-1)
+
+
+def exact_mean_linear1(sched: Schedule, a, b, u0, h0, h1, lag):
+    """K3: exact ensemble-mean recurrence of the C1/C5 model under EM (split or not):
+    E[u_{n+1}] = (1 + a dt_n) E[u_n] + b dt_n E[u~(t_n - tau)]   (SURVEY.md section 8(c) K3)."""
+    N = sched.n_steps
+    m = np.empty(N + 1)
+    m[0] = u0
+    for n in range(N):
+        mode = sched.lk_mode[n, 0]
+        if mode == LK_PRE:
+            ml = h0 + h1 * sched.lk_theta[n, 0]
+        elif mode == LK_EXACT:
+            ml = m[sched.lk_idx[n, 0]]
+        else:
+            i = sched.lk_idx[n, 0]; th = sched.lk_theta[n, 0]
+            ml = (1.0 - th) * m[i - 1] + th * m[i]
+        m[n + 1] = m[n] + sched.dt[n] * (a * m[n] + b * ml)
+    return m

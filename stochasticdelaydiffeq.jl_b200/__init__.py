@@ -1,0 +1,21 @@
+"""B200-native ensemble integrator for constant-lag stochastic delay differential equations.
+
+Drop-in for ONE path of SciML/StochasticDelayDiffEq.jl: ``solve(EnsembleProblem(SDDEProblem(...)), EM()/RKMil(),
+EnsembleB200(); dt, saveat, trajectories)`` -- host code here only marshals a descriptor across the C ABI of
+``libsdde_b200.so`` (include/sdde_b200.h); all arithmetic runs in hand-written sm_100a CUDA kernels
+(csrc/sdde_kernels.cuh).  There is no CPU fallback.
+"""
+from . import _capi
+from ._capi import SddeError, get_context, lib
+from .ensemble import (EnsembleB200, EnsembleSolution, Schedule, expand_saveat, merge_moments, schedule, shard_range,
+                       solve, timepoint_meanvar, timeseries_steps_mean, timeseries_steps_meanvar)
+from .problem import (EM, AffineHistory, ConstantHistory, EnsembleProblem, Model, RKMil, SDDEProblem, UserModel, hayes,
+                      linear1, linsys, linsys_params, mackey_glass, scalar_add, sir)
+
+__all__ = [
+    "EM", "RKMil", "SDDEProblem", "EnsembleProblem", "EnsembleB200", "EnsembleSolution", "solve", "schedule", "Schedule",
+    "expand_saveat", "merge_moments", "shard_range", "timeseries_steps_meanvar", "timeseries_steps_mean",
+    "timepoint_meanvar", "AffineHistory", "ConstantHistory", "Model", "UserModel", "linear1", "hayes", "mackey_glass",
+    "sir", "scalar_add", "linsys", "linsys_params", "SddeError", "get_context", "lib",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,693 @@
+// sdde_api.cu -- C ABI of libsdde_b200.so (see include/sdde_b200.h): descriptor validation, host schedule,
+// wave loop over trajectories, launches of the sm_100a step kernels, moments, D2H of the saved paths.
+//
+// Replaces the ensemble dispatch [EXT] SciMLBase.__solve(::AbstractEnsembleProblem, alg, ensemblealg; trajectories)
+// -> per trajectory DiffEqBase.__solve (/root/reference/src/solve.jl:1-9) for the fixed-step constant-lag case.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sdde_b200.h"
+#include "schedule.hpp"
+#include "sdde_dispatch.cuh"
+#include "user_model.hpp"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[2048];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_CHECK(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(SDDE_ERR_CUDA - (int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                             \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct sdde_ctx {
+    int device = 0;
+    cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
+    cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
+    DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
+    std::mutex mu;
+    int64_t opt_wave_traj = 0;     // 0 = auto
+    int64_t opt_batch = 0;         // 0 = compiled-in depth
+    int64_t opt_chunk_steps = 128;
+    sdde::UserModels user;
+    int sm_count = 148;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small kernels owned by the API layer
+// ------------------------------------------------------------------------------------------------
+namespace sdde {
+
+// (count, mean, M2) of one row of `out` per block: deterministic two-pass reduction.
+// Device side of [EXT] SciMLBase.EnsembleAnalysis.timeseries_steps_meanvar.
+__global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__ out, long long pitch, long long off,
+                                                      long long n, double *__restrict__ mom) {
+    __shared__ double sh[8];
+    __shared__ double s_mean;
+    const double *row = out + (long long)blockIdx.x * pitch + off;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) s += row[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sh[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        s_mean = t / (double)n;
+    }
+    __syncthreads();
+    const double mean = s_mean;
+    double q = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) { const double d = row[i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    __syncthreads();
+    if (lane == 0) sh[warp] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        mom[blockIdx.x * 3 + 0] = (double)n;
+        mom[blockIdx.x * 3 + 1] = mean;
+        mom[blockIdx.x * 3 + 2] = t;
+    }
+}
+
+// test hook: the normals the step kernels would draw, laid out [n][c][traj]
+__global__ void philox_dump_kernel(double *out, long long n_traj, long long traj_off, long long n_steps, int nc, u32 k0,
+                                   u32 k1) {
+    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= n_traj) return;
+    const long long nq = n_steps * nc;
+    for (long long call = 0; call * 2 < nq; ++call) {
+        double z0, z1;
+        philox_normal_pair((u64)(traj_off + tr), (u64)call, k0, k1, z0, z1);
+        out[(2 * call) * n_traj + tr] = z0;
+        if (2 * call + 1 < nq) out[(2 * call + 1) * n_traj + tr] = z1;
+    }
+}
+
+// FP64 FMA throughput micro-benchmark: 8 independent chains per thread
+__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+}  // namespace sdde
+
+// ------------------------------------------------------------------------------------------------
+// descriptor -> schedule input / kernel selection
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int check_desc(const sdde_desc *d) {
+    if (!d) return fail(SDDE_ERR_BAD_DESC, "descriptor is NULL");
+    if (d->struct_size != (int32_t)sizeof(sdde_desc))
+        return fail(SDDE_ERR_BAD_DESC, "sdde_desc.struct_size = %d, library expects %d (ABI mismatch)", d->struct_size,
+                    (int)sizeof(sdde_desc));
+    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_RKMIL_STRAT)
+        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil fixed-step only)", d->alg);
+    if (d->n_lag < 1 || d->n_lag > SDDE_MAX_LAG) return fail(SDDE_ERR_BAD_DESC, "n_lag = %d out of range", d->n_lag);
+    if (d->n_state < 1 || d->n_state > SDDE_MAX_STATE) return fail(SDDE_ERR_BAD_DESC, "n_state = %d out of range", d->n_state);
+    if (d->n_noise < 1 || d->n_noise > SDDE_MAX_NOISE) return fail(SDDE_ERR_BAD_DESC, "n_noise = %d out of range", d->n_noise);
+    if (d->n_param < 0 || d->n_param > SDDE_MAX_PARAM) return fail(SDDE_ERR_BAD_DESC, "n_param = %d out of range", d->n_param);
+    if (d->n_param > 0 && !d->params) return fail(SDDE_ERR_BAD_DESC, "params is NULL");
+    if (!d->u0) return fail(SDDE_ERR_BAD_DESC, "u0 is NULL");
+    if (d->n_saveat < 0 || (d->n_saveat > 0 && !d->saveat)) return fail(SDDE_ERR_BAD_DESC, "saveat array missing");
+    if (d->n_tstops < 0 || (d->n_tstops > 0 && !d->tstops)) return fail(SDDE_ERR_BAD_DESC, "tstops array missing");
+    if (d->n_traj < 0) return fail(SDDE_ERR_BAD_DESC, "n_traj < 0");
+    if (d->history_mode != SDDE_HISTORY_DENSE)
+        return fail(SDDE_ERR_UNSUPPORTED, "only the dense history mode exists on the GPU path (SURVEY.md H1)");
+    if (d->noise_mode < SDDE_NOISE_PHILOX || d->noise_mode > SDDE_NOISE_SUPPLIED_GRID)
+        return fail(SDDE_ERR_BAD_DESC, "noise_mode = %d", d->noise_mode);
+    if (d->noise_mode != SDDE_NOISE_PHILOX && !d->noise && d->n_traj > 0)
+        return fail(SDDE_ERR_BAD_DESC, "noise_mode is SUPPLIED but noise is NULL");
+    if (d->param_stride != 0 && d->param_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "param_stride < n_traj");
+    if (d->u0_stride != 0 && d->u0_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "u0_stride < n_traj");
+    return SDDE_OK;
+}
+
+int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
+    sdde::ScheduleInput in;
+    in.t0 = d->t0; in.tf = d->tf; in.dt = d->dt;
+    in.lags.assign(d->lags, d->lags + d->n_lag);
+    in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT) ? 2 : 1;
+    in.order_discontinuity_t0 = d->order_discontinuity_t0;
+    in.constant_lags_declared = d->constant_lags_declared != 0;
+    if (d->n_saveat > 0) in.saveat.assign(d->saveat, d->saveat + d->n_saveat);
+    if (d->n_tstops > 0) in.tstops.assign(d->tstops, d->tstops + d->n_tstops);
+    in.save_start = d->save_start != 0;
+    in.save_end = d->save_end != 0;
+    in.save_everystep = d->save_everystep != 0;
+    std::string err = sdde::build_schedule(in, S);
+    if (!err.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", err.c_str());
+    // src/solve.jl:581-585: dt > minimum(constant_lags) is an error for every algorithm but EM
+    if (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT) {
+        double minlag = d->lags[0];
+        for (int l = 1; l < d->n_lag; ++l) minlag = std::min(minlag, d->lags[l]);
+        for (double x : S.dt)
+            if (x > minlag)
+                return fail(SDDE_ERR_UNSUPPORTED,
+                            "dt > minimum(constant_lags). This is not allowed by the integrator. Please dt `dtmax` "
+                            "less than the minimum lag or use `EM`.");
+    }
+    return SDDE_OK;
+}
+
+int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
+    const bool ptraj = d->param_stride != 0;
+    const int alg = d->alg, nz = d->noise_mode;
+    switch (d->model_id) {
+        case SDDE_MODEL_LINEAR1: k = sdde::select_linear1(alg, nz, ptraj); break;
+        case SDDE_MODEL_HAYES: k = sdde::select_hayes(alg, nz, ptraj); break;
+        case SDDE_MODEL_MACKEY_GLASS: k = sdde::select_mackey_glass(alg, nz, ptraj); break;
+        case SDDE_MODEL_SCALAR_ADD: k = sdde::select_scalar_add(alg, nz, ptraj); break;
+        case SDDE_MODEL_SIR: k = sdde::select_sir(alg, nz, ptraj); break;
+        case SDDE_MODEL_LINSYS: k = sdde::select_linsys(d->n_state, d->n_lag, d->n_noise, alg, nz, ptraj); break;
+        default:
+            if (d->model_id >= SDDE_MODEL_USER_BASE && ctx) {
+                std::string err;
+                if (!ctx->user.select(d->model_id, alg, nz, ptraj, k, err))
+                    return fail(SDDE_ERR_UNSUPPORTED, "%s", err.c_str());
+                break;
+            }
+            return fail(SDDE_ERR_UNSUPPORTED, "unknown model id %d", d->model_id);
+    }
+    if (!k.fn) {
+        if ((alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMIL_STRAT))
+            return fail(SDDE_ERR_UNSUPPORTED, "RKMil requires diagonal noise (model %d has a non-diagonal noise matrix)",
+                        d->model_id);
+        return fail(SDDE_ERR_UNSUPPORTED, "no kernel for model %d shape (%d states, %d lags, %d noise) alg %d", d->model_id,
+                    d->n_state, d->n_lag, d->n_noise, alg);
+    }
+    if (k.n_state != d->n_state || k.n_lag != d->n_lag || k.n_noise != d->n_noise)
+        return fail(SDDE_ERR_BAD_DESC, "model %d expects (n_state,n_lag,n_noise) = (%d,%d,%d), descriptor has (%d,%d,%d)",
+                    d->model_id, k.n_state, k.n_lag, k.n_noise, d->n_state, d->n_lag, d->n_noise);
+    if (k.n_param != d->n_param)
+        return fail(SDDE_ERR_BAD_DESC, "model %d expects %d parameters, descriptor has %d", d->model_id, k.n_param, d->n_param);
+    return SDDE_OK;
+}
+
+void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, std::vector<unsigned char> &steps,
+                 std::vector<sdde::SaveRec> &saves) {
+    const int64_t N = S.n_steps();
+    const int L = S.n_lag;
+    const int R = S.ring_slots;
+    steps.assign((size_t)N * k.rec_size, 0);
+    std::vector<int> nsave((size_t)N, 0);
+    saves.resize(S.save_t.size());
+    for (size_t i = 0; i < S.save_t.size(); ++i) {
+        saves[i].step = (int)S.save_step[i];
+        saves[i].exact = S.save_exact[i];
+        saves[i].theta = S.save_theta[i];
+        if (S.save_step[i] >= 0) nsave[(size_t)S.save_step[i]]++;
+    }
+    for (int64_t n = 0; n < N; ++n) {
+        unsigned char *rec = steps.data() + (size_t)n * k.rec_size;
+        double hdr[3] = {S.t[(size_t)n], S.dt[(size_t)n], S.sqdt[(size_t)n]};
+        memcpy(rec, hdr, 24);
+        int ns[2] = {nsave[(size_t)n], 0};
+        memcpy(rec + 24, ns, 8);
+        for (int l = 0; l < L; ++l) {
+            const size_t e = (size_t)n * L + l;
+            const int mode = S.lk_mode[e];
+            int slot = 0;
+            if (mode == sdde::LK_EXACT) slot = (int)(S.lk_idx[e] % R);
+            else if (mode == sdde::LK_INTERP) slot = (int)((S.lk_idx[e] - 1) % R);
+            unsigned char *lk = rec + 32 + 16 * l;
+            memcpy(lk, &S.lk_theta[e], 8);
+            memcpy(lk + 8, &slot, 4);
+            memcpy(lk + 12, &mode, 4);
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sdde_b200_version(void) { return SDDE_B200_VERSION; }
+
+const char *sdde_b200_last_error(void) { return g_last_error.c_str(); }
+
+int sdde_b200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SDDE_ERR_CUDA - (int)e, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+sdde_ctx *sdde_b200_create(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        fail(SDDE_ERR_CUDA - (int)e, "no CUDA device available (%s); libsdde_b200 has no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { fail(SDDE_ERR_BAD_DESC, "device %d out of range (0..%d)", device, n - 1); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(SDDE_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        fail(SDDE_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    sdde_ctx *c = new sdde_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&c->ev_k0) == cudaSuccess && cudaEventCreate(&c->ev_k1) == cudaSuccess &&
+              cudaEventCreate(&c->ev_c0) == cudaSuccess && cudaEventCreate(&c->ev_c1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaEventCreateWithFlags(&c->ev_kdone[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { fail(SDDE_ERR_CUDA, "stream/event creation failed"); sdde_b200_destroy(c); return nullptr; }
+    return c;
+}
+
+void sdde_b200_destroy(sdde_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
+    c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
+    c->user.clear();
+    if (c->compute) cudaStreamDestroy(c->compute);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
+    cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_c0, c->ev_c1, c->ev_in, c->ev_kdone[0], c->ev_kdone[1],
+                         c->ev_copied[0], c->ev_copied[1]};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
+    if (!c || !key) return fail(SDDE_ERR_BAD_DESC, "NULL context or key");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!strcmp(key, "wave_traj")) c->opt_wave_traj = value;
+    else if (!strcmp(key, "batch")) c->opt_batch = value;
+    else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
+    else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
+    return SDDE_OK;
+}
+
+int sdde_b200_schedule(const sdde_desc *d, sdde_schedule *o) {
+    if (!o) return fail(SDDE_ERR_BAD_DESC, "output schedule is NULL");
+    memset(o, 0, sizeof(*o));
+    int rc = check_desc(d);
+    if (rc) return rc;
+    sdde::Schedule S;
+    rc = make_schedule(d, S);
+    if (rc) return rc;
+    auto dupd = [](const std::vector<double> &v) { double *p = (double *)malloc(sizeof(double) * std::max<size_t>(1, v.size())); if (p && !v.empty()) memcpy(p, v.data(), sizeof(double) * v.size()); return p; };
+    auto dupl = [](const std::vector<int64_t> &v) { int64_t *p = (int64_t *)malloc(sizeof(int64_t) * std::max<size_t>(1, v.size())); if (p && !v.empty()) memcpy(p, v.data(), sizeof(int64_t) * v.size()); return p; };
+    auto dupi = [](const std::vector<int32_t> &v) { int32_t *p = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(1, v.size())); if (p && !v.empty()) memcpy(p, v.data(), sizeof(int32_t) * v.size()); return p; };
+    o->n_steps = S.n_steps();
+    o->n_save = (int64_t)S.save_t.size();
+    o->n_lag = S.n_lag;
+    o->ring_slots = S.ring_slots;
+    o->min_gap = S.min_gap;
+    o->n_tstops_hit = (int32_t)S.tstops_hit.size();
+    o->t = dupd(S.t); o->dt = dupd(S.dt); o->sqdt = dupd(S.sqdt);
+    o->lk_mode = dupi(S.lk_mode); o->lk_idx = dupl(S.lk_idx); o->lk_theta = dupd(S.lk_theta);
+    o->save_t = dupd(S.save_t); o->save_step = dupl(S.save_step); o->save_theta = dupd(S.save_theta);
+    o->save_exact = dupi(S.save_exact); o->tstops_hit = dupd(S.tstops_hit);
+    if (!o->t || !o->dt || !o->sqdt || !o->lk_mode || !o->lk_idx || !o->lk_theta || !o->save_t || !o->save_step ||
+        !o->save_theta || !o->save_exact || !o->tstops_hit) {
+        sdde_b200_schedule_free(o);
+        return fail(SDDE_ERR_NOMEM, "out of host memory");
+    }
+    return SDDE_OK;
+}
+
+void sdde_b200_schedule_free(sdde_schedule *s) {
+    if (!s) return;
+    free(s->t); free(s->dt); free(s->sqdt); free(s->lk_mode); free(s->lk_idx); free(s->lk_theta);
+    free(s->save_t); free(s->save_step); free(s->save_theta); free(s->save_exact); free(s->tstops_hit);
+    memset(s, 0, sizeof(*s));
+}
+
+int sdde_b200_merge_moments(double *a, const double *b, int64_t n) {
+    if (!a || !b || n < 0) return fail(SDDE_ERR_BAD_DESC, "bad arguments");
+    for (int64_t i = 0; i < n; ++i) {
+        const double na = a[3 * i], ma = a[3 * i + 1], sa = a[3 * i + 2];
+        const double nb = b[3 * i], mb = b[3 * i + 1], sb = b[3 * i + 2];
+        const double nn = na + nb;
+        if (nn <= 0) { a[3 * i] = 0; a[3 * i + 1] = 0; a[3 * i + 2] = 0; continue; }
+        const double dlt = mb - ma;
+        a[3 * i] = nn;
+        a[3 * i + 1] = ma + dlt * (nb / nn);
+        a[3 * i + 2] = sa + sb + dlt * dlt * (na * nb / nn);
+    }
+    return SDDE_OK;
+}
+
+int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm) {
+    const auto wall0 = std::chrono::steady_clock::now();
+    if (tm) memset(tm, 0, sizeof(*tm));
+    if (!c) return fail(SDDE_ERR_CUDA, "NULL context (no CUDA device? libsdde_b200 has no CPU fallback)");
+    int rc = check_desc(d);
+    if (rc) return rc;
+    if (d->want_paths && !out) return fail(SDDE_ERR_BAD_DESC, "want_paths set but out is NULL");
+    if (d->want_moments && !moments) return fail(SDDE_ERR_BAD_DESC, "want_moments set but moments is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_CHECK(cudaSetDevice(c->device));
+
+    sdde::KernelInfo K;
+    rc = select_kernel(c, d, K);
+    if (rc) return rc;
+    sdde::Schedule S;
+    rc = make_schedule(d, S);
+    if (rc) return rc;
+
+    const int64_t N = S.n_steps();
+    const int64_t n_save = (int64_t)S.save_t.size();
+    const int NS = K.n_state, NC = K.n_chan;
+    const int64_t rows = n_save * NS;
+    const int64_t NT = d->n_traj;
+    if (N >= (int64_t)1 << 30) return fail(SDDE_ERR_UNSUPPORTED, "more than 2^30 steps");
+    if (tm) {
+        tm->n_steps = N; tm->n_save = n_save; tm->ring_slots = S.ring_slots; tm->block_threads = SDDE_BLOCK;
+        tm->traj_per_thread = K.tpt;
+        snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_solve_kernel<%s,alg%d,noise%d,ptraj%d,tpt%d,B%d>", K.name,
+                 d->alg, d->noise_mode, d->param_stride != 0, K.tpt, K.batch);
+        cudaFuncAttributes fa;
+        if (!K.is_user && cudaFuncGetAttributes(&fa, K.fn) == cudaSuccess) tm->regs_per_thread = fa.numRegs;
+        else cudaGetLastError();
+    }
+    if (moments) for (int64_t i = 0; i < rows * 3; ++i) moments[i] = 0.0;
+    if (NT == 0) {
+        if (tm) tm->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        return SDDE_OK;
+    }
+
+    // ---- schedule tables -> device ----
+    std::vector<unsigned char> h_steps;
+    std::vector<sdde::SaveRec> h_saves;
+    pack_tables(S, K, h_steps, h_saves);
+    CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
+    CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
+    int64_t h2d = 0, d2h = 0;
+    if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
+    if (!h_saves.empty()) CU_CHECK(cudaMemcpyAsync(c->saves.p, h_saves.data(), h_saves.size() * sizeof(sdde::SaveRec), cudaMemcpyHostToDevice, c->compute));
+    h2d += (int64_t)h_steps.size() + (int64_t)(h_saves.size() * sizeof(sdde::SaveRec));
+
+    // ---- wave geometry ----
+    const int64_t per_block = (int64_t)SDDE_BLOCK * K.tpt;
+    size_t free_b = 0, total_b = 0;
+    CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->ring.cap + c->out[0].cap + c->out[1].cap + c->noise.cap;   // our own cached workspaces are reusable
+    const bool out_dev = d->want_paths && d->out_mem == SDDE_MEM_DEVICE;
+    const bool need_stage = (d->want_paths && !out_dev) || (!d->want_paths && d->want_moments);
+    const bool noise_host = d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem == SDDE_MEM_HOST;
+    const int64_t noise_rows = (d->noise_mode == SDDE_NOISE_PHILOX) ? 0 : (N + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * NC;
+    const double bytes_per_traj = 8.0 * ((double)S.ring_slots * NS + (need_stage ? 2.0 * rows : 0.0) + (noise_host ? (double)noise_rows : 0.0) + NS + K.n_param) + 1.0;
+    int64_t wave = c->opt_wave_traj > 0 ? c->opt_wave_traj : ((int64_t)1 << 20);
+    if (c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > ((int64_t)1 << 18)) wave = (int64_t)1 << 18;  // pipeline D2H
+    const int64_t mem_cap = (int64_t)((double)free_b * 0.80 / bytes_per_traj);
+    wave = std::min(wave, std::max<int64_t>(per_block, mem_cap));
+    wave = std::max<int64_t>(per_block, (wave / per_block) * per_block);
+    wave = std::min(wave, ((NT + per_block - 1) / per_block) * per_block);
+    const int64_t pitch = wave;   // multiple of per_block => every thread of the grid owns in-bounds ring columns
+    const int n_waves = (int)((NT + wave - 1) / wave);
+
+    CU_CHECK(c->ring.reserve((size_t)S.ring_slots * NS * pitch * 8));
+    if (need_stage) {
+        CU_CHECK(c->out[0].reserve((size_t)std::max<int64_t>(1, rows) * pitch * 8));
+        if (n_waves > 1 && d->want_paths) CU_CHECK(c->out[1].reserve((size_t)std::max<int64_t>(1, rows) * pitch * 8));
+    }
+    if (noise_host) CU_CHECK(c->noise.reserve((size_t)std::max<int64_t>(1, noise_rows) * pitch * 8));
+    if (d->u0_stride != 0) CU_CHECK(c->u0.reserve((size_t)NS * pitch * 8));
+    if (d->param_stride != 0) CU_CHECK(c->ptraj.reserve((size_t)std::max(1, K.n_param) * pitch * 8));
+    if (status) CU_CHECK(c->status.reserve((size_t)pitch));
+    if (d->want_moments) CU_CHECK(c->mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves));
+    if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
+
+    const int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
+    const size_t smem = (size_t)chunk * K.rec_size;
+    int batch = K.batch;
+    if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
+    batch = std::max(1, std::min(batch, S.min_gap + 1));   // prefetched nodes must be older than the batch
+
+    sdde::KArgs A;
+    memset(&A, 0, sizeof(A));
+    A.steps = (const unsigned char *)c->steps.p;
+    A.saves = (const sdde::SaveRec *)c->saves.p;
+    A.ring = (double *)c->ring.p;
+    A.ring_pitch = pitch;
+    A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
+    A.noise_kind = d->noise_mode;
+    A.seed_lo = (sdde::u32)(d->seed & 0xffffffffu); A.seed_hi = (sdde::u32)(d->seed >> 32);
+    for (int j = 0; j < NS; ++j) { A.hist_c0[j] = d->hist_c0[j]; A.hist_c1[j] = d->hist_c1[j]; }
+    if (d->u0_stride == 0) for (int j = 0; j < NS; ++j) A.u0c[j] = d->u0[j];
+    if (d->param_stride == 0) for (int i = 0; i < K.n_param; ++i) A.p[i] = d->params[i];
+
+    std::vector<double> h_mom;
+    if (d->want_moments) h_mom.resize((size_t)rows * 3 * n_waves);
+    int launches = 0;
+    float kernel_ms = 0.f;
+    CU_CHECK(cudaEventRecord(c->ev_c0, c->copy_out));
+    bool first_kernel = true;
+
+    for (int w = 0; w < n_waves; ++w) {
+        const int64_t off = (int64_t)w * wave;
+        const int64_t nt = std::min(wave, NT - off);
+        const int buf = w & 1;
+        // inputs of this wave
+        if (d->u0_stride != 0 || d->param_stride != 0 || noise_host) {
+            if (w > 0) CU_CHECK(cudaStreamSynchronize(c->compute));   // single input buffer: previous wave must be done
+            if (d->u0_stride != 0) {
+                CU_CHECK(cudaMemcpy2DAsync(c->u0.p, pitch * 8, d->u0 + off, d->u0_stride * 8, nt * 8, NS, cudaMemcpyHostToDevice, c->copy_in));
+                h2d += nt * 8 * NS;
+            }
+            if (d->param_stride != 0 && K.n_param > 0) {
+                CU_CHECK(cudaMemcpy2DAsync(c->ptraj.p, pitch * 8, d->params + off, d->param_stride * 8, nt * 8, K.n_param, cudaMemcpyHostToDevice, c->copy_in));
+                h2d += nt * 8 * K.n_param;
+            }
+            if (noise_host) {
+                CU_CHECK(cudaMemcpy2DAsync(c->noise.p, pitch * 8, d->noise + off, NT * 8, nt * 8, noise_rows, cudaMemcpyHostToDevice, c->copy_in));
+                h2d += nt * 8 * noise_rows;
+            }
+            CU_CHECK(cudaEventRecord(c->ev_in, c->copy_in));
+            CU_CHECK(cudaStreamWaitEvent(c->compute, c->ev_in, 0));
+        }
+        A.u0 = d->u0_stride != 0 ? (const double *)c->u0.p : nullptr; A.u0_pitch = pitch;
+        A.ptraj = d->param_stride != 0 ? (const double *)c->ptraj.p : nullptr; A.p_pitch = pitch;
+        if (d->noise_mode != SDDE_NOISE_PHILOX) {
+            if (noise_host) { A.noise = (const double *)c->noise.p; A.noise_pitch = pitch; A.noise_off = 0; }
+            else { A.noise = d->noise; A.noise_pitch = NT; A.noise_off = off; }
+        }
+        A.status = status ? (unsigned char *)c->status.p : nullptr;
+        A.n_traj = nt;
+        A.traj_gid0 = d->traj_offset + off;
+        if (out_dev) {
+            A.out = out; A.out_pitch = NT; A.out_off = off;
+            A.out_vec_ok = ((NT % 2) == 0 && (off % 2) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+        } else if (need_stage) {
+            const int b = (d->want_paths && n_waves > 1) ? buf : 0;
+            if (d->want_paths && w >= 2) CU_CHECK(cudaStreamWaitEvent(c->compute, c->ev_copied[b], 0));  // staging buffer free again
+            A.out = (double *)c->out[b].p; A.out_pitch = pitch; A.out_off = 0; A.out_vec_ok = 1;
+        } else {
+            A.out = nullptr;
+        }
+        const unsigned grid = (unsigned)((nt + per_block - 1) / per_block);
+        if (first_kernel) { CU_CHECK(cudaEventRecord(c->ev_k0, c->compute)); first_kernel = false; }
+        if (K.is_user) {
+            std::string err;
+            if (!c->user.launch(K, grid, SDDE_BLOCK, smem, c->compute, &A, sizeof(A), err)) return fail(SDDE_ERR_CUDA, "%s", err.c_str());
+        } else {
+            void *args[] = {(void *)&A};
+            CU_CHECK(cudaLaunchKernel(K.fn, dim3(grid), dim3(SDDE_BLOCK), args, smem, c->compute));
+        }
+        ++launches;
+        if (d->want_moments && rows > 0) {
+            double *dm = (double *)c->mom.p + (size_t)w * rows * 3;
+            sdde::moments_kernel<<<(unsigned)rows, 256, 0, c->compute>>>(A.out, A.out_pitch, A.out_off, nt, dm);
+            CU_CHECK(cudaGetLastError());
+            ++launches;
+        }
+        CU_CHECK(cudaEventRecord(c->ev_kdone[buf], c->compute));
+        // outputs of this wave
+        if (d->want_paths && !out_dev && rows > 0) {
+            CU_CHECK(cudaStreamWaitEvent(c->copy_out, c->ev_kdone[buf], 0));
+            CU_CHECK(cudaMemcpy2DAsync(out + off, NT * 8, A.out, pitch * 8, nt * 8, rows, cudaMemcpyDeviceToHost, c->copy_out));
+            CU_CHECK(cudaEventRecord(c->ev_copied[buf], c->copy_out));
+            d2h += nt * 8 * rows;
+        }
+        if (status) {
+            CU_CHECK(cudaMemcpyAsync(status + off, c->status.p, (size_t)nt, cudaMemcpyDeviceToHost, c->compute));
+            d2h += nt;
+        }
+    }
+    CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
+    if (d->want_moments && rows > 0) {
+        CU_CHECK(cudaMemcpyAsync(h_mom.data(), c->mom.p, h_mom.size() * 8, cudaMemcpyDeviceToHost, c->compute));
+        d2h += (int64_t)h_mom.size() * 8;
+    }
+    CU_CHECK(cudaEventRecord(c->ev_c1, c->copy_out));
+    CU_CHECK(cudaStreamSynchronize(c->compute));
+    CU_CHECK(cudaStreamSynchronize(c->copy_out));
+    CU_CHECK(cudaStreamSynchronize(c->copy_in));
+    CU_CHECK(cudaGetLastError());
+    if (d->want_moments && rows > 0) {
+        memcpy(moments, h_mom.data(), (size_t)rows * 3 * 8);
+        for (int w = 1; w < n_waves; ++w) sdde_b200_merge_moments(moments, h_mom.data() + (size_t)w * rows * 3, rows);
+    }
+    if (tm) {
+        float ms = 0.f;
+        if (!first_kernel && cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1) == cudaSuccess) kernel_ms = ms;
+        tm->kernel_ms = kernel_ms;
+        if (cudaEventElapsedTime(&ms, c->ev_c0, c->ev_c1) == cudaSuccess) tm->d2h_ms = ms;
+        tm->h2d_bytes = h2d; tm->d2h_bytes = d2h; tm->launches = launches;
+        tm->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    }
+    return SDDE_OK;
+}
+
+int sdde_b200_compile_model(sdde_ctx *c, const char *source, int32_t *model_id) {
+    if (!c || !source || !model_id) return fail(SDDE_ERR_BAD_DESC, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_CHECK(cudaSetDevice(c->device));
+    std::string err;
+    int id = c->user.compile(source, err);
+    if (id < 0) return fail(SDDE_ERR_COMPILE, "%s", err.c_str());
+    *model_id = id;
+    return SDDE_OK;
+}
+
+int sdde_b200_philox_normals(sdde_ctx *c, uint64_t seed, int64_t traj_offset, int64_t n_traj, int64_t n_steps, int32_t n_noise,
+                             double *out_host) {
+    if (!c || !out_host || n_traj <= 0 || n_steps <= 0 || n_noise <= 0) return fail(SDDE_ERR_BAD_DESC, "bad arguments");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_CHECK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n_steps * n_noise * n_traj * 8;
+    CU_CHECK(c->out[0].reserve(bytes));
+    sdde::philox_dump_kernel<<<(unsigned)((n_traj + 127) / 128), 128, 0, c->compute>>>(
+        (double *)c->out[0].p, n_traj, traj_offset, n_steps, n_noise, (sdde::u32)(seed & 0xffffffffu), (sdde::u32)(seed >> 32));
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(out_host, c->out[0].p, bytes, cudaMemcpyDeviceToHost, c->compute));
+    CU_CHECK(cudaStreamSynchronize(c->compute));
+    return SDDE_OK;
+}
+
+int sdde_b200_dfma_peak(sdde_ctx *c, double *tflops) {
+    if (!c || !tflops) return fail(SDDE_ERR_BAD_DESC, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_CHECK(cudaSetDevice(c->device));
+    const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+    CU_CHECK(c->out[0].reserve((size_t)blocks * threads * 8));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_CHECK(cudaEventRecord(c->ev_k0, c->compute));
+        sdde::dfma_kernel<<<blocks, threads, 0, c->compute>>>((double *)c->out[0].p, iters, 0.999999, 1e-9);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
+        CU_CHECK(cudaStreamSynchronize(c->compute));
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
+        const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return SDDE_OK;
+}
+
+int sdde_b200_hbm_peak(sdde_ctx *c, double *gbs) {
+    if (!c || !gbs) return fail(SDDE_ERR_BAD_DESC, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_CHECK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)1 << 30;
+    CU_CHECK(c->out[0].reserve(bytes));
+    CU_CHECK(c->out[1].reserve(bytes));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU_CHECK(cudaEventRecord(c->ev_k0, c->compute));
+        sdde::copy_kernel<<<c->sm_count * 16, 256, 0, c->compute>>>((const uint4 *)c->out[0].p, (uint4 *)c->out[1].p, (long long)(bytes / 16));
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
+        CU_CHECK(cudaStreamSynchronize(c->compute));
+        float ms = 0.f;
+        CU_CHECK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
+        if (rep > 0) best = std::max(best, 2.0 * (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    *gbs = best;
+    return SDDE_OK;
+}
+
+void *sdde_b200_alloc_pinned(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(SDDE_ERR_CUDA - (int)e, "cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+void sdde_b200_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

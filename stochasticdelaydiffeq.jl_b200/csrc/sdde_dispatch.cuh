@@ -1,0 +1,61 @@
+// sdde_dispatch.cuh -- compile-time instantiation table: (model, alg, noise, per-trajectory params) -> kernel.
+#pragma once
+#include "sdde_kernels.cuh"
+#include "sdde_models.cuh"
+
+namespace sdde {
+
+struct KernelInfo {
+    const void *fn = nullptr;   // __global__ entry for cudaLaunchKernel
+    int tpt = 1;                // trajectories per thread
+    int batch = 1;              // prefetch depth B compiled into the kernel
+    int rec_size = 0;           // sizeof(StepRec<NL>)
+    int n_state = 0, n_lag = 0, n_chan = 0, n_noise = 0, n_param = 0;
+    bool diag = true;
+    bool is_user = false;       // fn is a cudaKernel_t obtained from an NVRTC-built library
+    const char *name = "";
+};
+
+template <class M, int ALG, int NOISE, bool PT>
+inline KernelInfo make_info(const char *name) {
+    KernelInfo k;
+    k.fn = (const void *)&sdde_solve_kernel<M, ALG, NOISE, PT, Tune<M>::TPT, Tune<M>::B>;
+    k.tpt = Tune<M>::TPT;
+    k.batch = Tune<M>::B;
+    k.rec_size = (int)sizeof(StepRec<M::NL>);
+    k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = M::DIAG ? M::NS : M::NW; k.n_param = M::NP;
+    k.diag = M::DIAG;
+    k.name = name;
+    return k;
+}
+
+#define SDDE_SEL3(M, NAME, A, NZ)                                                   \
+    if (alg == A && noise == NZ) return ptraj ? make_info<M, A, NZ, true>(NAME) : make_info<M, A, NZ, false>(NAME);
+#define SDDE_SEL_ALG(M, NAME, A) \
+    SDDE_SEL3(M, NAME, A, K_NOISE_PHILOX) SDDE_SEL3(M, NAME, A, K_NOISE_DW) SDDE_SEL3(M, NAME, A, K_NOISE_GRID)
+
+// all four algorithms (diagonal-noise models)
+#define SDDE_DEFINE_SELECT_DIAG(FUNC, M, NAME)                  \
+    KernelInfo FUNC(int alg, int noise, bool ptraj) {           \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EM_SPLIT)                   \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EM_NOSPLIT)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_ITO)                  \
+        SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_STRAT)                \
+        return KernelInfo();                                    \
+    }
+// EM only (non-diagonal noise: [EXT] RKMil requires diagonal noise)
+#define SDDE_DEFINE_SELECT_EM(FUNC, M, NAME)                    \
+    KernelInfo FUNC(int alg, int noise, bool ptraj) {           \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EM_SPLIT)                   \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EM_NOSPLIT)                 \
+        return KernelInfo();                                    \
+    }
+
+KernelInfo select_linear1(int alg, int noise, bool ptraj);
+KernelInfo select_hayes(int alg, int noise, bool ptraj);
+KernelInfo select_mackey_glass(int alg, int noise, bool ptraj);
+KernelInfo select_scalar_add(int alg, int noise, bool ptraj);
+KernelInfo select_sir(int alg, int noise, bool ptraj);
+KernelInfo select_linsys(int ns, int nl, int nw, int alg, int noise, bool ptraj);
+
+}  // namespace sdde

@@ -1,0 +1,435 @@
+// sdde_kernels.cuh -- the sm_100a step kernels of the ensemble SDDE path (device code, NVRTC-clean).
+//
+// One launch integrates one WAVE of trajectories over the WHOLE time span.  It replaces, for every trajectory of
+// the wave at once, the reference's per-trajectory
+//     __init            /root/reference/src/solve.jl:11-572      (register init from the descriptor)
+//     solve! hot loop   /root/reference/src/solve.jl:574-610
+//     loopheader!       /root/reference/src/integrators/interface.jl:1-30    (accept, next dW)
+//     perform_step!     [EXT] StochasticDiffEq EM / RKMil, call site src/solve.jl:586
+//     loopfooter!       /root/reference/src/integrators/interface.jl:70-85
+//     savevalues!       /root/reference/src/integrators/interface.jl:357-430
+//     HistoryFunction   [EXT] DelayDiffEq, wired at /root/reference/src/utils.jl:246
+//     WienerProcess     [EXT] DiffEqNoiseProcess, set up at /root/reference/src/solve.jl:304-339
+//
+// Data layout in HBM (all float64):
+//   ring   [ring_slots][NS][ring_pitch]   node j of the dense history lives in slot j % ring_slots; trajectory-contiguous
+//   out    [n_save][NS][out_pitch]        time-major, trajectory-contiguous (the caller's array when it is on the device)
+//   noise  [n][NC][noise_pitch]           supplied increments / grid values (validation modes only)
+//   steps  packed StepRec<NL>[n_steps]    trajectory-independent schedule (schedule.cpp), staged through shared memory
+//   saves  SaveRec[n_save]
+// Thread mapping: one thread integrates TPT adjacent trajectories (TPT = 2 -> every ring/out access is a 128-bit
+// double2 access, a warp touches 512 contiguous bytes, and the two independent recurrences give the FP64 pipe ILP).
+#pragma once
+
+namespace sdde {
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+enum { K_LK_PRE = 0, K_LK_EXACT = 1, K_LK_INTERP = 2 };
+enum { K_NOISE_PHILOX = 0, K_NOISE_DW = 1, K_NOISE_GRID = 2 };
+enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3 };
+
+#define SDDE_K_MAX_STATE 8
+#define SDDE_K_MAX_PARAM 128
+#define SDDE_BLOCK 128
+
+struct SaveRec {
+    int step;       // step whose end produces this save (-1: initial condition)
+    int exact;      // 1: take u_{n+1} verbatim
+    double theta;   // else (1-theta) u_n + theta u_{n+1}
+};
+
+template <int NL>
+struct StepRec {
+    double t, dt, sqdt;
+    int nsave;      // number of SaveRec produced by this step
+    int pad;
+    struct Lk {
+        double theta;   // interpolation weight, or the lookup time for prehistory
+        int slot_lo;    // ring slot of the lower node (of THE node when exact)
+        int mode;
+    } lk[NL];
+};
+
+struct KArgs {
+    const unsigned char *steps;
+    const SaveRec *saves;
+    double *ring;
+    double *out;
+    const double *noise;
+    const double *u0;        // per-trajectory initial state [NS][pitch] (wave local) or nullptr
+    const double *ptraj;     // per-trajectory parameters   [NP][pitch] (wave local) or nullptr
+    unsigned char *status;
+    long long ring_pitch, out_pitch, out_off, noise_pitch, noise_off, u0_pitch, p_pitch;
+    long long n_traj;        // valid trajectories of this wave
+    long long traj_gid0;     // global id of the wave's first trajectory
+    int n_steps, n_saves, ring_slots, chunk_steps, batch, noise_kind;
+    int out_vec_ok;          // out rows are 16-byte aligned for double2 stores
+    int pad0;
+    u32 seed_lo, seed_hi;
+    double hist_c0[SDDE_K_MAX_STATE], hist_c1[SDDE_K_MAX_STATE];
+    double u0c[SDDE_K_MAX_STATE];
+    double p[SDDE_K_MAX_PARAM];
+};
+
+// tuning knobs per model shape
+template <class M> struct Tune {
+    static constexpr int TPT = (M::NS == 1) ? 2 : 1;
+    static constexpr int FOOT = M::NS * M::NL * TPT;              // doubles per prefetched step (one node set)
+    static constexpr int B = FOOT <= 2 ? 4 : (FOOT <= 4 ? 2 : 1);
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) + Box-Muller in float64.
+// Stream layout: counter = (traj_id_lo, traj_id_hi, call_lo, call_hi), key = (seed_lo, seed_hi);
+// normal number q = step*NC + channel of a trajectory is half (q & 1) of call (q >> 1).
+// Replaces Xoroshiro128Plus + randn of /root/reference/src/solve.jl:313-336 (the bit stream is NOT reproduced,
+// the distribution is: independent N(0,1), scaled by sqrt|dt_n| like [EXT] DiffEqNoiseProcess WHITE_NOISE_DIST).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 (&o)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u64 p0 = (u64)0xD2511F53u * c0;
+        const u64 p1 = (u64)0xCD9E8D57u * c2;
+        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0;
+        const u32 n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (u32)p1;
+        c3 = (u32)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__device__ __forceinline__ void philox_normal_pair(u64 gid, u64 call, u32 k0, u32 k1, double &z0, double &z1) {
+    u32 w[4];
+    philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), k0, k1, w);
+    // 52-bit uniforms in (0,1): u = (m + 0.5) * 2^-52, built without an int->double conversion
+    const double x1 = __hiloint2double((int)(0x3FF00000u | (w[1] & 0xFFFFFu)), (int)w[0]);  // 1 + m*2^-52
+    const double x2 = __hiloint2double((int)(0x3FF00000u | (w[3] & 0xFFFFFu)), (int)w[2]);
+    const double one_m = 0.99999999999999988897769753748;  // 1 - 2^-53
+    const double u1 = x1 - one_m;
+    const double u2 = x2 - one_m;
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter accessors: kernel-argument constants (uniform) or per-trajectory registers (prob_func use case)
+// ------------------------------------------------------------------------------------------------
+struct ConstParams {
+    const double *p;
+    __device__ __forceinline__ double operator[](int i) const { return p[i]; }
+};
+template <int NP>
+struct RegParams {
+    double v[NP > 0 ? NP : 1];
+    __device__ __forceinline__ double operator[](int i) const { return v[i]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// one step of one trajectory: [EXT] StochasticDiffEq perform_step! for EMConstantCache / RKMilConstantCache
+// (SURVEY.md section 3.3).  ul = delayed states (same for every f/g evaluation of the step).
+// ------------------------------------------------------------------------------------------------
+template <class M, int ALG, class P>
+__device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&ul)[M::NL][M::NS], const P &p, double t,
+                                         double dt, double sq, const double *dw) {
+    constexpr int NS = M::NS;
+    double du[NS], K[NS];
+    M::f(du, u, ul, p, t);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) K[j] = u[j] + dt * du[j];
+    if (ALG == K_ALG_EM_SPLIT || ALG == K_ALG_EM_NOSPLIT) {
+        if (M::DIAG) {
+            double gv[NS];
+            if (ALG == K_ALG_EM_SPLIT) M::g(gv, K, ul, p, t); else M::g(gv, u, ul, p, t);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) u[j] = K[j] + gv[j] * dw[j];
+        } else {
+            constexpr int NW = M::NW;
+            double gv[NS * NW];
+            if (ALG == K_ALG_EM_SPLIT) M::g(gv, K, ul, p, t); else M::g(gv, u, ul, p, t);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                double noise = gv[i * NW] * dw[0];
+#pragma unroll
+                for (int j = 1; j < NW; ++j) noise = noise + gv[i * NW + j] * dw[j];
+                u[i] = K[i] + noise;
+            }
+        }
+    } else {
+        // RKMil, diagonal noise only (the host rejects the non-diagonal combination)
+        double L[NS], ut[NS], g2[NS];
+        M::g(L, u, ul, p, t);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) ut[j] = (ALG == K_ALG_RKMIL_ITO ? K[j] : u[j]) + L[j] * sq;
+        M::g(g2, ut, ul, p, t);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            const double ggp = (g2[j] - L[j]) / sq;
+            const double w2 = (ALG == K_ALG_RKMIL_ITO) ? (dw[j] * dw[j] - fabs(dt)) : (dw[j] * dw[j]);
+            const double mil = ggp * w2 / 2.0;
+            u[j] = (K[j] + L[j] * dw[j]) + mil;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector helpers: TPT adjacent trajectories per thread
+// ------------------------------------------------------------------------------------------------
+template <int TPT> __device__ __forceinline__ void ld_traj(const double *p, double (&v)[TPT]);
+template <> __device__ __forceinline__ void ld_traj<1>(const double *p, double (&v)[1]) { v[0] = *p; }
+template <> __device__ __forceinline__ void ld_traj<2>(const double *p, double (&v)[2]) {
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+template <int TPT> __device__ __forceinline__ void st_traj(double *p, const double (&v)[TPT]);
+template <> __device__ __forceinline__ void st_traj<1>(double *p, const double (&v)[1]) { *p = v[0]; }
+template <> __device__ __forceinline__ void st_traj<2>(double *p, const double (&v)[2]) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+}
+
+__device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+// ------------------------------------------------------------------------------------------------
+// the step kernel: thread-per-trajectory (x TPT), whole time span in one launch
+// ------------------------------------------------------------------------------------------------
+template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
+__global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_constant__ KArgs a) {
+    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
+    typedef StepRec<NL> Rec;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Rec *srec = reinterpret_cast<Rec *>(smem_raw);
+
+    const long long tr0 = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) * TPT;  // wave-local trajectory index
+    const long long last = a.n_traj - 1;
+
+    // ---- per-trajectory "__init": state, parameters, noise state (src/solve.jl:137, 302-339) ----
+    double u[TPT][NS];
+#pragma unroll
+    for (int tt = 0; tt < TPT; ++tt) {
+        const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) u[tt][j] = a.u0 ? a.u0[j * a.u0_pitch + tr] : a.u0c[j];
+    }
+    RegParams<PTRAJ ? NP : 0> preg[TPT];
+    if (PTRAJ) {
+#pragma unroll
+        for (int tt = 0; tt < TPT; ++tt) {
+            const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) preg[tt].v[PTRAJ ? i : 0] = a.ptraj[i * a.p_pitch + tr];
+        }
+    }
+    const ConstParams pconst{a.p};
+
+    double zc[TPT][2];
+    u64 zcall = ~0ull;
+    double curW[TPT][NC];
+#pragma unroll
+    for (int tt = 0; tt < TPT; ++tt) {
+        zc[tt][0] = zc[tt][1] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) curW[tt][c] = 0.0;
+    }
+    if (NOISE == K_NOISE_GRID) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double w[TPT];
+#pragma unroll
+            for (int tt = 0; tt < TPT; ++tt) {
+                const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+                w[tt] = a.noise[(long long)c * a.noise_pitch + a.noise_off + tr];
+                curW[tt][c] = w[tt];
+            }
+        }
+    }
+
+    // ---- node 0 of the history = u0 (src/utils.jl:143-247: sol.t=[t0], sol.u=[u0]) ----
+    double *ringp = a.ring + tr0;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        double v[TPT];
+#pragma unroll
+        for (int tt = 0; tt < TPT; ++tt) v[tt] = u[tt][j];
+        st_traj<TPT>(ringp + (long long)j * a.ring_pitch, v);
+    }
+    int wslot = (a.ring_slots > 1) ? 1 : 0;   // slot of the next node to be written
+
+    bool bad[TPT];
+#pragma unroll
+    for (int tt = 0; tt < TPT; ++tt) bad[tt] = false;
+    const bool out_vec = (TPT == 1) || (a.out_vec_ok && (tr0 + TPT - 1 <= last));
+    int ks = 0;
+    // save_start (src/solve.jl:355-363)
+    while (ks < a.n_saves && a.saves[ks].step < 0) {
+        if (a.out) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                double *op = a.out + ((long long)ks * NS + j) * a.out_pitch + a.out_off + tr0;
+                if (out_vec) {
+                    double v[TPT];
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) v[tt] = u[tt][j];
+                    if (tr0 <= last) st_traj<TPT>(op, v);
+                } else {
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt)
+                        if (tr0 + tt <= last) op[tt] = u[tt][j];
+                }
+            }
+        }
+        ++ks;
+    }
+
+    const int bw = a.batch < B ? (a.batch < 1 ? 1 : a.batch) : B;
+    for (int n0 = 0; n0 < a.n_steps; n0 += a.chunk_steps) {
+        const int cnt = (a.n_steps - n0 < a.chunk_steps) ? (a.n_steps - n0) : a.chunk_steps;
+        __syncthreads();
+        {   // stage this chunk of the schedule in shared memory
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
+            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+            const int nvec = cnt * (int)(sizeof(Rec) / 16);
+            for (int i = threadIdx.x; i < nvec; i += SDDE_BLOCK) dst[i] = src[i];
+        }
+        __syncthreads();
+
+        for (int nb = 0; nb < cnt; nb += bw) {
+            // ---- prefetch the delayed-state nodes of the next bw steps (all loads independent of the recurrence) ----
+            double xlo[B][NL][NS][TPT], xhi[B][NL][NS][TPT];
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                if (k < bw && nb + k < cnt) {
+                    const Rec &r = srec[nb + k];
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) {
+                        const int mode = r.lk[l].mode;
+                        if (mode != K_LK_PRE) {
+                            const int slo = r.lk[l].slot_lo;
+                            const int shi = (slo + 1 == a.ring_slots) ? 0 : slo + 1;
+#pragma unroll
+                            for (int j = 0; j < NS; ++j) {
+                                ld_traj<TPT>(ringp + ((long long)slo * NS + j) * a.ring_pitch, xlo[k][l][j]);
+                                if (mode == K_LK_INTERP)
+                                    ld_traj<TPT>(ringp + ((long long)shi * NS + j) * a.ring_pitch, xhi[k][l][j]);
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- the steps ----
+#pragma unroll
+            for (int k = 0; k < B; ++k) {
+                if (k < bw && nb + k < cnt) {
+                    const Rec &r = srec[nb + k];
+                    const int n = n0 + nb + k;
+                    const double tn = r.t, dtn = r.dt, sq = r.sqdt;
+                    // delayed states: [EXT] HistoryFunction regimes
+                    double ul[TPT][NL][NS];
+#pragma unroll
+                    for (int l = 0; l < NL; ++l) {
+                        const int mode = r.lk[l].mode;
+                        const double th = r.lk[l].theta;
+#pragma unroll
+                        for (int j = 0; j < NS; ++j)
+#pragma unroll
+                            for (int tt = 0; tt < TPT; ++tt) {
+                                if (mode == K_LK_PRE) ul[tt][l][j] = a.hist_c0[j] + a.hist_c1[j] * th;
+                                else if (mode == K_LK_EXACT) ul[tt][l][j] = xlo[k][l][j][tt];
+                                else ul[tt][l][j] = (1.0 - th) * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
+                            }
+                    }
+                    // increments: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454)
+                    double dw[TPT][NC];
+                    if (NOISE == K_NOISE_PHILOX) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const u64 q = (u64)n * NC + c;
+                            const u64 call = q >> 1;
+                            if (call != zcall) {
+#pragma unroll
+                                for (int tt = 0; tt < TPT; ++tt)
+                                    philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.seed_lo, a.seed_hi,
+                                                       zc[tt][0], zc[tt][1]);
+                                zcall = call;
+                            }
+#pragma unroll
+                            for (int tt = 0; tt < TPT; ++tt) dw[tt][c] = sq * ((q & 1) ? zc[tt][1] : zc[tt][0]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c)
+#pragma unroll
+                            for (int tt = 0; tt < TPT; ++tt) {
+                                const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+                                const long long row = (NOISE == K_NOISE_GRID) ? ((long long)(n + 1) * NC + c)
+                                                                               : ((long long)n * NC + c);
+                                const double w = a.noise[row * a.noise_pitch + a.noise_off + tr];
+                                if (NOISE == K_NOISE_GRID) { dw[tt][c] = w - curW[tt][c]; curW[tt][c] += dw[tt][c]; }
+                                else dw[tt][c] = w;
+                            }
+                    }
+                    // perform_step!
+                    double uold[TPT][NS];
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) {
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) uold[tt][j] = u[tt][j];
+                        if (PTRAJ) sde_step<M, ALG>(u[tt], ul[tt], preg[tt], tn, dtn, sq, dw[tt]);
+                        else sde_step<M, ALG>(u[tt], ul[tt], pconst, tn, dtn, sq, dw[tt]);
+                    }
+                    // dense history: node n+1 (save_everystep push of src/integrators/interface.jl:406-417)
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        double v[TPT];
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) v[tt] = u[tt][j];
+                        st_traj<TPT>(ringp + ((long long)wslot * NS + j) * a.ring_pitch, v);
+                    }
+                    wslot = (wslot + 1 == a.ring_slots) ? 0 : wslot + 1;
+                    // savevalues! (src/integrators/interface.jl:357-430)
+                    for (int s = 0; s < r.nsave; ++s) {
+                        const SaveRec sr = a.saves[ks];
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) {
+                            double v[TPT];
+#pragma unroll
+                            for (int tt = 0; tt < TPT; ++tt) {
+                                v[tt] = sr.exact ? u[tt][j] : ((1.0 - sr.theta) * uold[tt][j] + sr.theta * u[tt][j]);
+                                bad[tt] = bad[tt] || !finite_d(v[tt]);
+                            }
+                            if (a.out) {
+                                double *op = a.out + ((long long)ks * NS + j) * a.out_pitch + a.out_off + tr0;
+                                if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
+                                else {
+#pragma unroll
+                                    for (int tt = 0; tt < TPT; ++tt)
+                                        if (tr0 + tt <= last) op[tt] = v[tt];
+                                }
+                            }
+                        }
+                        ++ks;
+                    }
+                }
+            }
+        }
+    }
+    // [EXT] check_error! (src/solve.jl:578): NaN/Inf -> ReturnCode.Unstable, reported per trajectory
+    if (a.status) {
+#pragma unroll
+        for (int tt = 0; tt < TPT; ++tt) {
+            bool b = bad[tt];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) b = b || !finite_d(u[tt][j]);
+            if (tr0 + tt <= last) a.status[tr0 + tt] = b ? 1 : 0;
+        }
+    }
+}
+
+}  // namespace sdde

@@ -1,0 +1,138 @@
+// sdde_models.cuh -- built-in model zoo (device code).
+//
+// Each model is the device-side form of what the reference builds at
+// /root/reference/src/functionwrapper.jl:8-9,35-36: f(u,p,t) := f(u,h,p,t), g(u,p,t) := g(u,h,p,t), where the
+// history function h has already been evaluated at t - lags[l] for every constant lag (ul[l][*]); that value is
+// the same for every f/g call inside one step.
+//
+// Interface (also the contract for NVRTC user models, see sdde_b200_compile_model):
+//   NS states, NL lags, NW noise channels, NP parameters, DIAG (diagonal noise: gv[NS]; else gv[NS*NW] row-major)
+//   f(du, u, ul, p, t), g(gv, u, ul, p, t);  p[i] is either a kernel-argument constant or a per-trajectory register.
+// This header is NVRTC-clean (no host includes).
+#pragma once
+
+namespace sdde {
+
+// x^n, right-to-left binary exponentiation; the multiplication order is part of the model definition
+// (the oracle uses the same order).
+__device__ __forceinline__ double ipow(double x, int n) {
+    if (n == 10) {  // same products, same order as the loop below (x^2 * x^8), without the loop overhead
+        const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+        return x2 * x8;
+    }
+    double result = 1.0, base = x;
+    bool first = true;
+    while (n > 0) {
+        if (n & 1) { result = first ? base : result * base; first = false; }
+        n >>= 1;
+        if (n) base = base * base;
+    }
+    return result;
+}
+
+// du = (a u + b u(t-tau)) dt + s u dW              BASELINE.json configs[0], configs[4]
+struct ModelLinear1 {
+    static constexpr int NS = 1, NL = 1, NW = 1, NP = 3;
+    static constexpr bool DIAG = true;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
+        du[0] = p[0] * u[0] + p[1] * ul[0][0];
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*)[NS], const P &p, double) {
+        gv[0] = p[2] * u[0];
+    }
+};
+
+// Hayes equation of the reference tests: test/test_prob_sol.jl:6-13, test/analyticless_convergence_tests.jl:6-13 (beta = 0)
+struct ModelHayes {
+    static constexpr int NS = 1, NL = 1, NW = 1, NP = 7;
+    static constexpr bool DIAG = true;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
+        du[0] = (p[1] * u[0] + p[2] * ul[0][0]) + p[3];
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*ul)[NS], const P &p, double) {
+        gv[0] = (p[4] * u[0] + p[5] * ul[0][0]) + p[6];
+    }
+};
+
+// stochastic Mackey-Glass: BASELINE.json configs[1], configs[2]
+struct ModelMackeyGlass {
+    static constexpr int NS = 1, NL = 1, NW = 1, NP = 4;
+    static constexpr bool DIAG = true;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
+        const double x = ul[0][0];
+        const double xn = ipow(x, (int)p[2]);
+        du[0] = (p[0] * x) / (1.0 + xn) - p[1] * u[0];
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*)[NS], const P &p, double) {
+        gv[0] = p[3] * u[0];
+    }
+};
+
+// n-state linear delay system with n x m noise: BASELINE.json configs[3]
+//   du = (A u + sum_l B_l u(t-tau_l) + c) dt + G(u) dW,  G_ij = M_ij u_i + N_ij
+//   p = A[NS*NS], B_0..B_{NL-1}[NS*NS], c[NS], M[NS*NW], N[NS*NW]   (row-major)
+template <int NS_, int NL_, int NW_>
+struct ModelLinSys {
+    static constexpr int NS = NS_, NL = NL_, NW = NW_, NP = NS_ * NS_ * (1 + NL_) + NS_ + 2 * NS_ * NW_;
+    static constexpr bool DIAG = false;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double acc = p[i * NS] * u[0];
+#pragma unroll
+            for (int j = 1; j < NS; ++j) acc = acc + p[i * NS + j] * u[j];
+#pragma unroll
+            for (int l = 0; l < NL; ++l)
+#pragma unroll
+                for (int j = 0; j < NS; ++j) acc = acc + p[NS * NS * (1 + l) + i * NS + j] * ul[l][j];
+            du[i] = acc + p[NS * NS * (1 + NL) + i];
+        }
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*)[NS], const P &p, double) {
+        constexpr int offM = NS * NS * (1 + NL) + NS, offN = offM + NS * NW;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+            for (int j = 0; j < NW; ++j) gv[i * NW + j] = p[offM + i * NW + j] * u[i] + p[offN + i * NW + j];
+    }
+};
+
+// delayed SIR with 3x2 sparse noise: test/nondiagonal_sparse_noise.jl:5-43
+struct ModelSIR {
+    static constexpr int NS = 3, NL = 1, NW = 2, NP = 3;
+    static constexpr bool DIAG = false;
+    template <class P> __device__ __forceinline__ static void rates(double &infection, double &recovery, const double *u,
+                                                                    const double (*ul)[NS], const P &p) {
+        const double N = (u[0] + u[1]) + u[2];
+        infection = ((p[0] * p[1]) * u[1]) / N * u[0];
+        const double Nd = (ul[0][0] + ul[0][1]) + ul[0][2];
+        recovery = ((p[0] * p[1]) * ul[0][1]) / Nd * ul[0][0];
+    }
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
+        double inf, rec;
+        rates(inf, rec, u, ul, p);
+        du[0] = -inf; du[1] = inf - rec; du[2] = rec;
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*ul)[NS], const P &p, double) {
+        double inf, rec;
+        rates(inf, rec, u, ul, p);
+        const double si = sqrt(fmax(0.0, inf)), sr = sqrt(fmax(0.0, rec));
+        gv[0] = -si; gv[1] = 0.0;
+        gv[2] = si;  gv[3] = -sr;
+        gv[4] = 0.0; gv[5] = sr;
+    }
+};
+
+// scalar additive-noise delay equation: test/events.jl:4-5
+struct ModelScalarAdd {
+    static constexpr int NS = 1, NL = 1, NW = 1, NP = 2;
+    static constexpr bool DIAG = true;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *, const double (*ul)[NS], const P &p, double) {
+        du[0] = p[0] * ul[0][0];
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *, const double (*)[NS], const P &p, double) {
+        gv[0] = p[1];
+    }
+};
+
+}  // namespace sdde

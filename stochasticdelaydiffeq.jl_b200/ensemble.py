@@ -1,0 +1,461 @@
+"""``solve(EnsembleProblem, EM()/RKMil(), EnsembleB200(); dt, saveat, trajectories, ...)`` -> ``EnsembleSolution``.
+
+Host-side mirror of the dispatch a Julia maintainer would add (julia/EnsembleB200.jl):
+``SciMLBase.__solve(::AbstractEnsembleProblem{<:SDDEProblem}, ::Union{EM,RKMil}, ::EnsembleB200; trajectories, dt, saveat, ...)``
+which replaces the per-trajectory loop over ``DiffEqBase.__solve`` (/root/reference/src/solve.jl:1-9).  Keyword names and
+defaults follow ``__init`` (/root/reference/src/solve.jl:18-77) for the keywords that exist on this path; everything
+else raises.  All numerical work happens in libsdde_b200.so; this module only marshals the descriptor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi as capi
+from .problem import EM, RKMil, EnsembleProblem, SDDEProblem, UserModel, _as_history
+
+
+@dataclass
+class EnsembleB200:
+    """The ensemble algorithm: where SciML has EnsembleThreads()/EnsembleDistributed(), this path has EnsembleB200().
+
+    device       CUDA device of this process (default: LOCAL_RANK under torchrun, else 0)
+    distributed  shard trajectories over the ranks of the initialised torch.distributed group (one process per GPU)
+                 and merge ensemble moments over NCCL; paths stay on the rank that computed them
+    output       'host' -> numpy arrays (D2H inside the call) | 'device' -> torch CUDA tensors (no D2H)
+    """
+    device: int | None = None
+    distributed: bool = False
+    output: str = "host"
+    wave_traj: int | None = None
+
+
+# ---------------------------------------------------------------------------------------------
+# saveat expansion: /root/reference/src/solve.jl:32-34, 411-415, 659-677
+# ---------------------------------------------------------------------------------------------
+def _julia_range(a: float, s: float, b: float) -> np.ndarray:
+    """Elements of the Julia range a:s:b.  Julia lifts (a, s) to a common rational grid and evaluates each element
+    in twice precision; for decimal inputs that equals (na + k*ns)/d with na = a*d, ns = s*d integers."""
+    for d in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
+        na, ns = round(a * d), round(s * d)
+        if na / d == a and ns / d == s and ns > 0:
+            n = int(math.floor((b * d - na) / ns + 1e-9))
+            return np.array([(na + k * ns) / d for k in range(n + 1)], dtype=np.float64)
+    n = int(math.floor((b - a) / s + 1e-9))
+    return np.array([a + k * s for k in range(n + 1)], dtype=np.float64)
+
+
+def expand_saveat(saveat, t0: float, tf: float):
+    """-> (saveat times pushed to the heap, save_start default, save_end default)."""
+    if saveat is None:
+        return np.zeros(0), True, True
+    if np.isscalar(saveat):
+        s = float(saveat)
+        if s <= 0:
+            raise ValueError("saveat must be positive")
+        pts = _julia_range(t0, s, tf)
+        sv = pts[1:] if pts[-1] == tf else np.array([x for x in pts[1:] if x <= tf - s])
+        return np.asarray(sv, dtype=np.float64), True, True
+    arr = np.asarray(list(saveat), dtype=np.float64)
+    if arr.size == 0:
+        return np.zeros(0), True, True
+    return np.sort(arr[(arr > t0) & (arr < tf)]), bool(np.any(arr == t0)), bool(np.any(arr == tf))
+
+
+# ---------------------------------------------------------------------------------------------
+# descriptor marshalling
+# ---------------------------------------------------------------------------------------------
+class _Marshalled:
+    """Keeps every numpy buffer the descriptor points to alive (the Julia side uses GC.@preserve)."""
+
+    def __init__(self):
+        self.desc = capi.SddeDesc()
+        self.keep = []
+
+
+def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
+             n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
+             want_moments) -> _Marshalled:
+    if not isinstance(alg, (EM, RKMil)):
+        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM and RKMil, fixed step)")
+    if adaptive is None:
+        adaptive = isinstance(alg, RKMil)      # [EXT] isadaptive(RKMil) = true, src/solve.jl:40
+    if adaptive:
+        raise NotImplementedError("adaptive stepping is outside this path: pass adaptive=False (RKMil is adaptive by "
+                                  "default in the reference, src/solve.jl:40)")
+    t0, tf = prob.tspan
+    m = _Marshalled()
+    d = m.desc
+    d.struct_size = C.sizeof(capi.SddeDesc)
+    d.model_id, d.alg = model.model_id, alg.alg_id
+    d.n_state, d.n_noise, d.n_lag, d.n_param = model.n_state, model.n_noise, model.n_lag, model.n_param
+    if len(prob.lags) != model.n_lag:
+        raise ValueError(f"model {model.name} looks up {model.n_lag} lag(s), problem declares {len(prob.lags)}")
+    if prob.u0.size != model.n_state:
+        raise ValueError(f"u0 has {prob.u0.size} states, model {model.name} has {model.n_state}")
+    if prob.p.size != model.n_param:
+        raise ValueError(f"p has {prob.p.size} entries, model {model.name} takes {model.n_param}")
+    d.order_discontinuity_t0 = prob.order_discontinuity_t0
+    d.constant_lags_declared = 1 if len(prob.constant_lags) > 0 else 0
+    sv, ss_def, se_def = expand_saveat(saveat, t0, tf)
+    no_saveat = saveat is None or (not np.isscalar(saveat) and len(saveat) == 0)
+    if save_everystep is None:
+        save_everystep = no_saveat                                   # src/solve.jl:25
+    if save_start is None:
+        save_start = True if (save_everystep or no_saveat or np.isscalar(saveat)) else ss_def   # :32-34
+    if save_end is None:
+        save_end = True if (save_everystep or no_saveat or np.isscalar(saveat)) else se_def     # :411-415
+    d.save_start, d.save_end, d.save_everystep = int(save_start), int(save_end), int(save_everystep)
+    d.t0, d.tf, d.dt = t0, tf, float(dt)
+    for i, lag in enumerate(prob.lags):
+        d.lags[i] = lag
+    hist = _as_history(prob.h, prob.p, t0, model.n_state)
+    for j in range(model.n_state):
+        d.hist_c0[j], d.hist_c1[j] = hist.c0[j], hist.c1[j]
+    sv = np.ascontiguousarray(sv, dtype=np.float64)
+    ts = np.ascontiguousarray(np.asarray(list(tstops), dtype=np.float64))
+    m.keep += [sv, ts]
+    d.saveat, d.n_saveat = capi.np_ptr(sv).value if sv.size else None, sv.size
+    d.tstops, d.n_tstops = capi.np_ptr(ts).value if ts.size else None, ts.size
+    if p_batch is not None:
+        if p_batch.shape != (model.n_param, n_traj):
+            raise ValueError(f"p_batch must have shape ({model.n_param}, {n_traj})")
+        m.keep.append(p_batch)
+        d.params, d.param_stride = capi.np_ptr(p_batch).value, n_traj
+    else:
+        pp = np.ascontiguousarray(prob.p)
+        m.keep.append(pp)
+        d.params, d.param_stride = (capi.np_ptr(pp).value if pp.size else None), 0
+    if u0_batch is not None:
+        if u0_batch.shape != (model.n_state, n_traj):
+            raise ValueError(f"u0_batch must have shape ({model.n_state}, {n_traj})")
+        m.keep.append(u0_batch)
+        d.u0, d.u0_stride = capi.np_ptr(u0_batch).value, n_traj
+    else:
+        uu = np.ascontiguousarray(prob.u0)
+        m.keep.append(uu)
+        d.u0, d.u0_stride = capi.np_ptr(uu).value, 0
+    d.noise_mode, d.noise_mem = noise_mode, noise_mem
+    d.noise = noise
+    d.out_mem = out_mem
+    d.history_mode = 0
+    d.want_paths, d.want_moments = int(want_paths), int(want_moments)
+    d.n_traj, d.traj_offset = int(n_traj), int(traj_offset)
+    d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return m
+
+
+@dataclass
+class Schedule:
+    t: np.ndarray
+    dt: np.ndarray
+    sqdt: np.ndarray
+    lk_mode: np.ndarray
+    lk_idx: np.ndarray
+    lk_theta: np.ndarray
+    save_t: np.ndarray
+    save_step: np.ndarray
+    save_theta: np.ndarray
+    save_exact: np.ndarray
+    tstops_hit: np.ndarray
+    ring_slots: int
+    min_gap: int
+
+    @property
+    def n_steps(self):
+        return len(self.dt)
+
+
+def _resolve_model(prob, ctx):
+    model = prob.model
+    if isinstance(model, UserModel):
+        if ctx is None:
+            raise RuntimeError("a UserModel needs a GPU context to be compiled")
+        model = model.resolve(ctx)
+    return model
+
+
+def schedule(prob: SDDEProblem, alg, *, dt, saveat=None, save_everystep=None, save_start=None, save_end=None,
+             tstops=(), adaptive=None) -> Schedule:
+    """The trajectory-independent step/lookup/save schedule the library will use (host only, no GPU needed)."""
+    model = prob.model
+    if isinstance(model, UserModel):
+        ns, nl, nw, npar, diag = model._shape
+        from .problem import Model
+        model = Model(model.name, capi.MODEL_USER_BASE, ns, nl, nw, npar, diag)
+    m = _marshal(prob, model, alg, dt=dt, saveat=saveat, save_everystep=save_everystep, save_start=save_start,
+                 save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=0, traj_offset=0, seed=0, p_batch=None,
+                 u0_batch=None, noise=None, noise_mode=capi.NOISE_PHILOX, noise_mem=0, out_mem=0, want_paths=0,
+                 want_moments=0)
+    s = capi.SddeSchedule()
+    capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(s)))
+    try:
+        N, K, L = s.n_steps, s.n_save, s.n_lag
+
+        def arr(ptr, n, dtype):
+            return np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].astype(dtype, copy=True)
+
+        return Schedule(
+            t=arr(s.t, N + 1, np.float64), dt=arr(s.dt, N, np.float64), sqdt=arr(s.sqdt, N, np.float64),
+            lk_mode=arr(s.lk_mode, N * L, np.int32).reshape(N, L), lk_idx=arr(s.lk_idx, N * L, np.int64).reshape(N, L),
+            lk_theta=arr(s.lk_theta, N * L, np.float64).reshape(N, L),
+            save_t=arr(s.save_t, K, np.float64), save_step=arr(s.save_step, K, np.int64),
+            save_theta=arr(s.save_theta, K, np.float64), save_exact=arr(s.save_exact, K, np.int32),
+            tstops_hit=arr(s.tstops_hit, s.n_tstops_hit, np.float64), ring_slots=s.ring_slots, min_gap=s.min_gap)
+    finally:
+        capi.lib().sdde_b200_schedule_free(C.byref(s))
+
+
+# ---------------------------------------------------------------------------------------------
+# solutions
+# ---------------------------------------------------------------------------------------------
+class RODESolution:
+    """Lazy per-trajectory view: ``sol.t``, ``sol.u`` (list-of-states like Julia's Vector{uType}), ``sol.retcode``."""
+
+    def __init__(self, ens, i):
+        self._e, self._i = ens, i
+
+    @property
+    def t(self):
+        return self._e.t
+
+    @property
+    def u(self):
+        x = self._e.out[:, :, self._i]
+        if hasattr(x, "cpu"):
+            x = x.cpu().numpy()
+        return x[:, 0] if self._e.scalar_state else x
+
+    @property
+    def retcode(self):
+        st = self._e.status
+        return "Success" if st is None or st[self._i] == 0 else "Unstable"
+
+    def __getitem__(self, k):
+        return self.u[k]
+
+
+class EnsembleSolution:
+    """What the ensemble solve returns: dense ``out[n_save, n_state, trajectories]`` (time-major, trajectory
+    contiguous) plus lazy per-trajectory ``RODESolution`` views (materialising 10^6 solution objects would cost more
+    than the solve)."""
+
+    def __init__(self, t, out, status, moments, scalar_state, elapsed, timing, traj_offset=0, n_total=None):
+        self.t = t
+        self.out = out
+        self.status = status
+        self.moments = moments          # [n_save, n_state, 3] (count, mean, M2) or None
+        self.scalar_state = scalar_state
+        self.elapsedTime = elapsed
+        self.timing = timing
+        self.traj_offset = traj_offset
+        self.n_total = n_total
+        self.converged = True
+
+    def __len__(self):
+        return 0 if self.out is None else self.out.shape[2]
+
+    def __getitem__(self, i):
+        if self.out is None:
+            raise IndexError("paths were not requested (want_paths=False)")
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        return RODESolution(self, i)
+
+    @property
+    def u(self):
+        return _LazyList(self)
+
+    @property
+    def retcodes(self):
+        return None if self.status is None else np.where(self.status == 0, "Success", "Unstable")
+
+
+class _LazyList:
+    def __init__(self, e):
+        self._e = e
+
+    def __len__(self):
+        return len(self._e)
+
+    def __getitem__(self, i):
+        return self._e[i]
+
+    def __iter__(self):
+        return (self._e[i] for i in range(len(self._e)))
+
+
+# [EXT] SciMLBase.EnsembleAnalysis
+def timeseries_steps_meanvar(sim: EnsembleSolution):
+    """-> (mean[n_save, n_state], var[n_save, n_state]) over the WHOLE ensemble (all ranks when distributed)."""
+    if sim.moments is None:
+        raise ValueError("solve(..., moments=True) first")
+    cnt, mean, m2 = sim.moments[..., 0], sim.moments[..., 1], sim.moments[..., 2]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        var = m2 / (cnt - 1.0)
+    return mean, var
+
+
+def timeseries_steps_mean(sim):
+    return timeseries_steps_meanvar(sim)[0]
+
+
+def timepoint_meanvar(sim, t):
+    k = int(np.argmin(np.abs(sim.t - t)))
+    if sim.t[k] != t:
+        raise ValueError(f"t={t} is not a saved time point")
+    mean, var = timeseries_steps_meanvar(sim)
+    return mean[k], var[k]
+
+
+def merge_moments(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Chan merge of two (count, mean, M2) arrays through the library (host code of libsdde_b200)."""
+    a = np.ascontiguousarray(a, dtype=np.float64).copy()
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    capi.check(capi.lib().sdde_b200_merge_moments(capi.np_ptr(a), capi.np_ptr(b), a.size // 3))
+    return a
+
+
+# ---------------------------------------------------------------------------------------------
+# solve
+# ---------------------------------------------------------------------------------------------
+def _default_device():
+    import os
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """Contiguous global-id range of rank r: [r*ceil(N/R), min(N, (r+1)*ceil(N/R)))  (SURVEY.md section 8(e))."""
+    per = -(-n_total // world)
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, trajectories=1, saveat=None,
+          save_everystep=None, save_start=None, save_end=None, tstops=(), adaptive=None, seed=0, moments=False,
+          paths=True, noise_increments=None, noise_grid=None, out=None, callback=None, save_idxs=None, **kwargs):
+    """Ensemble solve on the B200 path.  ``prob`` is an ``EnsembleProblem`` (or an ``SDDEProblem`` -> one trajectory).
+
+    noise_increments[n_steps, n_chan, trajectories]  supplied dW (validation; reference: prob.noise branch src/solve.jl:340-353)
+    noise_grid[n_steps+1, n_chan, trajectories]      W on the schedule's nodes (NoiseGrid semantics)
+    out                                               preallocated result buffer: numpy (ideally pinned) or torch CUDA tensor
+    """
+    if callback is not None:
+        raise NotImplementedError("callbacks are outside this path (SURVEY.md section 8(f))")
+    if save_idxs is not None:
+        raise NotImplementedError("save_idxs is not implemented on this path yet")
+    if kwargs:
+        raise TypeError(f"unsupported keyword(s) on the EnsembleB200 path: {sorted(kwargs)}")
+    single = isinstance(prob, SDDEProblem)
+    eprob = EnsembleProblem(prob) if single else prob
+    ea = ensemblealg or EnsembleB200()
+    base = eprob.prob
+    n_total = int(trajectories)
+    rank, world = 0, 1
+    if ea.distributed:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_range(n_total, rank, world)
+    n_traj = hi - lo
+
+    device = ea.device if ea.device is not None else _default_device()
+    ctx = capi.get_context(device)
+    if ea.wave_traj:
+        ctx.set_option("wave_traj", ea.wave_traj)
+    model = _resolve_model(base, ctx)
+    if seed == 0:
+        seed = base.seed if base.seed != 0 else int(np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0])  # src/solve.jl:302
+    p_batch, u0_batch = eprob.batches(n_traj, lo)
+
+    t0w = time.perf_counter()
+    noise_mode, noise_mem, noise_ptr, keep = capi.NOISE_PHILOX, capi.MEM_HOST, None, []
+    nz = noise_increments if noise_increments is not None else noise_grid
+    if nz is not None:
+        noise_mode = capi.NOISE_SUPPLIED_DW if noise_increments is not None else capi.NOISE_SUPPLIED_GRID
+        if hasattr(nz, "data_ptr"):                    # torch tensor
+            if not nz.is_cuda or not nz.is_contiguous() or str(nz.dtype) != "torch.float64":
+                raise ValueError("device noise must be a contiguous float64 CUDA tensor")
+            noise_mem, noise_ptr = capi.MEM_DEVICE, nz.data_ptr()
+        else:
+            nz = np.ascontiguousarray(nz, dtype=np.float64)
+            noise_ptr = capi.np_ptr(nz).value
+        keep.append(nz)
+        if nz.shape[1] != model.n_chan or nz.shape[2] != n_traj:
+            raise ValueError(f"supplied noise must have shape [n, {model.n_chan}, {n_traj}]")
+
+    m = _marshal(base, model, alg, dt=dt, saveat=saveat, save_everystep=save_everystep, save_start=save_start,
+                 save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=lo, seed=seed,
+                 p_batch=p_batch, u0_batch=u0_batch, noise=noise_ptr, noise_mode=noise_mode, noise_mem=noise_mem,
+                 out_mem=capi.MEM_DEVICE if ea.output == "device" else capi.MEM_HOST, want_paths=paths,
+                 want_moments=moments)
+    sch = capi.SddeSchedule()
+    capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(sch)))
+    n_save, n_steps = sch.n_save, sch.n_steps
+    save_t = np.ctypeslib.as_array(sch.save_t, shape=(max(n_save, 1),))[:n_save].copy()
+    capi.lib().sdde_b200_schedule_free(C.byref(sch))
+    if nz is not None:
+        need = n_steps + (1 if noise_mode == capi.NOISE_SUPPLIED_GRID else 0)
+        if nz.shape[0] < need:
+            raise ValueError(f"supplied noise has {nz.shape[0]} rows, the schedule needs {need}")
+
+    out_arr, out_ptr = None, None
+    if paths:
+        shape = (n_save, model.n_state, n_traj)
+        if out is not None:
+            out_arr = out
+            if tuple(out_arr.shape) != shape:
+                raise ValueError(f"out must have shape {shape}")
+        elif ea.output == "device":
+            import torch
+            out_arr = torch.empty(shape, dtype=torch.float64, device=f"cuda:{device}")
+        else:
+            out_arr = np.empty(shape, dtype=np.float64)
+        if hasattr(out_arr, "data_ptr"):
+            if out_arr.is_cuda != (ea.output == "device"):
+                raise ValueError("out tensor residency does not match EnsembleB200(output=...)")
+            if not out_arr.is_contiguous():
+                raise ValueError("out must be contiguous")
+            out_ptr = out_arr.data_ptr()
+        else:
+            if not out_arr.flags.c_contiguous or out_arr.dtype != np.float64:
+                raise ValueError("out must be a C-contiguous float64 array")
+            out_ptr = capi.np_ptr(out_arr).value
+    mom = np.zeros((n_save, model.n_state, 3), dtype=np.float64) if moments else None
+    status = np.zeros(n_traj, dtype=np.uint8)
+    tm = capi.SddeTiming()
+    capi.check(capi.lib().sdde_b200_solve(ctx.handle, C.byref(m.desc), out_ptr,
+                                          capi.np_ptr(mom).value if moments else None, capi.np_ptr(status).value,
+                                          C.byref(tm)))
+    if moments and ea.distributed and world > 1:
+        mom = _allgather_merge_moments(mom, device)
+    if hasattr(out_arr, "data_ptr") and not out_arr.is_cuda:
+        out_arr = out_arr.numpy()
+    sim = EnsembleSolution(save_t, out_arr, status, mom, base.scalar_state, time.perf_counter() - t0w, tm.as_dict(),
+                           traj_offset=lo, n_total=n_total)
+    sim.seed = seed
+    if single:
+        return sim[0] if paths else sim
+    return sim
+
+
+def _allgather_merge_moments(mom: np.ndarray, device: int) -> np.ndarray:
+    """The path's single collective: all-gather the per-rank (count, mean, M2) triples over
+    NCCL (gloo on CPU in tests) and Chan-merge them in rank order, so every rank ends with identical moments."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    dev = torch.device(f"cuda:{device}") if backend == "nccl" else torch.device("cpu")
+    local = torch.from_numpy(mom).to(dev)
+    parts = [torch.empty_like(local) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, local)
+    acc = parts[0].cpu().numpy().copy()
+    for r in range(1, len(parts)):
+        acc = merge_moments(acc.reshape(-1, 3), parts[r].cpu().numpy().reshape(-1, 3)).reshape(mom.shape)
+    return acc
