@@ -1,0 +1,152 @@
+"""-m gpu: per-path parity of the CUDA path against the oracle under shared (supplied) Brownian increments.
+
+Tolerance: 1e-12 relative in float64 (BASELINE.json north_star).  The CUDA kernels contract a*b+c into FMA like
+Julia's @muladd does in the reference's step functions (bit identity with the un-fused oracle is not expected)."""
+import numpy as np
+import pytest
+
+import cases
+import sdde_b200 as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def run_case(case, n_traj, **extra):
+    sch = case.oracle_schedule()
+    nchan = case.model.n_chan
+    dW = cases.increments(sch, nchan, n_traj)
+    sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0),
+                  trajectories=n_traj, noise_increments=dW, moments=True, **case.solve_kwargs(), **extra)
+    ref, st = case.oracle(dW)
+    assert sim.out.shape == ref.shape
+    assert np.array_equal(sim.t, sch.save_t)
+    return sim, ref, st
+
+
+@pytest.mark.parametrize("alg", [0, 1, 2, 3])
+def test_c1_linear_all_algs(alg):
+    case = cases.c1().with_(alg=alg)
+    sim, ref, st = run_case(case, 1000)
+    assert cases.scaled_err(sim.out, ref) < TOL
+    assert np.array_equal(sim.status, st)
+
+
+def test_c1_save_everystep():
+    case = cases.c1(saveat=None)
+    sim, ref, _ = run_case(case, 300)
+    assert sim.out.shape[0] == 1002
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+@pytest.mark.parametrize("alg", [0, 1])
+def test_c2_mackey_glass_em(alg):
+    case = cases.c2(alg=alg)
+    sim, ref, _ = run_case(case, 4096)
+    assert sim.timing["n_steps"] == 2001
+    assert cases.relerr(sim.out, ref) < TOL
+
+
+@pytest.mark.parametrize("order0", [0, 2])
+@pytest.mark.parametrize("alg", [2, 3])
+def test_c3_nongrid_lag_rkmil(order0, alg):
+    case = cases.c3(order0=order0, alg=alg)
+    sim, ref, _ = run_case(case, 4096)
+    assert sim.timing["n_steps"] == (2002 if order0 == 0 else 2001)
+    assert cases.relerr(sim.out, ref) < TOL
+
+
+def test_c4_four_state_two_lags_nondiagonal():
+    case = cases.c4()
+    sim, ref, _ = run_case(case, 2048)
+    assert sim.timing["n_steps"] == 2003
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_hayes_time_dependent_history():
+    case = cases.hayes(T=3.0, dt=2.0 ** -6, beta=-1.2, saveat=0.25)   # test_prob_sol.jl g with the delayed term
+    sim, ref, _ = run_case(case, 512)
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_sir_sparse_noise_undeclared_lag():
+    case = cases.sir(T=20.0, dt=0.02)    # without the reference test's callback EM stays finite on this span only
+    sim, ref, _ = run_case(case, 512)
+    assert sim.timing["n_steps"] == 1001
+    assert cases.scaled_err(sim.out, ref) < 1e-11    # sqrt(max(0,x)) near 0 amplifies rounding differences
+
+
+def test_scalar_additive_noise():
+    case = cases.scalar_add()
+    sim, ref, _ = run_case(case, 512)
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_moments_match_numpy():
+    import sdde_oracle as O
+    case = cases.c2(T=40.0)
+    sim, ref, _ = run_case(case, 3001)      # odd count: exercises the scalar-store tail
+    om = O.moments(ref)
+    assert np.allclose(sim.moments[..., 0], 3001)
+    assert np.allclose(sim.moments[..., 1], om[..., 1], rtol=1e-12, atol=1e-14)
+    assert np.allclose(sim.moments[..., 2], om[..., 2], rtol=1e-9, atol=1e-14)
+
+
+def test_waves_and_device_output_agree():
+    import torch
+    case = cases.c2(T=30.0)
+    sch = case.oracle_schedule()
+    dW = cases.increments(sch, 1, 1500)
+    kw = dict(trajectories=1500, noise_increments=dW, **case.solve_kwargs())
+    a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+    b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, wave_traj=512), moments=True, **kw)
+    c = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device", wave_traj=512), **kw)
+    S.get_context(0).set_option("wave_traj", 0)
+    assert b.timing["waves"] == 3
+    assert np.array_equal(a.out, b.out)
+    assert np.array_equal(a.out, c.out.cpu().numpy())
+    dWd = torch.from_numpy(dW).cuda()
+    d = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=1500,
+                noise_increments=dWd, **case.solve_kwargs())
+    assert np.array_equal(a.out, d.out)
+
+
+def test_noise_grid_mode():
+    case = cases.c1(T=4.0)
+    sch = case.oracle_schedule()
+    dW = cases.increments(sch, 1, 256)
+    W = np.concatenate([np.zeros((1, 1, 256)), np.cumsum(dW, axis=0)], axis=0)
+    sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=256, noise_grid=W,
+                  **case.solve_kwargs())
+    # the increments the kernel reconstructs: dW_n = W[n+1] - curW, curW += dW_n
+    cur = np.zeros((1, 256)); dWg = np.empty_like(dW)
+    for n in range(sch.n_steps):
+        dWg[n] = W[n + 1] - cur
+        cur = cur + dWg[n]
+    ref, _ = case.oracle(dWg)
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_per_trajectory_params_and_u0():
+    case = cases.c1(T=5.0)
+    n = 700
+    rng = np.random.default_rng(5)
+    pb = np.stack([-1.0 + 0.2 * rng.random(n), 0.5 + 0.1 * rng.random(n), 0.2 * np.ones(n)])
+    ub = 1.0 + 0.1 * rng.random((1, n))
+    sch = case.oracle_schedule()
+    dW = cases.increments(sch, 1, n)
+    sim = S.solve(S.EnsembleProblem(case.problem(), p_batch=pb, u0_batch=ub), S.EM(), S.EnsembleB200(device=0),
+                  trajectories=n, noise_increments=dW, **case.solve_kwargs())
+    ref, _ = case.oracle(dW, params=pb, u0=ub)
+    assert cases.scaled_err(sim.out, ref) < TOL
+    # prob_func form (the reference's EnsembleProblem interface)
+    ep = S.EnsembleProblem(case.problem(), prob_func=lambda prob, i, rep: prob.remake(p=pb[:, i - 1], u0=ub[:, i - 1]))
+    sim2 = S.solve(ep, S.EM(), S.EnsembleB200(device=0), trajectories=n, noise_increments=dW, **case.solve_kwargs())
+    assert np.array_equal(sim.out, sim2.out)
+
+
+def test_unstable_trajectories_flagged():
+    case = cases.c1(T=10.0).with_(p=np.array([300.0, 0.5, 0.2]))   # explicit Euler blows up -> Inf/NaN
+    sim, ref, st = run_case(case, 64)
+    assert np.all(sim.status == 1) and np.all(st == 1)
+    assert sim.retcodes[0] == "Unstable"
