@@ -1,0 +1,342 @@
+// sdde_oracle.cpp -- CPU restatement (C++) of the reference's per-trajectory solve.  TEST INFRASTRUCTURE ONLY.
+//
+// PARITY UNPINNED: like oracle/sdde_oracle.py this follows the reference's algorithm (file:line below), but the
+// reference itself (Julia) cannot be run in this environment and ships no golden vectors for this path.
+//
+// This is the "CPU restatement stand-in" of BASELINE.md section 2: one trajectory at a time, the way
+// StochasticDelayDiffEq.jl does it, parallelised over trajectories with std::thread in static chunks (what
+// [EXT] SciMLBase EnsembleThreads' Threads.@threads does).  Per trajectory it deliberately keeps the reference's
+// work: its own tstop / discontinuity / saveat heaps (src/solve.jl:613-713), a growing dense history
+// (sol.t / sol.u push per step, src/integrators/interface.jl:406-417), a binary search + linear interpolation per
+// delayed-state lookup PER f/g EVALUATION ([EXT] HistoryFunction -> sde_interpolation, wired at src/utils.jl:246;
+// f and g each call h(p, t - tau), src/functionwrapper.jl:8-9,35-36) and one normal draw per step and channel
+// (src/integrators/interface.jl:449-454).  It has none of Julia's __init / deepcopy / dynamic-dispatch overhead, so
+// speed-ups quoted against it are conservative.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may load this library.
+// Build: make -C oracle   (g++ -O2 -ffp-contract=off; no FMA so it is bit-identical to the numpy oracle).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <queue>
+#include <thread>
+#include <vector>
+
+#include "../include/sdde_b200.h"
+
+namespace {
+
+inline double jl_eps(double x) {
+    x = std::fabs(x);
+    return std::nextafter(x, std::numeric_limits<double>::infinity()) - x;
+}
+
+// ---- Philox4x32-10 + Box-Muller: same stream definition as the GPU kernels (csrc/sdde_kernels.cuh) ----
+inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t o[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+inline void normal_pair(uint64_t gid, uint64_t call, uint64_t seed, double &z0, double &z1) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), w);
+    const uint64_t m1 = ((uint64_t)(w[1] & 0xFFFFFu) << 32) | w[0], m2 = ((uint64_t)(w[3] & 0xFFFFFu) << 32) | w[2];
+    const double u1 = ((double)m1 + 0.5) * 0x1p-52, u2 = ((double)m2 + 0.5) * 0x1p-52;
+    const double r = std::sqrt(-2.0 * std::log(u1));
+    const double ang = 2.0 * M_PI * u2;
+    z0 = r * std::cos(ang); z1 = r * std::sin(ang);
+}
+
+inline double ipow(double x, int n) {   // same multiplication order as oracle/sdde_oracle.py::ipow
+    double result = 1.0, base = x;
+    bool first = true;
+    while (n > 0) {
+        if (n & 1) { result = first ? base : result * base; first = false; }
+        n >>= 1;
+        if (n) base = base * base;
+    }
+    return result;
+}
+
+struct Traj;
+typedef void (*LagFn)(Traj &, double t, int l, double *out);   // h(p, t - tau_l)
+
+// ---- model zoo: f(du,u,h,p,t) / g(du,u,h,p,t) written against a history callback like the reference's closures ----
+struct Model {
+    int ns, nl, nw;
+    bool diag;
+    std::function<void(double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double t)> f, g;
+};
+
+Model make_model(const sdde_desc *d) {
+    Model m;
+    m.ns = d->n_state; m.nl = d->n_lag; m.nw = d->n_noise;
+    switch (d->model_id) {
+        case SDDE_MODEL_LINEAR1:
+            m.diag = true;
+            m.f = [](double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double ul; h(0, &ul); du[0] = p[0] * u[0] + p[1] * ul; };
+            m.g = [](double *du, const double *u, const std::function<void(int, double *)> &, const double *p, double) {
+                du[0] = p[2] * u[0]; };
+            break;
+        case SDDE_MODEL_HAYES:
+            m.diag = true;
+            m.f = [](double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double ul; h(0, &ul); du[0] = (p[1] * u[0] + p[2] * ul) + p[3]; };
+            m.g = [](double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double ul; h(0, &ul); du[0] = (p[4] * u[0] + p[5] * ul) + p[6]; };
+            break;
+        case SDDE_MODEL_MACKEY_GLASS:
+            m.diag = true;
+            m.f = [](double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double x; h(0, &x); const double xn = ipow(x, (int)p[2]); du[0] = (p[0] * x) / (1.0 + xn) - p[1] * u[0]; };
+            m.g = [](double *du, const double *u, const std::function<void(int, double *)> &, const double *p, double) {
+                du[0] = p[3] * u[0]; };
+            break;
+        case SDDE_MODEL_SCALAR_ADD:
+            m.diag = true;
+            m.f = [](double *du, const double *, const std::function<void(int, double *)> &h, const double *p, double) {
+                double ul; h(0, &ul); du[0] = p[0] * ul; };
+            m.g = [](double *du, const double *u, const std::function<void(int, double *)> &, const double *p, double) {
+                du[0] = p[1] + 0.0 * u[0]; };
+            break;
+        case SDDE_MODEL_SIR: {
+            m.diag = false;
+            auto rates = [](const double *u, const std::function<void(int, double *)> &h, const double *p, double &inf, double &rec) {
+                const double N = (u[0] + u[1]) + u[2];
+                inf = ((p[0] * p[1]) * u[1]) / N * u[0];
+                double ud[3]; h(0, ud);
+                const double Nd = (ud[0] + ud[1]) + ud[2];
+                rec = ((p[0] * p[1]) * ud[1]) / Nd * ud[0];
+            };
+            m.f = [rates](double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double inf, rec; rates(u, h, p, inf, rec); du[0] = -inf; du[1] = inf - rec; du[2] = rec; };
+            m.g = [rates](double *gv, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double inf, rec; rates(u, h, p, inf, rec);
+                const double si = std::sqrt(std::max(0.0, inf)), sr = std::sqrt(std::max(0.0, rec));
+                gv[0] = -si; gv[1] = 0.0; gv[2] = si; gv[3] = -sr; gv[4] = 0.0; gv[5] = sr; };
+            break;
+        }
+        case SDDE_MODEL_LINSYS: {
+            m.diag = false;
+            const int ns = d->n_state, nl = d->n_lag, nw = d->n_noise;
+            m.f = [ns, nl](double *du, const double *u, const std::function<void(int, double *)> &h, const double *p, double) {
+                double ul[SDDE_MAX_LAG][SDDE_MAX_STATE];
+                for (int l = 0; l < nl; ++l) h(l, ul[l]);
+                for (int i = 0; i < ns; ++i) {
+                    double acc = p[i * ns] * u[0];
+                    for (int j = 1; j < ns; ++j) acc = acc + p[i * ns + j] * u[j];
+                    for (int l = 0; l < nl; ++l)
+                        for (int j = 0; j < ns; ++j) acc = acc + p[ns * ns * (1 + l) + i * ns + j] * ul[l][j];
+                    du[i] = acc + p[ns * ns * (1 + nl) + i];
+                } };
+            m.g = [ns, nl, nw](double *gv, const double *u, const std::function<void(int, double *)> &, const double *p, double) {
+                const int offM = ns * ns * (1 + nl) + ns, offN = offM + ns * nw;
+                for (int i = 0; i < ns; ++i)
+                    for (int j = 0; j < nw; ++j) gv[i * nw + j] = p[offM + i * nw + j] * u[i] + p[offN + i * nw + j]; };
+            break;
+        }
+        default: m.ns = 0;
+    }
+    return m;
+}
+
+struct Disc { double t; int order2; };
+struct DiscLater { bool operator()(const Disc &a, const Disc &b) const { return a.t > b.t; } };
+typedef std::priority_queue<double, std::vector<double>, std::greater<double>> TimeHeap;
+typedef std::priority_queue<Disc, std::vector<Disc>, DiscLater> DiscHeap;
+
+// One trajectory, following src/solve.jl:11-610 for the fixed-step constant-lag case.
+// Returns number of steps taken.
+int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double *dW, int64_t n_steps_noise,
+                  double *out, int64_t n_save_expected, uint8_t *status) {
+    const int ns = M.ns, nl = M.nl, nc = M.diag ? M.ns : M.nw;
+    const int64_t NT = d->n_traj;
+    const double t0 = d->t0, tf = d->tf, dt = d->dt;
+    const int alg = d->alg;
+    const int alg_order2 = (alg >= 2) ? 2 : 1;
+    double p[SDDE_MAX_PARAM];
+    for (int i = 0; i < d->n_param; ++i) p[i] = d->param_stride ? d->params[i * d->param_stride + traj] : d->params[i];
+    double u[SDDE_MAX_STATE], uprev[SDDE_MAX_STATE], u0[SDDE_MAX_STATE];
+    for (int j = 0; j < ns; ++j) u0[j] = u[j] = d->u0_stride ? d->u0[j * d->u0_stride + traj] : d->u0[j];
+
+    // ---- __init: queues (src/solve.jl:613-713) ----
+    const int order0_2 = 2 * d->order_discontinuity_t0;
+    const bool add_prop = order0_2 <= alg_order2 && d->constant_lags_declared && nl > 0;
+    TimeHeap tst, sv;
+    DiscHeap disc;
+    if (!add_prop && d->n_tstops == 0) tst.push(tf);
+    else {
+        for (int i = 0; i < d->n_tstops; ++i) if (t0 < d->tstops[i] && d->tstops[i] <= tf) tst.push(d->tstops[i]);
+        if (add_prop) for (int l = 0; l < nl; ++l) if (d->lags[l] < tf - t0) tst.push(t0 + d->lags[l]);
+        tst.push(tf);
+    }
+    if (add_prop) for (int l = 0; l < nl; ++l) if (d->lags[l] < tf - t0) disc.push(Disc{t0 + d->lags[l], order0_2 + 1});
+    for (int i = 0; i < d->n_saveat; ++i) sv.push(d->saveat[i]);
+
+    // ---- dense history = solution arrays (src/utils.jl:143-247, src/solve.jl:465-482) ----
+    std::vector<double> ht, hu;
+    ht.reserve(1024); hu.reserve(1024 * ns);
+    ht.push_back(t0);
+    for (int j = 0; j < ns; ++j) hu.push_back(u[j]);
+
+    int64_t ks = 0;
+    bool bad = false;
+    auto save = [&](const double *v) {
+        if (ks < n_save_expected)
+            for (int j = 0; j < ns; ++j) { out[(ks * ns + j) * NT + traj] = v[j]; bad = bad || !std::isfinite(v[j]); }
+        ++ks;
+    };
+    if (d->save_start) save(u);
+
+    double t = t0;
+    // [EXT] HistoryFunction(p, t): prehistory | interpolation of the dense solution | constant u0
+    auto hist = [&](double tl, double *o) {
+        if (tl < ht.front()) { for (int j = 0; j < ns; ++j) o[j] = d->hist_c0[j] + d->hist_c1[j] * tl; return; }
+        if (tl <= ht.back()) {
+            const size_t i = std::lower_bound(ht.begin(), ht.end(), tl) - ht.begin();   // searchsortedfirst
+            if (ht[i] == tl) { for (int j = 0; j < ns; ++j) o[j] = hu[i * ns + j]; return; }
+            const double th = (tl - ht[i - 1]) / (ht[i] - ht[i - 1]);
+            for (int j = 0; j < ns; ++j) o[j] = (1.0 - th) * hu[(i - 1) * ns + j] + th * hu[i * ns + j];
+            return;
+        }
+        for (int j = 0; j < ns; ++j) o[j] = u0[j];
+    };
+    const std::function<void(int, double *)> hcb = [&](int l, double *o) { hist(t - d->lags[l], o); };
+
+    int64_t n = 0;
+    double zc0 = 0, zc1 = 0; uint64_t zcall = ~0ull;
+    double curW[SDDE_MAX_NOISE] = {0};
+    if (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID) for (int c = 0; c < nc; ++c) curW[c] = dW[(int64_t)c * NT + traj];
+    double du[SDDE_MAX_STATE], K[SDDE_MAX_STATE], gv[SDDE_MAX_STATE * SDDE_MAX_NOISE], g2[SDDE_MAX_STATE], ut[SDDE_MAX_STATE], dw[SDDE_MAX_NOISE];
+    while (!tst.empty()) {
+        while (t < tst.top()) {
+            // loopheader! / apply_step!: uprev <- u, dt_n <- min(dt, tstop - t), draw dW ~ N(0,|dt_n|)
+            const double top = tst.top();
+            const double dtn = dt != 0.0 ? std::min(dt, top - t) : top - t;
+            const double sq = std::sqrt(std::fabs(dtn));
+            for (int j = 0; j < ns; ++j) uprev[j] = u[j];
+            for (int c = 0; c < nc; ++c) {
+                if (d->noise_mode == SDDE_NOISE_PHILOX) {
+                    const uint64_t q = (uint64_t)n * nc + c, call = q >> 1;
+                    if (call != zcall) { normal_pair((uint64_t)(d->traj_offset + traj), call, d->seed, zc0, zc1); zcall = call; }
+                    dw[c] = sq * ((q & 1) ? zc1 : zc0);
+                } else if (d->noise_mode == SDDE_NOISE_SUPPLIED_DW) {
+                    dw[c] = n < n_steps_noise ? dW[(n * nc + c) * NT + traj] : 0.0;
+                } else {
+                    const double w = dW[((n + 1) * nc + c) * NT + traj];
+                    dw[c] = w - curW[c]; curW[c] += dw[c];
+                }
+            }
+            // perform_step! ([EXT] StochasticDiffEq, call site src/solve.jl:586)
+            M.f(du, uprev, hcb, p, t);
+            for (int j = 0; j < ns; ++j) K[j] = uprev[j] + dtn * du[j];
+            if (alg == SDDE_ALG_EM_SPLIT || alg == SDDE_ALG_EM_NOSPLIT) {
+                M.g(gv, alg == SDDE_ALG_EM_SPLIT ? K : uprev, hcb, p, t);
+                if (M.diag) for (int j = 0; j < ns; ++j) u[j] = K[j] + gv[j] * dw[j];
+                else for (int i = 0; i < ns; ++i) {
+                    double noise = gv[i * M.nw] * dw[0];
+                    for (int j = 1; j < M.nw; ++j) noise = noise + gv[i * M.nw + j] * dw[j];
+                    u[i] = K[i] + noise;
+                }
+            } else {
+                M.g(gv, uprev, hcb, p, t);
+                for (int j = 0; j < ns; ++j) ut[j] = (alg == SDDE_ALG_RKMIL_ITO ? K[j] : uprev[j]) + gv[j] * sq;
+                M.g(g2, ut, hcb, p, t);
+                for (int j = 0; j < ns; ++j) {
+                    const double ggp = (g2[j] - gv[j]) / sq;
+                    const double w2 = alg == SDDE_ALG_RKMIL_ITO ? (dw[j] * dw[j] - std::fabs(dtn)) : (dw[j] * dw[j]);
+                    const double mil = ggp * w2 / 2.0;
+                    u[j] = (K[j] + gv[j] * dw[j]) + mil;
+                }
+            }
+            // loopfooter! non-adaptive (src/integrators/interface.jl:70-85)
+            const double ttmp = t + dtn, tprev = t;
+            t = (std::fabs(ttmp - top) < 10.0 * jl_eps(std::max(t, top))) ? top : ttmp;
+            // savevalues! (src/integrators/interface.jl:357-430)
+            while (!sv.empty() && sv.top() <= t) {
+                const double curt = sv.top(); sv.pop();
+                if (curt != t) {
+                    const double th = (curt - tprev) / dtn;
+                    double val[SDDE_MAX_STATE];
+                    for (int j = 0; j < ns; ++j) val[j] = (1.0 - th) * uprev[j] + th * u[j];
+                    save(val);
+                } else save(u);
+            }
+            if (d->save_everystep) save(u);
+            ht.push_back(t);
+            for (int j = 0; j < ns; ++j) hu.push_back(u[j]);
+            ++n;
+            if (tst.empty()) break;
+        }
+        // handle_tstop! / handle_discontinuities! / add_next_discontinuities! (src/integrators/utils.jl)
+        if (!tst.empty()) {
+            if (t == tst.top()) tst.pop();
+            if (!disc.empty()) {
+                int order2 = disc.top().order2; disc.pop();
+                while (!disc.empty() && disc.top().t == t) { order2 = std::min(order2, disc.top().order2); disc.pop(); }
+                const double maxdt = 10.0 * jl_eps(t);
+                while (!disc.empty() && std::fabs(disc.top().t - t) < maxdt) { order2 = std::min(order2, disc.top().order2); disc.pop(); }
+                while (!tst.empty() && std::fabs(tst.top() - t) < maxdt) tst.pop();
+                const int next2 = order2 + 1;
+                if (next2 <= alg_order2 + 1 && d->constant_lags_declared)
+                    for (int l = 0; l < nl; ++l)
+                        if (d->lags[l] < tf - t) { disc.push(Disc{t + d->lags[l], next2}); tst.push(t + d->lags[l]); }
+            }
+        }
+    }
+    // postamble! (src/integrators/interface.jl:100-117)
+    if (d->save_end) {
+        // last saved time != t  <=>  the final state was not saved by saveat/save_everystep
+        bool already = d->save_everystep;
+        if (!already && d->n_saveat > 0) {
+            double mx = d->saveat[0];
+            for (int i = 1; i < d->n_saveat; ++i) mx = std::max(mx, d->saveat[i]);
+            already = (mx == t);
+        }
+        if (!already && n == 0 && d->save_start) already = true;
+        if (!already) save(u);
+    }
+    for (int j = 0; j < ns; ++j) bad = bad || !std::isfinite(u[j]);
+    if (status) status[traj] = bad ? 1 : 0;
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+// out: [n_save][n_state][n_traj] (host).  noise: as in sdde_desc (host).  Returns 0, or -2 for an unknown model.
+__attribute__((visibility("default"))) int sdde_oracle_solve(const sdde_desc *d, int64_t n_save, int64_t n_steps_noise, double *out,
+                                                              uint8_t *status, int n_threads, double *elapsed_s, int64_t *steps_taken) {
+    Model M = make_model(d);
+    if (M.ns == 0) return -2;
+    if (n_threads < 1) n_threads = 1;
+    const int64_t NT = d->n_traj;
+    std::vector<int64_t> steps((size_t)n_threads, 0);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int w = 0; w < n_threads; ++w) {
+        th.emplace_back([&, w]() {
+            const int64_t lo = NT * w / n_threads, hi = NT * (w + 1) / n_threads;   // static chunks (Threads.@threads)
+            int64_t s = 0;
+            for (int64_t i = lo; i < hi; ++i) s = solve_one(d, M, i, d->noise, n_steps_noise, out, n_save, status);
+            steps[(size_t)w] = s;
+        });
+    }
+    for (auto &t : th) t.join();
+    if (elapsed_s) *elapsed_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (steps_taken) { *steps_taken = 0; for (int64_t s : steps) *steps_taken = std::max(*steps_taken, s); }
+    return 0;
+}
+
+}  // extern "C"

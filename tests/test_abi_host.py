@@ -1,0 +1,181 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/sdde_b200.h; the host-side schedule builder of the
+product equals the oracle's replay bit for bit; descriptor validation and the reference's error behaviour; host logic
+of the SciML-surface mirror.  No compute entry point is exercised here (no GPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import sdde_b200 as S
+import sdde_oracle as O
+from sdde_b200 import _capi as capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sdde_b200.h")).read()
+    declared = sorted(set(re.findall(r"SDDE_API[^;(]*?\b(sdde_b200_\w+)\s*\(", hdr)))
+    assert declared == sorted(capi.EXPORTS) and len(declared) == 16
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.sdde_b200_version() == 100
+
+
+def test_struct_layout_matches_header():
+    src = '#include "sdde_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(sdde_desc),sizeof(sdde_schedule),sizeof(sdde_timing),offsetof(sdde_desc,params),offsetof(sdde_desc,seed));}'
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "a.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "a.c"), "-o", os.path.join(td, "a")], check=True)
+        out = subprocess.run([os.path.join(td, "a")], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [C.sizeof(capi.SddeDesc), C.sizeof(capi.SddeSchedule), C.sizeof(capi.SddeTiming),
+                                     capi.SddeDesc.params.offset, capi.SddeDesc.seed.offset]
+
+
+SCHED_CASES = [
+    (lambda: cases.c1(), {}), (lambda: cases.c1(saveat=None), {}), (lambda: cases.c2(), {}), (lambda: cases.c2(T=500.0), {}),
+    (lambda: cases.c3(0), {}), (lambda: cases.c3(2), {}), (lambda: cases.c3(0, alg=0), {}), (lambda: cases.c4(), {}),
+    (lambda: cases.hayes(T=10.0, dt=2.0 ** -8), {}), (lambda: cases.sir(), {}), (lambda: cases.scalar_add(), {}),
+    (lambda: cases.c1(T=3.3, saveat=[0.0, 0.7, 1.0, 2.2, 3.3]), {}), (lambda: cases.c1(T=3.3, saveat=[0.5, 1.5]), {}),
+    (lambda: cases.c1(T=0.5, saveat=0.2), {}),                       # tf < tau: never reads its own past
+    (lambda: cases.c1(T=2.0, saveat=0.003), {}),                     # several saves per step
+    (lambda: cases.c1(T=5.0).with_(dt=1.7, lags=[1.0]), {}),         # dt > tau (allowed for EM)
+]
+
+
+@pytest.mark.parametrize("mk,kw", SCHED_CASES)
+def test_product_schedule_equals_oracle_bitwise(mk, kw):
+    c = mk()
+    s = S.schedule(c.problem(), cases.ALG_MAP[c.alg], **c.solve_kwargs())
+    o = c.oracle_schedule()
+    for k in ["t", "dt", "sqdt", "lk_mode", "lk_idx", "lk_theta", "save_t", "save_step", "save_theta", "save_exact"]:
+        a, b = getattr(s, k), getattr(o, k)
+        assert a.shape == b.shape and np.array_equal(a, b), k
+    assert list(s.tstops_hit) == o.tstops_hit
+    # ring capacity: no node that a later lookup needs is overwritten
+    for n in range(s.n_steps):
+        for l in range(s.lk_mode.shape[1]):
+            if s.lk_mode[n, l] != 0:
+                lo = s.lk_idx[n, l] - (1 if s.lk_mode[n, l] == 2 else 0)
+                assert n - lo < s.ring_slots and n - s.lk_idx[n, l] >= s.min_gap
+
+
+def test_user_tstops_and_quirk():
+    c = cases.c1(T=3.0)
+    s = S.schedule(c.problem(), S.EM(), dt=0.01, saveat=0.5, tstops=[0.333, 2.0, 7.0])
+    o = O.build_schedule(0.0, 3.0, 0.01, [1.0], 0, saveat_times=O.expand_saveat(0.5, 0, 3.0)[0], tstops=[0.333, 2.0, 7.0])
+    assert np.array_equal(s.t, o.t) and list(s.tstops_hit) == o.tstops_hit and 0.333 in s.t
+
+
+def test_saveat_expansion_rules():
+    sv, ss, se = S.expand_saveat(1.0, 0.0, 500.0)
+    assert len(sv) == 500 and sv[0] == 1.0 and sv[-1] == 500.0 and ss and se
+    sv, _, _ = S.expand_saveat(0.3, 0.0, 1.0)          # (t0:s:tf)[end] != tf -> stops at tf - s
+    assert np.allclose(sv, [0.3, 0.6]) and sv[-1] <= 1.0 - 0.3
+    sv, ss, se = S.expand_saveat([0.0, 0.5, 2.0, 9.0], 0.0, 2.0)
+    assert list(sv) == [0.5] and ss and se
+    sv, ss, se = S.expand_saveat([0.5], 0.0, 2.0)
+    assert list(sv) == [0.5] and not ss and not se
+    for case in [(0.1, 0.0, 10.0), (0.5, 0.0, 20.0), (1.0, 0.0, 100.0)]:
+        assert np.array_equal(S.expand_saveat(*case)[0], O.expand_saveat(*case)[0])
+
+
+def _desc_rc(prob, alg, **kw):
+    try:
+        S.schedule(prob, alg, **kw)
+        return 0
+    except S.SddeError as e:
+        return e.code
+
+
+def test_error_behaviour_mirrors_reference_guards():
+    c = cases.c1()
+    # src/solve.jl:121-123
+    with pytest.raises(S.SddeError, match="Fixed timestep methods require a choice of dt"):
+        S.schedule(c.problem(), S.EM(), dt=0.0)
+    # RKMil is adaptive by default in the reference (src/solve.jl:40): this path needs adaptive=False
+    with pytest.raises(NotImplementedError, match="adaptive"):
+        S.schedule(c.problem(), S.RKMil(), dt=0.01)
+    # src/solve.jl:581-585
+    with pytest.raises(S.SddeError, match=r"dt > minimum\(constant_lags\)"):
+        S.schedule(c.problem(), S.RKMil(), dt=1.5, adaptive=False)
+    assert _desc_rc(c.problem(), S.EM(), dt=1.5) == 0       # EM is exempt
+    with pytest.raises(S.SddeError):
+        S.schedule(c.with_(tspan=(1.0, 0.0)).problem(), S.EM(), dt=0.1)
+    with pytest.raises(NotImplementedError):
+        S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, (0, 1), (1, 1, 1), constant_lags=(1.0,), neutral=True)
+    with pytest.raises(TypeError):
+        S.SDDEProblem(lambda u, h, p, t: u, S.linear1.g, 1.0, 1.0, (0, 1), (1, 1, 1), constant_lags=(1.0,))
+    with pytest.raises(ValueError):
+        S.SDDEProblem(S.linear1.f, S.hayes.g, 1.0, 1.0, (0, 1), (1, 1, 1), constant_lags=(1.0,))
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = capi.lib()
+    assert L.sdde_b200_device_count() < 0
+    assert not L.sdde_b200_create(0)
+    assert b"no CPU fallback" in L.sdde_b200_last_error()
+    d = capi.SddeDesc()
+    assert L.sdde_b200_solve(None, C.byref(d), None, None, None, None) <= capi.lib().sdde_b200_version() * 0 - 100
+    with pytest.raises(S.SddeError):
+        S.solve(cases.c1().problem(), S.EM(), dt=0.01)
+
+
+def test_abi_rejects_bad_descriptors():
+    L = capi.lib()
+    sch = capi.SddeSchedule()
+    d = capi.SddeDesc()
+    assert L.sdde_b200_schedule(C.byref(d), C.byref(sch)) == -1 and b"struct_size" in L.sdde_b200_last_error()
+    d.struct_size = C.sizeof(capi.SddeDesc)
+    d.alg = 9
+    assert L.sdde_b200_schedule(C.byref(d), C.byref(sch)) == -2
+    assert L.sdde_b200_schedule(None, C.byref(sch)) == -1
+
+
+def test_history_function_forms():
+    from sdde_b200.problem import _as_history
+    h = _as_history(lambda p, t: np.ones(1) + t, None, 0.0, 1)     # the reference tests' h(p,t) = 1 + t
+    assert h.c0 == (1.0,) and h.c1 == (1.0,)
+    assert _as_history(1.2, None, 0.0, 1).c0 == (1.2,)
+    with pytest.raises(NotImplementedError):
+        _as_history(lambda p, t: np.sin(t) * np.ones(1), None, 0.0, 1)
+
+
+def test_shard_ranges_cover_exactly():
+    for n, w in [(10 ** 6, 8), (10, 3), (7, 8), (0, 2), (10 ** 8, 4)]:
+        rs = [S.shard_range(n, r, w) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+
+
+def test_merge_moments_matches_oracle():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((4, 2, 900))
+    a, b = O.moments(x[..., :301]), O.moments(x[..., 301:])
+    got = S.merge_moments(a.reshape(-1, 3), b.reshape(-1, 3)).reshape(a.shape)
+    assert np.allclose(got, O.merge_moments(a, b), rtol=1e-15)
+    assert np.allclose(got, O.moments(x), rtol=1e-12)
+    z = np.zeros_like(a)
+    assert np.array_equal(S.merge_moments(z.reshape(-1, 3), a.reshape(-1, 3)).reshape(a.shape), a)
+
+
+def test_ensemble_problem_batches_and_prob_func():
+    c = cases.c1()
+    pb = np.arange(30, dtype=float).reshape(3, 10)
+    ep = S.EnsembleProblem(c.problem(), p_batch=pb)
+    p, u = ep.batches(4, first=3)
+    assert np.array_equal(p, pb[:, 3:7]) and u is None
+    ep = S.EnsembleProblem(c.problem(), prob_func=lambda prob, i, rep: prob.remake(p=[i, 0, 0], u0=[2.0 * i]))
+    p, u = ep.batches(3, first=2)
+    assert np.array_equal(p[0], [3, 4, 5]) and np.array_equal(u[0], [6.0, 8.0, 10.0])     # 1-based like Julia
+    with pytest.raises(NotImplementedError):
+        S.EnsembleProblem(c.problem(), output_func=lambda sol, i: (sol, False))

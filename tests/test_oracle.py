@@ -1,0 +1,183 @@
+"""CPU: the oracle against hand-derived known answers, the Random123 Philox known-answer
+vectors, the committed golden fixtures, and the C++ restatement against the numpy restatement (bit for bit)."""
+import os
+
+import numpy as np
+import pytest
+
+import c_oracle
+import cases
+import sdde_oracle as O
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+
+
+def test_philox_known_answer_vectors():
+    # Random123 kat_vectors for philox4x32_10
+    def kat(c, k):
+        r = O.philox4x32_10(*[np.array([x]) for x in c], k[0], k[1])
+        return [int(x[0]) for x in r]
+    assert kat([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normals_golden_and_moments():
+    z = O.philox_normals(GOLD["philox_ids"], 6, 3, 0xB2000001)
+    assert np.array_equal(z, GOLD["philox_z"])
+    z = O.philox_normals(np.arange(40000), 10, 1, 99)
+    assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 6 * np.sqrt(2 / z.size)
+    assert abs((z ** 4).mean() - 3) < 0.1
+
+
+def _one_step(alg):
+    m = O.Model(99, 1, 1, 1, True, 0, lambda u, ul, p, t: u, lambda u, ul, p, t: u)
+    s = O.Schedule(t=np.array([0, 0.1]), dt=np.array([0.1]), sqdt=np.sqrt(np.array([0.1])),
+                   lk_mode=np.zeros((1, 1), np.int32), lk_idx=-np.ones((1, 1), np.int64), lk_theta=np.zeros((1, 1)),
+                   lk_time=np.zeros((1, 1)), save_t=np.array([0.1]), save_step=np.array([0]),
+                   save_theta=np.array([1.0]), save_exact=np.array([1], np.int32))
+    out, _ = O.solve_ensemble(m, [], [1.0], [0.0], [0.0], [1.0], s, alg, np.full((1, 1, 1), 0.2))
+    return out[0, 0, 0]
+
+
+def test_k1_one_step_known_answers():
+    # f=u, g=u, u=1, dt=0.1, dW=0.2
+    assert _one_step(O.ALG_EM_SPLIT) == pytest.approx(1.32, rel=1e-15)
+    assert _one_step(O.ALG_EM_NOSPLIT) == pytest.approx(1.30, rel=1e-15)
+    sq = np.sqrt(0.1)
+    ggp = ((1.1 + sq) - 1.0) / sq
+    assert _one_step(O.ALG_RKMIL_ITO) == pytest.approx(1.1 + 0.2 + ggp * (0.04 - 0.1) / 2, rel=1e-15)
+    assert _one_step(O.ALG_RKMIL_ITO) == pytest.approx(1.260513167019495, rel=1e-14)
+    assert _one_step(O.ALG_RKMIL_STRAT) == pytest.approx(1.32, rel=1e-15)
+
+
+def test_k2_zero_noise_is_explicit_euler_for_the_dde():
+    c = cases.c1(T=3.0, saveat=None)
+    sch = c.oracle_schedule()
+    out, _ = c.oracle(np.zeros((sch.n_steps, 1, 1)))
+    a, b = -1.0, 0.5
+    u = [1.0]
+    for n in range(sch.n_steps):
+        tl = sch.t[n] - 1.0
+        if tl < 0:
+            ul = 1.0
+        else:
+            i = int(sch.lk_idx[n, 0]); th = sch.lk_theta[n, 0]
+            ul = u[i] if sch.lk_mode[n, 0] == O.LK_EXACT else (1 - th) * u[i - 1] + th * u[i]
+        u.append(u[n] + sch.dt[n] * (a * u[n] + b * ul))
+    assert np.allclose(out[:, 0, 0], np.array(u), rtol=1e-14)
+
+
+def test_k3_exact_mean_recurrence_matches_ensemble_mean():
+    c = cases.c1(T=4.0, saveat=None)
+    sch = c.oracle_schedule()
+    n = 20000
+    dW = O.philox_normals(np.arange(n), sch.n_steps, 1, 5) * sch.sqdt[:, None, None]
+    out, _ = c.oracle(dW)
+    m = O.exact_mean_linear1(sch, -1.0, 0.5, 1.0, 1.0, 0.0, 1.0)
+    se = out[:, 0, :].std(axis=1) / np.sqrt(n)
+    assert np.all(np.abs(out[:, 0, :].mean(axis=1) - m)[1:] < 5 * se[1:] + 1e-12)
+
+
+def test_k4_schedule_facts():
+    s = O.build_schedule(0, 100, 0.05, [17.0], O.ALG_EM_SPLIT)
+    assert s.n_steps == 2001 and s.tstops_hit == [17.0, 34.0, 100.0]
+    assert s.dt[-1] == pytest.approx(3.75e-12, rel=0.01)
+    short = [i for i in range(s.n_steps) if abs(s.dt[i] - 0.05) > 1e-15]
+    assert short == [339, 679, 2000]
+    assert int(np.sum(s.lk_mode[:, 0] == O.LK_EXACT)) == 3          # "3 exact of 1661"
+    assert int(np.sum(s.lk_mode[:, 0] != O.LK_PRE)) == 1661
+    s = O.build_schedule(0, 10, 0.01, [1.0], O.ALG_EM_SPLIT)
+    assert s.n_steps == 1001 and s.dt[-1] == pytest.approx(1.7e-13, rel=0.01)
+    s = O.build_schedule(0, 500, 0.05, [17.0], O.ALG_EM_SPLIT)
+    assert s.n_steps == 10000
+    s = O.build_schedule(0, 100, 0.05, [17.02], O.ALG_RKMIL_ITO)
+    assert s.n_steps == 2002 and s.tstops_hit == [17.02, 34.04, 51.06, 100.0]
+    s2 = O.build_schedule(0, 100, 0.05, [17.02], O.ALG_EM_SPLIT)
+    assert s2.tstops_hit == [17.02, 34.04, 100.0]                   # EM tracks {tau}, {2 tau} only
+    s = O.build_schedule(0, 100, 0.05, [17.02], O.ALG_RKMIL_ITO, order_discontinuity_t0=2)
+    assert s.n_steps == 2001 and s.tstops_hit == [100.0] and s.dt[-1] == pytest.approx(3.5e-12, rel=0.02)
+    assert s.lk_theta[400, 0] == pytest.approx(0.6, abs=1e-9)
+    s = O.build_schedule(0, 20, 0.01, [1.0, 2.5], O.ALG_EM_SPLIT)
+    assert s.n_steps == 2003 and s.tstops_hit == [1.0, 2.0, 2.5, 3.5, 5.0, 20.0]
+    tiny = [s.dt[i] for i in range(s.n_steps) if s.dt[i] < 1e-10]
+    assert len(tiny) == 3 and all(1e-15 < x < 1e-13 for x in tiny)
+
+
+def test_k5_history_edge():
+    # lookup at exactly t0 returns u0 even if h(p,t0) != u0; at t0 - eps returns h
+    m = O.get_model(O.MODEL_LINEAR1)
+    sch = O.build_schedule(0.0, 1.5, 0.5, [1.0], O.ALG_EM_SPLIT, save_everystep=True)
+    assert sch.lk_mode[2, 0] == O.LK_EXACT and sch.lk_idx[2, 0] == 0          # t=1.0 - 1.0 == t0
+    out, _ = O.solve_ensemble(m, [0.0, 1.0, 0.0], [2.0], [5.0], [0.0], [1.0], sch, O.ALG_EM_SPLIT,
+                              np.zeros((sch.n_steps, 1, 1)))
+    # f = u(t-1): steps 0,1 read h = 5, step 2 reads u0 = 2
+    assert np.allclose(out[:, 0, 0], [2.0, 4.5, 7.0, 8.0])
+
+
+def test_k7_saveat_alias_hazard():
+    # H1: with saveat > tau the reference's delayed state is u0 once past the last saved point
+    c = cases.c1(T=6.0, saveat=2.0)
+    sch = c.oracle_schedule()
+    dW = np.zeros((sch.n_steps, 1, 1))
+    dense, _ = c.oracle(dW)
+    alias, _ = c.oracle(dW, history_mode="reference_saveat_alias")
+    assert not np.allclose(dense, alias, rtol=1e-6)
+    # in alias mode with zero noise the delayed value is always u0=1 (prehistory 1, saved points only at 0,2,4,6 and
+    # lookups beyond the last saved point return u0): u' = -u + 0.5 -> fixed point 0.5
+    u = 1.0
+    for n in range(sch.n_steps):
+        u = u + sch.dt[n] * (-1.0 * u + 0.5 * 1.0)
+        if abs(sch.t[n + 1] - 2.0) < 1e-12:
+            assert alias[1, 0, 0] == pytest.approx(u, rel=1e-9)
+
+
+def test_golden_fixtures_reproduce():
+    for name, tau, alg, order0 in [("c2_em", 17.0, 0, 0), ("c3_rkmil_o0", 17.02, 2, 0), ("c3_rkmil_o2", 17.02, 2, 2)]:
+        sv = O.expand_saveat(1.0, 0.0, 40.0)[0]
+        sch = O.build_schedule(0.0, 40.0, 0.05, [tau], alg, order_discontinuity_t0=order0, saveat_times=sv)
+        assert np.array_equal(sch.t, GOLD[name + "_t"]) and np.array_equal(sch.dt, GOLD[name + "_dt"])
+        out, _ = O.solve_ensemble(O.get_model(O.MODEL_MACKEY_GLASS), [0.2, 0.1, 10.0, 0.1], [1.2], [1.2], [0.0], [tau],
+                                  sch, alg, GOLD[name + "_xi"] * sch.sqdt[:, None, None])
+        assert np.array_equal(out, GOLD[name + "_out"])
+
+
+@pytest.mark.parametrize("mk,n", [
+    (lambda: cases.c1(), 200), (lambda: cases.c1(saveat=None), 50), (lambda: cases.c2(T=60.0), 128),
+    (lambda: cases.c2(T=60.0, alg=1), 64), (lambda: cases.c3(0, T=60.0), 128), (lambda: cases.c3(2, T=60.0, alg=3), 128),
+    (lambda: cases.c4(T=8.0), 64), (lambda: cases.hayes(T=3.0, beta=-1.2, saveat=0.25), 64),
+    (lambda: cases.sir(T=20.0, dt=0.02), 64), (lambda: cases.scalar_add(), 64)])
+def test_cpp_restatement_equals_numpy_restatement_bitwise(mk, n):
+    c = mk()
+    sch = c.oracle_schedule()
+    dW = cases.increments(sch, c.model.n_chan, n)
+    ref, st = c.oracle(dW)
+    sv, ss, se = O.expand_saveat(c.saveat, *c.tspan)
+    out, st2, _, steps = c_oracle.solve(c.omodel.mid, c.alg, c.omodel.n_state, c.omodel.n_lag, c.omodel.n_noise, c.p,
+                                        c.u0, c.h0, c.h1, c.lags, c.tspan[0], c.tspan[1], c.dt, sv, len(sch.save_t),
+                                        save_start=ss, save_end=se, save_everystep=c.saveat is None, order0=c.order0,
+                                        declared=c.declared, n_traj=n, dW=dW, n_threads=3)
+    assert steps == sch.n_steps
+    assert np.array_equal(out, ref) and np.array_equal(st, st2)
+
+
+def test_cpp_philox_stream_matches_numpy():
+    c = cases.c1(T=2.0)
+    sch = c.oracle_schedule()
+    n = 64
+    z = O.philox_normals(np.arange(1000, 1000 + n), sch.n_steps, 1, 0xB2000001)
+    ref, _ = c.oracle(z * sch.sqdt[:, None, None])
+    sv, ss, se = O.expand_saveat(c.saveat, *c.tspan)
+    out, _, _, _ = c_oracle.solve(c.omodel.mid, 0, 1, 1, 1, c.p, c.u0, c.h0, c.h1, c.lags, 0.0, 2.0, c.dt, sv,
+                                  len(sch.save_t), n_traj=n, traj_offset=1000, seed=0xB2000001)
+    assert cases.scaled_err(out, ref) < 1e-12      # libm vs numpy log/sin/cos differ by ulps
+
+
+def test_moment_merge_is_associative_enough():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 2, 1000)) * 5 + 100
+    full = O.moments(x)
+    a, b, c = O.moments(x[..., :100]), O.moments(x[..., 100:550]), O.moments(x[..., 550:])
+    m = O.merge_moments(O.merge_moments(a, b), c)
+    assert np.allclose(m, full, rtol=1e-12)
