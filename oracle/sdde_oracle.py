@@ -466,23 +466,31 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def philox_normal_pair(traj_id, call, seed):
-    """Two N(0,1) float64 variates for (global trajectory id, call index):
-    counter = (traj_lo, traj_hi, call_lo, call_hi), key = (seed_lo, seed_hi);
-    m1 = (w1 & 0xFFFFF)<<32 | w0 (52 bits), u1 = (m1 + 0.5) * 2^-52 in (0,1); u2 likewise from (w2,w3);
-    z0 = sqrt(-2 ln u1) cos(2 pi u2), z1 = sqrt(-2 ln u1) sin(2 pi u2)."""
+    """Two N(0,1) float64 variates for (global trajectory id, call index) -- Box-Muller on one Philox4x32-10 block:
+    counter = (traj_lo, traj_hi, call_lo, call_hi), key = (seed_lo, seed_hi) -> words w0..w3;
+      radius:  m = (w1 & 0xFFFFF)<<32 | w0 (52 bits), u = (m + 0.5) * 2^-52 in (0,1), r = sqrt(-2 ln u)
+      angle :  q = w3 >> 30 (quadrant), f = (w3 & 0x3FFFFFFF)<<22 | w2>>10 (52 bits), x = f * 2^-52 - 1/2 in [-1/2, 1/2),
+               theta = (pi/2) (q + x)
+      z0 = r cos(theta), z1 = r sin(theta).
+    (same definition as csrc/sdde_kernels.cuh::philox_normal_pair; the kernel evaluates it with range-restricted
+    polynomials, here numpy's log/sin/cos are used, so the two agree to a few ulp, not bit for bit)."""
     traj_id = np.asarray(traj_id, dtype=np.uint64)
     call = np.asarray(call, dtype=np.uint64)
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     w0, w1, w2, w3 = philox4x32_10(traj_id & _MASK32, traj_id >> np.uint64(32),
                                    call & _MASK32, call >> np.uint64(32),
                                    seed & 0xFFFFFFFF, seed >> 32)
-    m1 = ((w1 & np.uint64(0xFFFFF)) << np.uint64(32)) | w0
-    m2 = ((w3 & np.uint64(0xFFFFF)) << np.uint64(32)) | w2
-    u1 = (m1.astype(np.float64) + 0.5) * 2.0 ** -52
-    u2 = (m2.astype(np.float64) + 0.5) * 2.0 ** -52
-    r = np.sqrt(-2.0 * np.log(u1))
-    ang = 2.0 * np.pi * u2
-    return r * np.cos(ang), r * np.sin(ang)
+    m = ((w1 & np.uint64(0xFFFFF)) << np.uint64(32)) | w0
+    u = (m.astype(np.float64) + 0.5) * 2.0 ** -52
+    r = np.sqrt(-2.0 * np.log(u))
+    q = (w3 >> np.uint64(30)).astype(np.int64)
+    f = ((w3 & np.uint64(0x3FFFFFFF)) << np.uint64(22)) | (w2 >> np.uint64(10))
+    x = f.astype(np.float64) * 2.0 ** -52 - 0.5
+    s, c = np.sin((np.pi / 2) * x), np.cos((np.pi / 2) * x)
+    # rotate by the quadrant exactly: q=0 (c,s), 1 (-s,c), 2 (-c,-s), 3 (s,-c)
+    cq = np.where(q == 0, c, np.where(q == 1, -s, np.where(q == 2, -c, s)))
+    sq = np.where(q == 0, s, np.where(q == 1, c, np.where(q == 2, -s, -c)))
+    return r * cq, r * sq
 
 
 def philox_normals(traj_ids, n_steps: int, n_noise: int, seed) -> np.ndarray:

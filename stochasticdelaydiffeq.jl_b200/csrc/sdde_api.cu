@@ -119,12 +119,17 @@ __global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__
 // test hook: the normals the step kernels would draw, laid out [n][c][traj]
 __global__ void philox_dump_kernel(double *out, long long n_traj, long long traj_off, long long n_steps, int nc, u32 k0,
                                    u32 k1) {
+    __shared__ double2 ltab[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) ltab[i] = RNG_LOG_TAB[i];
+    __syncthreads();
+    u32 rk[20];
+    philox_round_keys(k0, k1, rk);
     const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tr >= n_traj) return;
     const long long nq = n_steps * nc;
     for (long long call = 0; call * 2 < nq; ++call) {
         double z0, z1;
-        philox_normal_pair((u64)(traj_off + tr), (u64)call, k0, k1, z0, z1);
+        philox_normal_pair((u64)(traj_off + tr), (u64)call, rk, ltab, z0, z1);
         out[(2 * call) * n_traj + tr] = z0;
         if (2 * call + 1 < nq) out[(2 * call + 1) * n_traj + tr] = z1;
     }
@@ -490,7 +495,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
 
     const int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
-    const size_t smem = (size_t)chunk * K.rec_size;
+    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)chunk * K.rec_size;
     int batch = K.batch;
     if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
     batch = std::max(1, std::min(batch, S.min_gap + 1));   // prefetched nodes must be older than the batch
@@ -504,6 +509,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
     A.seed_lo = (sdde::u32)(d->seed & 0xffffffffu); A.seed_hi = (sdde::u32)(d->seed >> 32);
+    for (int r = 0; r < 10; ++r) { A.rk[2 * r] = A.seed_lo + (sdde::u32)r * 0x9E3779B9u; A.rk[2 * r + 1] = A.seed_hi + (sdde::u32)r * 0xBB67AE85u; }
     for (int j = 0; j < NS; ++j) { A.hist_c0[j] = d->hist_c0[j]; A.hist_c1[j] = d->hist_c1[j]; }
     if (d->u0_stride == 0) for (int j = 0; j < NS; ++j) A.u0c[j] = d->u0[j];
     if (d->param_stride == 0) for (int i = 0; i < K.n_param; ++i) A.p[i] = d->params[i];

@@ -20,6 +20,7 @@
 // Thread mapping: one thread integrates TPT adjacent trajectories (TPT = 2 -> every ring/out access is a 128-bit
 // double2 access, a warp touches 512 contiguous bytes, and the two independent recurrences give the FP64 pipe ILP).
 #pragma once
+#include "sdde_rng_tables.cuh"
 
 namespace sdde {
 
@@ -33,6 +34,7 @@ enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMI
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
 #define SDDE_BLOCK 128
+#define SDDE_RNG_SMEM_BYTES 2048
 
 struct SaveRec {
     int step;       // step whose end produces this save (-1: initial condition)
@@ -68,6 +70,7 @@ struct KArgs {
     int out_vec_ok;          // out rows are 16-byte aligned for double2 stores
     int pad0;
     u32 seed_lo, seed_hi;
+    u32 rk[20];              // Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 (host precomputed)
     double hist_c0[SDDE_K_MAX_STATE], hist_c1[SDDE_K_MAX_STATE];
     double u0c[SDDE_K_MAX_STATE];
     double p[SDDE_K_MAX_PARAM];
@@ -87,37 +90,97 @@ template <class M> struct Tune {
 // Replaces Xoroshiro128Plus + randn of /root/reference/src/solve.jl:313-336 (the bit stream is NOT reproduced,
 // the distribution is: independent N(0,1), scaled by sqrt|dt_n| like [EXT] DiffEqNoiseProcess WHITE_NOISE_DIST).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 (&o)[4]) {
+__device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, const u32 *__restrict__ rk, u32 (&o)[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const u64 p0 = (u64)0xD2511F53u * c0;
         const u64 p1 = (u64)0xCD9E8D57u * c2;
-        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ k0;
-        const u32 n2 = (u32)(p0 >> 32) ^ c3 ^ k1;
+        const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ rk[2 * r];
+        const u32 n2 = (u32)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
         c1 = (u32)p1;
         c3 = (u32)p0;
         c0 = n0;
         c2 = n2;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-__device__ __forceinline__ void philox_normal_pair(u64 gid, u64 call, u32 k0, u32 k1, double &z0, double &z1) {
+__device__ __forceinline__ void philox_round_keys(u32 k0, u32 k1, u32 *rk) {
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0 + (u32)r * 0x9E3779B9u; rk[2 * r + 1] = k1 + (u32)r * 0xBB67AE85u; }
+}
+
+__device__ __forceinline__ double rsqrt_approx(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// Two N(0,1) variates from one Philox block (w0..w3).  Definition (identical in oracle/sdde_oracle.py):
+//   radius: m = (w1 & 0xFFFFF)<<32 | w0, u = (m + 1/2) 2^-52 in (0,1), r = sqrt(-2 ln u)
+//   angle : q = w3 >> 30, f = (w3 & 0x3FFFFFFF)<<22 | w2>>10, x = f 2^-52 - 1/2, theta = (pi/2)(q + x)
+//   z0 = r cos(theta), z1 = r sin(theta)
+// Evaluation: every argument range is known, so no special cases and no libm calls:
+//   -2 ln u  : u = 2^e' * M', 128-entry table {1/c_k, -2 ln c'_k} in shared memory (k = top 7 mantissa bits),
+//              rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-8, degree-7 log1p polynomial (abs. error < 2^-66)
+//   sqrt     : MUFU.RSQ64H seed + one coupled Newton step + residual correction (<= 1 ulp on [2^-53, 74])
+//   sin, cos : Taylor in (pi/2 x), |x| <= 1/2, degree 15 / 16 (truncation < 5e-17), exact quadrant rotation
+__device__ __forceinline__ void normal_pair_from_words(const u32 (&w)[4], const double2 *__restrict__ ltab, double &z0,
+                                                       double &z1) {
+    // ---- radius ----
+    const double X = __hiloint2double((int)(0x3FF00000u | (w[1] & 0xFFFFFu)), (int)w[0]);   // 1 + m 2^-52
+    const double U = X - 0.99999999999999988897769753748;                                    // (m + 1/2) 2^-52, exact
+    const int hi = __double2hiint(U);
+    const int k = (hi >> 13) & 127;
+    const int n = 1023 - (hi >> 20) - ((hi >> 19) & 1);                                      // -e' in [0, 53]
+    const double M = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(U));    // mantissa in [1,2)
+    const double2 te = ltab[k];
+    const double rho = fma(M, te.x, -1.0);
+    const double dn = __hiloint2double(0x43300000, n) - 4503599627370496.0;                  // (double)n
+    double P = fma(rho, RNG_LOG1P_C[5], RNG_LOG1P_C[4]);
+    P = fma(rho, P, RNG_LOG1P_C[3]);
+    P = fma(rho, P, RNG_LOG1P_C[2]);
+    P = fma(rho, P, RNG_LOG1P_C[1]);
+    P = fma(rho, P, RNG_LOG1P_C[0]);
+    const double l1p = fma(rho * rho, P, rho);
+    double t = fma(dn, SDDE_RNG_TWO_LN2, te.y);
+    t = fma(-2.0, l1p, t);                                                                   // -2 ln u  > 0
+    const double y = rsqrt_approx(t);
+    double g = t * y, h = 0.5 * y;
+    const double e1 = fma(-h, g, 0.5);
+    g = fma(g, e1, g);
+    h = fma(h, e1, h);
+    const double e2 = fma(-g, g, t);
+    g = fma(e2, h, g);                                                                       // sqrt(t)
+    // ---- angle ----
+    const u32 q = w[3] >> 30;
+    const double D = __hiloint2double((int)(0x3FF00000u | ((w[3] >> 10) & 0xFFFFFu)), (int)((w[3] << 22) | (w[2] >> 10)));
+    const double x = D - 1.5;
+    const double zz = x * x;
+    double sp = fma(zz, RNG_SIN_C[7], RNG_SIN_C[6]);
+    double cp = fma(zz, RNG_COS_C[8], RNG_COS_C[7]);
+    sp = fma(zz, sp, RNG_SIN_C[5]); cp = fma(zz, cp, RNG_COS_C[6]);
+    sp = fma(zz, sp, RNG_SIN_C[4]); cp = fma(zz, cp, RNG_COS_C[5]);
+    sp = fma(zz, sp, RNG_SIN_C[3]); cp = fma(zz, cp, RNG_COS_C[4]);
+    sp = fma(zz, sp, RNG_SIN_C[2]); cp = fma(zz, cp, RNG_COS_C[3]);
+    sp = fma(zz, sp, RNG_SIN_C[1]); cp = fma(zz, cp, RNG_COS_C[2]);
+    sp = fma(zz, sp, RNG_SIN_C[0]); cp = fma(zz, cp, RNG_COS_C[1]);
+    cp = fma(zz, cp, RNG_COS_C[0]);
+    const double sn = x * sp;
+    // quadrant rotation: q=0 (c,s), 1 (-s,c), 2 (-c,-s), 3 (s,-c); signs folded into the radius
+    const bool odd = (q & 1u) != 0;
+    const double cc = odd ? sn : cp, ss = odd ? cp : sn;
+    const int ghi = __double2hiint(g), glo = __double2loint(g);
+    const double gc = __hiloint2double(ghi ^ (int)(((q + 1u) & 2u) << 30), glo);
+    const double gs = __hiloint2double(ghi ^ (int)((q & 2u) << 30), glo);
+    z0 = gc * cc;
+    z1 = gs * ss;
+}
+
+__device__ __forceinline__ void philox_normal_pair(u64 gid, u64 call, const u32 *__restrict__ rk,
+                                                   const double2 *__restrict__ ltab, double &z0, double &z1) {
     u32 w[4];
-    philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), k0, k1, w);
-    // 52-bit uniforms in (0,1): u = (m + 0.5) * 2^-52, built without an int->double conversion
-    const double x1 = __hiloint2double((int)(0x3FF00000u | (w[1] & 0xFFFFFu)), (int)w[0]);  // 1 + m*2^-52
-    const double x2 = __hiloint2double((int)(0x3FF00000u | (w[3] & 0xFFFFFu)), (int)w[2]);
-    const double one_m = 0.99999999999999988897769753748;  // 1 - 2^-53
-    const double u1 = x1 - one_m;
-    const double u2 = x2 - one_m;
-    const double r = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), rk, w);
+    normal_pair_from_words(w, ltab, z0, z1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,7 +268,11 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_con
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
     typedef StepRec<NL> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Rec *srec = reinterpret_cast<Rec *>(smem_raw);
+    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);                  // 2 KB log table of the normal generator
+    Rec *srec = reinterpret_cast<Rec *>(smem_raw + SDDE_RNG_SMEM_BYTES);
+    if (NOISE == K_NOISE_PHILOX) {
+        for (int i = threadIdx.x; i < 128; i += SDDE_BLOCK) ltab[i] = RNG_LOG_TAB[i];
+    }
 
     const long long tr0 = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) * TPT;  // wave-local trajectory index
     const long long last = a.n_traj - 1;
@@ -294,7 +361,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_con
         __syncthreads();
         {   // stage this chunk of the schedule in shared memory
             const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
-            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + SDDE_RNG_SMEM_BYTES);
             const int nvec = cnt * (int)(sizeof(Rec) / 16);
             for (int i = threadIdx.x; i < nvec; i += SDDE_BLOCK) dst[i] = src[i];
         }
@@ -355,8 +422,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_con
                             if (call != zcall) {
 #pragma unroll
                                 for (int tt = 0; tt < TPT; ++tt)
-                                    philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.seed_lo, a.seed_hi,
-                                                       zc[tt][0], zc[tt][1]);
+                                    philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, zc[tt][0], zc[tt][1]);
                                 zcall = call;
                             }
 #pragma unroll

@@ -27,10 +27,11 @@ std::string nvrtc_log(nvrtcProgram prog) {
 // Compile `src` with one kernel instantiation named by `expr`; returns cubin + lowered name.
 bool compile_one(const std::string &src, const std::string &expr, std::vector<char> &cubin, std::string &lowered,
                  std::string &err) {
-    const char *hdr_src[] = {(const char *)embedded_sdde_kernels_cuh, (const char *)embedded_sdde_models_cuh};
-    const char *hdr_names[] = {"sdde_kernels.cuh", "sdde_models.cuh"};
+    const char *hdr_src[] = {(const char *)embedded_sdde_kernels_cuh, (const char *)embedded_sdde_models_cuh,
+                             (const char *)embedded_sdde_rng_tables_cuh};
+    const char *hdr_names[] = {"sdde_kernels.cuh", "sdde_models.cuh", "sdde_rng_tables.cuh"};
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, src.c_str(), "sdde_user_model.cu", 2, hdr_src, hdr_names) != NVRTC_SUCCESS) {
+    if (nvrtcCreateProgram(&prog, src.c_str(), "sdde_user_model.cu", 3, hdr_src, hdr_names) != NVRTC_SUCCESS) {
         err = "nvrtcCreateProgram failed";
         return false;
     }

@@ -1,0 +1,121 @@
+"""-m gpu: the in-kernel noise (Philox4x32-10 + float64 Box-Muller) against the oracle's numpy implementation of the
+same stream definition, per-path parity in PHILOX mode, partition invariance, ensemble moments against the exact mean
+recurrence (K3) and the reference's own strong-order convergence test (K6)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import sdde_b200 as S
+import sdde_oracle as O
+from sdde_b200 import _capi as capi
+
+pytestmark = pytest.mark.gpu
+
+
+def device_normals(seed, off, n_traj, n_steps, n_noise):
+    out = np.empty((n_steps, n_noise, n_traj))
+    ctx = S.get_context(0)
+    capi.check(capi.lib().sdde_b200_philox_normals(ctx.handle, seed, off, n_traj, n_steps, n_noise, capi.np_ptr(out)))
+    return out
+
+
+@pytest.mark.parametrize("seed,off,nn", [(0xB2000001, 0, 1), (7, 2 ** 32 - 100, 1), (2 ** 63 + 12345, 10 ** 9, 3), (1, 5, 2)])
+def test_device_normals_match_oracle_stream(seed, off, nn):
+    n_traj, n_steps = 4096, 33
+    z = device_normals(seed, off, n_traj, n_steps, nn)
+    ref = O.philox_normals(np.arange(off, off + n_traj, dtype=np.uint64), n_steps, nn, seed)
+    # same bits -> same (u, q, x); evaluation differs by a few ulp (polynomials vs numpy libm)
+    assert np.max(np.abs(z - ref) / np.maximum(1.0, np.abs(ref))) < 4e-15
+
+
+def test_device_normals_distribution():
+    z = device_normals(99, 0, 1 << 16, 64, 1).ravel()
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((z ** 3).mean()) < 5 * np.sqrt(15 / n)
+    assert abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / n)
+    # tails: P(|z| > 4) = 6.33e-5
+    tail = np.mean(np.abs(z) > 4)
+    assert abs(tail - 6.334e-5) < 5 * np.sqrt(6.334e-5 / n)
+    # independence of consecutive draws of a trajectory and of neighbouring trajectories
+    zz = z.reshape(64, -1)
+    assert abs(np.mean(zz[:-1] * zz[1:])) < 5 / np.sqrt(zz[:-1].size)
+    assert abs(np.mean(zz[:, :-1] * zz[:, 1:])) < 5 / np.sqrt(zz[:, :-1].size)
+
+
+@pytest.mark.parametrize("mk", [lambda: cases.c2(T=60.0), lambda: cases.c3(0, T=60.0), lambda: cases.c4(T=6.0),
+                                lambda: cases.c1(T=5.0)])
+def test_philox_mode_paths_match_oracle_with_same_stream(mk):
+    case = mk()
+    n_traj, off, seed = 2050, 123456, 0xB2000001
+    sch = case.oracle_schedule()
+    nchan = case.model.n_chan
+    sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0),
+                  trajectories=n_traj, seed=seed, **case.solve_kwargs())
+    z = O.philox_normals(np.arange(n_traj, dtype=np.uint64), sch.n_steps, nchan, seed)
+    ref, _ = case.oracle(z * sch.sqdt[:, None, None])
+    assert cases.scaled_err(sim.out, ref) < 1e-11
+    # partition invariance: a slice solved with traj_offset reproduces the same paths bit for bit
+    ea = S.EnsembleB200(device=0, wave_traj=256)
+    sim2 = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], ea, trajectories=n_traj, seed=seed,
+                   **case.solve_kwargs())
+    S.get_context(0).set_option("wave_traj", 0)
+    assert np.array_equal(sim.out, sim2.out)
+
+
+def test_k3_ensemble_mean_against_exact_recurrence():
+    case = cases.c1(T=10.0, saveat=1.0)
+    n = 400_000
+    sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, seed=3, moments=True,
+                  paths=False, **case.solve_kwargs())
+    sch = case.oracle_schedule()
+    m = O.exact_mean_linear1(sch, -1.0, 0.5, 1.0, 1.0, 0.0, 1.0)
+    mean, var = S.timeseries_steps_meanvar(sim)
+    idx = [int(np.argmin(np.abs(sch.t - t))) for t in sim.t]
+    se = np.sqrt(var[:, 0] / n)
+    assert np.all(np.abs(mean[:, 0] - m[idx])[1:] < 5 * se[1:] + 1e-13)      # tolerance: 5 standard errors
+    assert sim.moments[0, 0, 2] == 0.0 and sim.moments[0, 0, 1] == 1.0
+
+
+def _strong_order(alg, algid):
+    """test/analyticless_convergence_tests.jl:30-36,52-61: Hayes, dts = 2^-8..2^-4, fine 2^-9, 300 paths, shared noise:
+    coarse increments are sums of the fine Brownian path's increments."""
+    n, T = 300, 10.0
+    fine = 2.0 ** -9
+    rng = np.random.default_rng(2026)
+    nf = int(round(T / fine))
+    dWf = rng.standard_normal((nf, 1, n)) * np.sqrt(fine)
+
+    def run(dt):
+        case = cases.hayes(T=T, dt=dt, alg=algid)
+        sch = case.oracle_schedule()
+        # the schedule is the uniform grid here (tau = 1 and all dts are powers of two: tstops land on the grid)
+        assert sch.n_steps == int(round(T / dt)) and np.all(sch.dt == dt)
+        k = int(round(dt / fine))
+        dW = dWf.reshape(sch.n_steps, k, 1, n).sum(axis=1)
+        kw = case.solve_kwargs(); kw["saveat"] = [T]
+        sim = S.solve(S.EnsembleProblem(case.problem()), alg, S.EnsembleB200(device=0), trajectories=n,
+                      noise_increments=dW, save_start=False, **kw)
+        return sim.out[-1, 0, :]
+
+    ref = run(fine)
+    dts = 2.0 ** -np.arange(8, 3, -1)
+    errs = np.array([np.mean(np.abs(run(dt) - ref)) for dt in dts])
+    slope = np.polyfit(np.log(dts), np.log(errs), 1)[0]
+    return slope
+
+
+def test_k6_strong_order_em():
+    assert abs(_strong_order(S.EM(), 0) - 0.5) < 0.3
+
+
+def test_k6_strong_order_rkmil_ito():
+    assert abs(_strong_order(S.RKMil(), 2) - 1.0) < 0.3
+
+
+def test_k6_strong_order_rkmil_stratonovich():
+    # the Stratonovich solution differs from the Ito one, but the scheme's own order is 1.0 (same assertion as the reference)
+    assert abs(_strong_order(S.RKMil("Stratonovich"), 3) - 1.0) < 0.3
