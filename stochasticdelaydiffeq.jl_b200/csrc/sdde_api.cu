@@ -248,11 +248,12 @@ int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
     return SDDE_OK;
 }
 
-void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, std::vector<unsigned char> &steps,
+void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pitch, std::vector<unsigned char> &steps,
                  std::vector<sdde::SaveRec> &saves) {
     const int64_t N = S.n_steps();
     const int L = S.n_lag;
-    const int R = S.ring_slots;
+    const int64_t R = S.ring_slots;
+    const int64_t slot_bytes = (int64_t)k.n_state * pitch * 8;     // one ring slot = [n_state][pitch] doubles
     steps.assign((size_t)N * k.rec_size, 0);
     std::vector<int> nsave((size_t)N, 0);
     saves.resize(S.save_t.size());
@@ -266,19 +267,26 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, std::vector
         unsigned char *rec = steps.data() + (size_t)n * k.rec_size;
         double hdr[3] = {S.t[(size_t)n], S.dt[(size_t)n], S.sqdt[(size_t)n]};
         memcpy(rec, hdr, 24);
-        int ns[2] = {nsave[(size_t)n], 0};
-        memcpy(rec + 24, ns, 8);
+        int mask = 0;
         for (int l = 0; l < L; ++l) {
             const size_t e = (size_t)n * L + l;
             const int mode = S.lk_mode[e];
-            int slot = 0;
-            if (mode == sdde::LK_EXACT) slot = (int)(S.lk_idx[e] % R);
-            else if (mode == sdde::LK_INTERP) slot = (int)((S.lk_idx[e] - 1) % R);
-            unsigned char *lk = rec + 32 + 16 * l;
-            memcpy(lk, &S.lk_theta[e], 8);
-            memcpy(lk + 8, &slot, 4);
-            memcpy(lk + 12, &mode, 4);
+            long long off_lo = 0, off_hi = 0;
+            double theta = S.lk_theta[e];
+            if (mode == sdde::LK_EXACT) {            // exact node: lo = hi = node, theta = 1  ->  fma(1, hi, 0*lo) == hi
+                off_lo = off_hi = (S.lk_idx[e] % R) * slot_bytes; theta = 1.0; mask |= 1 << l;
+            } else if (mode == sdde::LK_INTERP) {
+                off_lo = ((S.lk_idx[e] - 1) % R) * slot_bytes; off_hi = (S.lk_idx[e] % R) * slot_bytes; mask |= 1 << l;
+            }
+            unsigned char *lk = rec + 48 + 32 * l;
+            memcpy(lk, &theta, 8);
+            memcpy(lk + 8, &off_lo, 8);
+            memcpy(lk + 16, &off_hi, 8);
         }
+        int ns[2] = {nsave[(size_t)n], mask};
+        memcpy(rec + 24, ns, 8);
+        const long long off_store = ((n + 1) % R) * slot_bytes;
+        memcpy(rec + 32, &off_store, 8);
     }
 }
 
@@ -453,15 +461,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     }
 
     // ---- schedule tables -> device ----
-    std::vector<unsigned char> h_steps;
-    std::vector<sdde::SaveRec> h_saves;
-    pack_tables(S, K, h_steps, h_saves);
-    CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
-    CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
     int64_t h2d = 0, d2h = 0;
-    if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
-    if (!h_saves.empty()) CU_CHECK(cudaMemcpyAsync(c->saves.p, h_saves.data(), h_saves.size() * sizeof(sdde::SaveRec), cudaMemcpyHostToDevice, c->compute));
-    h2d += (int64_t)h_steps.size() + (int64_t)(h_saves.size() * sizeof(sdde::SaveRec));
 
     // ---- wave geometry ----
     const int64_t per_block = (int64_t)SDDE_BLOCK * K.tpt;
@@ -482,6 +482,16 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     const int64_t pitch = wave;   // multiple of per_block => every thread of the grid owns in-bounds ring columns
     const int n_waves = (int)((NT + wave - 1) / wave);
 
+    // ---- schedule tables -> device (byte offsets depend on the wave pitch) ----
+    std::vector<unsigned char> h_steps;
+    std::vector<sdde::SaveRec> h_saves;
+    pack_tables(S, K, pitch, h_steps, h_saves);
+    CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
+    CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
+    if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
+    if (!h_saves.empty()) CU_CHECK(cudaMemcpyAsync(c->saves.p, h_saves.data(), h_saves.size() * sizeof(sdde::SaveRec), cudaMemcpyHostToDevice, c->compute));
+    h2d += (int64_t)h_steps.size() + (int64_t)(h_saves.size() * sizeof(sdde::SaveRec));
+
     CU_CHECK(c->ring.reserve((size_t)S.ring_slots * NS * pitch * 8));
     if (need_stage) {
         CU_CHECK(c->out[0].reserve((size_t)std::max<int64_t>(1, rows) * pitch * 8));
@@ -494,11 +504,12 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (d->want_moments) CU_CHECK(c->mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves));
     if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
 
-    const int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
+    int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
+    if (chunk >= 8) chunk -= chunk % 8;   // batches (B <= 8) never straddle a chunk; step index of a batch start stays even
     const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)chunk * K.rec_size;
     int batch = K.batch;
     if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
-    batch = std::max(1, std::min(batch, S.min_gap + 1));   // prefetched nodes must be older than the batch
+    if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step
 
     sdde::KArgs A;
     memset(&A, 0, sizeof(A));

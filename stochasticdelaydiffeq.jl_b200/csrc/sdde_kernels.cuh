@@ -45,12 +45,15 @@ struct SaveRec {
 template <int NL>
 struct StepRec {
     double t, dt, sqdt;
-    int nsave;      // number of SaveRec produced by this step
-    int pad;
+    int nsave;            // number of SaveRec produced by this step
+    int ring_mask;        // bit l set: lag l reads the history ring; clear: prehistory h(p, t - tau_l)
+    long long off_store;  // BYTE offset (from the trajectory's ring column) of the slot that receives node n+1
+    long long pad;
     struct Lk {
-        double theta;   // interpolation weight, or the lookup time for prehistory
-        int slot_lo;    // ring slot of the lower node (of THE node when exact)
-        int mode;
+        double theta;         // interpolation weight; for prehistory: the lookup time t_n - tau_l
+        long long off_lo;     // byte offsets of the two bracketing nodes; an exact hit is (lo = hi = node, theta = 1)
+        long long off_hi;
+        long long pad;
     } lk[NL];
 };
 
@@ -263,6 +266,133 @@ __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931
 // ------------------------------------------------------------------------------------------------
 // the step kernel: thread-per-trajectory (x TPT), whole time span in one launch
 // ------------------------------------------------------------------------------------------------
+template <class M, int TPT, bool PTRAJ>
+struct TrajState {
+    static constexpr int NS = M::NS, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
+    double u[TPT][NS];
+    RegParams<PTRAJ ? NP : 0> preg[TPT];
+    double zc[TPT][2];        // cached normal pair of the current Philox call
+    u64 zcall;                // its call index
+    double curW[TPT][NC];     // NoiseGrid mode: current W
+    bool bad[TPT];
+    int ks;                   // next SaveRec
+};
+
+// BW consecutive steps starting at global step index n (recs[0..BW)).  BW > 1: the delayed-state nodes of all BW
+// steps are loaded up front (the host guarantees they are older than the batch) and n*NC is even, so which half of
+// a Philox pair a step consumes is a compile-time fact.
+template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW>
+__device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL> *recs, int n,
+                                          char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec) {
+    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW;
+    constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 2 == 0);
+    typedef StepRec<NL> Rec;
+    double xlo[BW][NL][NS][TPT], xhi[BW][NL][NS][TPT];
+#pragma unroll
+    for (int k = 0; k < BW; ++k) {
+        const Rec &r = recs[k];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (r.ring_mask & (1 << l)) {
+                const char *plo = ringb + r.lk[l].off_lo, *phi = ringb + r.lk[l].off_hi;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    ld_traj<TPT>(reinterpret_cast<const double *>(plo + (long long)j * a.ring_pitch * 8), xlo[k][l][j]);
+                    ld_traj<TPT>(reinterpret_cast<const double *>(phi + (long long)j * a.ring_pitch * 8), xhi[k][l][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BW; ++k) {
+        const Rec &r = recs[k];
+        const double tn = r.t, dtn = r.dt, sq = r.sqdt;
+        // delayed states: [EXT] HistoryFunction regimes
+        double ul[TPT][NL][NS];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const double th = r.lk[l].theta;
+            const bool ring = (r.ring_mask & (1 << l)) != 0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+#pragma unroll
+                for (int tt = 0; tt < TPT; ++tt)
+                    ul[tt][l][j] = ring ? ((1.0 - th) * xlo[k][l][j][tt] + th * xhi[k][l][j][tt])
+                                        : (a.hist_c0[j] + a.hist_c1[j] * th);
+        }
+        // increments: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454)
+        double dw[TPT][NC];
+        if (NOISE == K_NOISE_PHILOX) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const u64 q = (u64)(n + k) * NC + c;
+                const u64 call = q >> 1;
+                const bool fresh = STATIC_RNG ? (((k * NC + c) & 1) == 0) : (call != st.zcall);
+                if (fresh) {
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt)
+                        philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt][0], st.zc[tt][1]);
+                    st.zcall = call;
+                }
+                const bool odd = STATIC_RNG ? (((k * NC + c) & 1) != 0) : ((q & 1) != 0);
+#pragma unroll
+                for (int tt = 0; tt < TPT; ++tt) dw[tt][c] = sq * (odd ? st.zc[tt][1] : st.zc[tt][0]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int tt = 0; tt < TPT; ++tt) {
+                    const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+                    const long long row = (NOISE == K_NOISE_GRID) ? ((long long)(n + k + 1) * NC + c) : ((long long)(n + k) * NC + c);
+                    const double w = a.noise[row * a.noise_pitch + a.noise_off + tr];
+                    if (NOISE == K_NOISE_GRID) { dw[tt][c] = w - st.curW[tt][c]; st.curW[tt][c] += dw[tt][c]; }
+                    else dw[tt][c] = w;
+                }
+        }
+        // perform_step!
+        double uold[TPT][NS];
+#pragma unroll
+        for (int tt = 0; tt < TPT; ++tt) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) uold[tt][j] = st.u[tt][j];
+            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, dw[tt]);
+            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, dw[tt]);
+        }
+        // dense history: node n+1 (the save_everystep push of src/integrators/interface.jl:406-417)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            double v[TPT];
+#pragma unroll
+            for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
+            st_traj<TPT>(reinterpret_cast<double *>(ringb + r.off_store + (long long)j * a.ring_pitch * 8), v);
+        }
+        // savevalues! (src/integrators/interface.jl:357-430)
+        for (int s = 0; s < r.nsave; ++s) {
+            const SaveRec sr = a.saves[st.ks];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                double v[TPT];
+#pragma unroll
+                for (int tt = 0; tt < TPT; ++tt) {
+                    v[tt] = sr.exact ? st.u[tt][j] : ((1.0 - sr.theta) * uold[tt][j] + sr.theta * st.u[tt][j]);
+                    st.bad[tt] = st.bad[tt] || !finite_d(v[tt]);
+                }
+                if (a.out) {
+                    double *op = a.out + ((long long)st.ks * NS + j) * a.out_pitch + a.out_off + tr0;
+                    if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
+                    else {
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt)
+                            if (tr0 + tt <= last) op[tt] = v[tt];
+                    }
+                }
+            }
+            ++st.ks;
+        }
+    }
+}
+
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
 __global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
@@ -278,84 +408,58 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_con
     const long long last = a.n_traj - 1;
 
     // ---- per-trajectory "__init": state, parameters, noise state (src/solve.jl:137, 302-339) ----
-    double u[TPT][NS];
+    TrajState<M, TPT, PTRAJ> st;
 #pragma unroll
     for (int tt = 0; tt < TPT; ++tt) {
         const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
 #pragma unroll
-        for (int j = 0; j < NS; ++j) u[tt][j] = a.u0 ? a.u0[j * a.u0_pitch + tr] : a.u0c[j];
-    }
-    RegParams<PTRAJ ? NP : 0> preg[TPT];
-    if (PTRAJ) {
+        for (int j = 0; j < NS; ++j) st.u[tt][j] = a.u0 ? a.u0[j * a.u0_pitch + tr] : a.u0c[j];
+        if (PTRAJ) {
 #pragma unroll
-        for (int tt = 0; tt < TPT; ++tt) {
-            const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) preg[tt].v[PTRAJ ? i : 0] = a.ptraj[i * a.p_pitch + tr];
+            for (int i = 0; i < NP; ++i) st.preg[tt].v[PTRAJ ? i : 0] = a.ptraj[i * a.p_pitch + tr];
         }
+        st.zc[tt][0] = st.zc[tt][1] = 0.0;
+        st.bad[tt] = false;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            st.curW[tt][c] = (NOISE == K_NOISE_GRID) ? a.noise[(long long)c * a.noise_pitch + a.noise_off + tr] : 0.0;
     }
-    const ConstParams pconst{a.p};
-
-    double zc[TPT][2];
-    u64 zcall = ~0ull;
-    double curW[TPT][NC];
-#pragma unroll
-    for (int tt = 0; tt < TPT; ++tt) {
-        zc[tt][0] = zc[tt][1] = 0.0;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) curW[tt][c] = 0.0;
-    }
-    if (NOISE == K_NOISE_GRID) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            double w[TPT];
-#pragma unroll
-            for (int tt = 0; tt < TPT; ++tt) {
-                const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
-                w[tt] = a.noise[(long long)c * a.noise_pitch + a.noise_off + tr];
-                curW[tt][c] = w[tt];
-            }
-        }
-    }
+    st.zcall = ~0ull;
+    st.ks = 0;
 
     // ---- node 0 of the history = u0 (src/utils.jl:143-247: sol.t=[t0], sol.u=[u0]) ----
-    double *ringp = a.ring + tr0;
+    char *ringb = reinterpret_cast<char *>(a.ring + tr0);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         double v[TPT];
 #pragma unroll
-        for (int tt = 0; tt < TPT; ++tt) v[tt] = u[tt][j];
-        st_traj<TPT>(ringp + (long long)j * a.ring_pitch, v);
+        for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
+        st_traj<TPT>(reinterpret_cast<double *>(ringb + (long long)j * a.ring_pitch * 8), v);
     }
-    int wslot = (a.ring_slots > 1) ? 1 : 0;   // slot of the next node to be written
 
-    bool bad[TPT];
-#pragma unroll
-    for (int tt = 0; tt < TPT; ++tt) bad[tt] = false;
     const bool out_vec = (TPT == 1) || (a.out_vec_ok && (tr0 + TPT - 1 <= last));
-    int ks = 0;
     // save_start (src/solve.jl:355-363)
-    while (ks < a.n_saves && a.saves[ks].step < 0) {
+    while (st.ks < a.n_saves && a.saves[st.ks].step < 0) {
         if (a.out) {
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                double *op = a.out + ((long long)ks * NS + j) * a.out_pitch + a.out_off + tr0;
+                double *op = a.out + ((long long)st.ks * NS + j) * a.out_pitch + a.out_off + tr0;
                 if (out_vec) {
                     double v[TPT];
 #pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt) v[tt] = u[tt][j];
+                    for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
                     if (tr0 <= last) st_traj<TPT>(op, v);
                 } else {
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt)
-                        if (tr0 + tt <= last) op[tt] = u[tt][j];
+                        if (tr0 + tt <= last) op[tt] = st.u[tt][j];
                 }
             }
         }
-        ++ks;
+        ++st.ks;
     }
 
-    const int bw = a.batch < B ? (a.batch < 1 ? 1 : a.batch) : B;
+    const bool batched = (B > 1) && (a.batch >= B);   // host: batch = min(B, min_gap + 1); chunk_steps % B == 0
     for (int n0 = 0; n0 < a.n_steps; n0 += a.chunk_steps) {
         const int cnt = (a.n_steps - n0 < a.chunk_steps) ? (a.n_steps - n0) : a.chunk_steps;
         __syncthreads();
@@ -366,133 +470,21 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_con
             for (int i = threadIdx.x; i < nvec; i += SDDE_BLOCK) dst[i] = src[i];
         }
         __syncthreads();
-
-        for (int nb = 0; nb < cnt; nb += bw) {
-            // ---- prefetch the delayed-state nodes of the next bw steps (all loads independent of the recurrence) ----
-            double xlo[B][NL][NS][TPT], xhi[B][NL][NS][TPT];
-#pragma unroll
-            for (int k = 0; k < B; ++k) {
-                if (k < bw && nb + k < cnt) {
-                    const Rec &r = srec[nb + k];
-#pragma unroll
-                    for (int l = 0; l < NL; ++l) {
-                        const int mode = r.lk[l].mode;
-                        if (mode != K_LK_PRE) {
-                            const int slo = r.lk[l].slot_lo;
-                            const int shi = (slo + 1 == a.ring_slots) ? 0 : slo + 1;
-#pragma unroll
-                            for (int j = 0; j < NS; ++j) {
-                                ld_traj<TPT>(ringp + ((long long)slo * NS + j) * a.ring_pitch, xlo[k][l][j]);
-                                if (mode == K_LK_INTERP)
-                                    ld_traj<TPT>(ringp + ((long long)shi * NS + j) * a.ring_pitch, xhi[k][l][j]);
-                            }
-                        }
-                    }
-                }
-            }
-            // ---- the steps ----
-#pragma unroll
-            for (int k = 0; k < B; ++k) {
-                if (k < bw && nb + k < cnt) {
-                    const Rec &r = srec[nb + k];
-                    const int n = n0 + nb + k;
-                    const double tn = r.t, dtn = r.dt, sq = r.sqdt;
-                    // delayed states: [EXT] HistoryFunction regimes
-                    double ul[TPT][NL][NS];
-#pragma unroll
-                    for (int l = 0; l < NL; ++l) {
-                        const int mode = r.lk[l].mode;
-                        const double th = r.lk[l].theta;
-#pragma unroll
-                        for (int j = 0; j < NS; ++j)
-#pragma unroll
-                            for (int tt = 0; tt < TPT; ++tt) {
-                                if (mode == K_LK_PRE) ul[tt][l][j] = a.hist_c0[j] + a.hist_c1[j] * th;
-                                else if (mode == K_LK_EXACT) ul[tt][l][j] = xlo[k][l][j][tt];
-                                else ul[tt][l][j] = (1.0 - th) * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
-                            }
-                    }
-                    // increments: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454)
-                    double dw[TPT][NC];
-                    if (NOISE == K_NOISE_PHILOX) {
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            const u64 q = (u64)n * NC + c;
-                            const u64 call = q >> 1;
-                            if (call != zcall) {
-#pragma unroll
-                                for (int tt = 0; tt < TPT; ++tt)
-                                    philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, zc[tt][0], zc[tt][1]);
-                                zcall = call;
-                            }
-#pragma unroll
-                            for (int tt = 0; tt < TPT; ++tt) dw[tt][c] = sq * ((q & 1) ? zc[tt][1] : zc[tt][0]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < NC; ++c)
-#pragma unroll
-                            for (int tt = 0; tt < TPT; ++tt) {
-                                const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
-                                const long long row = (NOISE == K_NOISE_GRID) ? ((long long)(n + 1) * NC + c)
-                                                                               : ((long long)n * NC + c);
-                                const double w = a.noise[row * a.noise_pitch + a.noise_off + tr];
-                                if (NOISE == K_NOISE_GRID) { dw[tt][c] = w - curW[tt][c]; curW[tt][c] += dw[tt][c]; }
-                                else dw[tt][c] = w;
-                            }
-                    }
-                    // perform_step!
-                    double uold[TPT][NS];
-#pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt) {
-#pragma unroll
-                        for (int j = 0; j < NS; ++j) uold[tt][j] = u[tt][j];
-                        if (PTRAJ) sde_step<M, ALG>(u[tt], ul[tt], preg[tt], tn, dtn, sq, dw[tt]);
-                        else sde_step<M, ALG>(u[tt], ul[tt], pconst, tn, dtn, sq, dw[tt]);
-                    }
-                    // dense history: node n+1 (save_everystep push of src/integrators/interface.jl:406-417)
-#pragma unroll
-                    for (int j = 0; j < NS; ++j) {
-                        double v[TPT];
-#pragma unroll
-                        for (int tt = 0; tt < TPT; ++tt) v[tt] = u[tt][j];
-                        st_traj<TPT>(ringp + ((long long)wslot * NS + j) * a.ring_pitch, v);
-                    }
-                    wslot = (wslot + 1 == a.ring_slots) ? 0 : wslot + 1;
-                    // savevalues! (src/integrators/interface.jl:357-430)
-                    for (int s = 0; s < r.nsave; ++s) {
-                        const SaveRec sr = a.saves[ks];
-#pragma unroll
-                        for (int j = 0; j < NS; ++j) {
-                            double v[TPT];
-#pragma unroll
-                            for (int tt = 0; tt < TPT; ++tt) {
-                                v[tt] = sr.exact ? u[tt][j] : ((1.0 - sr.theta) * uold[tt][j] + sr.theta * u[tt][j]);
-                                bad[tt] = bad[tt] || !finite_d(v[tt]);
-                            }
-                            if (a.out) {
-                                double *op = a.out + ((long long)ks * NS + j) * a.out_pitch + a.out_off + tr0;
-                                if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
-                                else {
-#pragma unroll
-                                    for (int tt = 0; tt < TPT; ++tt)
-                                        if (tr0 + tt <= last) op[tt] = v[tt];
-                                }
-                            }
-                        }
-                        ++ks;
-                    }
-                }
-            }
+        int nb = 0;
+        if (batched) {
+            for (; nb + B <= cnt; nb += B)
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, B>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec);
         }
+        for (; nb < cnt; ++nb)
+            run_batch<M, ALG, NOISE, PTRAJ, TPT, 1>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec);
     }
     // [EXT] check_error! (src/solve.jl:578): NaN/Inf -> ReturnCode.Unstable, reported per trajectory
     if (a.status) {
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
-            bool b = bad[tt];
+            bool b = st.bad[tt];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) b = b || !finite_d(u[tt][j]);
+            for (int j = 0; j < NS; ++j) b = b || !finite_d(st.u[tt][j]);
             if (tr0 + tt <= last) a.status[tr0 + tt] = b ? 1 : 0;
         }
     }
