@@ -74,7 +74,7 @@ EXPORTS = [
     "sdde_b200_hbm_peak", "sdde_b200_alloc_pinned", "sdde_b200_free_pinned",
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdde_b200.so")
+LIB_PATH = os.environ.get("SDDE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdde_b200.so")
 _lib = None
 
 

@@ -220,7 +220,10 @@ int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
     switch (d->model_id) {
         case SDDE_MODEL_LINEAR1: k = sdde::select_linear1(alg, nz, ptraj); break;
         case SDDE_MODEL_HAYES: k = sdde::select_hayes(alg, nz, ptraj); break;
-        case SDDE_MODEL_MACKEY_GLASS: k = sdde::select_mackey_glass(alg, nz, ptraj); break;
+        case SDDE_MODEL_MACKEY_GLASS:
+            if (!ptraj && d->n_param == 4 && d->params && d->params[2] == 10.0) k = sdde::select_mackey_glass10(alg, nz, ptraj);
+            else k = sdde::select_mackey_glass(alg, nz, ptraj);
+            break;
         case SDDE_MODEL_SCALAR_ADD: k = sdde::select_scalar_add(alg, nz, ptraj); break;
         case SDDE_MODEL_SIR: k = sdde::select_sir(alg, nz, ptraj); break;
         case SDDE_MODEL_LINSYS: k = sdde::select_linsys(d->n_state, d->n_lag, d->n_noise, alg, nz, ptraj); break;

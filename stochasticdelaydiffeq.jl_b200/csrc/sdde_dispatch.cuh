@@ -54,6 +54,7 @@ inline KernelInfo make_info(const char *name) {
 KernelInfo select_linear1(int alg, int noise, bool ptraj);
 KernelInfo select_hayes(int alg, int noise, bool ptraj);
 KernelInfo select_mackey_glass(int alg, int noise, bool ptraj);
+KernelInfo select_mackey_glass10(int alg, int noise, bool ptraj);
 KernelInfo select_scalar_add(int alg, int noise, bool ptraj);
 KernelInfo select_sir(int alg, int noise, bool ptraj);
 KernelInfo select_linsys(int ns, int nl, int nw, int alg, int noise, bool ptraj);

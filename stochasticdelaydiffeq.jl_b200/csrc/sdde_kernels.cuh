@@ -80,10 +80,16 @@ struct KArgs {
 };
 
 // tuning knobs per model shape
+#ifndef SDDE_TUNE_B_SCALAR
+#define SDDE_TUNE_B_SCALAR 4
+#endif
+#ifndef SDDE_MIN_BLOCKS
+#define SDDE_MIN_BLOCKS 5
+#endif
 template <class M> struct Tune {
     static constexpr int TPT = (M::NS == 1) ? 2 : 1;
     static constexpr int FOOT = M::NS * M::NL * TPT;              // doubles per prefetched step (one node set)
-    static constexpr int B = FOOT <= 2 ? 4 : (FOOT <= 4 ? 2 : 1);
+    static constexpr int B = FOOT <= 2 ? SDDE_TUNE_B_SCALAR : (FOOT <= 4 ? 2 : 1);
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -287,22 +293,28 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW;
     constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 2 == 0);
     typedef StepRec<NL> Rec;
+    const long long jstride = a.ring_pitch * 8;
+    // ---- all delayed-state loads of the batch, unconditionally (prehistory records point at slot 0) ----
     double xlo[BW][NL][NS][TPT], xhi[BW][NL][NS][TPT];
 #pragma unroll
     for (int k = 0; k < BW; ++k) {
-        const Rec &r = recs[k];
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            if (r.ring_mask & (1 << l)) {
-                const char *plo = ringb + r.lk[l].off_lo, *phi = ringb + r.lk[l].off_hi;
+            const char *plo = ringb + recs[k].lk[l].off_lo, *phi = ringb + recs[k].lk[l].off_hi;
 #pragma unroll
-                for (int j = 0; j < NS; ++j) {
-                    ld_traj<TPT>(reinterpret_cast<const double *>(plo + (long long)j * a.ring_pitch * 8), xlo[k][l][j]);
-                    ld_traj<TPT>(reinterpret_cast<const double *>(phi + (long long)j * a.ring_pitch * 8), xhi[k][l][j]);
-                }
+            for (int j = 0; j < NS; ++j) {
+                ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
+                ld_traj<TPT>(reinterpret_cast<const double *>(phi + j * jstride), xhi[k][l][j]);
             }
         }
     }
+    // ---- the steps: straight-line code (no branch inside the batch, so the scheduler can overlap the BW x TPT
+    //      independent pieces: delayed-state drift terms, normal generation, the u recurrences) ----
+    double useq[BW + 1][TPT][NS];     // states at the batch's nodes (for the deferred savevalues!)
+#pragma unroll
+    for (int tt = 0; tt < TPT; ++tt)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) useq[0][tt][j] = st.u[tt][j];
 #pragma unroll
     for (int k = 0; k < BW; ++k) {
         const Rec &r = recs[k];
@@ -313,12 +325,16 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         for (int l = 0; l < NL; ++l) {
             const double th = r.lk[l].theta;
             const bool ring = (r.ring_mask & (1 << l)) != 0;
+            const double omt = 1.0 - th;
 #pragma unroll
-            for (int j = 0; j < NS; ++j)
+            for (int j = 0; j < NS; ++j) {
+                const double hv = a.hist_c0[j] + a.hist_c1[j] * th;
 #pragma unroll
-                for (int tt = 0; tt < TPT; ++tt)
-                    ul[tt][l][j] = ring ? ((1.0 - th) * xlo[k][l][j][tt] + th * xhi[k][l][j][tt])
-                                        : (a.hist_c0[j] + a.hist_c1[j] * th);
+                for (int tt = 0; tt < TPT; ++tt) {
+                    const double iv = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
+                    ul[tt][l][j] = ring ? iv : hv;
+                }
+            }
         }
         // increments: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454)
         double dw[TPT][NC];
@@ -351,13 +367,12 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 }
         }
         // perform_step!
-        double uold[TPT][NS];
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
-#pragma unroll
-            for (int j = 0; j < NS; ++j) uold[tt][j] = st.u[tt][j];
             if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, dw[tt]);
             else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, dw[tt]);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) useq[k + 1][tt][j] = st.u[tt][j];
         }
         // dense history: node n+1 (the save_everystep push of src/integrators/interface.jl:406-417)
 #pragma unroll
@@ -365,17 +380,20 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
             double v[TPT];
 #pragma unroll
             for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
-            st_traj<TPT>(reinterpret_cast<double *>(ringb + r.off_store + (long long)j * a.ring_pitch * 8), v);
+            st_traj<TPT>(reinterpret_cast<double *>(ringb + r.off_store + j * jstride), v);
         }
-        // savevalues! (src/integrators/interface.jl:357-430)
-        for (int s = 0; s < r.nsave; ++s) {
+    }
+    // ---- savevalues! (src/integrators/interface.jl:357-430), after the batch ----
+#pragma unroll
+    for (int k = 0; k < BW; ++k) {
+        for (int s = 0; s < recs[k].nsave; ++s) {
             const SaveRec sr = a.saves[st.ks];
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
                 double v[TPT];
 #pragma unroll
                 for (int tt = 0; tt < TPT; ++tt) {
-                    v[tt] = sr.exact ? st.u[tt][j] : ((1.0 - sr.theta) * uold[tt][j] + sr.theta * st.u[tt][j]);
+                    v[tt] = sr.exact ? useq[k + 1][tt][j] : ((1.0 - sr.theta) * useq[k][tt][j] + sr.theta * useq[k + 1][tt][j]);
                     st.bad[tt] = st.bad[tt] || !finite_d(v[tt]);
                 }
                 if (a.out) {
@@ -394,7 +412,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 }
 
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
-__global__ void __launch_bounds__(SDDE_BLOCK) sdde_solve_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(SDDE_BLOCK, SDDE_MIN_BLOCKS) sdde_solve_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
     typedef StepRec<NL> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
