@@ -308,8 +308,43 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
             }
         }
     }
+    // ---- increments of the whole batch first: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454).
+    //      This work is independent of the loads above, so it covers their latency. ----
+    double dwb[BW][TPT][NC];
+#pragma unroll
+    for (int k = 0; k < BW; ++k) {
+        const double sq = recs[k].sqdt;
+        if (NOISE == K_NOISE_PHILOX) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const u64 q = (u64)(n + k) * NC + c;
+                const u64 call = q >> 1;
+                const bool fresh = STATIC_RNG ? (((k * NC + c) & 1) == 0) : (call != st.zcall);
+                if (fresh) {
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt)
+                        philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt][0], st.zc[tt][1]);
+                    st.zcall = call;
+                }
+                const bool odd = STATIC_RNG ? (((k * NC + c) & 1) != 0) : ((q & 1) != 0);
+#pragma unroll
+                for (int tt = 0; tt < TPT; ++tt) dwb[k][tt][c] = sq * (odd ? st.zc[tt][1] : st.zc[tt][0]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int tt = 0; tt < TPT; ++tt) {
+                    const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+                    const long long row = (NOISE == K_NOISE_GRID) ? ((long long)(n + k + 1) * NC + c) : ((long long)(n + k) * NC + c);
+                    const double w = a.noise[row * a.noise_pitch + a.noise_off + tr];
+                    if (NOISE == K_NOISE_GRID) { dwb[k][tt][c] = w - st.curW[tt][c]; st.curW[tt][c] += dwb[k][tt][c]; }
+                    else dwb[k][tt][c] = w;
+                }
+        }
+    }
     // ---- the steps: straight-line code (no branch inside the batch, so the scheduler can overlap the BW x TPT
-    //      independent pieces: delayed-state drift terms, normal generation, the u recurrences) ----
+    //      independent pieces: delayed-state drift terms and the u recurrences) ----
     double useq[BW + 1][TPT][NS];     // states at the batch's nodes (for the deferred savevalues!)
 #pragma unroll
     for (int tt = 0; tt < TPT; ++tt)
@@ -336,36 +371,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 }
             }
         }
-        // increments: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454)
-        double dw[TPT][NC];
-        if (NOISE == K_NOISE_PHILOX) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const u64 q = (u64)(n + k) * NC + c;
-                const u64 call = q >> 1;
-                const bool fresh = STATIC_RNG ? (((k * NC + c) & 1) == 0) : (call != st.zcall);
-                if (fresh) {
-#pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt)
-                        philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt][0], st.zc[tt][1]);
-                    st.zcall = call;
-                }
-                const bool odd = STATIC_RNG ? (((k * NC + c) & 1) != 0) : ((q & 1) != 0);
-#pragma unroll
-                for (int tt = 0; tt < TPT; ++tt) dw[tt][c] = sq * (odd ? st.zc[tt][1] : st.zc[tt][0]);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-#pragma unroll
-                for (int tt = 0; tt < TPT; ++tt) {
-                    const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
-                    const long long row = (NOISE == K_NOISE_GRID) ? ((long long)(n + k + 1) * NC + c) : ((long long)(n + k) * NC + c);
-                    const double w = a.noise[row * a.noise_pitch + a.noise_off + tr];
-                    if (NOISE == K_NOISE_GRID) { dw[tt][c] = w - st.curW[tt][c]; st.curW[tt][c] += dw[tt][c]; }
-                    else dw[tt][c] = w;
-                }
-        }
+        double (&dw)[TPT][NC] = dwb[k];
         // perform_step!
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
