@@ -226,7 +226,14 @@ int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
             break;
         case SDDE_MODEL_SCALAR_ADD: k = sdde::select_scalar_add(alg, nz, ptraj); break;
         case SDDE_MODEL_SIR: k = sdde::select_sir(alg, nz, ptraj); break;
-        case SDDE_MODEL_LINSYS: k = sdde::select_linsys(d->n_state, d->n_lag, d->n_noise, alg, nz, ptraj); break;
+        case SDDE_MODEL_LINSYS:
+            if (d->lanes_per_traj > 1) {
+                if (ptraj) return fail(SDDE_ERR_UNSUPPORTED, "the cooperative-lanes kernel takes shared parameters only");
+                k = sdde::select_linsys_coop(d->n_state, d->n_lag, d->n_noise, alg, nz);
+                if (k.fn && k.lanes != d->lanes_per_traj) return fail(SDDE_ERR_UNSUPPORTED, "lanes_per_traj must be 0, 1 or n_state (%d)", d->n_state);
+                if (!k.fn) return fail(SDDE_ERR_UNSUPPORTED, "no cooperative-lanes kernel for this model shape / algorithm");
+            } else k = sdde::select_linsys(d->n_state, d->n_lag, d->n_noise, alg, nz, ptraj);
+            break;
         default:
             if (d->model_id >= SDDE_MODEL_USER_BASE && ctx) {
                 std::string err;
@@ -451,7 +458,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (tm) {
         tm->n_steps = N; tm->n_save = n_save; tm->ring_slots = S.ring_slots; tm->block_threads = SDDE_BLOCK;
         tm->traj_per_thread = K.tpt;
-        snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_solve_kernel<%s,alg%d,noise%d,ptraj%d,tpt%d,B%d>", K.name,
+        if (K.lanes > 1) snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_coop_kernel<%s,alg%d,noise%d,lanes%d>", K.name, d->alg, d->noise_mode, K.lanes);
+        else snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_solve_kernel<%s,alg%d,noise%d,ptraj%d,tpt%d,B%d>", K.name,
                  d->alg, d->noise_mode, d->param_stride != 0, K.tpt, K.batch);
         cudaFuncAttributes fa;
         if (!K.is_user && cudaFuncGetAttributes(&fa, K.fn) == cudaSuccess) tm->regs_per_thread = fa.numRegs;
@@ -467,7 +475,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     int64_t h2d = 0, d2h = 0;
 
     // ---- wave geometry ----
-    const int64_t per_block = (int64_t)SDDE_BLOCK * K.tpt;
+    const int64_t per_block = (int64_t)SDDE_BLOCK * K.tpt / K.lanes;
     size_t free_b = 0, total_b = 0;
     CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
     free_b += c->ring.cap + c->out[0].cap + c->out[1].cap + c->noise.cap;   // our own cached workspaces are reusable

@@ -2,6 +2,7 @@
 #pragma once
 #include "sdde_kernels.cuh"
 #include "sdde_models.cuh"
+#include "sdde_coop.cuh"
 
 namespace sdde {
 
@@ -12,6 +13,7 @@ struct KernelInfo {
     int rec_size = 0;           // sizeof(StepRec<NL>)
     int n_state = 0, n_lag = 0, n_chan = 0, n_noise = 0, n_param = 0;
     bool diag = true;
+    int lanes = 1;              // lanes per trajectory (cooperative kernel: n_state)
     bool is_user = false;       // fn is a cudaKernel_t obtained from an NVRTC-built library
     const char *name = "";
 };
@@ -25,6 +27,18 @@ inline KernelInfo make_info(const char *name) {
     k.rec_size = (int)sizeof(StepRec<M::NL>);
     k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = M::DIAG ? M::NS : M::NW; k.n_param = M::NP;
     k.diag = M::DIAG;
+    k.name = name;
+    return k;
+}
+
+template <class M, int ALG, int NOISE>
+inline KernelInfo make_coop_info(const char *name) {
+    KernelInfo k;
+    k.fn = (const void *)&sdde_coop_kernel<M, ALG, NOISE>;
+    k.tpt = 1; k.batch = 1; k.lanes = M::NS;
+    k.rec_size = (int)sizeof(StepRec<M::NL>);
+    k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = M::NW; k.n_param = M::NP;
+    k.diag = false;
     k.name = name;
     return k;
 }
@@ -58,5 +72,6 @@ KernelInfo select_mackey_glass10(int alg, int noise, bool ptraj);
 KernelInfo select_scalar_add(int alg, int noise, bool ptraj);
 KernelInfo select_sir(int alg, int noise, bool ptraj);
 KernelInfo select_linsys(int ns, int nl, int nw, int alg, int noise, bool ptraj);
+KernelInfo select_linsys_coop(int ns, int nl, int nw, int alg, int noise);
 
 }  // namespace sdde

@@ -114,6 +114,23 @@ struct ModelLinSys {
 #pragma unroll
             for (int j = 0; j < NW; ++j) gv[i * NW + j] = p[offM + i * NW + j] * u[i] + p[offN + i * NW + j];
     }
+    // row-wise interface for the cooperative-lanes kernel (sdde_coop.cuh): row i of f and of G, same operation order
+    static constexpr bool HAS_ROWS = true;
+    template <class P> __device__ __forceinline__ static double f_row(int i, const double *u, const double (*ul)[NS], const P &p, double) {
+        double acc = p[i * NS] * u[0];
+#pragma unroll
+        for (int j = 1; j < NS; ++j) acc = acc + p[i * NS + j] * u[j];
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+#pragma unroll
+            for (int j = 0; j < NS; ++j) acc = acc + p[NS * NS * (1 + l) + i * NS + j] * ul[l][j];
+        return acc + p[NS * NS * (1 + NL) + i];
+    }
+    template <class P> __device__ __forceinline__ static void g_row(int i, double *grow, const double *, double ui, const double (*)[NS], const P &p, double) {
+        constexpr int offM = NS * NS * (1 + NL) + NS, offN = offM + NS * NW;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) grow[j] = p[offM + i * NW + j] * ui + p[offN + i * NW + j];
+    }
 };
 
 // delayed SIR with 3x2 sparse noise: test/nondiagonal_sparse_noise.jl:5-43

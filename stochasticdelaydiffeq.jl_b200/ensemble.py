@@ -32,6 +32,7 @@ class EnsembleB200:
     distributed: bool = False
     output: str = "host"
     wave_traj: int | None = None
+    lanes_per_traj: int = 0      # 0/1: thread per trajectory; n_state (4): cooperative lanes (models with a row-wise form)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -79,7 +80,7 @@ class _Marshalled:
 
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
-             want_moments) -> _Marshalled:
+             want_moments, lanes_per_traj=0) -> _Marshalled:
     if not isinstance(alg, (EM, RKMil)):
         raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM and RKMil, fixed step)")
     if adaptive is None:
@@ -143,6 +144,7 @@ def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_
     d.noise = noise
     d.out_mem = out_mem
     d.history_mode = 0
+    d.lanes_per_traj = int(lanes_per_traj)
     d.want_paths, d.want_moments = int(want_paths), int(want_moments)
     d.n_traj, d.traj_offset = int(n_traj), int(traj_offset)
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -394,7 +396,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
                  save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=lo, seed=seed,
                  p_batch=p_batch, u0_batch=u0_batch, noise=noise_ptr, noise_mode=noise_mode, noise_mem=noise_mem,
                  out_mem=capi.MEM_DEVICE if ea.output == "device" else capi.MEM_HOST, want_paths=paths,
-                 want_moments=moments)
+                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj)
     sch = capi.SddeSchedule()
     capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(sch)))
     n_save, n_steps = sch.n_save, sch.n_steps

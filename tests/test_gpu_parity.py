@@ -150,3 +150,25 @@ def test_unstable_trajectories_flagged():
     sim, ref, st = run_case(case, 64)
     assert np.all(sim.status == 1) and np.all(st == 1)
     assert sim.retcodes[0] == "Unstable"
+
+
+def test_c4_cooperative_lanes_kernel_matches_oracle_and_thread_kernel():
+    """BASELINE.json configs[3]: 4 lanes of a warp per trajectory (sdde_coop.cuh) vs thread-per-trajectory."""
+    case = cases.c4()
+    sch = case.oracle_schedule()
+    n = 1000
+    dW = cases.increments(sch, 2, n)
+    kw = dict(trajectories=n, noise_increments=dW, **case.solve_kwargs())
+    a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+    b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, lanes_per_traj=4), moments=True, **kw)
+    assert "coop" in b.timing["kernel_name"] and "coop" not in a.timing["kernel_name"]
+    ref, st = case.oracle(dW)
+    assert cases.scaled_err(b.out, ref) < TOL
+    assert cases.scaled_err(b.out, a.out) < 1e-13
+    assert np.array_equal(b.status, st)
+    # Philox mode: identical streams in both mappings
+    kw = dict(trajectories=n, seed=5, **case.solve_kwargs())
+    a = S.solve(S.EnsembleProblem(case.problem()), S.EM(False), S.EnsembleB200(device=0), **kw)
+    b = S.solve(S.EnsembleProblem(case.problem()), S.EM(False), S.EnsembleB200(device=0, lanes_per_traj=4, wave_traj=320), **kw)
+    S.get_context(0).set_option("wave_traj", 0)
+    assert cases.scaled_err(b.out, a.out) < 1e-13
