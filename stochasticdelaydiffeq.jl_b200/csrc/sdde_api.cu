@@ -576,7 +576,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         A.traj_gid0 = d->traj_offset + off;
         if (out_dev) {
             A.out = out; A.out_pitch = NT; A.out_off = off;
-            A.out_vec_ok = ((NT % 2) == 0 && (off % 2) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+            A.out_vec_ok = ((NT % 4) == 0 && (off % 4) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
         } else if (need_stage) {
             const int b = (d->want_paths && n_waves > 1) ? buf : 0;
             if (d->want_paths && w >= 2) CU_CHECK(cudaStreamWaitEvent(c->compute, c->ev_copied[b], 0));  // staging buffer free again

@@ -83,13 +83,19 @@ struct KArgs {
 #ifndef SDDE_TUNE_B_SCALAR
 #define SDDE_TUNE_B_SCALAR 4
 #endif
+#ifndef SDDE_TUNE_TPT_SCALAR
+#define SDDE_TUNE_TPT_SCALAR 2
+#endif
+#ifndef SDDE_TUNE_FOOT_B2
+#define SDDE_TUNE_FOOT_B2 4
+#endif
 #ifndef SDDE_MIN_BLOCKS
 #define SDDE_MIN_BLOCKS 5
 #endif
 template <class M> struct Tune {
-    static constexpr int TPT = (M::NS == 1) ? 2 : 1;
+    static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : 1;
     static constexpr int FOOT = M::NS * M::NL * TPT;              // doubles per prefetched step (one node set)
-    static constexpr int B = FOOT <= 2 ? SDDE_TUNE_B_SCALAR : (FOOT <= 4 ? 2 : 1);
+    static constexpr int B = (M::NS == 1 && M::NL == 1) ? SDDE_TUNE_B_SCALAR : (FOOT <= SDDE_TUNE_FOOT_B2 ? 2 : 1);
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -261,10 +267,19 @@ template <> __device__ __forceinline__ void ld_traj<2>(const double *p, double (
     const double2 t = *reinterpret_cast<const double2 *>(p);
     v[0] = t.x; v[1] = t.y;
 }
+template <> __device__ __forceinline__ void ld_traj<4>(const double *p, double (&v)[4]) {
+    const double2 t0 = *reinterpret_cast<const double2 *>(p), t1 = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y;
+}
 template <int TPT> __device__ __forceinline__ void st_traj(double *p, const double (&v)[TPT]);
 template <> __device__ __forceinline__ void st_traj<1>(double *p, const double (&v)[1]) { *p = v[0]; }
 template <> __device__ __forceinline__ void st_traj<2>(double *p, const double (&v)[2]) {
     *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+}
+
+template <> __device__ __forceinline__ void st_traj<4>(double *p, const double (&v)[4]) {
+    *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(v[2], v[3]);
 }
 
 __device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
