@@ -123,6 +123,7 @@ typedef struct sdde_desc {
     int64_t n_traj;                   /* trajectories solved by THIS call */
     int64_t traj_offset;              /* global id of the first one (partition-invariant RNG streams) */
     uint64_t seed;
+    int64_t out_pitch;                /* elements between consecutive rows of `out`; 0 = n_traj (dense) */
 } sdde_desc;
 
 /* Host-side schedule (trajectory independent): the replay of src/solve.jl:574-610 time stepping with
@@ -186,6 +187,14 @@ SDDE_API void sdde_b200_schedule_free(sdde_schedule *s);
  *   status   [n_traj] bytes, host memory, 0 = ok, 1 = non-finite state seen (-> ReturnCode.Unstable), may be NULL
  *   tm       optional timing/launch report                                                          */
 SDDE_API int sdde_b200_solve(sdde_ctx *ctx, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm);
+
+/* Same as sdde_b200_solve, over several GPUs from ONE host process (the Julia `ccall` case): the trajectories are split
+ * into contiguous global-id ranges [r*ceil(N/R), ...), one per context, each range is solved concurrently on its GPU
+ * (one host thread per context), paths land in the caller's `out` (host memory only), and the per-GPU moment triples
+ * are Chan-merged on the host in rank order.  Results are identical to a single-GPU solve (partition-invariant Philox
+ * streams).  Under torchrun (one process per GPU) use sdde_b200_solve per rank + an NCCL all-gather of the triples. */
+SDDE_API int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc *d, double *out, double *moments,
+                                   uint8_t *status, sdde_timing *tm /* [n_ctx] or NULL */);
 
 /* Merge two (count, mean, M2) arrays of n triples: a <- merge(a, b)  (Chan et al.); host only. */
 SDDE_API int sdde_b200_merge_moments(double *a, const double *b, int64_t n);

@@ -42,6 +42,7 @@ Base.@kwdef mutable struct SddeDesc
     u0::Ptr{Float64} = C_NULL; u0_stride::Int64 = 0
     saveat::Ptr{Float64} = C_NULL; tstops::Ptr{Float64} = C_NULL; noise::Ptr{Float64} = C_NULL
     n_traj::Int64 = 0; traj_offset::Int64 = 0; seed::UInt64 = 0
+    out_pitch::Int64 = 0
 end
 
 alg_id(::EM{true}) = Int32(0); alg_id(::EM{false}) = Int32(1)

@@ -24,7 +24,7 @@ class Desc(C.Structure):
         ("lags", C.c_double * 4), ("hist_c0", C.c_double * 8), ("hist_c1", C.c_double * 8),
         ("params", C.c_void_p), ("param_stride", C.c_int64), ("u0", C.c_void_p), ("u0_stride", C.c_int64),
         ("saveat", C.c_void_p), ("tstops", C.c_void_p), ("noise", C.c_void_p),
-        ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64),
+        ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64), ("out_pitch", C.c_int64),
     ]
 
 

@@ -49,11 +49,17 @@ inline void normal_pair(uint64_t gid, uint64_t call, uint64_t seed, double &z0, 
     uint32_t w[4];
     philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)seed,
                   (uint32_t)(seed >> 32), w);
-    const uint64_t m1 = ((uint64_t)(w[1] & 0xFFFFFu) << 32) | w[0], m2 = ((uint64_t)(w[3] & 0xFFFFFu) << 32) | w[2];
-    const double u1 = ((double)m1 + 0.5) * 0x1p-52, u2 = ((double)m2 + 0.5) * 0x1p-52;
-    const double r = std::sqrt(-2.0 * std::log(u1));
-    const double ang = 2.0 * M_PI * u2;
-    z0 = r * std::cos(ang); z1 = r * std::sin(ang);
+    // same definition as oracle/sdde_oracle.py::philox_normal_pair and csrc/sdde_kernels.cuh::normal_pair_from_words
+    const uint64_t m = ((uint64_t)(w[1] & 0xFFFFFu) << 32) | w[0];
+    const double u = ((double)m + 0.5) * 0x1p-52;
+    const double r = std::sqrt(-2.0 * std::log(u));
+    const unsigned q = w[3] >> 30;
+    const uint64_t f = ((uint64_t)(w[3] & 0x3FFFFFFFu) << 22) | (w[2] >> 10);
+    const double x = (double)f * 0x1p-52 - 0.5;
+    const double s = std::sin((M_PI / 2) * x), c = std::cos((M_PI / 2) * x);
+    const double cq = q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s));
+    const double sq = q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c));
+    z0 = r * cq; z1 = r * sq;
 }
 
 inline double ipow(double x, int n) {   // same multiplication order as oracle/sdde_oracle.py::ipow

@@ -36,7 +36,7 @@ class SddeDesc(C.Structure):
         ("params", C.c_void_p), ("param_stride", C.c_int64),
         ("u0", C.c_void_p), ("u0_stride", C.c_int64),
         ("saveat", C.c_void_p), ("tstops", C.c_void_p), ("noise", C.c_void_p),
-        ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64),
+        ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64), ("out_pitch", C.c_int64),
     ]
 
 
@@ -69,7 +69,7 @@ class SddeTiming(C.Structure):
 # every symbol include/sdde_b200.h declares (tests check that the library exports them all)
 EXPORTS = [
     "sdde_b200_version", "sdde_b200_device_count", "sdde_b200_last_error", "sdde_b200_create", "sdde_b200_destroy",
-    "sdde_b200_set_option", "sdde_b200_schedule", "sdde_b200_schedule_free", "sdde_b200_solve",
+    "sdde_b200_set_option", "sdde_b200_schedule", "sdde_b200_schedule_free", "sdde_b200_solve", "sdde_b200_solve_multi",
     "sdde_b200_merge_moments", "sdde_b200_compile_model", "sdde_b200_philox_normals", "sdde_b200_dfma_peak",
     "sdde_b200_hbm_peak", "sdde_b200_alloc_pinned", "sdde_b200_free_pinned",
 ]
@@ -106,6 +106,7 @@ def lib():
     L.sdde_b200_schedule_free.argtypes = [C.POINTER(SddeSchedule)]
     L.sdde_b200_schedule_free.restype = None
     L.sdde_b200_solve.argtypes = [C.c_void_p, C.POINTER(SddeDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SddeTiming)]
+    L.sdde_b200_solve_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(SddeDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sdde_b200_merge_moments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.sdde_b200_compile_model.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)]
     L.sdde_b200_philox_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]

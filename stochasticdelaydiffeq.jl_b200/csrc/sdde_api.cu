@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -454,6 +455,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     const int NS = K.n_state, NC = K.n_chan;
     const int64_t rows = n_save * NS;
     const int64_t NT = d->n_traj;
+    const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;      // row pitch of the caller's out array
+    if (d->out_pitch != 0 && d->out_pitch < NT) return fail(SDDE_ERR_BAD_DESC, "out_pitch < n_traj");
     if (N >= (int64_t)1 << 30) return fail(SDDE_ERR_UNSUPPORTED, "more than 2^30 steps");
     if (tm) {
         tm->n_steps = N; tm->n_save = n_save; tm->ring_slots = S.ring_slots; tm->block_threads = SDDE_BLOCK;
@@ -485,7 +488,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     const int64_t noise_rows = (d->noise_mode == SDDE_NOISE_PHILOX) ? 0 : (N + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * NC;
     const double bytes_per_traj = 8.0 * ((double)S.ring_slots * NS + (need_stage ? 2.0 * rows : 0.0) + (noise_host ? (double)noise_rows : 0.0) + NS + K.n_param) + 1.0;
     int64_t wave = c->opt_wave_traj > 0 ? c->opt_wave_traj : ((int64_t)1 << 20);
-    if (c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > ((int64_t)1 << 18)) wave = (int64_t)1 << 18;  // pipeline D2H
+    if (c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > ((int64_t)1 << 19)) wave = (int64_t)1 << 19;  // pipeline D2H (PCIe-bound: few, wide waves)
     const int64_t mem_cap = (int64_t)((double)free_b * 0.80 / bytes_per_traj);
     wave = std::min(wave, std::max<int64_t>(per_block, mem_cap));
     wave = std::max<int64_t>(per_block, (wave / per_block) * per_block);
@@ -575,8 +578,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         A.n_traj = nt;
         A.traj_gid0 = d->traj_offset + off;
         if (out_dev) {
-            A.out = out; A.out_pitch = NT; A.out_off = off;
-            A.out_vec_ok = ((NT % 4) == 0 && (off % 4) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+            A.out = out; A.out_pitch = OP; A.out_off = off;
+            A.out_vec_ok = ((OP % 4) == 0 && (off % 4) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
         } else if (need_stage) {
             const int b = (d->want_paths && n_waves > 1) ? buf : 0;
             if (d->want_paths && w >= 2) CU_CHECK(cudaStreamWaitEvent(c->compute, c->ev_copied[b], 0));  // staging buffer free again
@@ -604,7 +607,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         // outputs of this wave
         if (d->want_paths && !out_dev && rows > 0) {
             CU_CHECK(cudaStreamWaitEvent(c->copy_out, c->ev_kdone[buf], 0));
-            CU_CHECK(cudaMemcpy2DAsync(out + off, NT * 8, A.out, pitch * 8, nt * 8, rows, cudaMemcpyDeviceToHost, c->copy_out));
+            CU_CHECK(cudaMemcpy2DAsync(out + off, OP * 8, A.out, pitch * 8, nt * 8, rows, cudaMemcpyDeviceToHost, c->copy_out));
             CU_CHECK(cudaEventRecord(c->ev_copied[buf], c->copy_out));
             d2h += nt * 8 * rows;
         }
@@ -634,6 +637,67 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         if (cudaEventElapsedTime(&ms, c->ev_c0, c->ev_c1) == cudaSuccess) tm->d2h_ms = ms;
         tm->h2d_bytes = h2d; tm->d2h_bytes = d2h; tm->launches = launches;
         tm->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    }
+    return SDDE_OK;
+}
+
+int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc *d, double *out, double *moments, uint8_t *status,
+                          sdde_timing *tm) {
+    if (!ctxs || n_ctx < 1) return fail(SDDE_ERR_BAD_DESC, "no contexts");
+    int rc = check_desc(d);
+    if (rc) return rc;
+    if (d->out_mem != SDDE_MEM_HOST || (d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem != SDDE_MEM_HOST))
+        return fail(SDDE_ERR_UNSUPPORTED, "sdde_b200_solve_multi takes host buffers only");
+    if (d->model_id >= SDDE_MODEL_USER_BASE) return fail(SDDE_ERR_UNSUPPORTED, "user models are compiled per context: use one context per call");
+    if (n_ctx == 1) return sdde_b200_solve(ctxs[0], d, out, moments, status, tm);
+    // trajectory-independent sizes
+    sdde::KernelInfo K;
+    rc = select_kernel(ctxs[0], d, K);
+    if (rc) return rc;
+    sdde::Schedule S;
+    rc = make_schedule(d, S);
+    if (rc) return rc;
+    const int64_t rows = (int64_t)S.save_t.size() * d->n_state, NT = d->n_traj;
+    const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;
+    const int64_t per = (NT + n_ctx - 1) / n_ctx;
+    const int64_t noise_rows = (S.n_steps() + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * (int64_t)K.n_chan;
+    std::vector<int> rcs((size_t)n_ctx, 0);
+    std::vector<std::string> errs((size_t)n_ctx);
+    std::vector<std::vector<double>> moms((size_t)n_ctx);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_ctx; ++r) {
+        th.emplace_back([&, r]() {
+            const int64_t lo = std::min(NT, (int64_t)r * per), hi = std::min(NT, lo + per), n = hi - lo;
+            if (n == 0) return;
+            sdde_desc dr = *d;
+            dr.n_traj = n; dr.traj_offset = d->traj_offset + lo; dr.out_pitch = OP;
+            // per-trajectory inputs are [row][stride] arrays: the slice of this GPU starts at column lo.  params/u0 keep
+            // their stride; supplied noise is re-packed densely (its row pitch is n_traj by definition).
+            std::vector<double> nz;
+            if (d->param_stride) dr.params = d->params + lo;
+            if (d->u0_stride) dr.u0 = d->u0 + lo;
+            if (d->noise_mode != SDDE_NOISE_PHILOX) {
+                nz.resize((size_t)std::max<int64_t>(1, noise_rows * n));
+                for (int64_t k = 0; k < noise_rows; ++k) memcpy(nz.data() + k * n, d->noise + k * NT + lo, (size_t)n * 8);
+                dr.noise = nz.data();
+            }
+            if (d->want_moments) moms[(size_t)r].assign((size_t)std::max<int64_t>(1, rows * 3), 0.0);
+            rcs[(size_t)r] = sdde_b200_solve(ctxs[r], &dr, d->want_paths ? out + lo : nullptr,
+                                             d->want_moments ? moms[(size_t)r].data() : nullptr,
+                                             status ? status + lo : nullptr, tm ? tm + r : nullptr);
+            if (rcs[(size_t)r]) errs[(size_t)r] = g_last_error;     // thread-local -> hand to the caller's thread
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int r = 0; r < n_ctx; ++r)
+        if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "GPU %d: %s", r, errs[(size_t)r].c_str());
+    if (d->want_moments) {
+        bool first = true;
+        for (int r = 0; r < n_ctx; ++r) {
+            if (moms[(size_t)r].empty()) continue;
+            if (first) { memcpy(moments, moms[(size_t)r].data(), (size_t)rows * 3 * 8); first = false; }
+            else sdde_b200_merge_moments(moments, moms[(size_t)r].data(), rows);
+        }
     }
     return SDDE_OK;
 }

@@ -33,7 +33,9 @@ enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMI
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
+#ifndef SDDE_BLOCK
 #define SDDE_BLOCK 128
+#endif
 #define SDDE_RNG_SMEM_BYTES 2048
 
 struct SaveRec {

@@ -32,6 +32,7 @@ class EnsembleB200:
     distributed: bool = False
     output: str = "host"
     wave_traj: int | None = None
+    devices: tuple | None = None   # several GPUs driven from THIS process (sdde_b200_solve_multi); host output only
     lanes_per_traj: int = 0      # 0/1: thread per trajectory; n_state (4): cooperative lanes (models with a row-wise form)
 
 
@@ -367,7 +368,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     lo, hi = shard_range(n_total, rank, world)
     n_traj = hi - lo
 
-    device = ea.device if ea.device is not None else _default_device()
+    device = ea.device if ea.device is not None else (ea.devices[0] if ea.devices else _default_device())
     ctx = capi.get_context(device)
     if ea.wave_traj:
         ctx.set_option("wave_traj", ea.wave_traj)
@@ -432,9 +433,19 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     mom = np.zeros((n_save, model.n_state, 3), dtype=np.float64) if moments else None
     status = np.zeros(n_traj, dtype=np.uint8)
     tm = capi.SddeTiming()
-    capi.check(capi.lib().sdde_b200_solve(ctx.handle, C.byref(m.desc), out_ptr,
-                                          capi.np_ptr(mom).value if moments else None, capi.np_ptr(status).value,
-                                          C.byref(tm)))
+    if ea.devices and len(ea.devices) > 1:
+        if ea.output != "host":
+            raise ValueError("EnsembleB200(devices=...) returns host arrays")
+        hs = (C.c_void_p * len(ea.devices))(*[capi.get_context(dv).handle for dv in ea.devices])
+        tms = (capi.SddeTiming * len(ea.devices))()
+        capi.check(capi.lib().sdde_b200_solve_multi(hs, len(ea.devices), C.byref(m.desc), out_ptr,
+                                                    capi.np_ptr(mom).value if moments else None,
+                                                    capi.np_ptr(status).value, C.cast(tms, C.c_void_p)))
+        tm = tms[0]
+    else:
+        capi.check(capi.lib().sdde_b200_solve(ctx.handle, C.byref(m.desc), out_ptr,
+                                              capi.np_ptr(mom).value if moments else None, capi.np_ptr(status).value,
+                                              C.byref(tm)))
     if moments and ea.distributed and world > 1:
         mom = _allgather_merge_moments(mom, device)
     if hasattr(out_arr, "data_ptr") and not out_arr.is_cuda:
