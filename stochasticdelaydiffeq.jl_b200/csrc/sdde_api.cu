@@ -298,6 +298,8 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
         memcpy(rec + 24, ns, 8);
         const long long off_store = ((n + 1) % R) * slot_bytes;
         memcpy(rec + 32, &off_store, 8);
+        const double inv_sq = 1.0 / S.sqdt[(size_t)n];
+        memcpy(rec + 40, &inv_sq, 8);
     }
 }
 

@@ -50,7 +50,7 @@ struct StepRec {
     int nsave;            // number of SaveRec produced by this step
     int ring_mask;        // bit l set: lag l reads the history ring; clear: prehistory h(p, t - tau_l)
     long long off_store;  // BYTE offset (from the trajectory's ring column) of the slot that receives node n+1
-    long long pad;
+    double inv_sqdt;      // 1 / sqrt|dt_n| (RKMil's difference quotient multiplies instead of dividing)
     struct Lk {
         double theta;         // interpolation weight; for prehistory: the lookup time t_n - tau_l
         long long off_lo;     // byte offsets of the two bracketing nodes; an exact hit is (lo = hi = node, theta = 1)
@@ -219,7 +219,7 @@ struct RegParams {
 // ------------------------------------------------------------------------------------------------
 template <class M, int ALG, class P>
 __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&ul)[M::NL][M::NS], const P &p, double t,
-                                         double dt, double sq, const double *dw) {
+                                         double dt, double sq, double isq, const double *dw) {
     constexpr int NS = M::NS;
     double du[NS], K[NS];
     M::f(du, u, ul, p, t);
@@ -252,9 +252,9 @@ __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&ul)[
         M::g(g2, ut, ul, p, t);
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            const double ggp = (g2[j] - L[j]) / sq;
+            const double ggp = (g2[j] - L[j]) * isq;          // reference: ./ sqdt (1 ulp apart)
             const double w2 = (ALG == K_ALG_RKMIL_ITO) ? (dw[j] * dw[j] - fabs(dt)) : (dw[j] * dw[j]);
-            const double mil = ggp * w2 / 2.0;
+            const double mil = (ggp * w2) * 0.5;
             u[j] = (K[j] + L[j] * dw[j]) + mil;
         }
     }
@@ -370,7 +370,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #pragma unroll
     for (int k = 0; k < BW; ++k) {
         const Rec &r = recs[k];
-        const double tn = r.t, dtn = r.dt, sq = r.sqdt;
+        const double tn = r.t, dtn = r.dt, sq = r.sqdt, isq = r.inv_sqdt;
         // delayed states: [EXT] HistoryFunction regimes
         double ul[TPT][NL][NS];
 #pragma unroll
@@ -392,8 +392,8 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         // perform_step!
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
-            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, dw[tt]);
-            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, dw[tt]);
+            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, isq, dw[tt]);
+            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, isq, dw[tt]);
 #pragma unroll
             for (int j = 0; j < NS; ++j) useq[k + 1][tt][j] = st.u[tt][j];
         }
