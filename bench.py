@@ -46,16 +46,18 @@ def mg_problem(S):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler is started
+    before the warm-up (nvidia-smi takes a while to produce its first line); only samples whose timestamp falls inside
+    [mark_start, mark_end] are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.t0, self.t1 = gpu_index, None, [], None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -64,31 +66,41 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for ln in self.lines:
+        sm, mx, reasons, pw, n_all = [], [], set(), [], 0
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
+                continue
+            n_all += 1
+            if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts) + 0.06):
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                sm.append(float(f[2])); mx.append(float(f[3])); pw.append(float(f[4]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_total": n_all, "reasons": sorted(reasons)}
 
 
 def cpu_reference_run(steps, warmup, sample_paths=None):
@@ -118,7 +130,7 @@ def cpu_reference_run(steps, warmup, sample_paths=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trajectories", type=int, default=WORKLOAD["trajectories_per_gpu"])
@@ -175,11 +187,12 @@ def main():
 
     # ---- device-resident arm: value + roofline ----
     W, K = max(3, args.warmup), max(1, args.steps)
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(W):
         sim = one_pass(i, ea_dev, out_dev, False)
-    sampler = ClockSampler(local)
     barrier_sync()
-    sampler.start()
+    sampler.mark_start()
     t0 = time.perf_counter()
     kernel_ms, launches = [], 0
     for i in range(K):
@@ -188,6 +201,7 @@ def main():
         launches += sim.timing["launches"]
     barrier_sync()
     elapsed = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop()
     tmax = torch.tensor([elapsed, sum(kernel_ms) / K], dtype=torch.float64, device=dev)
     if world > 1:

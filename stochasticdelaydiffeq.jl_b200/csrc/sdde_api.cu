@@ -73,6 +73,10 @@ struct sdde_ctx {
     int64_t opt_chunk_steps = 128;
     sdde::UserModels user;
     int sm_count = 148;
+    // schedule cache: repeated solves of the same problem shape (ensemble sweeps, benchmarks) reuse the host schedule
+    // and the packed device tables instead of replaying the time stepping and re-uploading them
+    std::string sched_key, table_key;
+    sdde::Schedule sched;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -186,6 +190,20 @@ int check_desc(const sdde_desc *d) {
     if (d->param_stride != 0 && d->param_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "param_stride < n_traj");
     if (d->u0_stride != 0 && d->u0_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "u0_stride < n_traj");
     return SDDE_OK;
+}
+
+std::string schedule_key(const sdde_desc *d) {
+    std::string k;
+    auto add = [&k](const void *p, size_t n) { k.append((const char *)p, n); };
+    const int32_t ints[] = {d->alg, d->n_lag, d->order_discontinuity_t0, d->constant_lags_declared, d->save_start, d->save_end,
+                            d->save_everystep, d->n_saveat, d->n_tstops};
+    add(ints, sizeof(ints));
+    const double dbl[] = {d->t0, d->tf, d->dt};
+    add(dbl, sizeof(dbl));
+    add(d->lags, sizeof(double) * (size_t)d->n_lag);
+    if (d->n_saveat > 0) add(d->saveat, sizeof(double) * (size_t)d->n_saveat);
+    if (d->n_tstops > 0) add(d->tstops, sizeof(double) * (size_t)d->n_tstops);
+    return k;
 }
 
 int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
@@ -448,9 +466,14 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     sdde::KernelInfo K;
     rc = select_kernel(c, d, K);
     if (rc) return rc;
-    sdde::Schedule S;
-    rc = make_schedule(d, S);
-    if (rc) return rc;
+    const std::string skey = schedule_key(d);
+    if (skey != c->sched_key) {
+        c->sched_key.clear(); c->table_key.clear();
+        rc = make_schedule(d, c->sched);
+        if (rc) return rc;
+        c->sched_key = skey;
+    }
+    const sdde::Schedule &S = c->sched;
 
     const int64_t N = S.n_steps();
     const int64_t n_save = (int64_t)S.save_t.size();
@@ -501,12 +524,22 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     // ---- schedule tables -> device (byte offsets depend on the wave pitch) ----
     std::vector<unsigned char> h_steps;
     std::vector<sdde::SaveRec> h_saves;
-    pack_tables(S, K, pitch, h_steps, h_saves);
-    CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
-    CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
-    if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
-    if (!h_saves.empty()) CU_CHECK(cudaMemcpyAsync(c->saves.p, h_saves.data(), h_saves.size() * sizeof(sdde::SaveRec), cudaMemcpyHostToDevice, c->compute));
-    h2d += (int64_t)h_steps.size() + (int64_t)(h_saves.size() * sizeof(sdde::SaveRec));
+    {
+        std::string tkey = skey;
+        const int64_t tk[] = {pitch, (int64_t)K.rec_size, (int64_t)K.n_state};
+        tkey.append((const char *)tk, sizeof(tk));
+        if (tkey != c->table_key) {
+            c->table_key.clear();
+            pack_tables(S, K, pitch, h_steps, h_saves);
+            CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
+            CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
+            if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
+            if (!h_saves.empty()) CU_CHECK(cudaMemcpyAsync(c->saves.p, h_saves.data(), h_saves.size() * sizeof(sdde::SaveRec), cudaMemcpyHostToDevice, c->compute));
+            h2d += (int64_t)h_steps.size() + (int64_t)(h_saves.size() * sizeof(sdde::SaveRec));
+            CU_CHECK(cudaStreamSynchronize(c->compute));     // h_steps / h_saves are stack-owned
+            c->table_key = tkey;
+        }
+    }
 
     CU_CHECK(c->ring.reserve((size_t)S.ring_slots * NS * pitch * 8));
     if (need_stage) {

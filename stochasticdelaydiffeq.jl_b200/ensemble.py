@@ -329,6 +329,9 @@ def merge_moments(a: np.ndarray, b: np.ndarray) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------
 # solve
 # ---------------------------------------------------------------------------------------------
+_sched_cache: dict = {}     # (n_save, n_steps, save_t) of the last schedule: repeated solves skip the host replay
+
+
 def _default_device():
     import os
     return int(os.environ.get("LOCAL_RANK", "0"))
@@ -398,11 +401,16 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
                  p_batch=p_batch, u0_batch=u0_batch, noise=noise_ptr, noise_mode=noise_mode, noise_mem=noise_mem,
                  out_mem=capi.MEM_DEVICE if ea.output == "device" else capi.MEM_HOST, want_paths=paths,
                  want_moments=moments, lanes_per_traj=ea.lanes_per_traj)
-    sch = capi.SddeSchedule()
-    capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(sch)))
-    n_save, n_steps = sch.n_save, sch.n_steps
-    save_t = np.ctypeslib.as_array(sch.save_t, shape=(max(n_save, 1),))[:n_save].copy()
-    capi.lib().sdde_b200_schedule_free(C.byref(sch))
+    d = m.desc
+    skey = (d.alg, d.t0, d.tf, d.dt, tuple(d.lags[i] for i in range(d.n_lag)), d.order_discontinuity_t0,
+            d.constant_lags_declared, d.save_start, d.save_end, d.save_everystep, m.keep[0].tobytes(), m.keep[1].tobytes())
+    if _sched_cache.get("key") != skey:
+        sch = capi.SddeSchedule()
+        capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(sch)))
+        _sched_cache.update(key=skey, n_save=sch.n_save, n_steps=sch.n_steps,
+                            save_t=np.ctypeslib.as_array(sch.save_t, shape=(max(sch.n_save, 1),))[:sch.n_save].copy())
+        capi.lib().sdde_b200_schedule_free(C.byref(sch))
+    n_save, n_steps, save_t = _sched_cache["n_save"], _sched_cache["n_steps"], _sched_cache["save_t"].copy()
     if nz is not None:
         need = n_steps + (1 if noise_mode == capi.NOISE_SUPPLIED_GRID else 0)
         if nz.shape[0] < need:
