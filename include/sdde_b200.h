@@ -124,6 +124,9 @@ typedef struct sdde_desc {
     int64_t traj_offset;              /* global id of the first one (partition-invariant RNG streams) */
     uint64_t seed;
     int64_t out_pitch;                /* elements between consecutive rows of `out`; 0 = n_traj (dense) */
+    int32_t n_save_idxs;              /* save_idxs keyword (src/solve.jl:355-356): 0 = save every state, else the number of */
+    int32_t save_idxs[SDDE_MAX_STATE];/*   0-based state indices that are saved (out/moments then have n_save_idxs rows per save) */
+    int32_t reserved1;
 } sdde_desc;
 
 /* Host-side schedule (trajectory independent): the replay of src/solve.jl:574-610 time stepping with

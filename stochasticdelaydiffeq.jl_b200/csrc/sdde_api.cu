@@ -189,6 +189,11 @@ int check_desc(const sdde_desc *d) {
         return fail(SDDE_ERR_BAD_DESC, "noise_mode is SUPPLIED but noise is NULL");
     if (d->param_stride != 0 && d->param_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "param_stride < n_traj");
     if (d->u0_stride != 0 && d->u0_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "u0_stride < n_traj");
+    if (d->n_save_idxs < 0 || d->n_save_idxs > d->n_state) return fail(SDDE_ERR_BAD_DESC, "n_save_idxs out of range");
+    for (int i = 0; i < d->n_save_idxs; ++i) {
+        if (d->save_idxs[i] < 0 || d->save_idxs[i] >= d->n_state) return fail(SDDE_ERR_BAD_DESC, "save_idxs[%d] = %d out of range", i, d->save_idxs[i]);
+        for (int k = 0; k < i; ++k) if (d->save_idxs[k] == d->save_idxs[i]) return fail(SDDE_ERR_BAD_DESC, "duplicate entry in save_idxs");
+    }
     return SDDE_OK;
 }
 
@@ -478,7 +483,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     const int64_t N = S.n_steps();
     const int64_t n_save = (int64_t)S.save_t.size();
     const int NS = K.n_state, NC = K.n_chan;
-    const int64_t rows = n_save * NS;
+    const int NSAVED = d->n_save_idxs > 0 ? d->n_save_idxs : NS;
+    const int64_t rows = n_save * NSAVED;
     const int64_t NT = d->n_traj;
     const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;      // row pitch of the caller's out array
     if (d->out_pitch != 0 && d->out_pitch < NT) return fail(SDDE_ERR_BAD_DESC, "out_pitch < n_traj");
@@ -568,6 +574,9 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     A.ring_pitch = pitch;
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
+    A.n_saved = NSAVED;
+    for (int j = 0; j < SDDE_K_MAX_STATE; ++j) A.save_row[j] = d->n_save_idxs > 0 ? -1 : (j < NS ? j : -1);
+    for (int i = 0; i < d->n_save_idxs; ++i) A.save_row[d->save_idxs[i]] = i;
     A.seed_lo = (sdde::u32)(d->seed & 0xffffffffu); A.seed_hi = (sdde::u32)(d->seed >> 32);
     for (int r = 0; r < 10; ++r) { A.rk[2 * r] = A.seed_lo + (sdde::u32)r * 0x9E3779B9u; A.rk[2 * r + 1] = A.seed_hi + (sdde::u32)r * 0xBB67AE85u; }
     for (int j = 0; j < NS; ++j) { A.hist_c0[j] = d->hist_c0[j]; A.hist_c1[j] = d->hist_c1[j]; }
@@ -692,7 +701,7 @@ int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc 
     sdde::Schedule S;
     rc = make_schedule(d, S);
     if (rc) return rc;
-    const int64_t rows = (int64_t)S.save_t.size() * d->n_state, NT = d->n_traj;
+    const int64_t rows = (int64_t)S.save_t.size() * (d->n_save_idxs > 0 ? d->n_save_idxs : d->n_state), NT = d->n_traj;
     const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;
     const int64_t per = (NT + n_ctx - 1) / n_ctx;
     const int64_t noise_rows = (S.n_steps() + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * (int64_t)K.n_chan;

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_cons
     char *ringb = reinterpret_cast<char *>(a.ring + tr * NS + j);     // ring layout [slot][traj][NS]
     *reinterpret_cast<double *>(ringb) = u;                            // node 0
     while (ks < a.n_saves && a.saves[ks].step < 0) {
-        if (a.out && live) a.out[((long long)ks * NS + j) * a.out_pitch + a.out_off + tr] = u;
+        if (a.out && live && a.save_row[j] >= 0) a.out[((long long)ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr] = u;
         ++ks;
     }
     const double hc0 = a.hist_c0[j], hc1 = a.hist_c1[j];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_cons
                 const SaveRec sr = a.saves[ks];
                 const double v = sr.exact ? u : ((1.0 - sr.theta) * uold + sr.theta * u);
                 bad = bad || !finite_d(v);
-                if (a.out && live) a.out[((long long)ks * NS + j) * a.out_pitch + a.out_off + tr] = v;
+                if (a.out && live && a.save_row[j] >= 0) a.out[((long long)ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr] = v;
                 ++ks;
             }
         }

@@ -73,7 +73,8 @@ struct KArgs {
     long long traj_gid0;     // global id of the wave's first trajectory
     int n_steps, n_saves, ring_slots, chunk_steps, batch, noise_kind;
     int out_vec_ok;          // out rows are 16-byte aligned for double2 stores
-    int pad0;
+    int n_saved;             // states saved per save point (save_idxs)
+    int save_row[SDDE_K_MAX_STATE];   // state j -> row within a save point, or -1 (not saved)
     u32 seed_lo, seed_hi;
     u32 rk[20];              // Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 (host precomputed)
     double hist_c0[SDDE_K_MAX_STATE], hist_c1[SDDE_K_MAX_STATE];
@@ -419,8 +420,8 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                     v[tt] = sr.exact ? useq[k + 1][tt][j] : ((1.0 - sr.theta) * useq[k][tt][j] + sr.theta * useq[k + 1][tt][j]);
                     st.bad[tt] = st.bad[tt] || !finite_d(v[tt]);
                 }
-                if (a.out) {
-                    double *op = a.out + ((long long)st.ks * NS + j) * a.out_pitch + a.out_off + tr0;
+                if (a.out && a.save_row[j] >= 0) {
+                    double *op = a.out + ((long long)st.ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr0;
                     if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
                     else {
 #pragma unroll
@@ -484,7 +485,8 @@ __global__ void __launch_bounds__(SDDE_BLOCK, SDDE_MIN_BLOCKS) sdde_solve_kernel
         if (a.out) {
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                double *op = a.out + ((long long)st.ks * NS + j) * a.out_pitch + a.out_off + tr0;
+                if (a.save_row[j] < 0) continue;
+                double *op = a.out + ((long long)st.ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr0;
                 if (out_vec) {
                     double v[TPT];
 #pragma unroll

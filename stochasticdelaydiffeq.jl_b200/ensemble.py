@@ -81,7 +81,7 @@ class _Marshalled:
 
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
-             want_moments, lanes_per_traj=0) -> _Marshalled:
+             want_moments, lanes_per_traj=0, save_idxs=None) -> _Marshalled:
     if not isinstance(alg, (EM, RKMil)):
         raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM and RKMil, fixed step)")
     if adaptive is None:
@@ -146,6 +146,13 @@ def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_
     d.out_mem = out_mem
     d.history_mode = 0
     d.lanes_per_traj = int(lanes_per_traj)
+    if save_idxs is not None:
+        idx = [int(i) for i in np.atleast_1d(save_idxs)]
+        if not idx or any(i < 0 or i >= model.n_state for i in idx) or len(set(idx)) != len(idx):
+            raise ValueError("save_idxs must be distinct 0-based state indices")
+        d.n_save_idxs = len(idx)
+        for k, i in enumerate(idx):
+            d.save_idxs[k] = i
     d.want_paths, d.want_moments = int(want_paths), int(want_moments)
     d.n_traj, d.traj_offset = int(n_traj), int(traj_offset)
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -355,8 +362,6 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     """
     if callback is not None:
         raise NotImplementedError("callbacks are outside this path (SURVEY.md section 8(f))")
-    if save_idxs is not None:
-        raise NotImplementedError("save_idxs is not implemented on this path yet")
     if kwargs:
         raise TypeError(f"unsupported keyword(s) on the EnsembleB200 path: {sorted(kwargs)}")
     single = isinstance(prob, SDDEProblem)
@@ -400,7 +405,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
                  save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=lo, seed=seed,
                  p_batch=p_batch, u0_batch=u0_batch, noise=noise_ptr, noise_mode=noise_mode, noise_mem=noise_mem,
                  out_mem=capi.MEM_DEVICE if ea.output == "device" else capi.MEM_HOST, want_paths=paths,
-                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj)
+                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj, save_idxs=save_idxs)
     d = m.desc
     skey = (d.alg, d.t0, d.tf, d.dt, tuple(d.lags[i] for i in range(d.n_lag)), d.order_discontinuity_t0,
             d.constant_lags_declared, d.save_start, d.save_end, d.save_everystep, m.keep[0].tobytes(), m.keep[1].tobytes())
@@ -416,9 +421,10 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
         if nz.shape[0] < need:
             raise ValueError(f"supplied noise has {nz.shape[0]} rows, the schedule needs {need}")
 
+    n_saved = model.n_state if save_idxs is None else len(np.atleast_1d(save_idxs))
     out_arr, out_ptr = None, None
     if paths:
-        shape = (n_save, model.n_state, n_traj)
+        shape = (n_save, n_saved, n_traj)
         if out is not None:
             out_arr = out
             if tuple(out_arr.shape) != shape:
@@ -438,7 +444,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
             if not out_arr.flags.c_contiguous or out_arr.dtype != np.float64:
                 raise ValueError("out must be a C-contiguous float64 array")
             out_ptr = capi.np_ptr(out_arr).value
-    mom = np.zeros((n_save, model.n_state, 3), dtype=np.float64) if moments else None
+    mom = np.zeros((n_save, n_saved, 3), dtype=np.float64) if moments else None
     status = np.zeros(n_traj, dtype=np.uint8)
     tm = capi.SddeTiming()
     if ea.devices and len(ea.devices) > 1:
@@ -458,7 +464,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
         mom = _allgather_merge_moments(mom, device)
     if hasattr(out_arr, "data_ptr") and not out_arr.is_cuda:
         out_arr = out_arr.numpy()
-    sim = EnsembleSolution(save_t, out_arr, status, mom, base.scalar_state, time.perf_counter() - t0w, tm.as_dict(),
+    sim = EnsembleSolution(save_t, out_arr, status, mom, base.scalar_state and n_saved == 1, time.perf_counter() - t0w, tm.as_dict(),
                            traj_offset=lo, n_total=n_total)
     sim.seed = seed
     if single:

@@ -273,3 +273,21 @@ def test_full_size_properties_c2():
     assert np.allclose(sim.moments[..., 1], mean, rtol=1e-12)
     var = sim.out.var(dim=2, unbiased=True).cpu().numpy()
     assert np.allclose(sim.moments[..., 2] / (n - 1), var, rtol=1e-9)
+
+
+def test_save_idxs_subset_and_order():
+    """save_idxs keyword (src/solve.jl:355-356, interface.jl:386-391): only the listed states are saved, in list order."""
+    case = cases.c4(T=5.0)
+    sch = case.oracle_schedule()
+    n = 300
+    dW = cases.increments(sch, 2, n)
+    ref, _ = case.oracle(dW)
+    for lanes in (0, 4):
+        sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, lanes_per_traj=lanes),
+                      trajectories=n, noise_increments=dW, save_idxs=[2, 0], moments=True, **case.solve_kwargs())
+        assert sim.out.shape == (len(sch.save_t), 2, n)
+        assert cases.scaled_err(sim.out, ref[:, [2, 0], :]) < TOL
+        assert np.allclose(sim.moments[..., 1], ref[:, [2, 0], :].mean(axis=2), rtol=1e-12, atol=1e-15)
+    with pytest.raises(ValueError):
+        S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=4, save_idxs=[1, 1],
+                **case.solve_kwargs())
