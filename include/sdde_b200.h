@@ -57,7 +57,8 @@ extern "C" {
 enum { SDDE_ALG_EM_SPLIT = 0,      /* EM() == EM(true) */
        SDDE_ALG_EM_NOSPLIT = 1,    /* EM(false) */
        SDDE_ALG_RKMIL_ITO = 2,     /* RKMil(), adaptive=false */
-       SDDE_ALG_RKMIL_STRAT = 3 }; /* RKMil(interpretation=:Stratonovich), adaptive=false */
+       SDDE_ALG_RKMIL_STRAT = 3,   /* RKMil(interpretation=:Stratonovich), adaptive=false */
+       SDDE_ALG_EULER_HEUN = 4 };  /* EulerHeun() (Stratonovich): second f/g evaluation at t+dt (test/test_prob_sol.jl:34) */
 
 /* ---- built-in model zoo: the device-side replacement of the closures that
  *      src/functionwrapper.jl:8-9,35-36 builds around the user's f(u,h,p,t), g(u,h,p,t).
@@ -139,12 +140,14 @@ typedef struct sdde_schedule {
     int32_t ring_slots;        /* history ring capacity the kernels use */
     int32_t min_gap;           /* min over steps of (n - newest node a lookup touches) */
     int32_t n_tstops_hit;
+    int32_t n_stage;           /* history lookup times per step (2 for EulerHeun: t_n and t_n + dt_n) */
+    int32_t reserved;
     double *t;                 /* [n_steps+1] */
     double *dt;                /* [n_steps]   */
     double *sqdt;              /* [n_steps]   */
-    int32_t *lk_mode;          /* [n_steps*n_lag] 0 prehistory, 1 exact node, 2 interpolate */
-    int64_t *lk_idx;           /* [n_steps*n_lag] node index (upper node when interpolating), -1 prehistory */
-    double *lk_theta;          /* [n_steps*n_lag] theta, or the lookup time for prehistory */
+    int32_t *lk_mode;          /* [n_steps][n_stage][n_lag] 0 prehistory, 1 exact node, 2 interpolate, 3 constant u0 */
+    int64_t *lk_idx;           /* same shape: node index (upper node when interpolating), -1 otherwise */
+    double *lk_theta;          /* same shape: theta, or the lookup time for prehistory */
     double *save_t;            /* [n_save] */
     int64_t *save_step;        /* [n_save] step whose end produced the save, -1 = initial condition */
     double *save_theta;        /* [n_save] */

@@ -169,7 +169,7 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
     const int64_t NT = d->n_traj;
     const double t0 = d->t0, tf = d->tf, dt = d->dt;
     const int alg = d->alg;
-    const int alg_order2 = (alg >= 2) ? 2 : 1;
+    const int alg_order2 = (alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMIL_STRAT) ? 2 : 1;
     double p[SDDE_MAX_PARAM];
     for (int i = 0; i < d->n_param; ++i) p[i] = d->param_stride ? d->params[i * d->param_stride + traj] : d->params[i];
     double u[SDDE_MAX_STATE], uprev[SDDE_MAX_STATE], u0[SDDE_MAX_STATE];
@@ -217,7 +217,8 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
         }
         for (int j = 0; j < ns; ++j) o[j] = u0[j];
     };
-    const std::function<void(int, double *)> hcb = [&](int l, double *o) { hist(t - d->lags[l], o); };
+    double tq = t0;   // time at which the current f/g evaluation asks for its delayed states
+    const std::function<void(int, double *)> hcb = [&](int l, double *o) { hist(tq - d->lags[l], o); };
 
     int64_t n = 0;
     double zc0 = 0, zc1 = 0; uint64_t zcall = ~0ull;
@@ -244,9 +245,29 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
                 }
             }
             // perform_step! ([EXT] StochasticDiffEq, call site src/solve.jl:586)
+            tq = t;
             M.f(du, uprev, hcb, p, t);
             for (int j = 0; j < ns; ++j) K[j] = uprev[j] + dtn * du[j];
-            if (alg == SDDE_ALG_EM_SPLIT || alg == SDDE_ALG_EM_NOSPLIT) {
+            if (alg == SDDE_ALG_EULER_HEUN) {
+                // [EXT] EulerHeunConstantCache; second evaluation at t + dt
+                const int nwv = M.diag ? 1 : M.nw;
+                double g1[SDDE_MAX_STATE * SDDE_MAX_NOISE], gg2[SDDE_MAX_STATE * SDDE_MAX_NOISE], tmp[SDDE_MAX_STATE], f2[SDDE_MAX_STATE];
+                M.g(g1, uprev, hcb, p, t);
+                for (int i = 0; i < ns; ++i) {
+                    double noise = g1[i * nwv] * dw[M.diag ? i : 0];
+                    for (int j = 1; j < nwv; ++j) noise = noise + g1[i * nwv + j] * dw[j];
+                    tmp[i] = (uprev[i] + du[i] * dtn) + noise;
+                }
+                tq = t + dtn;
+                M.f(f2, tmp, hcb, p, t + dtn);
+                M.g(gg2, tmp, hcb, p, t + dtn);
+                tq = t;
+                for (int i = 0; i < ns; ++i) {
+                    double noise2 = (0.5 * (g1[i * nwv] + gg2[i * nwv])) * dw[M.diag ? i : 0];
+                    for (int j = 1; j < nwv; ++j) noise2 = noise2 + (0.5 * (g1[i * nwv + j] + gg2[i * nwv + j])) * dw[j];
+                    u[i] = (uprev[i] + (dtn * 0.5) * (du[i] + f2[i])) + noise2;
+                }
+            } else if (alg == SDDE_ALG_EM_SPLIT || alg == SDDE_ALG_EM_NOSPLIT) {
                 M.g(gv, alg == SDDE_ALG_EM_SPLIT ? K : uprev, hcb, p, t);
                 if (M.diag) for (int j = 0; j < ns; ++j) u[j] = K[j] + gv[j] * dw[j];
                 else for (int i = 0; i < ns; ++i) {

@@ -43,6 +43,7 @@ ALG_EM_SPLIT = 0      # EM()  == EM(true)   [EXT] default split-step
 ALG_EM_NOSPLIT = 1    # EM(false)
 ALG_RKMIL_ITO = 2     # RKMil()  (interpretation = :Ito)
 ALG_RKMIL_STRAT = 3   # RKMil(interpretation = :Stratonovich)
+ALG_EULER_HEUN = 4    # EulerHeun()  (Stratonovich; second f/g evaluation at t + dt)
 
 # [EXT] StochasticDiffEq.alg_order: EM 1//2, RKMil 1//1  (call site src/solve.jl:248)
 ALG_ORDER = {
@@ -50,12 +51,15 @@ ALG_ORDER = {
     ALG_EM_NOSPLIT: Fraction(1, 2),
     ALG_RKMIL_ITO: Fraction(1, 1),
     ALG_RKMIL_STRAT: Fraction(1, 1),
+    ALG_EULER_HEUN: Fraction(1, 2),
 }
+N_STAGE = {ALG_EM_SPLIT: 1, ALG_EM_NOSPLIT: 1, ALG_RKMIL_ITO: 1, ALG_RKMIL_STRAT: 1, ALG_EULER_HEUN: 2}
 
 # lookup modes in the schedule tables
 LK_PRE = 0      # t < t0            -> user history h(p, t)
 LK_EXACT = 1    # t == sol.t[i]     -> sol.u[i]
 LK_INTERP = 2   # t in (t[i-1],t[i]) -> (1-theta) u[i-1] + theta u[i]
+LK_U0 = 3       # t > sol.t[end]    -> the never-advanced history integrator's u = u0
 
 
 def _eps(x: float) -> float:
@@ -71,7 +75,7 @@ class Schedule:
     t: np.ndarray            # [N+1] node times, t[0] = t0
     dt: np.ndarray           # [N]   dt_n used by step n (after modify_dt_for_tstops!)
     sqdt: np.ndarray         # [N]   sqrt(|dt_n|)
-    lk_mode: np.ndarray      # [N, L] LK_*
+    lk_mode: np.ndarray      # [N, L] LK_*   ([N, n_stage*L] for two-stage algorithms, stage-major)
     lk_idx: np.ndarray       # [N, L] node index i (upper node for INTERP), -1 for PRE
     lk_theta: np.ndarray     # [N, L] theta for INTERP; lookup time for PRE
     lk_time: np.ndarray      # [N, L] t_n - lag (as computed in float64)
@@ -249,27 +253,34 @@ def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_
 
     N = len(dts)
     L = len(lags)
+    NSTG = N_STAGE[alg]
     tarr = np.array(ts, dtype=np.float64)
-    lk_mode = np.zeros((N, L), dtype=np.int32)
-    lk_idx = np.full((N, L), -1, dtype=np.int64)
-    lk_theta = np.zeros((N, L), dtype=np.float64)
-    lk_time = np.zeros((N, L), dtype=np.float64)
+    lk_mode = np.zeros((N, NSTG * L), dtype=np.int32)
+    lk_idx = np.full((N, NSTG * L), -1, dtype=np.int64)
+    lk_theta = np.zeros((N, NSTG * L), dtype=np.float64)
+    lk_time = np.zeros((N, NSTG * L), dtype=np.float64)
     for k in range(N):
         tn = ts[k]
-        for l, lag in enumerate(lags):
-            tl = tn - lag
-            lk_time[k, l] = tl
-            if tl < t0:
-                lk_mode[k, l] = LK_PRE; lk_theta[k, l] = tl
-                continue
-            # sde_interpolation on sol.t[1..k+1] (dense history: sol.t[end] == t_n)
-            i = bisect.bisect_left(ts, tl, 0, k + 1)         # searchsortedfirst
-            if ts[i] == tl:
-                lk_mode[k, l] = LK_EXACT; lk_idx[k, l] = i; lk_theta[k, l] = 1.0
-            else:
-                h_ = ts[i] - ts[i - 1]
-                lk_mode[k, l] = LK_INTERP; lk_idx[k, l] = i
-                lk_theta[k, l] = (tl - ts[i - 1]) / h_
+        for sg in range(NSTG):
+            tq = tn if sg == 0 else tn + dts[k]          # EulerHeun's second evaluation: f(tmp, p, t + dt)
+            for l, lag in enumerate(lags):
+                e = sg * L + l
+                tl = tq - lag
+                lk_time[k, e] = tl
+                if tl < t0:
+                    lk_mode[k, e] = LK_PRE; lk_theta[k, e] = tl
+                    continue
+                if tl > tn:                              # past sol.t[end] = t_n: constant u0 (HistoryFunction regime 3)
+                    lk_mode[k, e] = LK_U0
+                    continue
+                # sde_interpolation on sol.t[1..k+1] (dense history: sol.t[end] == t_n)
+                i = bisect.bisect_left(ts, tl, 0, k + 1)         # searchsortedfirst
+                if ts[i] == tl:
+                    lk_mode[k, e] = LK_EXACT; lk_idx[k, e] = i; lk_theta[k, e] = 1.0
+                else:
+                    h_ = ts[i] - ts[i - 1]
+                    lk_mode[k, e] = LK_INTERP; lk_idx[k, e] = i
+                    lk_theta[k, e] = (tl - ts[i - 1]) / h_
     dta = np.array(dts, dtype=np.float64)
     return Schedule(t=tarr, dt=dta, sqdt=np.sqrt(np.abs(dta)), lk_mode=lk_mode, lk_idx=lk_idx,
                     lk_theta=lk_theta, lk_time=lk_time,
@@ -584,7 +595,28 @@ def solve_ensemble(model: Model, params, u0, h0, h1, lags, sched: Schedule, alg,
         dw = dW[n]
         fu = model.f(u, ul, p, t)
         K = u + dt * fu
-        if alg in (ALG_EM_SPLIT, ALG_EM_NOSPLIT):
+        if alg == ALG_EULER_HEUN:
+            # [EXT] EulerHeunConstantCache: the second f/g evaluation happens at t + dt, so its delayed states are
+            # looked up at (t + dt) - tau in the history that still ends at t_n
+            ul2 = [lookup((t + dt) - float(lag)) for lag in lags]
+            g1 = model.g(u, ul, p, t)
+            if model.diagonal:
+                noise = g1 * dw
+            else:
+                noise = g1[:, 0, :] * dw[0]
+                for j in range(1, m):
+                    noise = noise + g1[:, j, :] * dw[j]
+            tmp = (u + fu * dt) + noise
+            f2 = model.f(tmp, ul2, p, t + dt)
+            g2 = model.g(tmp, ul2, p, t + dt)
+            if model.diagonal:
+                noise2 = (0.5 * (g1 + g2)) * dw
+            else:
+                noise2 = (0.5 * (g1[:, 0, :] + g2[:, 0, :])) * dw[0]
+                for j in range(1, m):
+                    noise2 = noise2 + (0.5 * (g1[:, j, :] + g2[:, j, :])) * dw[j]
+            unew = (u + (dt * 0.5) * (fu + f2)) + noise2
+        elif alg in (ALG_EM_SPLIT, ALG_EM_NOSPLIT):
             uc = K if alg == ALG_EM_SPLIT else u
             gv = model.g(uc, ul, p, t)
             if model.diagonal:

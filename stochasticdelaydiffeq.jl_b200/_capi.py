@@ -12,7 +12,7 @@ import numpy as np
 
 SDDE_MAX_STATE, SDDE_MAX_LAG, SDDE_MAX_NOISE, SDDE_MAX_PARAM = 8, 4, 8, 128
 
-ALG_EM_SPLIT, ALG_EM_NOSPLIT, ALG_RKMIL_ITO, ALG_RKMIL_STRAT = 0, 1, 2, 3
+ALG_EM_SPLIT, ALG_EM_NOSPLIT, ALG_RKMIL_ITO, ALG_RKMIL_STRAT, ALG_EULER_HEUN = 0, 1, 2, 3, 4
 MODEL_LINEAR1, MODEL_HAYES, MODEL_MACKEY_GLASS, MODEL_LINSYS, MODEL_SIR, MODEL_SCALAR_ADD = 0, 1, 2, 3, 4, 5
 MODEL_USER_BASE = 1000
 NOISE_PHILOX, NOISE_SUPPLIED_DW, NOISE_SUPPLIED_GRID = 0, 1, 2
@@ -44,7 +44,7 @@ class SddeDesc(C.Structure):
 class SddeSchedule(C.Structure):
     _fields_ = [
         ("n_steps", C.c_int64), ("n_save", C.c_int64), ("n_lag", C.c_int32), ("ring_slots", C.c_int32),
-        ("min_gap", C.c_int32), ("n_tstops_hit", C.c_int32),
+        ("min_gap", C.c_int32), ("n_tstops_hit", C.c_int32), ("n_stage", C.c_int32), ("reserved", C.c_int32),
         ("t", _dp), ("dt", _dp), ("sqdt", _dp),
         ("lk_mode", C.POINTER(C.c_int32)), ("lk_idx", C.POINTER(C.c_int64)), ("lk_theta", _dp),
         ("save_t", _dp), ("save_step", C.POINTER(C.c_int64)), ("save_theta", _dp),

@@ -131,31 +131,39 @@ std::string build_schedule(const ScheduleInput &in, Schedule &S) {
     }
 
     // History lookups: [EXT] HistoryFunction three regimes + LinearInterpolationData.
+    // Stage 0 looks up t_n - tau (every f/g call of EM and RKMil); stage 1 (EulerHeun's second evaluation, at t + dt)
+    // looks up (t_n + dt_n) - tau against the SAME dense history, which ends at t_n while the step is being taken.
     const int64_t N = n;
-    S.lk_mode.assign((size_t)N * L, LK_PRE);
-    S.lk_idx.assign((size_t)N * L, -1);
-    S.lk_theta.assign((size_t)N * L, 0.0);
+    const int NSTG = in.n_stage;
+    S.n_stage = NSTG;
+    S.lk_mode.assign((size_t)N * NSTG * L, LK_PRE);
+    S.lk_idx.assign((size_t)N * NSTG * L, -1);
+    S.lk_theta.assign((size_t)N * NSTG * L, 0.0);
     int64_t need = 1;                                    // max_m (m - lowest node needed by step m)
     int64_t gap = std::numeric_limits<int32_t>::max();
     for (int64_t k = 0; k < N; ++k) {
         const double tn = S.t[(size_t)k];
-        for (int l = 0; l < L; ++l) {
-            const double tl = tn - in.lags[(size_t)l];
-            const size_t e = (size_t)k * L + l;
-            if (tl < t0) { S.lk_theta[e] = tl; continue; }           // prehistory h(p, tl)
-            // searchsortedfirst(sol.t[1..k+1], tl): dense history ends at t_n
-            const auto beg = S.t.begin();
-            const int64_t i = std::lower_bound(beg, beg + k + 1, tl) - beg;
-            if (S.t[(size_t)i] == tl) {
-                S.lk_mode[e] = LK_EXACT; S.lk_idx[e] = i; S.lk_theta[e] = 1.0;
-                need = std::max(need, k - i);
-            } else {
-                const double h = S.t[(size_t)i] - S.t[(size_t)i - 1];
-                S.lk_mode[e] = LK_INTERP; S.lk_idx[e] = i;
-                S.lk_theta[e] = (tl - S.t[(size_t)i - 1]) / h;
-                need = std::max(need, k - (i - 1));
+        for (int sg = 0; sg < NSTG; ++sg) {
+            const double tq = sg == 0 ? tn : tn + S.dt[(size_t)k];
+            for (int l = 0; l < L; ++l) {
+                const double tl = tq - in.lags[(size_t)l];
+                const size_t e = ((size_t)k * NSTG + sg) * L + l;
+                if (tl < t0) { S.lk_theta[e] = tl; continue; }           // prehistory h(p, tl)
+                if (tl > tn) { S.lk_mode[e] = LK_U0; continue; }         // never-advanced stub integrator: u0
+                // searchsortedfirst(sol.t[1..k+1], tl): dense history ends at t_n
+                const auto beg = S.t.begin();
+                const int64_t i = std::lower_bound(beg, beg + k + 1, tl) - beg;
+                if (S.t[(size_t)i] == tl) {
+                    S.lk_mode[e] = LK_EXACT; S.lk_idx[e] = i; S.lk_theta[e] = 1.0;
+                    need = std::max(need, k - i);
+                } else {
+                    const double h = S.t[(size_t)i] - S.t[(size_t)i - 1];
+                    S.lk_mode[e] = LK_INTERP; S.lk_idx[e] = i;
+                    S.lk_theta[e] = (tl - S.t[(size_t)i - 1]) / h;
+                    need = std::max(need, k - (i - 1));
+                }
+                gap = std::min(gap, k - i);
             }
-            gap = std::min(gap, k - i);
         }
     }
     S.ring_slots = (int)std::max<int64_t>(2, need + 1);

@@ -19,12 +19,13 @@
 
 namespace sdde {
 
-enum { LK_PRE = 0, LK_EXACT = 1, LK_INTERP = 2 };
+enum { LK_PRE = 0, LK_EXACT = 1, LK_INTERP = 2, LK_U0 = 3 };   // LK_U0: past the end of the dense history -> constant u0
 
 struct ScheduleInput {
     double t0 = 0, tf = 0, dt = 0;
     std::vector<double> lags;
-    int alg_order2 = 1;                 // 2*alg_order: EM 1, RKMil 2  ([EXT] StochasticDiffEq.alg_order)
+    int alg_order2 = 1;                 // 2*alg_order: EM 1, RKMil 2, EulerHeun 1  ([EXT] StochasticDiffEq.alg_order)
+    int n_stage = 1;                    // history lookup times per step: stage 0 at t_n, stage 1 at t_n + dt_n (EulerHeun)
     int order_discontinuity_t0 = 0;
     bool constant_lags_declared = true;
     bool neutral = false;
@@ -36,8 +37,8 @@ struct ScheduleInput {
 
 struct Schedule {
     std::vector<double> t, dt, sqdt;
-    int n_lag = 0;
-    std::vector<int32_t> lk_mode;       // [n_steps*n_lag]
+    int n_lag = 0, n_stage = 1;
+    std::vector<int32_t> lk_mode;       // [n_steps][n_stage][n_lag]
     std::vector<int64_t> lk_idx;
     std::vector<double> lk_theta;
     std::vector<double> save_t, save_theta;

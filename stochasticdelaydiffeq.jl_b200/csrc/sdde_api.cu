@@ -170,8 +170,8 @@ int check_desc(const sdde_desc *d) {
     if (d->struct_size != (int32_t)sizeof(sdde_desc))
         return fail(SDDE_ERR_BAD_DESC, "sdde_desc.struct_size = %d, library expects %d (ABI mismatch)", d->struct_size,
                     (int)sizeof(sdde_desc));
-    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_RKMIL_STRAT)
-        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil fixed-step only)", d->alg);
+    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_EULER_HEUN)
+        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / EulerHeun, fixed step)", d->alg);
     if (d->n_lag < 1 || d->n_lag > SDDE_MAX_LAG) return fail(SDDE_ERR_BAD_DESC, "n_lag = %d out of range", d->n_lag);
     if (d->n_state < 1 || d->n_state > SDDE_MAX_STATE) return fail(SDDE_ERR_BAD_DESC, "n_state = %d out of range", d->n_state);
     if (d->n_noise < 1 || d->n_noise > SDDE_MAX_NOISE) return fail(SDDE_ERR_BAD_DESC, "n_noise = %d out of range", d->n_noise);
@@ -215,7 +215,8 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     sdde::ScheduleInput in;
     in.t0 = d->t0; in.tf = d->tf; in.dt = d->dt;
     in.lags.assign(d->lags, d->lags + d->n_lag);
-    in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT) ? 2 : 1;
+    in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT) ? 2 : 1;   // [EXT] alg_order: EM, EulerHeun 1//2
+    in.n_stage = d->alg == SDDE_ALG_EULER_HEUN ? 2 : 1;
     in.order_discontinuity_t0 = d->order_discontinuity_t0;
     in.constant_lags_declared = d->constant_lags_declared != 0;
     if (d->n_saveat > 0) in.saveat.assign(d->saveat, d->saveat + d->n_saveat);
@@ -226,7 +227,7 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     std::string err = sdde::build_schedule(in, S);
     if (!err.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", err.c_str());
     // src/solve.jl:581-585: dt > minimum(constant_lags) is an error for every algorithm but EM
-    if (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT) {
+    if (d->alg != SDDE_ALG_EM_SPLIT && d->alg != SDDE_ALG_EM_NOSPLIT) {
         double minlag = d->lags[0];
         for (int l = 1; l < d->n_lag; ++l) minlag = std::min(minlag, d->lags[l]);
         for (double x : S.dt)
@@ -302,8 +303,9 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
         double hdr[3] = {S.t[(size_t)n], S.dt[(size_t)n], S.sqdt[(size_t)n]};
         memcpy(rec, hdr, 24);
         int mask = 0;
-        for (int l = 0; l < L; ++l) {
-            const size_t e = (size_t)n * L + l;
+        const int NLK = L * S.n_stage;
+        for (int l = 0; l < NLK; ++l) {            // lookup l = stage * L + lag, same order as Schedule::lk_*
+            const size_t e = (size_t)n * NLK + l;
             const int mode = S.lk_mode[e];
             long long off_lo = 0, off_hi = 0;
             double theta = S.lk_theta[e];
@@ -311,6 +313,8 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
                 off_lo = off_hi = (S.lk_idx[e] % R) * slot_bytes; theta = 1.0; mask |= 1 << l;
             } else if (mode == sdde::LK_INTERP) {
                 off_lo = ((S.lk_idx[e] - 1) % R) * slot_bytes; off_hi = (S.lk_idx[e] % R) * slot_bytes; mask |= 1 << l;
+            } else if (mode == sdde::LK_U0) {
+                mask |= 0x10000 << l;
             }
             unsigned char *lk = rec + 48 + 32 * l;
             memcpy(lk, &theta, 8);
@@ -420,6 +424,7 @@ int sdde_b200_schedule(const sdde_desc *d, sdde_schedule *o) {
     o->n_steps = S.n_steps();
     o->n_save = (int64_t)S.save_t.size();
     o->n_lag = S.n_lag;
+    o->n_stage = S.n_stage;
     o->ring_slots = S.ring_slots;
     o->min_gap = S.min_gap;
     o->n_tstops_hit = (int32_t)S.tstops_hit.size();

@@ -13,6 +13,7 @@ struct KernelInfo {
     int rec_size = 0;           // sizeof(StepRec<NL>)
     int n_state = 0, n_lag = 0, n_chan = 0, n_noise = 0, n_param = 0;
     bool diag = true;
+    int n_stage = 1;            // history lookup sets per step (2: EulerHeun)
     int lanes = 1;              // lanes per trajectory (cooperative kernel: n_state)
     bool is_user = false;       // fn is a cudaKernel_t obtained from an NVRTC-built library
     const char *name = "";
@@ -21,10 +22,12 @@ struct KernelInfo {
 template <class M, int ALG, int NOISE, bool PT>
 inline KernelInfo make_info(const char *name) {
     KernelInfo k;
-    k.fn = (const void *)&sdde_solve_kernel<M, ALG, NOISE, PT, Tune<M>::TPT, Tune<M>::B>;
+    constexpr int BB = (alg_stages(ALG) > 1 && Tune<M>::B > 1) ? Tune<M>::B / 2 : Tune<M>::B;   // two lookup sets per step
+    k.fn = (const void *)&sdde_solve_kernel<M, ALG, NOISE, PT, Tune<M>::TPT, BB>;
     k.tpt = Tune<M>::TPT;
-    k.batch = Tune<M>::B;
-    k.rec_size = (int)sizeof(StepRec<M::NL>);
+    k.batch = BB;
+    k.n_stage = alg_stages(ALG);
+    k.rec_size = (int)sizeof(StepRec<M::NL * alg_stages(ALG)>);
     k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = M::DIAG ? M::NS : M::NW; k.n_param = M::NP;
     k.diag = M::DIAG;
     k.name = name;
@@ -55,6 +58,7 @@ inline KernelInfo make_coop_info(const char *name) {
         SDDE_SEL_ALG(M, NAME, K_ALG_EM_NOSPLIT)                 \
         SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_ITO)                  \
         SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_STRAT)                \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
         return KernelInfo();                                    \
     }
 // EM only (non-diagonal noise: [EXT] RKMil requires diagonal noise)
@@ -62,6 +66,7 @@ inline KernelInfo make_coop_info(const char *name) {
     KernelInfo FUNC(int alg, int noise, bool ptraj) {           \
         SDDE_SEL_ALG(M, NAME, K_ALG_EM_SPLIT)                   \
         SDDE_SEL_ALG(M, NAME, K_ALG_EM_NOSPLIT)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
         return KernelInfo();                                    \
     }
 

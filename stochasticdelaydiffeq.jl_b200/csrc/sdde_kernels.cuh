@@ -29,7 +29,9 @@ typedef unsigned long long u64;
 
 enum { K_LK_PRE = 0, K_LK_EXACT = 1, K_LK_INTERP = 2 };
 enum { K_NOISE_PHILOX = 0, K_NOISE_DW = 1, K_NOISE_GRID = 2 };
-enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3 };
+enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3, K_ALG_EULER_HEUN = 4 };
+// history lookup times per step: EulerHeun evaluates f and g a second time at t + dt
+__host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULER_HEUN ? 2 : 1; }
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
@@ -48,7 +50,8 @@ template <int NL>
 struct StepRec {
     double t, dt, sqdt;
     int nsave;            // number of SaveRec produced by this step
-    int ring_mask;        // bit l set: lag l reads the history ring; clear: prehistory h(p, t - tau_l)
+    int ring_mask;        // bit i (< 16) set: lookup i reads the history ring; bit 16+i set: constant u0 (past the end of
+                          // the dense history); neither: prehistory h(p, t - tau_l).  Lookup i = stage * NL + lag.
     long long off_store;  // BYTE offset (from the trajectory's ring column) of the slot that receives node n+1
     double inv_sqdt;      // 1 / sqrt|dt_n| (RKMil's difference quotient multiplies instead of dividing)
     struct Lk {
@@ -219,9 +222,35 @@ struct RegParams {
 // (SURVEY.md section 3.3).  ul = delayed states (same for every f/g evaluation of the step).
 // ------------------------------------------------------------------------------------------------
 template <class M, int ALG, class P>
-__device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&ul)[M::NL][M::NS], const P &p, double t,
-                                         double dt, double sq, double isq, const double *dw) {
+__device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)[alg_stages(ALG)][M::NL][M::NS], const P &p,
+                                         double t, double dt, double sq, double isq, const double *dw) {
     constexpr int NS = M::NS;
+    const double (&ul)[M::NL][M::NS] = uls[0];
+    if (ALG == K_ALG_EULER_HEUN) {
+        // [EXT] EulerHeunConstantCache: tmp = u + f dt + g dW;  u+ = u + dt/2 (f + f(tmp, t+dt)) + 1/2 (g + g(tmp, t+dt)) dW
+        constexpr int NW = M::DIAG ? 1 : M::NW, NG = M::DIAG ? NS : NS * M::NW;
+        const double (&ul2)[M::NL][M::NS] = uls[alg_stages(ALG) - 1];
+        double f1[NS], g1[NG], tmp[NS], f2[NS], g2[NG];
+        M::f(f1, u, ul, p, t);
+        M::g(g1, u, ul, p, t);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double noise = g1[i * NW] * dw[M::DIAG ? i : 0];
+#pragma unroll
+            for (int j = 1; j < NW; ++j) noise = noise + g1[i * NW + j] * dw[j];
+            tmp[i] = (u[i] + f1[i] * dt) + noise;
+        }
+        M::f(f2, tmp, ul2, p, t + dt);
+        M::g(g2, tmp, ul2, p, t + dt);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double noise2 = (0.5 * (g1[i * NW] + g2[i * NW])) * dw[M::DIAG ? i : 0];
+#pragma unroll
+            for (int j = 1; j < NW; ++j) noise2 = noise2 + (0.5 * (g1[i * NW + j] + g2[i * NW + j])) * dw[j];
+            u[i] = (u[i] + (dt * 0.5) * (f1[i] + f2[i])) + noise2;
+        }
+        return;
+    }
     double du[NS], K[NS];
     M::f(du, u, ul, p, t);
 #pragma unroll
@@ -306,18 +335,18 @@ struct TrajState {
 // steps are loaded up front (the host guarantees they are older than the batch) and n*NC is even, so which half of
 // a Philox pair a step consumes is a compile-time fact.
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW>
-__device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL> *recs, int n,
+__device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL * alg_stages(ALG)> *recs, int n,
                                           char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec) {
-    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW;
+    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NSTG = alg_stages(ALG), NLK = NL * NSTG;
     constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 2 == 0);
-    typedef StepRec<NL> Rec;
+    typedef StepRec<NLK> Rec;
     const long long jstride = a.ring_pitch * 8;
     // ---- all delayed-state loads of the batch, unconditionally (prehistory records point at slot 0) ----
-    double xlo[BW][NL][NS][TPT], xhi[BW][NL][NS][TPT];
+    double xlo[BW][NLK][NS][TPT], xhi[BW][NLK][NS][TPT];
 #pragma unroll
     for (int k = 0; k < BW; ++k) {
 #pragma unroll
-        for (int l = 0; l < NL; ++l) {
+        for (int l = 0; l < NLK; ++l) {
             const char *plo = ringb + recs[k].lk[l].off_lo, *phi = ringb + recs[k].lk[l].off_hi;
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
@@ -373,9 +402,9 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         const Rec &r = recs[k];
         const double tn = r.t, dtn = r.dt, sq = r.sqdt, isq = r.inv_sqdt;
         // delayed states: [EXT] HistoryFunction regimes
-        double ul[TPT][NL][NS];
+        double ul[TPT][NSTG][NL][NS];
 #pragma unroll
-        for (int l = 0; l < NL; ++l) {
+        for (int l = 0; l < NLK; ++l) {
             const double th = r.lk[l].theta;
             const bool ring = (r.ring_mask & (1 << l)) != 0;
             const double omt = 1.0 - th;
@@ -385,8 +414,17 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #pragma unroll
                 for (int tt = 0; tt < TPT; ++tt) {
                     const double iv = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
-                    ul[tt][l][j] = ring ? iv : hv;
+                    ul[tt][l / NL][l % NL][j] = ring ? iv : hv;
                 }
+            }
+            if (NSTG > 1 && (r.ring_mask & (0x10000 << l))) {   // second-stage lookup past the dense history: constant u0
+#pragma unroll
+                for (int j = 0; j < NS; ++j)
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) {
+                        const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+                        ul[tt][l / NL][l % NL][j] = a.u0 ? a.u0[j * a.u0_pitch + tr] : a.u0c[j];
+                    }
             }
         }
         double (&dw)[TPT][NC] = dwb[k];
@@ -438,7 +476,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
 __global__ void __launch_bounds__(SDDE_BLOCK, SDDE_MIN_BLOCKS) sdde_solve_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
-    typedef StepRec<NL> Rec;
+    typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *ltab = reinterpret_cast<double2 *>(smem_raw);                  // 2 KB log table of the normal generator
     Rec *srec = reinterpret_cast<Rec *>(smem_raw + SDDE_RNG_SMEM_BYTES);

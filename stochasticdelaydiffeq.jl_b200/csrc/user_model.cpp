@@ -13,7 +13,7 @@ namespace sdde {
 
 namespace {
 
-const int kAlgs = 4, kNoises = 3;
+const int kAlgs = 5, kNoises = 3;
 inline int variant_index(int alg, int noise, bool ptraj) { return (alg * kNoises + noise) * 2 + (ptraj ? 1 : 0); }
 
 std::string nvrtc_log(nvrtcProgram prog) {
@@ -123,13 +123,14 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
     const int idx = model_id - SDDE_MODEL_USER_BASE;
     if (idx < 0 || idx >= (int)entries_.size()) { err = "unknown user model id"; return false; }
     Entry &en = entries_[(size_t)idx];
-    if (!en.diag && alg >= 2) { k = KernelInfo(); return true; }   // caller reports "RKMil requires diagonal noise"
+    if (!en.diag && (alg == 2 || alg == 3)) { k = KernelInfo(); return true; }   // caller reports "RKMil requires diagonal noise"
     const int v = variant_index(alg, noise, ptraj);
     if (!en.kernels[(size_t)v]) {
         char expr[256];
         snprintf(expr, sizeof(expr),
-                 "sdde::sdde_solve_kernel<sdde::UserModel, %d, %d, %s, sdde::Tune<sdde::UserModel>::TPT, sdde::Tune<sdde::UserModel>::B>",
-                 alg, noise, ptraj ? "true" : "false");
+                 "sdde::sdde_solve_kernel<sdde::UserModel, %d, %d, %s, sdde::Tune<sdde::UserModel>::TPT, %s>",
+                 alg, noise, ptraj ? "true" : "false",
+                 alg == 4 ? "(sdde::Tune<sdde::UserModel>::B > 1 ? sdde::Tune<sdde::UserModel>::B / 2 : 1)" : "sdde::Tune<sdde::UserModel>::B");
         std::vector<char> cubin;
         std::string lowered;
         if (!compile_one(g_sources[(size_t)idx].src, expr, cubin, lowered, err)) return false;
@@ -145,7 +146,9 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
     k = KernelInfo();
     k.fn = en.kernels[(size_t)v];
     k.is_user = true;
-    k.tpt = en.tpt; k.batch = en.batch; k.rec_size = en.rec_size;
+    k.tpt = en.tpt; k.batch = (alg == 4 && en.batch > 1) ? en.batch / 2 : en.batch;
+    k.n_stage = alg == 4 ? 2 : 1;
+    k.rec_size = 48 + 32 * en.nl * k.n_stage;
     k.n_state = en.ns; k.n_lag = en.nl; k.n_noise = en.nw; k.n_chan = en.diag ? en.ns : en.nw; k.n_param = en.np;
     k.diag = en.diag;
     k.name = en.name.c_str();

@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi as capi
-from .problem import EM, RKMil, EnsembleProblem, SDDEProblem, UserModel, _as_history
+from .problem import EM, EulerHeun, RKMil, EnsembleProblem, SDDEProblem, UserModel, _as_history
 
 
 @dataclass
@@ -82,8 +82,8 @@ class _Marshalled:
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
              want_moments, lanes_per_traj=0, save_idxs=None) -> _Marshalled:
-    if not isinstance(alg, (EM, RKMil)):
-        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM and RKMil, fixed step)")
+    if not isinstance(alg, (EM, RKMil, EulerHeun)):
+        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil and EulerHeun, fixed step)")
     if adaptive is None:
         adaptive = isinstance(alg, RKMil)      # [EXT] isadaptive(RKMil) = true, src/solve.jl:40
     if adaptive:
@@ -204,7 +204,7 @@ def schedule(prob: SDDEProblem, alg, *, dt, saveat=None, save_everystep=None, sa
     s = capi.SddeSchedule()
     capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(s)))
     try:
-        N, K, L = s.n_steps, s.n_save, s.n_lag
+        N, K, L = s.n_steps, s.n_save, s.n_lag * s.n_stage
 
         def arr(ptr, n, dtype):
             return np.ctypeslib.as_array(ptr, shape=(max(n, 1),))[:n].astype(dtype, copy=True)

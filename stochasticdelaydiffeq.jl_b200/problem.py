@@ -43,6 +43,16 @@ class RKMil:
         return capi.ALG_RKMIL_ITO if self.interpretation == "Ito" else capi.ALG_RKMIL_STRAT
 
 
+@dataclass(frozen=True)
+class EulerHeun:
+    """Euler-Heun (Stratonovich), fixed step: second drift/diffusion evaluation at t + dt, i.e. a second set of
+    delayed-state lookups per step ([EXT] StochasticDiffEq EulerHeun; reference smoke test test/test_prob_sol.jl:34)."""
+
+    @property
+    def alg_id(self):
+        return capi.ALG_EULER_HEUN
+
+
 # ---------------------------------------------------------------------------------------------
 # model zoo handles: model.f / model.g are what the user passes as f and g
 # ---------------------------------------------------------------------------------------------

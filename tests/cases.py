@@ -3,7 +3,7 @@ import numpy as np
 import sdde_b200 as S
 import sdde_oracle as O
 
-ALG_MAP = {0: S.EM(True), 1: S.EM(False), 2: S.RKMil("Ito"), 3: S.RKMil("Stratonovich")}
+ALG_MAP = {0: S.EM(True), 1: S.EM(False), 2: S.RKMil("Ito"), 3: S.RKMil("Stratonovich"), 4: S.EulerHeun()}
 
 
 class Case:
@@ -22,7 +22,7 @@ class Case:
 
     def solve_kwargs(self):
         kw = dict(dt=self.dt, saveat=self.saveat)
-        if self.alg >= 2:
+        if self.alg in (2, 3):
             kw["adaptive"] = False
         return kw
 

@@ -46,6 +46,8 @@ SCHED_CASES = [
     (lambda: cases.c1(T=0.5, saveat=0.2), {}),                       # tf < tau: never reads its own past
     (lambda: cases.c1(T=2.0, saveat=0.003), {}),                     # several saves per step
     (lambda: cases.c1(T=5.0).with_(dt=1.7, lags=[1.0]), {}),         # dt > tau (allowed for EM)
+    (lambda: cases.c2(T=60.0, alg=4), {}), (lambda: cases.c4(T=8.0).with_(alg=4), {}),      # EulerHeun: two lookup sets
+    (lambda: cases.c1(T=5.0).with_(dt=0.25, lags=[0.25], alg=4), {}),                        # dt == tau: stage 2 lands on t_n
 ]
 
 

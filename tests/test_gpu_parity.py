@@ -291,3 +291,23 @@ def test_save_idxs_subset_and_order():
     with pytest.raises(ValueError):
         S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=4, save_idxs=[1, 1],
                 **case.solve_kwargs())
+
+
+# ---- EulerHeun: a second set of delayed-state lookups per step, at t + dt ----
+@pytest.mark.parametrize("mk,n", [
+    (lambda: cases.c1().with_(alg=4), 500), (lambda: cases.c2(T=100.0, alg=4), 2048), (lambda: cases.c3(0, T=60.0, alg=4), 1024),
+    (lambda: cases.c4(T=8.0).with_(alg=4), 512), (lambda: cases.sir(T=10.0, dt=0.02).with_(alg=4), 256),
+    (lambda: cases.hayes(T=3.0, beta=-1.2, saveat=0.25, alg=4), 256), (lambda: cases.scalar_add().with_(alg=4), 128)])
+def test_euler_heun_matches_oracle(mk, n):
+    case = mk()
+    sim, ref, st = run_case(case, n)
+    assert "alg4" in sim.timing["kernel_name"]
+    assert cases.scaled_err(sim.out, ref) < (1e-11 if case.name == "sir" else TOL)
+    assert np.array_equal(sim.status, st)
+
+
+def test_euler_heun_step_equal_to_lag_guard():
+    # src/solve.jl:581-585 applies to every algorithm but EM
+    case = cases.c1(T=5.0).with_(dt=1.5, alg=4)
+    with pytest.raises(S.SddeError, match="dt > minimum"):
+        S.solve(S.EnsembleProblem(case.problem()), S.EulerHeun(), S.EnsembleB200(device=0), trajectories=4, **case.solve_kwargs())

@@ -119,3 +119,8 @@ def test_k6_strong_order_rkmil_ito():
 def test_k6_strong_order_rkmil_stratonovich():
     # the Stratonovich solution differs from the Ito one, but the scheme's own order is 1.0 (same assertion as the reference)
     assert abs(_strong_order(S.RKMil("Stratonovich"), 3) - 1.0) < 0.3
+
+
+def test_k6_strong_order_euler_heun():
+    # test/analyticless_convergence_tests.jl:42-46 asserts 1.0 +- 0.3 for EulerHeun on the same problem
+    assert abs(_strong_order(S.EulerHeun(), 4) - 1.0) < 0.3

@@ -147,7 +147,9 @@ def test_golden_fixtures_reproduce():
     (lambda: cases.c1(), 200), (lambda: cases.c1(saveat=None), 50), (lambda: cases.c2(T=60.0), 128),
     (lambda: cases.c2(T=60.0, alg=1), 64), (lambda: cases.c3(0, T=60.0), 128), (lambda: cases.c3(2, T=60.0, alg=3), 128),
     (lambda: cases.c4(T=8.0), 64), (lambda: cases.hayes(T=3.0, beta=-1.2, saveat=0.25), 64),
-    (lambda: cases.sir(T=20.0, dt=0.02), 64), (lambda: cases.scalar_add(), 64)])
+    (lambda: cases.sir(T=20.0, dt=0.02), 64), (lambda: cases.scalar_add(), 64),
+    (lambda: cases.c2(T=60.0, alg=4), 64), (lambda: cases.c4(T=6.0).with_(alg=4), 32), (lambda: cases.sir(T=10.0, dt=0.02).with_(alg=4), 32),
+    (lambda: cases.hayes(T=3.0, beta=-1.2, saveat=0.25, alg=4), 32)])
 def test_cpp_restatement_equals_numpy_restatement_bitwise(mk, n):
     c = mk()
     sch = c.oracle_schedule()
@@ -181,3 +183,13 @@ def test_moment_merge_is_associative_enough():
     a, b, c = O.moments(x[..., :100]), O.moments(x[..., 100:550]), O.moments(x[..., 550:])
     m = O.merge_moments(O.merge_moments(a, b), c)
     assert np.allclose(m, full, rtol=1e-12)
+
+
+def test_euler_heun_known_answer_and_order():
+    # one step, f = u, g = u, u = 1, dt = 0.1, dW = 0.2 (no delay dependence): tmp = 1 + 0.1 + 0.2 = 1.3,
+    # u+ = 1 + 0.05 (1 + 1.3) + 0.5 (1 + 1.3) 0.2 = 1.345
+    assert _one_step(O.ALG_EULER_HEUN) == pytest.approx(1.345, rel=1e-15)
+    s = O.build_schedule(0, 5, 0.01, [1.0], O.ALG_EULER_HEUN)
+    assert s.lk_mode.shape == (501, 2) and s.tstops_hit == [1.0, 2.0, 5.0]          # alg_order 1/2 like EM
+    # the second-stage lookup of step n is (numerically almost) the first-stage lookup of step n+1
+    assert np.all(np.abs(s.lk_time[:-1, 1] - s.lk_time[1:, 0]) < 1e-12)
