@@ -74,11 +74,6 @@ std::string wrap_source(const char *user) {
 
 }  // namespace
 
-struct UserSource {
-    std::string src;
-};
-static std::vector<UserSource> g_sources;   // parallel to entries_ (kept outside the class to keep the header light)
-
 int UserModels::compile(const char *source, std::string &err) {
     const std::string src = wrap_source(source);
     // 1) probe compile: syntax check + model dimensions
@@ -113,9 +108,8 @@ int UserModels::compile(const char *source, std::string &err) {
     }
     en.kernels.assign((size_t)kAlgs * kNoises * 2, nullptr);
     en.name = "user" + std::to_string(entries_.size());
+    en.source = src;
     entries_.push_back(en);
-    while (g_sources.size() < entries_.size()) g_sources.push_back(UserSource());
-    g_sources[entries_.size() - 1].src = src;
     return SDDE_MODEL_USER_BASE + (int)entries_.size() - 1;
 }
 
@@ -133,7 +127,7 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
                  alg == 4 ? "(sdde::Tune<sdde::UserModel>::B > 1 ? sdde::Tune<sdde::UserModel>::B / 2 : 1)" : "sdde::Tune<sdde::UserModel>::B");
         std::vector<char> cubin;
         std::string lowered;
-        if (!compile_one(g_sources[(size_t)idx].src, expr, cubin, lowered, err)) return false;
+        if (!compile_one(en.source, expr, cubin, lowered, err)) return false;
         cudaLibrary_t lib = nullptr;
         cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
         if (e != cudaSuccess) { err = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); return false; }

@@ -29,6 +29,7 @@ class UserModels {
         int ns = 0, nl = 0, nw = 0, np = 0, tpt = 1, batch = 1, rec_size = 0;
         bool diag = true;
         std::string name;
+        std::string source;                   // wrapped program text (variants are compiled lazily from it)
     };
     std::vector<Entry> entries_;
     std::vector<void *> libs_;                // loaded cudaLibrary_t handles
