@@ -530,7 +530,20 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     wave = std::max<int64_t>(per_block, (wave / per_block) * per_block);
     wave = std::min(wave, ((NT + per_block - 1) / per_block) * per_block);
     const int64_t pitch = wave;   // multiple of per_block => every thread of the grid owns in-bounds ring columns
-    const int n_waves = (int)((NT + wave - 1) / wave);
+    // Wave list.  When the saved paths leave over PCIe (host output) the first waves are small and grow geometrically,
+    // so that the D2H stream starts after a few milliseconds instead of after a whole 2^19-trajectory wave.
+    std::vector<int64_t> wave_off, wave_cnt;
+    {
+        const bool ramp = c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > wave;
+        int64_t cur = ramp ? std::max<int64_t>(per_block, (((int64_t)1 << 16) / per_block) * per_block) : wave;
+        for (int64_t off = 0; off < NT;) {
+            const int64_t cnt = std::min(std::min(cur, wave), NT - off);
+            wave_off.push_back(off); wave_cnt.push_back(cnt);
+            off += cnt;
+            if (ramp) cur = std::min(wave, cur * 2);
+        }
+    }
+    const int n_waves = (int)wave_off.size();
 
     // ---- schedule tables -> device (byte offsets depend on the wave pitch) ----
     std::vector<unsigned char> h_steps;
@@ -596,8 +609,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     bool first_kernel = true;
 
     for (int w = 0; w < n_waves; ++w) {
-        const int64_t off = (int64_t)w * wave;
-        const int64_t nt = std::min(wave, NT - off);
+        const int64_t off = wave_off[(size_t)w];
+        const int64_t nt = wave_cnt[(size_t)w];
         const int buf = w & 1;
         // inputs of this wave
         if (d->u0_stride != 0 || d->param_stride != 0 || noise_host) {
