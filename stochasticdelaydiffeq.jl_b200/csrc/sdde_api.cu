@@ -298,6 +298,7 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
         saves[i].theta = S.save_theta[i];
         if (S.save_step[i] >= 0) nsave[(size_t)S.save_step[i]]++;
     }
+    std::vector<long long> prev_hi((size_t)std::max(1, L * S.n_stage), -1);     // byte offset of the previous step's upper node, -1: none
     for (int64_t n = 0; n < N; ++n) {
         unsigned char *rec = steps.data() + (size_t)n * k.rec_size;
         double hdr[3] = {S.t[(size_t)n], S.dt[(size_t)n], S.sqdt[(size_t)n]};
@@ -316,6 +317,10 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
             } else if (mode == sdde::LK_U0) {
                 mask |= 0x10000 << l;
             }
+            // consecutive steps usually bracket with a shared node: lo(n) == hi(n-1) -> the kernel keeps it in registers
+            const bool ring = mode == sdde::LK_EXACT || mode == sdde::LK_INTERP;
+            if (ring && prev_hi[(size_t)l] == off_lo) mask |= 0x100 << l;
+            prev_hi[(size_t)l] = ring ? off_hi : -1;
             unsigned char *lk = rec + 48 + 32 * l;
             memcpy(lk, &theta, 8);
             memcpy(lk + 8, &off_lo, 8);
@@ -579,7 +584,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
 
     int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
     if (chunk >= 8) chunk -= chunk % 8;   // batches (B <= 8) never straddle a chunk; step index of a batch start stays even
-    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)chunk * K.rec_size;
+    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 1) * K.rec_size;
     int batch = K.batch;
     if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
     if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step
@@ -593,6 +598,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
     A.n_saved = NSAVED;
+    A.prefetch = (S.min_gap >= 1) ? 1 : 0;
     for (int j = 0; j < SDDE_K_MAX_STATE; ++j) A.save_row[j] = d->n_save_idxs > 0 ? -1 : (j < NS ? j : -1);
     for (int i = 0; i < d->n_save_idxs; ++i) A.save_row[d->save_idxs[i]] = i;
     A.seed_lo = (sdde::u32)(d->seed & 0xffffffffu); A.seed_hi = (sdde::u32)(d->seed >> 32);

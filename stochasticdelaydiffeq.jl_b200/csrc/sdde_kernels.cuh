@@ -50,8 +50,9 @@ template <int NL>
 struct StepRec {
     double t, dt, sqdt;
     int nsave;            // number of SaveRec produced by this step
-    int ring_mask;        // bit i (< 16) set: lookup i reads the history ring; bit 16+i set: constant u0 (past the end of
-                          // the dense history); neither: prehistory h(p, t - tau_l).  Lookup i = stage * NL + lag.
+    int ring_mask;        // lookup i = stage * NL + lag (i < 8).  bit i: reads the history ring; bit 8+i: its lower node is the
+                          // upper node of the previous step's lookup i (kept in registers, not re-read); bit 16+i: constant
+                          // u0 (past the end of the dense history); neither bit i nor 16+i: prehistory h(p, t - tau_l).
     long long off_store;  // BYTE offset (from the trajectory's ring column) of the slot that receives node n+1
     double inv_sqdt;      // 1 / sqrt|dt_n| (RKMil's difference quotient multiplies instead of dividing)
     struct Lk {
@@ -77,6 +78,7 @@ struct KArgs {
     int n_steps, n_saves, ring_slots, chunk_steps, batch, noise_kind;
     int out_vec_ok;          // out rows are 16-byte aligned for double2 stores
     int n_saved;             // states saved per save point (save_idxs)
+    int prefetch;            // step-by-step kernels: next step's nodes are older than this step (min_gap >= 1) -> L1 prefetch
     int save_row[SDDE_K_MAX_STATE];   // state j -> row within a save point, or -1 (not saved)
     u32 seed_lo, seed_hi;
     u32 rk[20];              // Philox round keys: rk[2r] = seed_lo + r*W0, rk[2r+1] = seed_hi + r*W1 (host precomputed)
@@ -95,13 +97,19 @@ struct KArgs {
 #ifndef SDDE_TUNE_FOOT_B2
 #define SDDE_TUNE_FOOT_B2 4
 #endif
+#ifndef SDDE_TUNE_TPT_MULTI
+#define SDDE_TUNE_TPT_MULTI 2
+#endif
 #ifndef SDDE_MIN_BLOCKS
 #define SDDE_MIN_BLOCKS 5
 #endif
 template <class M> struct Tune {
-    static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : 1;
+    static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : (M::NS >= 4 ? SDDE_TUNE_TPT_MULTI : 1);
     static constexpr int FOOT = M::NS * M::NL * TPT;              // doubles per prefetched step (one node set)
     static constexpr int B = (M::NS == 1 && M::NL == 1) ? SDDE_TUNE_B_SCALAR : (FOOT <= SDDE_TUNE_FOOT_B2 ? 2 : 1);
+    // resident CTAs per SM the register allocation aims for: scalar models 5 (<= 102 registers); multi-state models
+    // with two trajectories per thread need the registers more than the occupancy (measured, profiles/README.md)
+    static constexpr int MINB = (M::NS >= 4 && TPT > 1) ? 3 : SDDE_MIN_BLOCKS;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -329,6 +337,7 @@ struct TrajState {
     double curW[TPT][NC];     // NoiseGrid mode: current W
     bool bad[TPT];
     int ks;                   // next SaveRec
+    double carry[M::NL * 2][NS][TPT];   // upper nodes of the previous step's lookups (consecutive steps share a node)
 };
 
 // BW consecutive steps starting at global step index n (recs[0..BW)).  BW > 1: the delayed-state nodes of all BW
@@ -336,7 +345,8 @@ struct TrajState {
 // a Philox pair a step consumes is a compile-time fact.
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW>
 __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL * alg_stages(ALG)> *recs, int n,
-                                          char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec) {
+                                          char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec,
+                                          bool prefetch_next) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NSTG = alg_stages(ALG), NLK = NL * NSTG;
     constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 2 == 0);
     typedef StepRec<NLK> Rec;
@@ -348,11 +358,32 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #pragma unroll
         for (int l = 0; l < NLK; ++l) {
             const char *plo = ringb + recs[k].lk[l].off_lo, *phi = ringb + recs[k].lk[l].off_hi;
+            const bool reuse = (recs[k].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1): already in registers
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
+                if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
                 ld_traj<TPT>(reinterpret_cast<const double *>(phi + j * jstride), xhi[k][l][j]);
+                if (reuse) {
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) xlo[k][l][j][tt] = (k == 0) ? st.carry[l][j][tt] : xhi[k > 0 ? k - 1 : 0][l][j][tt];
+                }
             }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NLK; ++l)
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+#pragma unroll
+            for (int tt = 0; tt < TPT; ++tt) st.carry[l][j][tt] = xhi[BW - 1][l][j][tt];
+    // step-by-step path (multi-state models): pull the NEXT step's upper nodes towards L1 while this step computes
+    // (they were written at least one step ago; recs[BW] is staged by the caller when prefetch_next is set)
+    if (BW == 1 && prefetch_next) {
+#pragma unroll
+        for (int l = 0; l < NLK; ++l) {
+            const char *phi = ringb + recs[BW].lk[l].off_hi;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) asm volatile("prefetch.global.L1 [%0];" ::"l"(phi + j * jstride));
         }
     }
     // ---- increments of the whole batch first: accept_step! draws dW ~ N(0,|dt_n|) (src/integrators/interface.jl:449-454).
@@ -474,7 +505,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 }
 
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
-__global__ void __launch_bounds__(SDDE_BLOCK, SDDE_MIN_BLOCKS) sdde_solve_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
     typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -506,6 +537,12 @@ __global__ void __launch_bounds__(SDDE_BLOCK, SDDE_MIN_BLOCKS) sdde_solve_kernel
     }
     st.zcall = ~0ull;
     st.ks = 0;
+#pragma unroll
+    for (int l = 0; l < NL * 2; ++l)
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+#pragma unroll
+            for (int tt = 0; tt < TPT; ++tt) st.carry[l][j][tt] = 0.0;
 
     // ---- node 0 of the history = u0 (src/utils.jl:143-247: sol.t=[t0], sol.u=[u0]) ----
     char *ringb = reinterpret_cast<char *>(a.ring + tr0);
@@ -543,21 +580,24 @@ __global__ void __launch_bounds__(SDDE_BLOCK, SDDE_MIN_BLOCKS) sdde_solve_kernel
     const bool batched = (B > 1) && (a.batch >= B);   // host: batch = min(B, min_gap + 1); chunk_steps % B == 0
     for (int n0 = 0; n0 < a.n_steps; n0 += a.chunk_steps) {
         const int cnt = (a.n_steps - n0 < a.chunk_steps) ? (a.n_steps - n0) : a.chunk_steps;
+        const int nrec = (a.n_steps - n0 > cnt) ? cnt + 1 : cnt;      // one record of look-ahead for the prefetch
         __syncthreads();
         {   // stage this chunk of the schedule in shared memory
             const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
             uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + SDDE_RNG_SMEM_BYTES);
-            const int nvec = cnt * (int)(sizeof(Rec) / 16);
+            const int nvec = nrec * (int)(sizeof(Rec) / 16);
             for (int i = threadIdx.x; i < nvec; i += SDDE_BLOCK) dst[i] = src[i];
         }
         __syncthreads();
         int nb = 0;
         if (batched) {
             for (; nb + B <= cnt; nb += B)
-                run_batch<M, ALG, NOISE, PTRAJ, TPT, B>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec);
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, B>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, false);
         }
+        const bool pf = (B == 1) && a.prefetch;
         for (; nb < cnt; ++nb)
-            run_batch<M, ALG, NOISE, PTRAJ, TPT, 1>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec);
+            run_batch<M, ALG, NOISE, PTRAJ, TPT, 1>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec,
+                                                    pf && (nb + 1 < nrec));
     }
     // [EXT] check_error! (src/solve.jl:578): NaN/Inf -> ReturnCode.Unstable, reported per trajectory
     if (a.status) {
