@@ -56,8 +56,10 @@ class ClockSampler:
         self.idx, self.proc, self.lines, self.t0, self.t1 = gpu_index, None, [], None, None
 
     def start(self):
+        if os.environ.get("SDDE_BENCH_NO_SAMPLER"):
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -130,7 +132,7 @@ def cpu_reference_run(steps, warmup, sample_paths=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--trajectories", type=int, default=WORKLOAD["trajectories_per_gpu"])

@@ -59,6 +59,20 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinnedBuf {       // page-locked host staging (small D2H results: status bytes, moment triples)
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace
 
 struct sdde_ctx {
@@ -67,6 +81,7 @@ struct sdde_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
     DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
+    PinnedBuf h_status, h_mom;
     std::mutex mu;
     int64_t opt_wave_traj = 0;     // 0 = auto
     int64_t opt_batch = 0;         // 0 = compiled-in depth
@@ -76,6 +91,8 @@ struct sdde_ctx {
     // schedule cache: repeated solves of the same problem shape (ensemble sweeps, benchmarks) reuse the host schedule
     // and the packed device tables instead of replaying the time stepping and re-uploading them
     std::string sched_key, table_key;
+    size_t mem_free_cached = 0;     // cudaMemGetInfo costs up to ~1.5 ms: refreshed only when the problem shape changes
+    std::string mem_key;
     sdde::Schedule sched;
 };
 
@@ -395,6 +412,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     cudaDeviceSynchronize();
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
+    c->h_status.release(); c->h_mom.release();
     c->user.clear();
     if (c->compute) cudaStreamDestroy(c->compute);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
@@ -469,6 +487,8 @@ int sdde_b200_merge_moments(double *a, const double *b, int64_t n) {
 
 int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm) {
     const auto wall0 = std::chrono::steady_clock::now();
+    static const bool dbg = getenv("SDDE_DEBUG_TIMING") != nullptr;
+    auto lap = [&](const char *what) { if (dbg) fprintf(stderr, "[sdde timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count()); };
     if (tm) memset(tm, 0, sizeof(*tm));
     if (!c) return fail(SDDE_ERR_CUDA, "NULL context (no CUDA device? libsdde_b200 has no CPU fallback)");
     int rc = check_desc(d);
@@ -521,8 +541,19 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     // ---- wave geometry ----
     const int64_t per_block = (int64_t)SDDE_BLOCK * K.tpt / K.lanes;
     size_t free_b = 0, total_b = 0;
-    CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    free_b += c->ring.cap + c->out[0].cap + c->out[1].cap + c->noise.cap;   // our own cached workspaces are reusable
+    {
+        std::string mkey = skey;
+        const int64_t mk[] = {NT, (int64_t)d->out_mem, (int64_t)d->want_paths, (int64_t)d->want_moments, (int64_t)d->noise_mode, (int64_t)NS};
+        mkey.append((const char *)mk, sizeof(mk));
+        if (mkey != c->mem_key || c->mem_free_cached == 0) {
+            CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
+            free_b += c->ring.cap + c->out[0].cap + c->out[1].cap + c->noise.cap;   // our own cached workspaces are reusable
+            c->mem_free_cached = free_b;
+            c->mem_key = mkey;
+        }
+        free_b = c->mem_free_cached;
+    }
+    lap("memory budget known");
     const bool out_dev = d->want_paths && d->out_mem == SDDE_MEM_DEVICE;
     const bool need_stage = (d->want_paths && !out_dev) || (!d->want_paths && d->want_moments);
     const bool noise_host = d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem == SDDE_MEM_HOST;
@@ -578,7 +609,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (noise_host) CU_CHECK(c->noise.reserve((size_t)std::max<int64_t>(1, noise_rows) * pitch * 8));
     if (d->u0_stride != 0) CU_CHECK(c->u0.reserve((size_t)NS * pitch * 8));
     if (d->param_stride != 0) CU_CHECK(c->ptraj.reserve((size_t)std::max(1, K.n_param) * pitch * 8));
-    if (status) CU_CHECK(c->status.reserve((size_t)pitch));
+    if (status) { CU_CHECK(c->status.reserve((size_t)pitch)); CU_CHECK(c->h_status.reserve((size_t)NT)); }
     if (d->want_moments) CU_CHECK(c->mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves));
     if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
 
@@ -607,8 +638,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (d->u0_stride == 0) for (int j = 0; j < NS; ++j) A.u0c[j] = d->u0[j];
     if (d->param_stride == 0) for (int i = 0; i < K.n_param; ++i) A.p[i] = d->params[i];
 
-    std::vector<double> h_mom;
-    if (d->want_moments) h_mom.resize((size_t)rows * 3 * n_waves);
+    double *h_mom = nullptr;
+    if (d->want_moments) { CU_CHECK(c->h_mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves)); h_mom = (double *)c->h_mom.p; }
     int launches = 0;
     float kernel_ms = 0.f;
     CU_CHECK(cudaEventRecord(c->ev_c0, c->copy_out));
@@ -680,23 +711,27 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
             d2h += nt * 8 * rows;
         }
         if (status) {
-            CU_CHECK(cudaMemcpyAsync(status + off, c->status.p, (size_t)nt, cudaMemcpyDeviceToHost, c->compute));
+            CU_CHECK(cudaMemcpyAsync((unsigned char *)c->h_status.p + off, c->status.p, (size_t)nt, cudaMemcpyDeviceToHost, c->compute));
             d2h += nt;
         }
     }
     CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
     if (d->want_moments && rows > 0) {
-        CU_CHECK(cudaMemcpyAsync(h_mom.data(), c->mom.p, h_mom.size() * 8, cudaMemcpyDeviceToHost, c->compute));
-        d2h += (int64_t)h_mom.size() * 8;
+        CU_CHECK(cudaMemcpyAsync(h_mom, c->mom.p, (size_t)rows * 3 * 8 * n_waves, cudaMemcpyDeviceToHost, c->compute));
+        d2h += (int64_t)rows * 3 * 8 * n_waves;
     }
     CU_CHECK(cudaEventRecord(c->ev_c1, c->copy_out));
+    lap("all work enqueued");
     CU_CHECK(cudaStreamSynchronize(c->compute));
+    lap("compute stream synced");
     CU_CHECK(cudaStreamSynchronize(c->copy_out));
     CU_CHECK(cudaStreamSynchronize(c->copy_in));
+    lap("copy streams synced");
     CU_CHECK(cudaGetLastError());
+    if (status) memcpy(status, c->h_status.p, (size_t)NT);
     if (d->want_moments && rows > 0) {
-        memcpy(moments, h_mom.data(), (size_t)rows * 3 * 8);
-        for (int w = 1; w < n_waves; ++w) sdde_b200_merge_moments(moments, h_mom.data() + (size_t)w * rows * 3, rows);
+        memcpy(moments, h_mom, (size_t)rows * 3 * 8);
+        for (int w = 1; w < n_waves; ++w) sdde_b200_merge_moments(moments, h_mom + (size_t)w * rows * 3, rows);
     }
     if (tm) {
         float ms = 0.f;

@@ -358,7 +358,11 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #pragma unroll
         for (int l = 0; l < NLK; ++l) {
             const char *plo = ringb + recs[k].lk[l].off_lo, *phi = ringb + recs[k].lk[l].off_hi;
+#ifdef SDDE_NO_CARRY
+            const bool reuse = false;
+#else
             const bool reuse = (recs[k].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1): already in registers
+#endif
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
                 if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
