@@ -311,3 +311,31 @@ def test_euler_heun_step_equal_to_lag_guard():
     case = cases.c1(T=5.0).with_(dt=1.5, alg=4)
     with pytest.raises(S.SddeError, match="dt > minimum"):
         S.solve(S.EnsembleProblem(case.problem()), S.EulerHeun(), S.EnsembleB200(device=0), trajectories=4, **case.solve_kwargs())
+
+
+def test_cooperative_kernel_with_per_trajectory_initial_states():
+    case = cases.c4(T=4.0)
+    sch = case.oracle_schedule()
+    n = 257
+    rng = np.random.default_rng(3)
+    ub = np.asarray(case.u0)[:, None] * (1.0 + 0.1 * rng.random((4, n)))
+    dW = cases.increments(sch, 2, n)
+    ref, _ = case.oracle(dW, u0=ub)
+    for lanes in (0, 4):
+        sim = S.solve(S.EnsembleProblem(case.problem(), u0_batch=ub), S.EM(), S.EnsembleB200(device=0, lanes_per_traj=lanes),
+                      trajectories=n, noise_increments=dW, **case.solve_kwargs())
+        assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_rkmil_with_per_trajectory_parameters():
+    case = cases.c3(0, T=40.0)
+    n = 600
+    rng = np.random.default_rng(8)
+    pb = np.stack([0.2 + 0.02 * rng.random(n), 0.1 * np.ones(n), 10.0 * np.ones(n), 0.05 + 0.1 * rng.random(n)])
+    sch = case.oracle_schedule()
+    dW = cases.increments(sch, 1, n)
+    sim = S.solve(S.EnsembleProblem(case.problem(), p_batch=pb), S.RKMil(), S.EnsembleB200(device=0), trajectories=n,
+                  noise_increments=dW, **case.solve_kwargs())
+    ref, _ = case.oracle(dW, params=pb)
+    assert "mackey_glass," in sim.timing["kernel_name"]          # generic-exponent kernel (parameters vary per path)
+    assert cases.relerr(sim.out, ref) < TOL

@@ -65,3 +65,29 @@ def test_nvrtc_compile_error_is_reported():
     with pytest.raises(S.SddeError) as ei:
         S.solve(S.EnsembleProblem(prob), S.EM(), S.EnsembleB200(device=0), dt=0.1, trajectories=4)
     assert ei.value.code == -4 and "NVRTC" in str(ei.value)
+
+
+def test_user_model_per_trajectory_params_noise_grid_and_rkmil():
+    """The JIT path compiles one variant per (algorithm, noise source, parameter mode): exercise per-trajectory
+    parameters + NoiseGrid + RKMil on the 2-state diagonal-noise user model."""
+    um = S.UserModel(SRC, 2, 1, 2, 3, True, name="delayed_oscillator")
+    om = O.Model(1000, 2, 1, 2, True, 3, _f, _g)
+    n = 333
+    rng = np.random.default_rng(9)
+    pb = np.stack([1.0 + 0.2 * rng.random(n), 0.5 * np.ones(n), 0.1 + 0.1 * rng.random(n)])
+    ub = np.stack([1.0 + 0.1 * rng.random(n), 0.05 * rng.random(n)])
+    prob = S.SDDEProblem(um.f, um.g, [1.0, 0.0], S.AffineHistory((1.0, 0.0), (0.1, 0.0)), (0.0, 4.0), [1.0, 0.5, 0.2],
+                         constant_lags=(0.7,))
+    sv = O.expand_saveat(0.5, 0.0, 4.0)[0]
+    osch = O.build_schedule(0.0, 4.0, 0.01, [0.7], 2, saveat_times=sv)
+    dW = cases.increments(osch, 2, n)
+    W = np.concatenate([np.zeros((1, 2, n)), np.cumsum(dW, axis=0)], axis=0)
+    cur = np.zeros((2, n)); dWg = np.empty_like(dW)
+    for k in range(osch.n_steps):
+        dWg[k] = W[k + 1] - cur
+        cur = cur + dWg[k]
+    sim = S.solve(S.EnsembleProblem(prob, p_batch=pb, u0_batch=ub), S.RKMil(), S.EnsembleB200(device=0), trajectories=n,
+                  noise_grid=W, dt=0.01, saveat=0.5, adaptive=False)
+    ref, _ = O.solve_ensemble(om, pb, ub, [1.0, 0.0], [0.1, 0.0], [0.7], osch, 2, dWg)
+    assert "ptraj1" in sim.timing["kernel_name"] and "noise2" in sim.timing["kernel_name"]
+    assert cases.scaled_err(sim.out, ref) < 1e-12
