@@ -107,7 +107,8 @@ typedef struct sdde_desc {
     int32_t out_mem;                  /* SDDE_MEM_* of `out` passed to sdde_b200_solve */
     int32_t history_mode;
     int32_t want_paths, want_moments;
-    int32_t lanes_per_traj;           /* 0 = auto; 1 = thread per trajectory; 4,8 = cooperative lanes (n_state >= 4) */
+    int32_t lanes_per_traj;           /* 0/1 = thread per trajectory (default); n_state (4) = cooperative lanes, one lane per
+                                         state (sdde_coop.cuh; models with a row-wise form, shared parameters) */
     int32_t n_saveat, n_tstops;
     int32_t reserved0;
     double t0, tf, dt;
@@ -180,7 +181,9 @@ SDDE_API const char *sdde_b200_last_error(void);                 /* thread-local
 /* One context drives one GPU (one process per GPU under torchrun; several contexts per process are fine). */
 SDDE_API sdde_ctx *sdde_b200_create(int device);
 SDDE_API void sdde_b200_destroy(sdde_ctx *ctx);
-SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value);  /* "wave_traj", "block", "batch", "chunk_steps" */
+SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value);  /* "wave_traj" (0 = auto), "batch" (0 = compiled-in
+                                                                                    prefetch depth), "chunk_steps" (schedule records staged per
+                                                                                    shared-memory refill, 1..1024) */
 
 /* Host only: builds the step/lookup/save schedule for a descriptor (no GPU needed). */
 SDDE_API int sdde_b200_schedule(const sdde_desc *d, sdde_schedule *out);

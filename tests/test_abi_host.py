@@ -181,3 +181,11 @@ def test_ensemble_problem_batches_and_prob_func():
     assert np.array_equal(p[0], [3, 4, 5]) and np.array_equal(u[0], [6.0, 8.0, 10.0])     # 1-based like Julia
     with pytest.raises(NotImplementedError):
         S.EnsembleProblem(c.problem(), output_func=lambda sol, i: (sol, False))
+
+
+def test_version_and_struct_guard_fields():
+    L = capi.lib()
+    assert L.sdde_b200_version() == 100
+    assert L.sdde_b200_set_option(None, b"wave_traj", 1) == -1      # NULL context is rejected, not dereferenced
+    d = capi.SddeDesc()
+    assert hasattr(d, "out_pitch") and hasattr(d, "n_save_idxs") and len(d.save_idxs) == 8
