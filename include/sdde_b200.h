@@ -182,7 +182,8 @@ SDDE_API const char *sdde_b200_last_error(void);                 /* thread-local
 SDDE_API sdde_ctx *sdde_b200_create(int device);
 SDDE_API void sdde_b200_destroy(sdde_ctx *ctx);
 SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value);  /* "wave_traj" (0 = auto), "batch" (0 = compiled-in
-                                                                                    prefetch depth), "chunk_steps" (schedule records staged per
+                                                                                    prefetch depth), "mem_limit" (bytes the device workspaces may use, 0 = 80 % of free memory),
+                                                                                    "chunk_steps" (schedule records staged per
                                                                                     shared-memory refill, 1..1024) */
 
 /* Host only: builds the step/lookup/save schedule for a descriptor (no GPU needed). */

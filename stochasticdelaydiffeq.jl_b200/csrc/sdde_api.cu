@@ -86,6 +86,7 @@ struct sdde_ctx {
     int64_t opt_wave_traj = 0;     // 0 = auto
     int64_t opt_batch = 0;         // 0 = compiled-in depth
     int64_t opt_chunk_steps = 128;
+    int64_t opt_mem_limit = 0;     // bytes the workspaces may use (0 = 80 % of the free device memory)
     sdde::UserModels user;
     int sm_count = 148;
     // schedule cache: repeated solves of the same problem shape (ensemble sweeps, benchmarks) reuse the host schedule
@@ -428,6 +429,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     std::lock_guard<std::mutex> lk(c->mu);
     if (!strcmp(key, "wave_traj")) c->opt_wave_traj = value;
     else if (!strcmp(key, "batch")) c->opt_batch = value;
+    else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
     return SDDE_OK;
@@ -552,6 +554,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
             c->mem_key = mkey;
         }
         free_b = c->mem_free_cached;
+        if (c->opt_mem_limit > 0) free_b = std::min<size_t>(free_b, (size_t)((double)c->opt_mem_limit / 0.80));
     }
     lap("memory budget known");
     const bool out_dev = d->want_paths && d->out_mem == SDDE_MEM_DEVICE;

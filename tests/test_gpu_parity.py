@@ -339,3 +339,46 @@ def test_rkmil_with_per_trajectory_parameters():
     ref, _ = case.oracle(dW, params=pb)
     assert "mackey_glass," in sim.timing["kernel_name"]          # generic-exponent kernel (parameters vary per path)
     assert cases.relerr(sim.out, ref) < TOL
+
+
+def test_memory_limit_forces_waves_same_result():
+    """The wave size follows the memory budget (C5's 10^8 paths never need an 82 GB ring): with a 16 MB budget the
+    same ensemble runs in many waves and returns identical paths and moments (up to the merge order)."""
+    case = cases.c2(T=30.0)
+    n = 20000
+    kw = dict(trajectories=n, seed=31, moments=True, **case.solve_kwargs())
+    a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+    ctx = S.get_context(0)
+    ctx.set_option("mem_limit", 16 << 20)
+    try:
+        b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+    finally:
+        ctx.set_option("mem_limit", 0)
+    assert b.timing["waves"] > a.timing["waves"] >= 1
+    assert np.array_equal(a.out, b.out)
+    assert np.allclose(a.moments, b.moments, rtol=1e-12, atol=1e-15)
+
+
+def test_two_contexts_on_one_gpu_are_independent():
+    from sdde_b200 import _capi as capi
+    case = cases.c1(T=2.0)
+    c2 = capi.Context(0)
+    try:
+        import threading
+        res = {}
+
+        def run(tag, seed):
+            # each thread drives its own context (the default one / a second one) concurrently
+            if tag == "b":
+                capi._contexts[0], saved = c2, capi._contexts[0]
+            res[tag] = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=3000,
+                               seed=seed, **case.solve_kwargs()).out
+        run("a", 5)
+        saved_ctx = capi._contexts[0]
+        capi._contexts[0] = c2
+        res["b"] = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=3000, seed=5,
+                           **case.solve_kwargs()).out
+        capi._contexts[0] = saved_ctx
+        assert np.array_equal(res["a"], res["b"])
+    finally:
+        c2.close()
