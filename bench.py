@@ -35,7 +35,7 @@ UNIT = "trajectory-steps/s"
 ALG_BYTES_PER_TRAJ_STEP = 16.4        # 8 B delayed-node read + 8 B new-node write + 8*501/10000 B saved output
 WORKLOAD = dict(workload="C2 stochastic Mackey-Glass beta=0.2 gamma=0.1 n=10 sigma=0.1 tau=17 u0=h=1.2, EM(split) dt=0.05, "
                          "t in [0,500] (10000 steps), saveat=1.0 (501 points)", trajectories_per_gpu=1_000_000,
-                noise="in-kernel Philox4x32-10 + float64 Box-Muller",
+                noise="in-kernel Philox4x32-10 (4 normals per call: 40-bit radius, 24-bit angle per Box-Muller pair) + float64 Box-Muller",
                 l2="working set 2.7 GB ring + 4.0 GB output per launch >> 126 MB L2 (no explicit flush needed)")
 T_END, DT, TAU = 500.0, 0.05, 17.0
 P_MG = (0.2, 0.1, 10.0, 0.1)

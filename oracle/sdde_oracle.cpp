@@ -45,21 +45,24 @@ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
-inline void normal_pair(uint64_t gid, uint64_t call, uint64_t seed, double &z0, double &z1) {
+// same definition as oracle/sdde_oracle.py::_box_muller_pair and csrc/sdde_kernels.cuh::normal_pair_from_words
+inline void box_muller_pair(uint32_t wa, uint32_t wb, double &z0, double &z1) {
+    const uint64_t m = ((uint64_t)(wb & 0xFFu) << 32) | wa;
+    const double u = ((double)m + 0.5) * 0x1p-40;
+    const double r = std::sqrt(-2.0 * std::log(u));
+    const unsigned q = wb >> 30;
+    const uint32_t f = (wb >> 8) & 0x3FFFFFu;
+    const double x = ((double)f + 0.5) * 0x1p-22 - 0.5;
+    const double s = std::sin((M_PI / 2) * x), c = std::cos((M_PI / 2) * x);
+    z0 = r * (q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s)));
+    z1 = r * (q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c)));
+}
+inline void normal_quad(uint64_t gid, uint64_t call, uint64_t seed, double z[4]) {
     uint32_t w[4];
     philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)call, (uint32_t)(call >> 32), (uint32_t)seed,
                   (uint32_t)(seed >> 32), w);
-    // same definition as oracle/sdde_oracle.py::philox_normal_pair and csrc/sdde_kernels.cuh::normal_pair_from_words
-    const uint64_t m = ((uint64_t)(w[1] & 0xFFFFFu) << 32) | w[0];
-    const double u = ((double)m + 0.5) * 0x1p-52;
-    const double r = std::sqrt(-2.0 * std::log(u));
-    const unsigned q = w[3] >> 30;
-    const uint64_t f = ((uint64_t)(w[3] & 0x3FFFFFFFu) << 22) | (w[2] >> 10);
-    const double x = (double)f * 0x1p-52 - 0.5;
-    const double s = std::sin((M_PI / 2) * x), c = std::cos((M_PI / 2) * x);
-    const double cq = q == 0 ? c : (q == 1 ? -s : (q == 2 ? -c : s));
-    const double sq = q == 0 ? s : (q == 1 ? c : (q == 2 ? -s : -c));
-    z0 = r * cq; z1 = r * sq;
+    box_muller_pair(w[0], w[1], z[0], z[1]);
+    box_muller_pair(w[2], w[3], z[2], z[3]);
 }
 
 inline double ipow(double x, int n) {   // same multiplication order as oracle/sdde_oracle.py::ipow
@@ -221,7 +224,7 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
     const std::function<void(int, double *)> hcb = [&](int l, double *o) { hist(tq - d->lags[l], o); };
 
     int64_t n = 0;
-    double zc0 = 0, zc1 = 0; uint64_t zcall = ~0ull;
+    double zc[4] = {0, 0, 0, 0}; uint64_t zcall = ~0ull;
     double curW[SDDE_MAX_NOISE] = {0};
     if (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID) for (int c = 0; c < nc; ++c) curW[c] = dW[(int64_t)c * NT + traj];
     double du[SDDE_MAX_STATE], K[SDDE_MAX_STATE], gv[SDDE_MAX_STATE * SDDE_MAX_NOISE], g2[SDDE_MAX_STATE], ut[SDDE_MAX_STATE], dw[SDDE_MAX_NOISE];
@@ -234,9 +237,9 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
             for (int j = 0; j < ns; ++j) uprev[j] = u[j];
             for (int c = 0; c < nc; ++c) {
                 if (d->noise_mode == SDDE_NOISE_PHILOX) {
-                    const uint64_t q = (uint64_t)n * nc + c, call = q >> 1;
-                    if (call != zcall) { normal_pair((uint64_t)(d->traj_offset + traj), call, d->seed, zc0, zc1); zcall = call; }
-                    dw[c] = sq * ((q & 1) ? zc1 : zc0);
+                    const uint64_t q = (uint64_t)n * nc + c, call = q >> 2;
+                    if (call != zcall) { normal_quad((uint64_t)(d->traj_offset + traj), call, d->seed, zc); zcall = call; }
+                    dw[c] = sq * zc[q & 3];
                 } else if (d->noise_mode == SDDE_NOISE_SUPPLIED_DW) {
                     dw[c] = n < n_steps_noise ? dW[(n * nc + c) * NT + traj] : 0.0;
                 } else {

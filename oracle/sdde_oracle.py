@@ -476,27 +476,17 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def philox_normal_pair(traj_id, call, seed):
-    """Two N(0,1) float64 variates for (global trajectory id, call index) -- Box-Muller on one Philox4x32-10 block:
-    counter = (traj_lo, traj_hi, call_lo, call_hi), key = (seed_lo, seed_hi) -> words w0..w3;
-      radius:  m = (w1 & 0xFFFFF)<<32 | w0 (52 bits), u = (m + 0.5) * 2^-52 in (0,1), r = sqrt(-2 ln u)
-      angle :  q = w3 >> 30 (quadrant), f = (w3 & 0x3FFFFFFF)<<22 | w2>>10 (52 bits), x = f * 2^-52 - 1/2 in [-1/2, 1/2),
-               theta = (pi/2) (q + x)
-      z0 = r cos(theta), z1 = r sin(theta).
-    (same definition as csrc/sdde_kernels.cuh::philox_normal_pair; the kernel evaluates it with range-restricted
-    polynomials, here numpy's log/sin/cos are used, so the two agree to a few ulp, not bit for bit)."""
-    traj_id = np.asarray(traj_id, dtype=np.uint64)
-    call = np.asarray(call, dtype=np.uint64)
-    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    w0, w1, w2, w3 = philox4x32_10(traj_id & _MASK32, traj_id >> np.uint64(32),
-                                   call & _MASK32, call >> np.uint64(32),
-                                   seed & 0xFFFFFFFF, seed >> 32)
-    m = ((w1 & np.uint64(0xFFFFF)) << np.uint64(32)) | w0
-    u = (m.astype(np.float64) + 0.5) * 2.0 ** -52
+def _box_muller_pair(wa, wb):
+    """One Box-Muller pair from two Philox words (same bit allocation as csrc/sdde_kernels.cuh::normal_pair_from_words):
+      radius:  m = (wb & 0xFF)<<32 | wa (40 bits), u = (m + 0.5) * 2^-40 in (0,1), r = sqrt(-2 ln u)
+      angle :  q = wb >> 30 (quadrant), f = (wb >> 8) & 0x3FFFFF (22 bits), x = (f + 0.5) * 2^-22 - 1/2,
+               theta = (pi/2) (q + x);   z0 = r cos(theta), z1 = r sin(theta)."""
+    m = ((wb & np.uint64(0xFF)) << np.uint64(32)) | wa
+    u = (m.astype(np.float64) + 0.5) * 2.0 ** -40
     r = np.sqrt(-2.0 * np.log(u))
-    q = (w3 >> np.uint64(30)).astype(np.int64)
-    f = ((w3 & np.uint64(0x3FFFFFFF)) << np.uint64(22)) | (w2 >> np.uint64(10))
-    x = f.astype(np.float64) * 2.0 ** -52 - 0.5
+    q = (wb >> np.uint64(30)).astype(np.int64)
+    f = (wb >> np.uint64(8)) & np.uint64(0x3FFFFF)
+    x = (f.astype(np.float64) + 0.5) * 2.0 ** -22 - 0.5
     s, c = np.sin((np.pi / 2) * x), np.cos((np.pi / 2) * x)
     # rotate by the quadrant exactly: q=0 (c,s), 1 (-s,c), 2 (-c,-s), 3 (s,-c)
     cq = np.where(q == 0, c, np.where(q == 1, -s, np.where(q == 2, -c, s)))
@@ -504,16 +494,32 @@ def philox_normal_pair(traj_id, call, seed):
     return r * cq, r * sq
 
 
+def philox_normal_quad(traj_id, call, seed):
+    """Four N(0,1) float64 variates for (global trajectory id, call index): one Philox4x32-10 block with
+    counter = (traj_lo, traj_hi, call_lo, call_hi), key = (seed_lo, seed_hi); pair A from (w0, w1), pair B from (w2, w3).
+    The kernel evaluates the same definition with range-restricted polynomials, here numpy's log/sin/cos are used, so
+    the two agree to a few ulp, not bit for bit."""
+    traj_id = np.asarray(traj_id, dtype=np.uint64)
+    call = np.asarray(call, dtype=np.uint64)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    w0, w1, w2, w3 = philox4x32_10(traj_id & _MASK32, traj_id >> np.uint64(32),
+                                   call & _MASK32, call >> np.uint64(32),
+                                   seed & 0xFFFFFFFF, seed >> 32)
+    z0, z1 = _box_muller_pair(w0, w1)
+    z2, z3 = _box_muller_pair(w2, w3)
+    return z0, z1, z2, z3
+
+
 def philox_normals(traj_ids, n_steps: int, n_noise: int, seed) -> np.ndarray:
-    """xi[n, c, traj]: normal number q = n*n_noise + c comes from call q>>1, half q&1."""
+    """xi[n, c, traj]: normal number q = n*n_noise + c comes from call q>>2, lane q&3."""
     traj_ids = np.asarray(traj_ids, dtype=np.uint64)
     nq = n_steps * n_noise
-    ncall = (nq + 1) // 2
+    ncall = (nq + 3) // 4
     calls = np.arange(ncall, dtype=np.uint64)[:, None]
-    z0, z1 = philox_normal_pair(traj_ids[None, :], calls, seed)
-    z = np.empty((ncall * 2, traj_ids.size), dtype=np.float64)
-    z[0::2] = z0
-    z[1::2] = z1
+    zs = philox_normal_quad(traj_ids[None, :], calls, seed)
+    z = np.empty((ncall * 4, traj_ids.size), dtype=np.float64)
+    for i in range(4):
+        z[i::4] = zs[i]
     return z[:nq].reshape(n_steps, n_noise, traj_ids.size)
 
 

@@ -150,11 +150,11 @@ __global__ void philox_dump_kernel(double *out, long long n_traj, long long traj
     const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tr >= n_traj) return;
     const long long nq = n_steps * nc;
-    for (long long call = 0; call * 2 < nq; ++call) {
-        double z0, z1;
-        philox_normal_pair((u64)(traj_off + tr), (u64)call, rk, ltab, z0, z1);
-        out[(2 * call) * n_traj + tr] = z0;
-        if (2 * call + 1 < nq) out[(2 * call + 1) * n_traj + tr] = z1;
+    for (long long call = 0; call * 4 < nq; ++call) {
+        double z[4];
+        philox_normal_quad((u64)(traj_off + tr), (u64)call, rk, ltab, z);
+        for (int i = 0; i < 4; ++i)
+            if (4 * call + i < nq) out[(4 * call + i) * n_traj + tr] = z[i];
     }
 }
 

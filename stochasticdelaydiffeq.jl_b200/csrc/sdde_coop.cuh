@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_cons
     const ConstParams p{a.p};
 
     double u = a.u0 ? a.u0[j * a.u0_pitch + trc] : a.u0c[j];
-    double zc0 = 0.0, zc1 = 0.0;
+    double zc[4] = {0.0, 0.0, 0.0, 0.0};
     u64 zcall = ~0ull;
     double curW[NW];
 #pragma unroll
@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_cons
 #pragma unroll
             for (int c = 0; c < NW; ++c) {
                 if (NOISE == K_NOISE_PHILOX) {
-                    const u64 q = (u64)n * NW + c, call = q >> 1;
-                    if (call != zcall) { philox_normal_pair((u64)(a.traj_gid0 + tr), call, a.rk, ltab, zc0, zc1); zcall = call; }
-                    dw[c] = sq * ((q & 1) ? zc1 : zc0);
+                    const u64 q = (u64)n * NW + c, call = q >> 2;
+                    if (call != zcall) { philox_normal_quad((u64)(a.traj_gid0 + tr), call, a.rk, ltab, zc); zcall = call; }
+                    const double zlo = (q & 1) ? zc[1] : zc[0], zhi = (q & 1) ? zc[3] : zc[2];
+                    dw[c] = sq * ((q & 2) ? zhi : zlo);
                 } else {
                     const long long row = (NOISE == K_NOISE_GRID) ? ((long long)(n + 1) * NW + c) : ((long long)n * NW + c);
                     const double w = a.noise[row * a.noise_pitch + a.noise_off + trc];

@@ -115,7 +115,7 @@ template <class M> struct Tune {
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) + Box-Muller in float64.
 // Stream layout: counter = (traj_id_lo, traj_id_hi, call_lo, call_hi), key = (seed_lo, seed_hi);
-// normal number q = step*NC + channel of a trajectory is half (q & 1) of call (q >> 1).
+// normal number q = step*NC + channel of a trajectory is lane (q & 3) of call (q >> 2): four normals per call.
 // Replaces Xoroshiro128Plus + randn of /root/reference/src/solve.jl:313-336 (the bit stream is NOT reproduced,
 // the distribution is: independent N(0,1), scaled by sqrt|dt_n| like [EXT] DiffEqNoiseProcess WHITE_NOISE_DIST).
 // ------------------------------------------------------------------------------------------------
@@ -144,23 +144,28 @@ __device__ __forceinline__ double rsqrt_approx(double x) {
     return y;
 }
 
-// Two N(0,1) variates from one Philox block (w0..w3).  Definition (identical in oracle/sdde_oracle.py):
-//   radius: m = (w1 & 0xFFFFF)<<32 | w0, u = (m + 1/2) 2^-52 in (0,1), r = sqrt(-2 ln u)
-//   angle : q = w3 >> 30, f = (w3 & 0x3FFFFFFF)<<22 | w2>>10, x = f 2^-52 - 1/2, theta = (pi/2)(q + x)
+// FOUR N(0,1) variates from one Philox block: two Box-Muller pairs, pair A from (w0, w1), pair B from (w2, w3).
+// Bit allocation per pair (wa, wb) -- identical in oracle/sdde_oracle.py and oracle/sdde_oracle.cpp:
+//   radius: m = (wb & 0xFF)<<32 | wa  (40 bits), u = (m + 1/2) 2^-40 in (0,1), r = sqrt(-2 ln u)   [|z| <= 7.5 sigma]
+//   angle : q = wb >> 30 (quadrant), f = (wb >> 8) & 0x3FFFFF (22 bits), x = (f + 1/2) 2^-22 - 1/2, theta = (pi/2)(q + x)
 //   z0 = r cos(theta), z1 = r sin(theta)
+// Why 40 + 24 bits and not 52 + 52: the 32x32->64-bit products of Philox share the FP64 datapath with DFMA on sm_100a
+// (profiles/README.md), so bits are expensive.  The angle only has to make averages over the circle exact: for any
+// smooth functional the mean over 2^24 equispaced directions is the trapezoidal rule of a smooth periodic function
+// (error beyond any power of 2^-24), so each z stays N(0,1) to far below float64 rounding; the radius keeps 40 bits
+// (tail truncated at 7.5 sigma, probability 5e-14 per draw; spacing of r at 6 sigma: 8e-5).
 // Evaluation: every argument range is known, so no special cases and no libm calls:
 //   -2 ln u  : u = 2^e' * M', 128-entry table {1/c_k, -2 ln c'_k} in shared memory (k = top 7 mantissa bits),
 //              rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-8, degree-7 log1p polynomial (abs. error < 2^-66)
-//   sqrt     : MUFU.RSQ64H seed + one coupled Newton step + residual correction (<= 1 ulp on [2^-53, 74])
+//   sqrt     : MUFU.RSQ64H seed + one coupled Newton step + residual correction (<= 1 ulp on [2^-41, 57])
 //   sin, cos : Taylor in (pi/2 x), |x| <= 1/2, degree 15 / 16 (truncation < 5e-17), exact quadrant rotation
-__device__ __forceinline__ void normal_pair_from_words(const u32 (&w)[4], const double2 *__restrict__ ltab, double &z0,
-                                                       double &z1) {
+__device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const double2 *__restrict__ ltab, double &z0, double &z1) {
     // ---- radius ----
-    const double X = __hiloint2double((int)(0x3FF00000u | (w[1] & 0xFFFFFu)), (int)w[0]);   // 1 + m 2^-52
-    const double U = X - 0.99999999999999988897769753748;                                    // (m + 1/2) 2^-52, exact
+    const double X = __hiloint2double((int)(0x3FF00000u | ((wb & 0xFFu) << 12) | (wa >> 20)), (int)(wa << 12));   // 1 + m 2^-40
+    const double U = X - 0.99999999999954525264911353588104248046875;                         // (m + 1/2) 2^-40, exact
     const int hi = __double2hiint(U);
     const int k = (hi >> 13) & 127;
-    const int n = 1023 - (hi >> 20) - ((hi >> 19) & 1);                                      // -e' in [0, 53]
+    const int n = 1023 - (hi >> 20) - ((hi >> 19) & 1);                                      // -e' in [0, 41]
     const double M = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(U));    // mantissa in [1,2)
     const double2 te = ltab[k];
     const double rho = fma(M, te.x, -1.0);
@@ -181,9 +186,9 @@ __device__ __forceinline__ void normal_pair_from_words(const u32 (&w)[4], const 
     const double e2 = fma(-g, g, t);
     g = fma(e2, h, g);                                                                       // sqrt(t)
     // ---- angle ----
-    const u32 q = w[3] >> 30;
-    const double D = __hiloint2double((int)(0x3FF00000u | ((w[3] >> 10) & 0xFFFFFu)), (int)((w[3] << 22) | (w[2] >> 10)));
-    const double x = D - 1.5;
+    const u32 q = wb >> 30;
+    const double D = __hiloint2double((int)(0x3FF00000u | ((wb >> 10) & 0xFFFFFu)), (int)((wb << 22) & 0xC0000000u));  // 1 + f 2^-22
+    const double x = D - 1.49999988079071044921875;                                          // (f + 1/2) 2^-22 - 1/2, exact
     const double zz = x * x;
     double sp = fma(zz, RNG_SIN_C[7], RNG_SIN_C[6]);
     double cp = fma(zz, RNG_COS_C[8], RNG_COS_C[7]);
@@ -205,11 +210,13 @@ __device__ __forceinline__ void normal_pair_from_words(const u32 (&w)[4], const 
     z1 = gs * ss;
 }
 
-__device__ __forceinline__ void philox_normal_pair(u64 gid, u64 call, const u32 *__restrict__ rk,
-                                                   const double2 *__restrict__ ltab, double &z0, double &z1) {
+// normals 4*call .. 4*call+3 of trajectory gid
+__device__ __forceinline__ void philox_normal_quad(u64 gid, u64 call, const u32 *__restrict__ rk,
+                                                   const double2 *__restrict__ ltab, double (&z)[4]) {
     u32 w[4];
     philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), rk, w);
-    normal_pair_from_words(w, ltab, z0, z1);
+    normal_pair_from_words(w[0], w[1], ltab, z[0], z[1]);
+    normal_pair_from_words(w[2], w[3], ltab, z[2], z[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,7 +339,7 @@ struct TrajState {
     static constexpr int NS = M::NS, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
     double u[TPT][NS];
     RegParams<PTRAJ ? NP : 0> preg[TPT];
-    double zc[TPT][2];        // cached normal pair of the current Philox call
+    double zc[TPT][4];        // cached normals of the current Philox call
     u64 zcall;                // its call index
     double curW[TPT][NC];     // NoiseGrid mode: current W
     bool bad[TPT];
@@ -348,7 +355,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                                           char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec,
                                           bool prefetch_next) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NSTG = alg_stages(ALG), NLK = NL * NSTG;
-    constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 2 == 0);
+    constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 4 == 0);   // batch start n*NC is then a multiple of 4 as well
     typedef StepRec<NLK> Rec;
     const long long jstride = a.ring_pitch * 8;
     // ---- all delayed-state loads of the batch, unconditionally (prehistory records point at slot 0) ----
@@ -400,17 +407,21 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const u64 q = (u64)(n + k) * NC + c;
-                const u64 call = q >> 1;
-                const bool fresh = STATIC_RNG ? (((k * NC + c) & 1) == 0) : (call != st.zcall);
+                const u64 call = q >> 2;
+                const bool fresh = STATIC_RNG ? (((k * NC + c) & 3) == 0) : (call != st.zcall);
                 if (fresh) {
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt)
-                        philox_normal_pair((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt][0], st.zc[tt][1]);
+                        philox_normal_quad((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt]);
                     st.zcall = call;
                 }
-                const bool odd = STATIC_RNG ? (((k * NC + c) & 1) != 0) : ((q & 1) != 0);
+                const int lane = STATIC_RNG ? ((k * NC + c) & 3) : (int)(q & 3);
 #pragma unroll
-                for (int tt = 0; tt < TPT; ++tt) dwb[k][tt][c] = sq * (odd ? st.zc[tt][1] : st.zc[tt][0]);
+                for (int tt = 0; tt < TPT; ++tt) {
+                    const double zlo = (lane & 1) ? st.zc[tt][1] : st.zc[tt][0];
+                    const double zhi = (lane & 1) ? st.zc[tt][3] : st.zc[tt][2];
+                    dwb[k][tt][c] = sq * ((lane & 2) ? zhi : zlo);
+                }
             }
         } else {
 #pragma unroll
@@ -533,7 +544,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(c
 #pragma unroll
             for (int i = 0; i < NP; ++i) st.preg[tt].v[PTRAJ ? i : 0] = a.ptraj[i * a.p_pitch + tr];
         }
-        st.zc[tt][0] = st.zc[tt][1] = 0.0;
+        st.zc[tt][0] = st.zc[tt][1] = st.zc[tt][2] = st.zc[tt][3] = 0.0;
         st.bad[tt] = false;
 #pragma unroll
         for (int c = 0; c < NC; ++c)
