@@ -168,6 +168,8 @@ typedef struct sdde_timing {
     int32_t regs_per_thread;
     int32_t block_threads;
     int32_t traj_per_thread;
+    int32_t moment_merge;      /* sdde_b200_solve_multi: 0 = none, 1 = host Chan merge, 2 = NCCL all-gather + device merge */
+    int32_t reserved;
     int64_t ring_bytes;
     char kernel_name[128];
 } sdde_timing;
@@ -201,7 +203,8 @@ SDDE_API int sdde_b200_solve(sdde_ctx *ctx, const sdde_desc *d, double *out, dou
 /* Same as sdde_b200_solve, over several GPUs from ONE host process (the Julia `ccall` case): the trajectories are split
  * into contiguous global-id ranges [r*ceil(N/R), ...), one per context, each range is solved concurrently on its GPU
  * (one host thread per context), paths land in the caller's `out` (host memory only), and the per-GPU moment triples
- * are Chan-merged on the host in rank order.  Results are identical to a single-GPU solve (partition-invariant Philox
+ * are all-gathered over NCCL (communicators from ncclCommInitAll, libnccl.so.2 resolved at run time) and Chan-merged in
+ * rank order on the device; without NCCL, or with option "nccl" = 0, they are merged on the host.  Results are identical to a single-GPU solve (partition-invariant Philox
  * streams).  Under torchrun (one process per GPU) use sdde_b200_solve per rank + an NCCL all-gather of the triples. */
 SDDE_API int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc *d, double *out, double *moments,
                                    uint8_t *status, sdde_timing *tm /* [n_ctx] or NULL */);

@@ -22,6 +22,7 @@
 #include "schedule.hpp"
 #include "sdde_dispatch.cuh"
 #include "user_model.hpp"
+#include "nccl_dyn.hpp"
 
 namespace {
 
@@ -82,6 +83,9 @@ struct sdde_ctx {
     cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
     DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
     PinnedBuf h_status, h_mom;
+    DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
+    bool keep_moments_on_device = false;   // set by solve_multi: leave the wave-merged triples in `mom` for the all-gather
+    int64_t opt_nccl = 1;          // solve_multi: 1 = merge moments with an NCCL all-gather + device merge, 0 = on the host
     std::mutex mu;
     int64_t opt_wave_traj = 0;     // 0 = auto
     int64_t opt_batch = 0;         // 0 = compiled-in depth
@@ -137,6 +141,26 @@ __global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__
         mom[blockIdx.x * 3 + 1] = mean;
         mom[blockIdx.x * 3 + 2] = t;
     }
+}
+
+// Chan merge of `parts` arrays of (count, mean, M2) triples, in order: dst[i] = merge(src[0][i], src[1][i], ...).
+// One thread per triple; used across trajectory waves and, after the NCCL all-gather, across GPUs.
+__global__ void merge_moments_kernel(const double *__restrict__ src, long long part_stride, int parts, long long n, double *__restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double cnt = src[3 * i], mean = src[3 * i + 1], m2 = src[3 * i + 2];
+    for (int p = 1; p < parts; ++p) {
+        const double *s = src + (long long)p * part_stride + 3 * i;
+        const double nb = s[0], mb = s[1], sb = s[2];
+        const double nn = cnt + nb;
+        if (nn > 0) {
+            const double dlt = mb - mean;
+            mean = mean + dlt * (nb / nn);
+            m2 = m2 + sb + dlt * dlt * (cnt * nb / nn);
+        }
+        cnt = nn;
+    }
+    dst[3 * i] = cnt; dst[3 * i + 1] = mean; dst[3 * i + 2] = m2;
 }
 
 // test hook: the normals the step kernels would draw, laid out [n][c][traj]
@@ -413,7 +437,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     cudaDeviceSynchronize();
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
-    c->h_status.release(); c->h_mom.release();
+    c->h_status.release(); c->h_mom.release(); c->gather.release();
     c->user.clear();
     if (c->compute) cudaStreamDestroy(c->compute);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
@@ -429,6 +453,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     std::lock_guard<std::mutex> lk(c->mu);
     if (!strcmp(key, "wave_traj")) c->opt_wave_traj = value;
     else if (!strcmp(key, "batch")) c->opt_batch = value;
+    else if (!strcmp(key, "nccl")) c->opt_nccl = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
@@ -719,7 +744,15 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         }
     }
     CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
-    if (d->want_moments && rows > 0) {
+    if (d->want_moments && rows > 0 && c->keep_moments_on_device) {
+        // multi-GPU path: wave merge on the device, result stays in mom[0..rows) for the NCCL all-gather
+        if (n_waves > 1) {
+            sdde::merge_moments_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c->compute>>>(
+                (const double *)c->mom.p, rows * 3, n_waves, rows, (double *)c->mom.p);
+            CU_CHECK(cudaGetLastError());
+            ++launches;
+        }
+    } else if (d->want_moments && rows > 0) {
         CU_CHECK(cudaMemcpyAsync(h_mom, c->mom.p, (size_t)rows * 3 * 8 * n_waves, cudaMemcpyDeviceToHost, c->compute));
         d2h += (int64_t)rows * 3 * 8 * n_waves;
     }
@@ -732,7 +765,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     lap("copy streams synced");
     CU_CHECK(cudaGetLastError());
     if (status) memcpy(status, c->h_status.p, (size_t)NT);
-    if (d->want_moments && rows > 0) {
+    if (d->want_moments && rows > 0 && !c->keep_moments_on_device) {
         memcpy(moments, h_mom, (size_t)rows * 3 * 8);
         for (int w = 1; w < n_waves; ++w) sdde_b200_merge_moments(moments, h_mom + (size_t)w * rows * 3, rows);
     }
@@ -747,9 +780,37 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     return SDDE_OK;
 }
 
+namespace {
+
+// NCCL communicators of a device group, created once per device list (ncclCommInitAll) and kept for the process.
+struct NcclGroup {
+    std::vector<int> devices;
+    std::vector<ncclComm_t> comms;
+};
+std::mutex g_nccl_mu;
+std::vector<NcclGroup *> g_nccl_groups;
+
+NcclGroup *nccl_group_for(const std::vector<int> &devices, std::string &err) {
+    const sdde::NcclApi &N = sdde::nccl_api();
+    if (!N.ok) { err = N.why; return nullptr; }
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    for (NcclGroup *g : g_nccl_groups)
+        if (g->devices == devices) return g;
+    NcclGroup *g = new NcclGroup();
+    g->devices = devices;
+    g->comms.assign(devices.size(), nullptr);
+    ncclResult_t r = N.CommInitAll(g->comms.data(), (int)devices.size(), devices.data());
+    if (r != ncclSuccess) { err = std::string("ncclCommInitAll: ") + N.GetErrorString(r); delete g; return nullptr; }
+    g_nccl_groups.push_back(g);
+    return g;
+}
+
+}  // namespace
+
 int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc *d, double *out, double *moments, uint8_t *status,
                           sdde_timing *tm) {
     if (!ctxs || n_ctx < 1) return fail(SDDE_ERR_BAD_DESC, "no contexts");
+    for (int r = 0; r < n_ctx; ++r) if (!ctxs[r]) return fail(SDDE_ERR_BAD_DESC, "context %d is NULL", r);
     int rc = check_desc(d);
     if (rc) return rc;
     if (d->out_mem != SDDE_MEM_HOST || (d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem != SDDE_MEM_HOST))
@@ -767,6 +828,19 @@ int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc 
     const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;
     const int64_t per = (NT + n_ctx - 1) / n_ctx;
     const int64_t noise_rows = (S.n_steps() + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * (int64_t)K.n_chan;
+
+    // The path's single collective: all-gather of the per-GPU moment triples over NCCL + device merge in rank order.
+    NcclGroup *grp = nullptr;
+    std::string nccl_why;
+    if (d->want_moments && rows > 0 && ctxs[0]->opt_nccl && (int64_t)(n_ctx - 1) * per < NT /* every GPU has work */) {
+        std::vector<int> devs;
+        for (int r = 0; r < n_ctx; ++r) devs.push_back(ctxs[r]->device);
+        bool distinct = true;
+        for (int r = 0; r < n_ctx && distinct; ++r) for (int q = 0; q < r; ++q) if (devs[q] == devs[r]) distinct = false;
+        if (distinct) grp = nccl_group_for(devs, nccl_why);
+    }
+    for (int r = 0; r < n_ctx; ++r) ctxs[r]->keep_moments_on_device = (grp != nullptr);
+
     std::vector<int> rcs((size_t)n_ctx, 0);
     std::vector<std::string> errs((size_t)n_ctx);
     std::vector<std::vector<double>> moms((size_t)n_ctx);
@@ -795,16 +869,47 @@ int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc 
         });
     }
     for (auto &t : th) t.join();
+    for (int r = 0; r < n_ctx; ++r) ctxs[r]->keep_moments_on_device = false;
     for (int r = 0; r < n_ctx; ++r)
         if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "GPU %d: %s", r, errs[(size_t)r].c_str());
-    if (d->want_moments) {
+    int merge_kind = 0;
+    if (d->want_moments && rows > 0 && grp) {
+        const sdde::NcclApi &N = sdde::nccl_api();
+        const size_t cnt = (size_t)rows * 3;
+        for (int r = 0; r < n_ctx; ++r) {
+            CU_CHECK(cudaSetDevice(ctxs[r]->device));
+            CU_CHECK(ctxs[r]->gather.reserve(cnt * 8 * (size_t)n_ctx));
+        }
+        ncclResult_t nr = N.GroupStart();
+        for (int r = 0; r < n_ctx && nr == ncclSuccess; ++r) {
+            CU_CHECK(cudaSetDevice(ctxs[r]->device));
+            nr = N.AllGather(ctxs[r]->mom.p, ctxs[r]->gather.p, cnt, ncclDouble, grp->comms[(size_t)r], ctxs[r]->compute);
+        }
+        const ncclResult_t ne = N.GroupEnd();
+        if (nr == ncclSuccess) nr = ne;
+        if (nr != ncclSuccess) return fail(SDDE_ERR_NCCL - (int)nr, "NCCL all-gather of the moment triples failed: %s", N.GetErrorString(nr));
+        // every GPU now holds all partial triples; merge in rank order on GPU 0 and read the result back
+        sdde_ctx *c0 = ctxs[0];
+        CU_CHECK(cudaSetDevice(c0->device));
+        sdde::merge_moments_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c0->compute>>>(
+            (const double *)c0->gather.p, (long long)cnt, n_ctx, rows, (double *)c0->gather.p);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaMemcpyAsync(moments, c0->gather.p, cnt * 8, cudaMemcpyDeviceToHost, c0->compute));
+        for (int r = 0; r < n_ctx; ++r) {
+            CU_CHECK(cudaSetDevice(ctxs[r]->device));
+            CU_CHECK(cudaStreamSynchronize(ctxs[r]->compute));
+        }
+        merge_kind = 2;
+    } else if (d->want_moments) {
         bool first = true;
         for (int r = 0; r < n_ctx; ++r) {
             if (moms[(size_t)r].empty()) continue;
             if (first) { memcpy(moments, moms[(size_t)r].data(), (size_t)rows * 3 * 8); first = false; }
             else sdde_b200_merge_moments(moments, moms[(size_t)r].data(), rows);
         }
+        merge_kind = 1;
     }
+    if (tm) for (int r = 0; r < n_ctx; ++r) tm[r].moment_merge = merge_kind;
     return SDDE_OK;
 }
 

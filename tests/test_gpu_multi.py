@@ -22,6 +22,14 @@ def test_two_gpus_one_process_equals_one_gpu():
     b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(devices=(0, 1)), **kw)
     assert np.array_equal(a.out, b.out) and np.array_equal(a.status, b.status)
     assert np.allclose(a.moments, b.moments, rtol=1e-12)
+    assert b.timing["moment_merge"] == 2          # NCCL all-gather over NVLink + device merge (the path's only collective)
+    ctx = S.get_context(0)
+    ctx.set_option("nccl", 0)
+    try:
+        c = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(devices=(0, 1)), **kw)
+    finally:
+        ctx.set_option("nccl", 1)
+    assert c.timing["moment_merge"] == 1 and np.allclose(c.moments, b.moments, rtol=1e-13)
     # supplied noise + per-trajectory parameters are sliced per GPU
     c1 = cases.c1(T=3.0)
     sch = c1.oracle_schedule()
