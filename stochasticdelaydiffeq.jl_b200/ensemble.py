@@ -333,6 +333,22 @@ def merge_moments(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return a
 
 
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (sdde_b200_alloc_pinned): pass it as ``solve(..., out=...)`` and reuse
+    it across solves -- D2H then runs at PCIe speed (~45-50 GB/s instead of ~5 GB/s into pageable memory; allocating it
+    costs ~0.4 ms/MB, so it only pays when reused).  Freed when the array (and every view of it) is garbage collected."""
+    import weakref
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = capi.lib().sdde_b200_alloc_pinned(max(nbytes, 1))
+    if not ptr:
+        raise capi.SddeError(-100, capi.lib().sdde_b200_last_error().decode(errors="replace"))
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, capi.lib().sdde_b200_free_pinned, ptr)
+    return arr
+
+
 # ---------------------------------------------------------------------------------------------
 # solve
 # ---------------------------------------------------------------------------------------------

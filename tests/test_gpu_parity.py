@@ -382,3 +382,18 @@ def test_two_contexts_on_one_gpu_are_independent():
         assert np.array_equal(res["a"], res["b"])
     finally:
         c2.close()
+
+
+def test_pinned_output_buffer_reused_across_solves():
+    case = cases.c2(T=20.0)
+    n = 4096
+    sch = case.oracle_schedule()
+    out = S.pinned_empty((len(sch.save_t), 1, n))
+    ref = None
+    for seed in (1, 2):
+        sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, seed=seed,
+                      out=out, **case.solve_kwargs())
+        assert sim.out is out or np.shares_memory(sim.out, out)
+        plain = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, seed=seed,
+                        **case.solve_kwargs())
+        assert np.array_equal(plain.out, out)
