@@ -85,6 +85,8 @@ struct sdde_ctx {
     PinnedBuf h_status, h_mom;
     DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
     bool keep_moments_on_device = false;   // set by solve_multi: leave the wave-merged triples in `mom` for the all-gather
+    int64_t opt_jit_linsys = 1;    // specialise the linear delay system's constants with NVRTC (zeros vanish, no LDCU per entry)
+    std::vector<std::pair<std::string, int>> linsys_jit;   // (shape + parameter bytes) -> user model id
     int64_t opt_nccl = 1;          // solve_multi: 1 = merge moments with an NCCL all-gather + device merge, 0 = on the host
     std::mutex mu;
     int64_t opt_wave_traj = 0;     // 0 = auto
@@ -281,6 +283,45 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     return SDDE_OK;
 }
 
+// CUDA source of the n-state linear delay system with THIS problem's matrices baked in as literals: zero entries
+// disappear at compile time and the remaining coefficients become immediates instead of one constant load (LDCU) per
+// matrix entry and step (tools/micro/ldcu.cu).  Same operation order as ModelLinSys, so results are unchanged
+// (a dropped term is +0*x).  Compiled once per (shape, parameters) and context through the user-model machinery.
+std::string linsys_jit_source(int ns, int nl, int nw, const double *p) {
+    char buf[128];
+    auto lit = [&](double v) { snprintf(buf, sizeof(buf), "%.17g", v); std::string t(buf); if (t.find_first_of(".eEn") == std::string::npos) t += ".0"; return t; };
+    const int offB = ns * ns, offC = ns * ns * (1 + nl), offM = offC + ns, offN = offM + ns * nw;
+    std::string src = "struct UserModel {\n";
+    snprintf(buf, sizeof(buf), "    static constexpr int NS = %d, NL = %d, NW = %d, NP = %d;\n", ns, nl, nw, offN + ns * nw);
+    src += buf;
+    src += "    static constexpr bool DIAG = false;\n";
+    src += "    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &, double) {\n";
+    for (int i = 0; i < ns; ++i) {
+        // acc = p[i*ns]*u[0] (+ ...)  -- keep the first product even when its coefficient is zero so that the
+        // accumulation starts exactly like the generic model
+        std::string e = "(" + lit(p[i * ns]) + " * u[0])";
+        for (int j = 1; j < ns; ++j) if (p[i * ns + j] != 0.0) e = "(" + e + " + " + lit(p[i * ns + j]) + " * u[" + std::to_string(j) + "])";
+        for (int l = 0; l < nl; ++l)
+            for (int j = 0; j < ns; ++j) {
+                const double v = p[offB + l * ns * ns + i * ns + j];
+                if (v != 0.0) e = "(" + e + " + " + lit(v) + " * ul[" + std::to_string(l) + "][" + std::to_string(j) + "])";
+            }
+        if (p[offC + i] != 0.0) e = "(" + e + " + " + lit(p[offC + i]) + ")";
+        src += "        du[" + std::to_string(i) + "] = " + e + ";\n";
+    }
+    src += "    }\n";
+    src += "    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*)[NS], const P &, double) {\n";
+    for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < nw; ++j) {
+            const double m = p[offM + i * nw + j], n0 = p[offN + i * nw + j];
+            std::string e = (m != 0.0) ? (lit(m) + " * u[" + std::to_string(i) + "]") : std::string("0.0");
+            if (n0 != 0.0) e = e + " + " + lit(n0);
+            src += "        gv[" + std::to_string(i * nw + j) + "] = " + e + ";\n";
+        }
+    src += "    }\n};\n";
+    return src;
+}
+
 int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
     const bool ptraj = d->param_stride != 0;
     const int alg = d->alg, nz = d->noise_mode;
@@ -299,7 +340,31 @@ int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
                 k = sdde::select_linsys_coop(d->n_state, d->n_lag, d->n_noise, alg, nz);
                 if (k.fn && k.lanes != d->lanes_per_traj) return fail(SDDE_ERR_UNSUPPORTED, "lanes_per_traj must be 0, 1 or n_state (%d)", d->n_state);
                 if (!k.fn) return fail(SDDE_ERR_UNSUPPORTED, "no cooperative-lanes kernel for this model shape / algorithm");
-            } else k = sdde::select_linsys(d->n_state, d->n_lag, d->n_noise, alg, nz, ptraj);
+            } else {
+                k = sdde::KernelInfo();
+                const int npar = d->n_state * d->n_state * (1 + d->n_lag) + d->n_state + 2 * d->n_state * d->n_noise;
+                bool finite = true;
+                if (!ptraj && d->params && d->n_param == npar)
+                    for (int i = 0; i < npar; ++i) finite = finite && std::isfinite(d->params[i]);
+                if (ctx && ctx->opt_jit_linsys && !ptraj && d->params && d->n_param == npar && finite) {
+                    std::string key;
+                    const int32_t shp[3] = {d->n_state, d->n_lag, d->n_noise};
+                    key.append((const char *)shp, sizeof(shp));
+                    key.append((const char *)d->params, sizeof(double) * (size_t)npar);
+                    int id = -1;
+                    for (auto &e : ctx->linsys_jit) if (e.first == key) id = e.second;
+                    std::string err;
+                    if (id < 0) {
+                        char nm[64];
+                        snprintf(nm, sizeof(nm), "linsys_%d_%d_%d_nvrtc_constants", d->n_state, d->n_lag, d->n_noise);
+                        id = ctx->user.compile(linsys_jit_source(d->n_state, d->n_lag, d->n_noise, d->params).c_str(), err, nm);
+                        ctx->linsys_jit.emplace_back(key, id);          // id < 0: remembered as "NVRTC unavailable", generic kernel below
+                    }
+                    if (id >= 0 && ctx->user.select(id, alg, nz, false, k, err)) k.n_param = d->n_param;
+                    else k = sdde::KernelInfo();
+                }
+                if (!k.fn) k = sdde::select_linsys(d->n_state, d->n_lag, d->n_noise, alg, nz, ptraj);
+            }
             break;
         default:
             if (d->model_id >= SDDE_MODEL_USER_BASE && ctx) {
@@ -454,6 +519,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     if (!strcmp(key, "wave_traj")) c->opt_wave_traj = value;
     else if (!strcmp(key, "batch")) c->opt_batch = value;
     else if (!strcmp(key, "nccl")) c->opt_nccl = value;
+    else if (!strcmp(key, "jit_linsys")) c->opt_jit_linsys = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
@@ -553,7 +619,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         else snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_solve_kernel<%s,alg%d,noise%d,ptraj%d,tpt%d,B%d>", K.name,
                  d->alg, d->noise_mode, d->param_stride != 0, K.tpt, K.batch);
         cudaFuncAttributes fa;
-        if (!K.is_user && cudaFuncGetAttributes(&fa, K.fn) == cudaSuccess) tm->regs_per_thread = fa.numRegs;
+        if (cudaFuncGetAttributes(&fa, K.fn) == cudaSuccess) tm->regs_per_thread = fa.numRegs;   // also accepts a cudaKernel_t
         else cudaGetLastError();
     }
     if (moments) for (int64_t i = 0; i < rows * 3; ++i) moments[i] = 0.0;

@@ -74,7 +74,7 @@ std::string wrap_source(const char *user) {
 
 }  // namespace
 
-int UserModels::compile(const char *source, std::string &err) {
+int UserModels::compile(const char *source, std::string &err, const char *name) {
     const std::string src = wrap_source(source);
     // 1) probe compile: syntax check + model dimensions
     std::vector<char> cubin;
@@ -107,7 +107,7 @@ int UserModels::compile(const char *source, std::string &err) {
         return -1;
     }
     en.kernels.assign((size_t)kAlgs * kNoises * 2, nullptr);
-    en.name = "user" + std::to_string(entries_.size());
+    en.name = name ? std::string(name) : "user" + std::to_string(entries_.size());
     en.source = src;
     entries_.push_back(en);
     return SDDE_MODEL_USER_BASE + (int)entries_.size() - 1;

@@ -17,7 +17,7 @@ namespace sdde {
 class UserModels {
    public:
     // returns model id (>= 1000) or -1 with err set
-    int compile(const char *source, std::string &err);
+    int compile(const char *source, std::string &err, const char *name = nullptr);
     bool select(int model_id, int alg, int noise, bool ptraj, KernelInfo &k, std::string &err);
     bool launch(const KernelInfo &k, unsigned grid, unsigned block, size_t smem, cudaStream_t st, const void *args,
                 size_t args_size, std::string &err);

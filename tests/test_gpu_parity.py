@@ -397,3 +397,24 @@ def test_pinned_output_buffer_reused_across_solves():
         plain = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, seed=seed,
                         **case.solve_kwargs())
         assert np.array_equal(plain.out, out)
+
+
+def test_linsys_nvrtc_constant_specialisation_equals_generic_kernel():
+    """The linear delay system's matrices are baked into an NVRTC-compiled kernel (zeros vanish); the generic
+    constant-bank kernel stays available (option jit_linsys = 0) and both give the same paths."""
+    case = cases.c4(T=5.0)
+    sch = case.oracle_schedule()
+    n = 500
+    dW = cases.increments(sch, 2, n)
+    kw = dict(trajectories=n, noise_increments=dW, **case.solve_kwargs())
+    a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+    ctx = S.get_context(0)
+    ctx.set_option("jit_linsys", 0)
+    try:
+        b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+    finally:
+        ctx.set_option("jit_linsys", 1)
+    assert "nvrtc_constants" in a.timing["kernel_name"] and "nvrtc" not in b.timing["kernel_name"]
+    assert cases.scaled_err(a.out, b.out) < 1e-13
+    ref, _ = case.oracle(dW)
+    assert cases.scaled_err(a.out, ref) < TOL and cases.scaled_err(b.out, ref) < TOL
