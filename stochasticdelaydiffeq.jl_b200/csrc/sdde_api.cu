@@ -168,8 +168,8 @@ __global__ void merge_moments_kernel(const double *__restrict__ src, long long p
 // test hook: the normals the step kernels would draw, laid out [n][c][traj]
 __global__ void philox_dump_kernel(double *out, long long n_traj, long long traj_off, long long n_steps, int nc, u32 k0,
                                    u32 k1) {
-    __shared__ double2 ltab[128];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) ltab[i] = RNG_LOG_TAB[i];
+    __shared__ double2 ltab[SDDE_RNG_TAB_ENTRIES];
+    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += blockDim.x) ltab[i] = RNG_TAB[i];
     __syncthreads();
     u32 rk[20];
     philox_round_keys(k0, k1, rk);

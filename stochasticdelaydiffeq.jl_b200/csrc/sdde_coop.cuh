@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_cons
     double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
     Rec *srec = reinterpret_cast<Rec *>(smem_raw + SDDE_RNG_SMEM_BYTES);
     if (NOISE == K_NOISE_PHILOX) {
-        for (int i = threadIdx.x; i < 128; i += SDDE_BLOCK) ltab[i] = RNG_LOG_TAB[i];
+        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += SDDE_BLOCK) ltab[i] = RNG_TAB[i];
     }
     const int j = threadIdx.x % LPT;                                                        // my state component
     const long long tr = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) / LPT;          // wave-local trajectory

@@ -38,7 +38,7 @@ __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULE
 #ifndef SDDE_BLOCK
 #define SDDE_BLOCK 128
 #endif
-#define SDDE_RNG_SMEM_BYTES 2048
+#define SDDE_RNG_SMEM_BYTES (SDDE_RNG_TAB_ENTRIES * 16)   // 12 KB: log + cos/sin tables of the normal generator
 
 struct SaveRec {
     int step;       // step whose end produces this save (-1: initial condition)
@@ -154,52 +154,51 @@ __device__ __forceinline__ double rsqrt_approx(double x) {
 // smooth functional the mean over 2^24 equispaced directions is the trapezoidal rule of a smooth periodic function
 // (error beyond any power of 2^-24), so each z stays N(0,1) to far below float64 rounding; the radius keeps 40 bits
 // (tail truncated at 7.5 sigma, probability 5e-14 per draw; spacing of r at 6 sigma: 8e-5).
-// Evaluation: every argument range is known, so no special cases and no libm calls:
-//   -2 ln u  : u = 2^e' * M', 128-entry table {1/c_k, -2 ln c'_k} in shared memory (k = top 7 mantissa bits),
-//              rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-8, degree-7 log1p polynomial (abs. error < 2^-66)
-//   sqrt     : MUFU.RSQ64H seed + one coupled Newton step + residual correction (<= 1 ulp on [2^-41, 57])
-//   sin, cos : Taylor in (pi/2 x), |x| <= 1/2, degree 15 / 16 (truncation < 5e-17), exact quadrant rotation
-__device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const double2 *__restrict__ ltab, double &z0, double &z1) {
+// Evaluation: every argument range is known, so no special cases and no libm calls; both transcendental parts are
+// "table + short polynomial" with one shared-memory table (RNG_TAB, 12 KB, staged per CTA):
+//   -2 ln u  : u = 2^e' * M'; k = top 9 mantissa bits -> {1/c_k, -2 ln c'_k}; rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-10,
+//              log1p(rho) = rho + rho^2 (L2 + L3 rho + L4 rho^2 + L5 rho^3)            (truncation < 2^-62)
+//   sqrt     : MUFU.RSQ64H seed y, e = 1 - t y^2, y <- y (1 + e/2 + 3 e^2/8) (cubic step), r = t y   (<= 1 ulp)
+//   sin, cos : i = top 8 bits of the angle fraction -> {cos, sin}(pi/2 x_i); residual d = x - x_i, |d| <= 2^-9,
+//              sin(pi/2 d) = d (S1 + S3 d^2 + S5 d^4), cos(pi/2 d) = 1 + C2 d^2 + C4 d^4 (truncation < 2e-18), angle
+//              addition, exact quadrant rotation
+// 29 FP64 instructions per pair (the Taylor-only version needed 39).
+__device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const double2 *__restrict__ tab, double &z0, double &z1) {
     // ---- radius ----
     const double X = __hiloint2double((int)(0x3FF00000u | ((wb & 0xFFu) << 12) | (wa >> 20)), (int)(wa << 12));   // 1 + m 2^-40
     const double U = X - 0.99999999999954525264911353588104248046875;                         // (m + 1/2) 2^-40, exact
     const int hi = __double2hiint(U);
-    const int k = (hi >> 13) & 127;
+    const int k = (hi >> 11) & 511;
     const int n = 1023 - (hi >> 20) - ((hi >> 19) & 1);                                      // -e' in [0, 41]
     const double M = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(U));    // mantissa in [1,2)
-    const double2 te = ltab[k];
+    const double2 te = tab[k];
+    // ---- angle: table lookup issued early ----
+    const u32 q = wb >> 30;
+    const u32 f = (wb >> 8) & 0x3FFFFFu;                                                     // 22-bit fraction
+    const double2 cs = tab[512 + (f >> 14)];
+    const u32 flow = f & 0x3FFFu;
+    const double D = __hiloint2double((int)(0x3FF00000u | (flow >> 2)), (int)((flow & 3u) << 30));   // 1 + flow 2^-22
+    const double dl = D - 1.00195300579071044921875;                                         // (flow + 1/2) 2^-22 - 2^-9, exact
+    // ---- -2 ln u ----
     const double rho = fma(M, te.x, -1.0);
     const double dn = __hiloint2double(0x43300000, n) - 4503599627370496.0;                  // (double)n
-    double P = fma(rho, RNG_LOG1P_C[5], RNG_LOG1P_C[4]);
-    P = fma(rho, P, RNG_LOG1P_C[3]);
-    P = fma(rho, P, RNG_LOG1P_C[2]);
+    double P = fma(rho, RNG_LOG1P_C[3], RNG_LOG1P_C[2]);
     P = fma(rho, P, RNG_LOG1P_C[1]);
     P = fma(rho, P, RNG_LOG1P_C[0]);
     const double l1p = fma(rho * rho, P, rho);
     double t = fma(dn, SDDE_RNG_TWO_LN2, te.y);
     t = fma(-2.0, l1p, t);                                                                   // -2 ln u  > 0
+    // ---- sqrt(t) ----
     const double y = rsqrt_approx(t);
-    double g = t * y, h = 0.5 * y;
-    const double e1 = fma(-h, g, 0.5);
-    g = fma(g, e1, g);
-    h = fma(h, e1, h);
-    const double e2 = fma(-g, g, t);
-    g = fma(e2, h, g);                                                                       // sqrt(t)
-    // ---- angle ----
-    const u32 q = wb >> 30;
-    const double D = __hiloint2double((int)(0x3FF00000u | ((wb >> 10) & 0xFFFFFu)), (int)((wb << 22) & 0xC0000000u));  // 1 + f 2^-22
-    const double x = D - 1.49999988079071044921875;                                          // (f + 1/2) 2^-22 - 1/2, exact
-    const double zz = x * x;
-    double sp = fma(zz, RNG_SIN_C[7], RNG_SIN_C[6]);
-    double cp = fma(zz, RNG_COS_C[8], RNG_COS_C[7]);
-    sp = fma(zz, sp, RNG_SIN_C[5]); cp = fma(zz, cp, RNG_COS_C[6]);
-    sp = fma(zz, sp, RNG_SIN_C[4]); cp = fma(zz, cp, RNG_COS_C[5]);
-    sp = fma(zz, sp, RNG_SIN_C[3]); cp = fma(zz, cp, RNG_COS_C[4]);
-    sp = fma(zz, sp, RNG_SIN_C[2]); cp = fma(zz, cp, RNG_COS_C[3]);
-    sp = fma(zz, sp, RNG_SIN_C[1]); cp = fma(zz, cp, RNG_COS_C[2]);
-    sp = fma(zz, sp, RNG_SIN_C[0]); cp = fma(zz, cp, RNG_COS_C[1]);
-    cp = fma(zz, cp, RNG_COS_C[0]);
-    const double sn = x * sp;
+    const double e = fma(-t, y * y, 1.0);
+    const double y1 = fma(y * e, fma(e, 0.375, 0.5), y);
+    const double g = t * y1;
+    // ---- sin / cos of (pi/2) x = (pi/2)(x_i + d) ----
+    const double d2 = dl * dl;
+    const double sd = dl * fma(d2, fma(d2, RNG_SINR_C[2], RNG_SINR_C[1]), RNG_SINR_C[0]);
+    const double cd = fma(d2, fma(d2, RNG_COSR_C[1], RNG_COSR_C[0]), 1.0);
+    const double cp = fma(-cs.y, sd, cs.x * cd);
+    const double sn = fma(cs.x, sd, cs.y * cd);
     // quadrant rotation: q=0 (c,s), 1 (-s,c), 2 (-c,-s), 3 (s,-c); signs folded into the radius
     const bool odd = (q & 1u) != 0;
     const double cc = odd ? sn : cp, ss = odd ? cp : sn;
@@ -524,10 +523,10 @@ __global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(c
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
     typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);                  // 2 KB log table of the normal generator
+    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);                  // tables of the normal generator
     Rec *srec = reinterpret_cast<Rec *>(smem_raw + SDDE_RNG_SMEM_BYTES);
     if (NOISE == K_NOISE_PHILOX) {
-        for (int i = threadIdx.x; i < 128; i += SDDE_BLOCK) ltab[i] = RNG_LOG_TAB[i];
+        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += SDDE_BLOCK) ltab[i] = RNG_TAB[i];
     }
 
     const long long tr0 = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) * TPT;  // wave-local trajectory index

@@ -5,8 +5,8 @@
 #include "../../stochasticdelaydiffeq.jl_b200/csrc/sdde_kernels.cuh"
 using namespace sdde;
 template <int MODE> __global__ void __launch_bounds__(128) k(double *o, int iters, u32 k0, u32 k1) {
-    __shared__ double2 ltab[128];
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) ltab[i] = RNG_LOG_TAB[i];
+    __shared__ double2 ltab[SDDE_RNG_TAB_ENTRIES];
+    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += blockDim.x) ltab[i] = RNG_TAB[i];
     __syncthreads();
     u32 rk[20]; philox_round_keys(k0, k1, rk);
     const u64 gid = blockIdx.x * blockDim.x + threadIdx.x;
