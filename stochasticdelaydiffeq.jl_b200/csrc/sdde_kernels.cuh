@@ -101,7 +101,7 @@ struct KArgs {
 #define SDDE_TUNE_TPT_MULTI 2
 #endif
 #ifndef SDDE_MIN_BLOCKS
-#define SDDE_MIN_BLOCKS 5
+#define SDDE_MIN_BLOCKS 4
 #endif
 template <class M> struct Tune {
     static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : (M::NS >= 4 ? SDDE_TUNE_TPT_MULTI : 1);
