@@ -210,12 +210,18 @@ __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const dou
 }
 
 // normals 4*call .. 4*call+3 of trajectory gid
+__device__ __forceinline__ void philox_words(u64 gid, u64 call, const u32 *__restrict__ rk, u32 (&w)[4]) {
+    philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), rk, w);
+}
+__device__ __forceinline__ void normal_quad_from_words(const u32 (&w)[4], const double2 *__restrict__ ltab, double (&z)[4]) {
+    normal_pair_from_words(w[0], w[1], ltab, z[0], z[1]);
+    normal_pair_from_words(w[2], w[3], ltab, z[2], z[3]);
+}
 __device__ __forceinline__ void philox_normal_quad(u64 gid, u64 call, const u32 *__restrict__ rk,
                                                    const double2 *__restrict__ ltab, double (&z)[4]) {
     u32 w[4];
-    philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), rk, w);
-    normal_pair_from_words(w[0], w[1], ltab, z[0], z[1]);
-    normal_pair_from_words(w[2], w[3], ltab, z[2], z[3]);
+    philox_words(gid, call, rk, w);
+    normal_quad_from_words(w, ltab, z);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,6 +346,8 @@ struct TrajState {
     RegParams<PTRAJ ? NP : 0> preg[TPT];
     double zc[TPT][4];        // cached normals of the current Philox call
     u64 zcall;                // its call index
+    u32 wn[TPT][4];           // Philox words of call wcall, computed one batch ahead (batched path): the 10-round
+    u64 wcall;                // dependent chain then has no consumer inside the batch and hides under its FP64 work
     double curW[TPT][NC];     // NoiseGrid mode: current W
     bool bad[TPT];
     int ks;                   // next SaveRec
@@ -409,9 +417,24 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 const u64 call = q >> 2;
                 const bool fresh = STATIC_RNG ? (((k * NC + c) & 3) == 0) : (call != st.zcall);
                 if (fresh) {
+                    if (STATIC_RNG && (k * NC + c) == 0) {
+                        // words of this call were produced during the previous batch (recomputed after a step-by-step
+                        // stretch); produce the words of the NEXT batch's first call now, nothing in this batch waits for them
+                        if (st.wcall != call) {
 #pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt)
-                        philox_normal_quad((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt]);
+                            for (int tt = 0; tt < TPT; ++tt) philox_words((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, st.wn[tt]);
+                        }
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) {
+                            normal_quad_from_words(st.wn[tt], ltab, st.zc[tt]);
+                            philox_words((u64)(a.traj_gid0 + tr0 + tt), call + (u64)(BW * NC / 4), a.rk, st.wn[tt]);
+                        }
+                        st.wcall = call + (u64)(BW * NC / 4);
+                    } else {
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt)
+                            philox_normal_quad((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt]);
+                    }
                     st.zcall = call;
                 }
                 const int lane = STATIC_RNG ? ((k * NC + c) & 3) : (int)(q & 3);
@@ -550,6 +573,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(c
             st.curW[tt][c] = (NOISE == K_NOISE_GRID) ? a.noise[(long long)c * a.noise_pitch + a.noise_off + tr] : 0.0;
     }
     st.zcall = ~0ull;
+    st.wcall = ~0ull;
     st.ks = 0;
 #pragma unroll
     for (int l = 0; l < NL * 2; ++l)
