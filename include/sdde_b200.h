@@ -212,6 +212,18 @@ SDDE_API int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const s
 /* Merge two (count, mean, M2) arrays of n triples: a <- merge(a, b)  (Chan et al.); host only. */
 SDDE_API int sdde_b200_merge_moments(double *a, const double *b, int64_t n);
 
+/* Order statistics across trajectories of saved rows, on the device: the reference side computes them with
+ * [EXT] SciMLBase EnsembleSummary -> EnsembleAnalysis.timeseries_steps_quantile / timeseries_steps_median ->
+ * Statistics.quantile(v, p) (alpha = beta = 1) / Statistics.median(v) on the per-time-point vectors of a solved ensemble.
+ *   paths   [n_rows][pitch] float64 (the `out` of sdde_b200_solve viewed as n_save*n_state rows, pitch = n_traj), host or
+ *           device memory according to `mem`; the first n_traj values of each row are used
+ *   probs   n_prob probabilities in [0, 1]
+ *   result  [n_rows][n_prob + (want_median != 0)] host memory; the median is the last column.  A row holding a NaN yields NaN.
+ *   kernel_ms  optional: CUDA-event time of the selection kernels
+ * Exact (bit-identical to selecting from the sorted row): radix selection on the order-preserving integer image. */
+SDDE_API int sdde_b200_quantiles(sdde_ctx *ctx, const double *paths, int32_t mem, int64_t n_rows, int64_t n_traj, int64_t pitch,
+                                 const double *probs, int32_t n_prob, int32_t want_median, double *result, double *kernel_ms);
+
 /* Register a user model from CUDA C++ source (NVRTC, sm_100a).  The source must define
  *   struct UserModel { static constexpr int NS, NL, NW, NP; static constexpr bool DIAG;
  *                      template<class P> __device__ static void f(double*du,const double*u,const double(*ul)[NS],const P&p,double t);

@@ -701,3 +701,56 @@ def exact_mean_linear1(sched: Schedule, a, b, u0, h0, h1, lag):
             ml = (1.0 - th) * m[i - 1] + th * m[i]
         m[n + 1] = m[n] + sched.dt[n] * (a * m[n] + b * ml)
     return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# Order statistics across trajectories: what [EXT] SciMLBase EnsembleSummary computes on the reference side with
+# EnsembleAnalysis.timeseries_steps_quantile / timeseries_steps_median -> [EXT] Statistics.quantile (alpha = beta = 1)
+# and Statistics.median.  Checker for sdde_b200_quantiles; a full sort per row, formulas restated from Statistics.jl.
+# ---------------------------------------------------------------------------------------------------
+def julia_quantile(v, p):
+    """Statistics.quantile(v, p) for a float64 vector (sorted internally)."""
+    v = np.sort(np.asarray(v, dtype=np.float64))
+    n = v.size
+    if not 0.0 <= p <= 1.0:
+        raise ValueError("input probability out of [0,1] range")
+    if np.isnan(v).any():
+        return np.nan                              # Julia raises; the device path reports NaN for such a row
+    if n == 1:
+        a = b = v[0]
+        gamma = 0.0
+    else:
+        m = np.float64(1.0) + np.float64(p) * (1.0 - 1.0 - 1.0)
+        aleph = np.float64(n) * np.float64(p) + m
+        j = int(min(max(int(np.trunc(aleph)), 1), n - 1))
+        gamma = float(min(max(aleph - j, 0.0), 1.0))
+        a, b = v[j - 1], v[j]
+    with np.errstate(invalid="ignore"):
+        if np.isfinite(a) and np.isfinite(b):
+            return a + np.float64(gamma) * (b - a)
+        return (1.0 - np.float64(gamma)) * a + np.float64(gamma) * b
+
+
+def julia_median(v):
+    """Statistics.median(v): middle order statistic, or middle(a, b) = a/2 + b/2 of the two central ones."""
+    v = np.sort(np.asarray(v, dtype=np.float64))
+    n = v.size
+    if np.isnan(v).any():
+        return np.nan
+    if n % 2 == 1:
+        return v[(n - 1) // 2]
+    with np.errstate(invalid="ignore"):
+        return v[n // 2 - 1] / 2 + v[n // 2] / 2
+
+
+def ensemble_quantiles(paths, probs, want_median=False):
+    """paths [n_rows, n_traj] -> [n_rows, len(probs) + want_median]."""
+    paths = np.asarray(paths, dtype=np.float64)
+    cols = len(probs) + (1 if want_median else 0)
+    res = np.empty((paths.shape[0], cols))
+    for i, row in enumerate(paths):
+        for j, p in enumerate(probs):
+            res[i, j] = julia_quantile(row, p)
+        if want_median:
+            res[i, -1] = julia_median(row)
+    return res

@@ -325,6 +325,64 @@ def timepoint_meanvar(sim, t):
     return mean[k], var[k]
 
 
+def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=None):
+    """[EXT] SciMLBase.EnsembleAnalysis.timeseries_steps_quantile (and _median): per saved time point and state, the
+    quantile(s) ``q`` across this solution's trajectories -- Statistics.quantile's definition, selected exactly on the
+    device (sdde_b200_quantiles; the paths stay in HBM when the solve ran with ``output='device'``).
+
+    -> array [n_save, n_state, len(q)] (``[n_save, n_state]`` for a scalar q); with ``median=True`` the median is
+    appended as the last entry of the last axis."""
+    if sim.out is None:
+        raise ValueError("solve(..., paths=True) first: order statistics need the saved paths")
+    probs = np.atleast_1d(np.asarray(q, dtype=np.float64)) if q is not None else np.zeros(0)
+    out = sim.out
+    n_save, n_state, n_traj = out.shape
+    on_dev = hasattr(out, "data_ptr")
+    if on_dev:
+        dev = out.device.index
+        ptr = out.data_ptr()
+    else:
+        dev = device if device is not None else _default_device()
+        out = np.ascontiguousarray(out, dtype=np.float64)
+        ptr = capi.np_ptr(out).value
+    ctx = capi.get_context(dev)
+    ncol = probs.size + (1 if median else 0)
+    res = np.empty((n_save * n_state, ncol), dtype=np.float64)
+    ms = C.c_double(0.0)
+    capi.check(capi.lib().sdde_b200_quantiles(ctx.handle, ptr, capi.MEM_DEVICE if on_dev else capi.MEM_HOST, n_save * n_state,
+                                              n_traj, n_traj, capi.np_ptr(probs).value if probs.size else None, probs.size,
+                                              1 if median else 0, capi.np_ptr(res).value, C.byref(ms)))
+    sim.timing["quantile_kernel_ms"] = ms.value
+    res = res.reshape(n_save, n_state, ncol)
+    if np.isscalar(q) and not median:
+        return res[..., 0]
+    return res
+
+
+def timeseries_steps_median(sim: EnsembleSolution):
+    return timeseries_steps_quantile(sim, None, median=True)[..., 0]
+
+
+class EnsembleSummary:
+    """[EXT] SciMLBase.EnsembleSummary(sim; quantiles=[0.05, 0.95]): mean ``u``, variance ``v``, median ``med`` and the
+    two quantile bands ``qlow``/``qhigh`` per saved time point, all computed on the device."""
+
+    def __init__(self, sim: EnsembleSolution, quantiles=(0.05, 0.95)):
+        if len(quantiles) != 2:
+            raise ValueError("quantiles must be (low, high)")
+        if sim.moments is not None:
+            self.u, self.v = timeseries_steps_meanvar(sim)
+        else:
+            o = sim.out.cpu().numpy() if hasattr(sim.out, "data_ptr") else sim.out
+            self.u, self.v = o.mean(axis=2), o.var(axis=2, ddof=1)
+        r = timeseries_steps_quantile(sim, list(quantiles), median=True)
+        self.qlow, self.qhigh, self.med = r[..., 0], r[..., 1], r[..., 2]
+        self.t = sim.t
+        self.num_monte = len(sim)
+        self.elapsedTime = sim.elapsedTime
+        self.converged = sim.converged
+
+
 def merge_moments(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     """Chan merge of two (count, mean, M2) arrays through the library (host code of libsdde_b200)."""
     a = np.ascontiguousarray(a, dtype=np.float64).copy()

@@ -193,3 +193,16 @@ def test_euler_heun_known_answer_and_order():
     assert s.lk_mode.shape == (501, 2) and s.tstops_hit == [1.0, 2.0, 5.0]          # alg_order 1/2 like EM
     # the second-stage lookup of step n is (numerically almost) the first-stage lookup of step n+1
     assert np.all(np.abs(s.lk_time[:-1, 1] - s.lk_time[1:, 0]) < 1e-12)
+
+
+def test_oracle_quantile_definition_known_answers():
+    """Statistics.quantile (alpha = beta = 1) hand-computed: v = 1..5 -> q(0.1) = 1.4, q(0.5) = 3, q(1) = 5;
+    v = 1..4 -> median 2.5, q(0.25) = 1.75."""
+    v5, v4 = np.array([5.0, 1.0, 4.0, 2.0, 3.0]), np.array([4.0, 1.0, 3.0, 2.0])
+    assert O.julia_quantile(v5, 0.1) == 1.4 and O.julia_quantile(v5, 0.5) == 3.0 and O.julia_quantile(v5, 1.0) == 5.0
+    assert O.julia_quantile(v5, 0.0) == 1.0 and O.julia_median(v5) == 3.0
+    assert O.julia_median(v4) == 2.5 and O.julia_quantile(v4, 0.25) == 1.75
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1001)
+    for p in (0.05, 0.3, 0.95):
+        assert abs(O.julia_quantile(x, p) - np.quantile(x, p)) < 1e-14      # numpy 'linear' = the same type-7 definition
