@@ -665,7 +665,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     wave = std::min(wave, ((NT + per_block - 1) / per_block) * per_block);
     const int64_t pitch = wave;   // multiple of per_block => every thread of the grid owns in-bounds ring columns
     // Wave list.  When the saved paths leave over PCIe (host output) the first waves are small and grow geometrically,
-    // so that the D2H stream starts after a few milliseconds instead of after a whole 2^19-trajectory wave.
+    // so that the D2H stream starts after a few milliseconds instead of after a whole 2^19-trajectory wave
+    // and then never idles (measured on C2: D2H engine busy from 4 ms to the end).
     std::vector<int64_t> wave_off, wave_cnt;
     {
         const bool ramp = c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > wave;
@@ -674,7 +675,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
             const int64_t cnt = std::min(std::min(cur, wave), NT - off);
             wave_off.push_back(off); wave_cnt.push_back(cnt);
             off += cnt;
-            if (ramp) cur = std::min(wave, cur * 2);
+            if (ramp) cur = std::min(wave, std::max<int64_t>(per_block, (cur * 3 / 2 / per_block) * per_block));   // x1.5: a wave's kernel must end before the previous wave's copy does (kernel ~25, PCIe ~14 trajectories/us on C2)
         }
     }
     const int n_waves = (int)wave_off.size();
@@ -707,7 +708,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (noise_host) CU_CHECK(c->noise.reserve((size_t)std::max<int64_t>(1, noise_rows) * pitch * 8));
     if (d->u0_stride != 0) CU_CHECK(c->u0.reserve((size_t)NS * pitch * 8));
     if (d->param_stride != 0) CU_CHECK(c->ptraj.reserve((size_t)std::max(1, K.n_param) * pitch * 8));
-    if (status) { CU_CHECK(c->status.reserve((size_t)pitch)); CU_CHECK(c->h_status.reserve((size_t)NT)); }
+    if (status) { CU_CHECK(c->status.reserve((size_t)NT + (size_t)pitch)); CU_CHECK(c->h_status.reserve((size_t)NT)); }   // all waves: ONE D2H at the end
     if (d->want_moments) CU_CHECK(c->mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves));
     if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
 
@@ -743,6 +744,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     CU_CHECK(cudaEventRecord(c->ev_c0, c->copy_out));
     bool first_kernel = true;
 
+    std::vector<cudaEvent_t> dbg_ev;                 // SDDE_DEBUG_TIMING: per wave (kernel start, kernel end, copy start, copy end)
+    auto dbg_mark = [&](cudaStream_t s) { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); dbg_ev.push_back(e); } };
     for (int w = 0; w < n_waves; ++w) {
         const int64_t off = wave_off[(size_t)w];
         const int64_t nt = wave_cnt[(size_t)w];
@@ -771,7 +774,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
             if (noise_host) { A.noise = (const double *)c->noise.p; A.noise_pitch = pitch; A.noise_off = 0; }
             else { A.noise = d->noise; A.noise_pitch = NT; A.noise_off = off; }
         }
-        A.status = status ? (unsigned char *)c->status.p : nullptr;
+        A.status = status ? (unsigned char *)c->status.p + off : nullptr;
         A.n_traj = nt;
         A.traj_gid0 = d->traj_offset + off;
         if (out_dev) {
@@ -786,6 +789,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         }
         const unsigned grid = (unsigned)((nt + per_block - 1) / per_block);
         if (first_kernel) { CU_CHECK(cudaEventRecord(c->ev_k0, c->compute)); first_kernel = false; }
+        dbg_mark(c->compute);
         if (K.is_user) {
             std::string err;
             if (!c->user.launch(K, grid, SDDE_BLOCK, smem, c->compute, &A, sizeof(A), err)) return fail(SDDE_ERR_CUDA, "%s", err.c_str());
@@ -801,19 +805,24 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
             ++launches;
         }
         CU_CHECK(cudaEventRecord(c->ev_kdone[buf], c->compute));
+        dbg_mark(c->compute);
         // outputs of this wave
         if (d->want_paths && !out_dev && rows > 0) {
             CU_CHECK(cudaStreamWaitEvent(c->copy_out, c->ev_kdone[buf], 0));
+            dbg_mark(c->copy_out);
             CU_CHECK(cudaMemcpy2DAsync(out + off, OP * 8, A.out, pitch * 8, nt * 8, rows, cudaMemcpyDeviceToHost, c->copy_out));
             CU_CHECK(cudaEventRecord(c->ev_copied[buf], c->copy_out));
+            dbg_mark(c->copy_out);
             d2h += nt * 8 * rows;
-        }
-        if (status) {
-            CU_CHECK(cudaMemcpyAsync((unsigned char *)c->h_status.p + off, c->status.p, (size_t)nt, cudaMemcpyDeviceToHost, c->compute));
-            d2h += nt;
         }
     }
     CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
+    // Status bytes leave in ONE copy after the last wave: a small D2H per wave on the compute stream would queue behind the
+    // wave's path copy in the D2H copy engine and stall the next wave's kernel until that copy ends (no overlap at all).
+    if (status) {
+        CU_CHECK(cudaMemcpyAsync(c->h_status.p, c->status.p, (size_t)NT, cudaMemcpyDeviceToHost, c->compute));
+        d2h += NT;
+    }
     if (d->want_moments && rows > 0 && c->keep_moments_on_device) {
         // multi-GPU path: wave merge on the device, result stays in mom[0..rows) for the NCCL all-gather
         if (n_waves > 1) {
@@ -834,6 +843,16 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     CU_CHECK(cudaStreamSynchronize(c->copy_in));
     lap("copy streams synced");
     CU_CHECK(cudaGetLastError());
+    if (dbg && !dbg_ev.empty()) {
+        const int per = (d->want_paths && !out_dev && rows > 0) ? 4 : 2;
+        for (size_t i = 0; i + per <= dbg_ev.size(); i += per) {
+            float t[4] = {0, 0, 0, 0};
+            for (int j = 0; j < per; ++j) cudaEventElapsedTime(&t[j], dbg_ev[0], dbg_ev[i + j]);
+            fprintf(stderr, "[sdde timing] wave %zu (%lld traj): kernel %.2f..%.2f ms  copy %.2f..%.2f ms\n", i / per,
+                    (long long)wave_cnt[i / per], t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : dbg_ev) cudaEventDestroy(e);
+    }
     if (status) memcpy(status, c->h_status.p, (size_t)NT);
     if (d->want_moments && rows > 0 && !c->keep_moments_on_device) {
         memcpy(moments, h_mom, (size_t)rows * 3 * 8);
