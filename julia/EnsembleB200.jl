@@ -102,4 +102,22 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM,
     return SciMLBase.EnsembleSolution(sols, 0.0, true)
 end
 
+"""
+    b200_quantiles(ea, out, probs; median = true) -> Array{Float64,3}  (n_col, n_state, n_save)
+
+Median and quantile bands across trajectories of the `out` array of an EnsembleB200 solve (host memory here), selected
+exactly on the device: what `EnsembleSummary(sim; quantiles)` computes with `timeseries_steps_quantile` /
+`timeseries_steps_median` (Statistics.quantile / Statistics.median per time point), without materialising the
+componentwise vectors.  Columns: one per probability, the median last.
+"""
+function b200_quantiles(ea::EnsembleB200, out::Array{Float64, 3}, probs::Vector{Float64}; median::Bool = true)
+    n_traj, n_state, n_save = size(out)
+    res = Array{Float64, 3}(undef, length(probs) + median, n_state, n_save)
+    rc = GC.@preserve out probs res ccall((:sdde_b200_quantiles, libsdde), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Cint, Int64, Int64, Int64, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+        context(ea.device), out, 0, n_state * n_save, n_traj, n_traj, probs, length(probs), median ? 1 : 0, res, C_NULL)
+    rc == 0 || error("libsdde_b200 ($rc): " * last_error())
+    return res
+end
+
 end # module
