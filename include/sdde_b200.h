@@ -228,6 +228,10 @@ SDDE_API int sdde_b200_quantiles(sdde_ctx *ctx, const double *paths, int32_t mem
  *   struct UserModel { static constexpr int NS, NL, NW, NP; static constexpr bool DIAG;
  *                      template<class P> __device__ static void f(double*du,const double*u,const double(*ul)[NS],const P&p,double t);
  *                      template<class P> __device__ static void g(double*gv,const double*u,const double(*ul)[NS],const P&p,double t); };
+ * Optional history function for t < t0 (any expression, not only affine): add
+ *   static constexpr bool HAS_H = true;
+ *   template<class P> __device__ static void h(double*out,const P&p,double t);
+ * to the struct; it then replaces the descriptor's hist_c0/hist_c1 (the reference's h(p, t), src/functionwrapper.jl:35-36).
  * Returns a model id >= SDDE_MODEL_USER_BASE in *model_id. */
 SDDE_API int sdde_b200_compile_model(sdde_ctx *ctx, const char *source, int32_t *model_id);
 

@@ -225,6 +225,15 @@ __device__ __forceinline__ void philox_normal_quad(u64 gid, u64 call, const u32 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Optional model-defined history function h(p, t) for t < t0 (user models: `static constexpr bool HAS_H = true;` and
+// `template <class P> __device__ static void h(double *out, const P &p, double t)`); models without it use the
+// descriptor's affine history c0 + c1*t.  The reference's h is an arbitrary callable (src/functionwrapper.jl:35-36).
+// ------------------------------------------------------------------------------------------------
+template <class...> struct VoidOf { typedef void type; };
+template <class M, class = void> struct HasHist { static constexpr bool value = false; };
+template <class M> struct HasHist<M, typename VoidOf<decltype(M::HAS_H)>::type> { static constexpr bool value = M::HAS_H; };
+
+// ------------------------------------------------------------------------------------------------
 // parameter accessors: kernel-argument constants (uniform) or per-trajectory registers (prob_func use case)
 // ------------------------------------------------------------------------------------------------
 struct ConstParams {
@@ -483,6 +492,18 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 for (int tt = 0; tt < TPT; ++tt) {
                     const double iv = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
                     ul[tt][l / NL][l % NL][j] = ring ? iv : hv;
+                }
+            }
+            if constexpr (HasHist<M>::value) {
+                if (!ring) {                                    // prehistory record (warp-uniform: the schedule is shared)
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) {
+                        double hv[NS];
+                        if (PTRAJ) M::h(hv, st.preg[tt], th);
+                        else M::h(hv, ConstParams{a.p}, th);
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) ul[tt][l / NL][l % NL][j] = hv[j];
+                    }
                 }
             }
             if (NSTG > 1 && (r.ring_mask & (0x10000 << l))) {   // second-stage lookup past the dense history: constant u0

@@ -117,8 +117,10 @@ class UserModel:
     ``source`` must define ``struct UserModel`` with the interface documented in include/sdde_b200.h.
     """
 
-    def __init__(self, source: str, n_state: int, n_lag: int, n_noise: int, n_param: int, diagonal: bool, name="user"):
+    def __init__(self, source: str, n_state: int, n_lag: int, n_noise: int, n_param: int, diagonal: bool, name="user",
+                 history: bool = False):
         self.source = source
+        self.history = bool(history)   # the source defines HAS_H = true and h(out, p, t): pass ``model.h`` as the problem's h
         self._shape = (n_state, n_lag, n_noise, n_param, diagonal)
         self.name = name
         self._ids: dict[int, int] = {}
@@ -141,6 +143,13 @@ class UserModel:
     def g(self):
         return ModelFunction(self, "g")
 
+    @property
+    def h(self):
+        """Handle of the model's own device history function (any h(p, t), not only affine)."""
+        if not self.history:
+            raise AttributeError("this UserModel was created without history=True")
+        return ModelFunction(self, "h")
+
 
 # ---------------------------------------------------------------------------------------------
 # history functions
@@ -161,6 +170,8 @@ def ConstantHistory(values) -> AffineHistory:
 
 
 def _as_history(h, p, t0, n_state) -> AffineHistory:
+    if isinstance(h, ModelFunction):                 # device history of a UserModel: the descriptor's affine slots are unused
+        return AffineHistory(tuple(0.0 for _ in range(n_state)), tuple(0.0 for _ in range(n_state)))
     if isinstance(h, AffineHistory):
         if len(h.c0) != n_state:
             raise ValueError("history has the wrong number of states")
@@ -194,6 +205,11 @@ class SDDEProblem:
             raise TypeError("f and g must be <model>.f and <model>.g handles of the device model zoo (or of a UserModel)")
         if f.model is not g.model:
             raise ValueError("f and g must come from the same model")
+        if isinstance(h, ModelFunction):
+            if h.role != "h" or h.model is not f.model:
+                raise ValueError("a device history must be <the same UserModel>.h")
+        elif getattr(f.model, "history", False):
+            raise ValueError("this UserModel defines its own history function: pass <model>.h as h")
         if dependent_lags:
             raise NotImplementedError("state-dependent lags are outside this path (SURVEY.md section 8(f))")
         if neutral:

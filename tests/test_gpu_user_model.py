@@ -91,3 +91,73 @@ def test_user_model_per_trajectory_params_noise_grid_and_rkmil():
     ref, _ = O.solve_ensemble(om, pb, ub, [1.0, 0.0], [0.1, 0.0], [0.7], osch, 2, dWg)
     assert "ptraj1" in sim.timing["kernel_name"] and "noise2" in sim.timing["kernel_name"]
     assert cases.scaled_err(sim.out, ref) < 1e-12
+
+
+SRC_H = r"""
+struct UserModel {
+    static constexpr int NS = 2, NL = 2, NW = 2, NP = 2;
+    static constexpr bool DIAG = true;
+    static constexpr bool HAS_H = true;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double t) {
+        du[0] = -p[0] * ul[0][0] + ul[1][1];
+        du[1] = -u[1] + ul[0][0] * ul[1][0];
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*ul)[NS], const P &p, double t) {
+        gv[0] = p[1] * u[0];
+        gv[1] = p[1] * ul[1][1];
+    }
+    template <class P> __device__ __forceinline__ static void h(double *out, const P &p, double t) {
+        out[0] = cos(p[0] * t);
+        out[1] = 0.5 + 0.1 * t * t;
+    }
+};
+"""
+
+
+@pytest.mark.parametrize("alg", [0, 3, 4])
+@pytest.mark.parametrize("ptraj", [False, True])
+def test_user_model_with_its_own_history_function(alg, ptraj):
+    """A non-affine h(p, t) (cosine and parabola, depending on p) evaluated on the device for every lookup before t0;
+    two lags, one of them off the step grid; EM / RKMil Stratonovich / EulerHeun; shared and per-trajectory p."""
+    um = S.UserModel(SRC_H, 2, 2, 2, 2, True, name="own_history", history=True)
+
+    def f(u, ul, p, t):
+        return np.stack([-p[0] * ul[0][0] + ul[1][1], -u[1] + ul[0][0] * ul[1][0]])
+
+    def g(u, ul, p, t):
+        return np.stack([p[1] * u[0], p[1] * ul[1][1]])
+
+    om = O.Model(1001, 2, 2, 2, True, 2, f, g)
+    n = 257
+    rng = np.random.default_rng(4)
+    p = np.array([1.3, 0.2])
+    pb = np.stack([1.0 + 0.5 * rng.random(n), 0.1 + 0.2 * rng.random(n)]) if ptraj else None
+    lags = (0.5, 1.23)
+    prob = S.SDDEProblem(um.f, um.g, [1.0, 0.5], um.h, (0.0, 3.0), p, constant_lags=lags)
+    kw = dict(dt=0.01, saveat=0.25)
+    if alg in (2, 3):
+        kw["adaptive"] = False
+    sv = O.expand_saveat(0.25, 0.0, 3.0)[0]
+    osch = O.build_schedule(0.0, 3.0, 0.01, list(lags), alg, saveat_times=sv)
+    dW = cases.increments(osch, 2, n)
+    sim = S.solve(S.EnsembleProblem(prob, p_batch=pb), cases.ALG_MAP[alg], S.EnsembleB200(device=0), trajectories=n,
+                  noise_increments=dW, **kw)
+
+    def hist(pp, t):
+        one = np.ones(n)
+        return np.stack([np.cos(pp[0] * t) * one, (0.5 + 0.1 * t * t) * one])
+
+    ref, _ = O.solve_ensemble(om, pb if ptraj else p, [1.0, 0.5], [0.0, 0.0], [0.0, 0.0], list(lags), osch, alg, dW, history_fn=hist)
+    assert cases.scaled_err(sim.out, ref) < 1e-12
+    # the history really matters: an affine stand-in gives different paths
+    ref_aff, _ = O.solve_ensemble(om, pb if ptraj else p, [1.0, 0.5], [1.0, 0.5], [0.0, 0.0], list(lags), osch, alg, dW)
+    assert cases.scaled_err(ref, ref_aff) > 1e-3
+
+
+def test_user_model_history_argument_checks():
+    um = S.UserModel(SRC_H, 2, 2, 2, 2, True, history=True)
+    plain = S.UserModel(SRC, 2, 1, 2, 3, True)
+    with pytest.raises(ValueError):
+        S.SDDEProblem(um.f, um.g, [1.0, 0.5], 1.0, (0.0, 1.0), [1.0, 0.1], constant_lags=(0.5, 1.0))
+    with pytest.raises(AttributeError):
+        plain.h

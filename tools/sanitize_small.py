@@ -1,0 +1,31 @@
+"""Small end-to-end workload for compute-sanitizer (memcheck / racecheck): every kernel family once, tiny sizes."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import numpy as np
+import sdde_b200 as S
+import cases
+
+def run(case, n=777, **kw):
+    return S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0), trajectories=n, seed=3,
+                   moments=True, **case.solve_kwargs(), **kw)
+
+for case in (cases.c1(T=3.0), cases.c2(T=40.0), cases.c3(T=40.0), cases.c3(order0=2, T=40.0, alg=3), cases.c2(T=30.0, alg=4),
+             cases.c4(T=4.0), cases.sir(T=4.0, dt=0.02), cases.scalar_add(T=3.0), cases.hayes(T=2.0)):
+    sim = run(case)
+    print(case.name, "ok", float(np.asarray(sim.out)[-1].mean()), flush=True)
+# supplied increments, per-trajectory parameters, several waves, device output, quantiles
+case = cases.c1(T=2.0)
+sch = case.oracle_schedule()
+dW = cases.increments(sch, 1, 300)
+sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, wave_traj=128), trajectories=300,
+              noise_increments=dW, **case.solve_kwargs())
+simd = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), trajectories=5000, seed=9,
+               **case.solve_kwargs())
+q = S.timeseries_steps_quantile(simd, [0.05, 0.95], median=True)
+print("quantiles ok", q.shape, flush=True)
+ea = S.EnsembleB200(device=0, lanes_per_traj=4)
+c4 = cases.c4(T=2.0)
+simc = S.solve(S.EnsembleProblem(c4.problem()), S.EM(), ea, trajectories=333, seed=3, **c4.solve_kwargs())
+print("coop ok", flush=True)
