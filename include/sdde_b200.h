@@ -129,6 +129,11 @@ typedef struct sdde_desc {
     int32_t n_save_idxs;              /* save_idxs keyword (src/solve.jl:355-356): 0 = save every state, else the number of */
     int32_t save_idxs[SDDE_MAX_STATE];/*   0-based state indices that are saved (out/moments then have n_save_idxs rows per save) */
     int32_t reserved1;
+    const double *noise_t;            /* SDDE_NOISE_SUPPLIED_GRID only: NULL = `noise` holds W on the schedule's own nodes
+                                         ([n_steps+1] rows per channel); else the n_noise_t ascending grid times of a
+                                         NoiseGrid(t, W) on ANY grid covering [t0, tf] -- W(t) is then interpolated
+                                         linearly at the step ends like [EXT] DiffEqNoiseProcess NoiseGrid does */
+    int64_t n_noise_t;
 } sdde_desc;
 
 /* Host-side schedule (trajectory independent): the replay of src/solve.jl:574-610 time stepping with

@@ -44,6 +44,7 @@ Base.@kwdef mutable struct SddeDesc
     n_traj::Int64 = 0; traj_offset::Int64 = 0; seed::UInt64 = 0
     out_pitch::Int64 = 0
     n_save_idxs::Int32 = 0; save_idxs::NTuple{8, Int32} = ntuple(_ -> Int32(0), 8); reserved1::Int32 = 0
+    noise_t::Ptr{Float64} = C_NULL; n_noise_t::Int64 = 0
 end
 
 alg_id(::EM{true}) = Int32(0); alg_id(::EM{false}) = Int32(1)

@@ -754,3 +754,40 @@ def ensemble_quantiles(paths, probs, want_median=False):
         if want_median:
             res[i, -1] = julia_median(row)
     return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# Supplied NoiseGrid(t, W) on its own time grid: [EXT] DiffEqNoiseProcess interpolate!(::NoiseGrid, u, p, t)
+# (searchsortedfirst at t - 10 eps, exact-node shortcuts, linear interpolant) and calculate_step!'s snap of the last
+# node (|t - ts[end]| < 100 eps), evaluated at the schedule's nodes.  Checker for the library's noise_regrid_kernel.
+# ---------------------------------------------------------------------------------------------------
+def noise_grid_on_nodes(ts, W, t_nodes):
+    """W[n_grid, c, traj] on grid ts -> W at t_nodes, [len(t_nodes), c, traj]."""
+    ts = np.asarray(ts, dtype=np.float64)
+    W = np.asarray(W, dtype=np.float64)
+    eps = np.finfo(np.float64).eps
+    out = np.empty((len(t_nodes),) + W.shape[1:], dtype=np.float64)
+    for k, t in enumerate(np.asarray(t_nodes, dtype=np.float64)):
+        if abs(t - ts[-1]) < 100.0 * eps:
+            t = ts[-1]
+        if t > ts[-1] or t < ts[0]:
+            raise ValueError("Solution interpolation cannot extrapolate past the final timepoint")
+        i = int(np.searchsorted(ts, t - 10.0 * eps, side="left"))
+        if i < len(ts) and ts[i] == t:
+            out[k] = W[i]
+        elif i > 0 and ts[i - 1] == t:
+            out[k] = W[i - 1]
+        else:
+            th = (t - ts[i - 1]) / (ts[i] - ts[i - 1])
+            out[k] = (1.0 - th) * W[i - 1] + th * W[i]
+    return out
+
+
+def noise_grid_increments(W_nodes):
+    """calculate_step!/accept_step! bookkeeping: dW_n = W(t_{n+1}) - curW, curW += dW_n (curW starts at W(t0))."""
+    cur = W_nodes[0].copy()
+    dW = np.empty((W_nodes.shape[0] - 1,) + W_nodes.shape[1:], dtype=np.float64)
+    for n in range(dW.shape[0]):
+        dW[n] = W_nodes[n + 1] - cur
+        cur = cur + dW[n]
+    return dW

@@ -38,6 +38,7 @@ class SddeDesc(C.Structure):
         ("saveat", C.c_void_p), ("tstops", C.c_void_p), ("noise", C.c_void_p),
         ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64), ("out_pitch", C.c_int64),
         ("n_save_idxs", C.c_int32), ("save_idxs", C.c_int32 * 8), ("reserved1", C.c_int32),
+        ("noise_t", C.c_void_p), ("n_noise_t", C.c_int64),
     ]
 
 

@@ -171,4 +171,27 @@ std::string build_schedule(const ScheduleInput &in, Schedule &S) {
     return std::string();
 }
 
+std::string plan_noise_grid(const std::vector<double> &t_nodes, const double *ts, int64_t n_ts, std::vector<GridNode> &out) {
+    out.clear();
+    if (n_ts < 2) return "a NoiseGrid needs at least two grid times";
+    for (int64_t i = 1; i < n_ts; ++i)
+        if (!(ts[i] > ts[i - 1])) return "NoiseGrid times must be strictly ascending";
+    const double eps64 = std::numeric_limits<double>::epsilon();
+    for (double t : t_nodes) {
+        if (std::fabs(t - ts[n_ts - 1]) < 100.0 * eps64) t = ts[n_ts - 1];        // calculate_step!(::NoiseGrid)
+        if (t > ts[n_ts - 1] || t < ts[0]) return "NoiseGrid does not cover the time span (cannot extrapolate)";
+        const int64_t i = std::lower_bound(ts, ts + n_ts, t - 10.0 * eps64) - ts;    // searchsortedfirst(ts, t - 10eps)
+        GridNode g;
+        if (i < n_ts && ts[i] == t) { g.lo = g.hi = (int32_t)i; g.theta = 1.0; }
+        else if (i > 0 && ts[i - 1] == t) { g.lo = g.hi = (int32_t)(i - 1); g.theta = 1.0; }
+        else {
+            if (i <= 0 || i >= n_ts) return "NoiseGrid does not cover the time span (cannot extrapolate)";
+            g.lo = (int32_t)(i - 1); g.hi = (int32_t)i;
+            g.theta = (t - ts[i - 1]) / (ts[i] - ts[i - 1]);
+        }
+        out.push_back(g);
+    }
+    return std::string();
+}
+
 }  // namespace sdde

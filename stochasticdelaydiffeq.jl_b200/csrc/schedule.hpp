@@ -53,4 +53,10 @@ struct Schedule {
 // Returns empty string on success, else an error message.
 std::string build_schedule(const ScheduleInput &in, Schedule &out);
 
+// Where the schedule's nodes t_0..t_N fall on the grid of a supplied NoiseGrid(ts, W): W(t_k) = W[lo] if lo == hi, else
+// (1 - theta) W[lo] + theta W[hi].  Mirrors [EXT] DiffEqNoiseProcess interpolate!(::NoiseGrid, u, p, t) (searchsortedfirst
+// at t - 10 eps, exact-node shortcuts, linear interpolant) and calculate_step!'s snap of the last node (100 eps).
+struct GridNode { int32_t lo, hi; double theta; };
+std::string plan_noise_grid(const std::vector<double> &t_nodes, const double *ts, int64_t n_ts, std::vector<GridNode> &out);
+
 }  // namespace sdde

@@ -84,6 +84,7 @@ struct sdde_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
     DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
+    DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
     PinnedBuf h_status, h_mom;
     DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
     DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
@@ -200,6 +201,18 @@ __global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, doubl
     out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// W on an arbitrary NoiseGrid -> W on the schedule's nodes (rows (k, c) of dst), linear in time; see plan_noise_grid.
+__global__ void __launch_bounds__(256) noise_regrid_kernel(const double *__restrict__ src, long long spitch, long long soff,
+                                                           const GridNode *__restrict__ nodes, int nc, long long nt,
+                                                           double *__restrict__ dst, long long dpitch) {
+    const long long row = blockIdx.y;                       // k * nc + c
+    const GridNode g = nodes[row / nc];
+    const int c = (int)(row % nc);
+    const double *lo = src + ((long long)g.lo * nc + c) * spitch + soff, *hi = src + ((long long)g.hi * nc + c) * spitch + soff;
+    for (long long tr = (long long)blockIdx.x * 256 + threadIdx.x; tr < nt; tr += (long long)gridDim.x * 256)
+        dst[row * dpitch + tr] = g.lo == g.hi ? hi[tr] : (1.0 - g.theta) * lo[tr] + g.theta * hi[tr];
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
@@ -234,6 +247,8 @@ int check_desc(const sdde_desc *d) {
         return fail(SDDE_ERR_BAD_DESC, "noise_mode = %d", d->noise_mode);
     if (d->noise_mode != SDDE_NOISE_PHILOX && !d->noise && d->n_traj > 0)
         return fail(SDDE_ERR_BAD_DESC, "noise_mode is SUPPLIED but noise is NULL");
+    if (d->noise_t && (d->noise_mode != SDDE_NOISE_SUPPLIED_GRID || d->n_noise_t < 2))
+        return fail(SDDE_ERR_BAD_DESC, "noise_t needs noise_mode = SDDE_NOISE_SUPPLIED_GRID and n_noise_t >= 2");
     if (d->param_stride != 0 && d->param_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "param_stride < n_traj");
     if (d->u0_stride != 0 && d->u0_stride < d->n_traj) return fail(SDDE_ERR_BAD_DESC, "u0_stride < n_traj");
     if (d->n_save_idxs < 0 || d->n_save_idxs > d->n_state) return fail(SDDE_ERR_BAD_DESC, "n_save_idxs out of range");
@@ -506,6 +521,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
     c->h_status.release(); c->h_mom.release(); c->gather.release();
+    c->noise_src.release(); c->noise_nodes.release();
     c->qs_rows.release(); c->qs_hist.release(); c->qs_paths.release(); c->qs_cand.release();
     c->user.clear();
     if (c->compute) cudaStreamDestroy(c->compute);
@@ -656,7 +672,16 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     const bool need_stage = (d->want_paths && !out_dev) || (!d->want_paths && d->want_moments);
     const bool noise_host = d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem == SDDE_MEM_HOST;
     const int64_t noise_rows = (d->noise_mode == SDDE_NOISE_PHILOX) ? 0 : (N + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * NC;
-    const double bytes_per_traj = 8.0 * ((double)S.ring_slots * NS + (need_stage ? 2.0 * rows : 0.0) + (noise_host ? (double)noise_rows : 0.0) + NS + K.n_param) + 1.0;
+    // NoiseGrid on its own time grid: W is interpolated onto the schedule's nodes on the device first (noise_regrid_kernel)
+    const bool regrid = d->noise_mode == SDDE_NOISE_SUPPLIED_GRID && d->noise_t != nullptr;
+    const int64_t src_rows = regrid ? d->n_noise_t * NC : noise_rows;
+    std::vector<sdde::GridNode> grid_nodes;
+    if (regrid) {
+        const std::string gerr = sdde::plan_noise_grid(S.t, d->noise_t, d->n_noise_t, grid_nodes);
+        if (!gerr.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", gerr.c_str());
+    }
+    const double bytes_per_traj = 8.0 * ((double)S.ring_slots * NS + (need_stage ? 2.0 * rows : 0.0) + (noise_host ? (double)src_rows : 0.0) +
+                                         (regrid ? (double)noise_rows : 0.0) + NS + K.n_param) + 1.0;
     int64_t wave = c->opt_wave_traj > 0 ? c->opt_wave_traj : ((int64_t)1 << 20);
     if (c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > ((int64_t)1 << 19)) wave = (int64_t)1 << 19;  // pipeline D2H (PCIe-bound: few, wide waves)
     const int64_t mem_cap = (int64_t)((double)free_b * 0.80 / bytes_per_traj);
@@ -705,7 +730,15 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         CU_CHECK(c->out[0].reserve((size_t)std::max<int64_t>(1, rows) * pitch * 8));
         if (n_waves > 1 && d->want_paths) CU_CHECK(c->out[1].reserve((size_t)std::max<int64_t>(1, rows) * pitch * 8));
     }
-    if (noise_host) CU_CHECK(c->noise.reserve((size_t)std::max<int64_t>(1, noise_rows) * pitch * 8));
+    DevBuf &noise_in = regrid ? c->noise_src : c->noise;      // where host-supplied rows are staged
+    if (noise_host) CU_CHECK(noise_in.reserve((size_t)std::max<int64_t>(1, src_rows) * pitch * 8));
+    if (regrid) {
+        CU_CHECK(c->noise.reserve((size_t)std::max<int64_t>(1, noise_rows) * pitch * 8));
+        CU_CHECK(c->noise_nodes.reserve(grid_nodes.size() * sizeof(sdde::GridNode)));
+        CU_CHECK(cudaMemcpyAsync(c->noise_nodes.p, grid_nodes.data(), grid_nodes.size() * sizeof(sdde::GridNode), cudaMemcpyHostToDevice, c->compute));
+        CU_CHECK(cudaStreamSynchronize(c->compute));
+        h2d += (int64_t)(grid_nodes.size() * sizeof(sdde::GridNode));
+    }
     if (d->u0_stride != 0) CU_CHECK(c->u0.reserve((size_t)NS * pitch * 8));
     if (d->param_stride != 0) CU_CHECK(c->ptraj.reserve((size_t)std::max(1, K.n_param) * pitch * 8));
     if (status) { CU_CHECK(c->status.reserve((size_t)NT + (size_t)pitch)); CU_CHECK(c->h_status.reserve((size_t)NT)); }   // all waves: ONE D2H at the end
@@ -762,8 +795,8 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
                 h2d += nt * 8 * K.n_param;
             }
             if (noise_host) {
-                CU_CHECK(cudaMemcpy2DAsync(c->noise.p, pitch * 8, d->noise + off, NT * 8, nt * 8, noise_rows, cudaMemcpyHostToDevice, c->copy_in));
-                h2d += nt * 8 * noise_rows;
+                CU_CHECK(cudaMemcpy2DAsync(noise_in.p, pitch * 8, d->noise + off, NT * 8, nt * 8, src_rows, cudaMemcpyHostToDevice, c->copy_in));
+                h2d += nt * 8 * src_rows;
             }
             CU_CHECK(cudaEventRecord(c->ev_in, c->copy_in));
             CU_CHECK(cudaStreamWaitEvent(c->compute, c->ev_in, 0));
@@ -771,8 +804,16 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         A.u0 = d->u0_stride != 0 ? (const double *)c->u0.p : nullptr; A.u0_pitch = pitch;
         A.ptraj = d->param_stride != 0 ? (const double *)c->ptraj.p : nullptr; A.p_pitch = pitch;
         if (d->noise_mode != SDDE_NOISE_PHILOX) {
-            if (noise_host) { A.noise = (const double *)c->noise.p; A.noise_pitch = pitch; A.noise_off = 0; }
+            if (noise_host) { A.noise = (const double *)noise_in.p; A.noise_pitch = pitch; A.noise_off = 0; }
             else { A.noise = d->noise; A.noise_pitch = NT; A.noise_off = off; }
+            if (regrid) {
+                const unsigned gx = (unsigned)std::min<int64_t>((nt + 255) / 256, 1024);
+                sdde::noise_regrid_kernel<<<dim3(gx, (unsigned)noise_rows), 256, 0, c->compute>>>(
+                    A.noise, A.noise_pitch, A.noise_off, (const sdde::GridNode *)c->noise_nodes.p, NC, nt, (double *)c->noise.p, pitch);
+                CU_CHECK(cudaGetLastError());
+                ++launches;
+                A.noise = (const double *)c->noise.p; A.noise_pitch = pitch; A.noise_off = 0;
+            }
         }
         A.status = status ? (unsigned char *)c->status.p + off : nullptr;
         A.n_traj = nt;
@@ -902,6 +943,7 @@ int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc 
     for (int r = 0; r < n_ctx; ++r) if (!ctxs[r]) return fail(SDDE_ERR_BAD_DESC, "context %d is NULL", r);
     int rc = check_desc(d);
     if (rc) return rc;
+    if (d->noise_t) return fail(SDDE_ERR_UNSUPPORTED, "sdde_b200_solve_multi takes supplied noise on the schedule's own nodes only");
     if (d->out_mem != SDDE_MEM_HOST || (d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem != SDDE_MEM_HOST))
         return fail(SDDE_ERR_UNSUPPORTED, "sdde_b200_solve_multi takes host buffers only");
     if (d->model_id >= SDDE_MODEL_USER_BASE) return fail(SDDE_ERR_UNSUPPORTED, "user models are compiled per context: use one context per call");

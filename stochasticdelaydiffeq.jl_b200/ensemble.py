@@ -81,7 +81,7 @@ class _Marshalled:
 
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
-             want_moments, lanes_per_traj=0, save_idxs=None) -> _Marshalled:
+             want_moments, lanes_per_traj=0, save_idxs=None, noise_t=None) -> _Marshalled:
     if not isinstance(alg, (EM, RKMil, EulerHeun)):
         raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil and EulerHeun, fixed step)")
     if adaptive is None:
@@ -143,6 +143,9 @@ def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_
         d.u0, d.u0_stride = capi.np_ptr(uu).value, 0
     d.noise_mode, d.noise_mem = noise_mode, noise_mem
     d.noise = noise
+    if noise_t is not None:
+        m.keep.append(noise_t)
+        d.noise_t, d.n_noise_t = capi.np_ptr(noise_t).value, noise_t.size
     d.out_mem = out_mem
     d.history_mode = 0
     d.lanes_per_traj = int(lanes_per_traj)
@@ -431,7 +434,9 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     """Ensemble solve on the B200 path.  ``prob`` is an ``EnsembleProblem`` (or an ``SDDEProblem`` -> one trajectory).
 
     noise_increments[n_steps, n_chan, trajectories]  supplied dW (validation; reference: prob.noise branch src/solve.jl:340-353)
-    noise_grid[n_steps+1, n_chan, trajectories]      W on the schedule's nodes (NoiseGrid semantics)
+    noise_grid[n_steps+1, n_chan, trajectories]      W on the schedule's nodes (NoiseGrid semantics), or a tuple
+                   (t[n_grid], W[n_grid, n_chan, trajectories]) = NoiseGrid(t, W) on any grid covering tspan (W is
+                   interpolated linearly at the step ends, like the reference's NoiseGrid)
     out                                               preallocated result buffer: numpy (ideally pinned) or torch CUDA tensor
     """
     if callback is not None:
@@ -461,6 +466,13 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
 
     t0w = time.perf_counter()
     noise_mode, noise_mem, noise_ptr, keep = capi.NOISE_PHILOX, capi.MEM_HOST, None, []
+    grid_t = None
+    if isinstance(noise_grid, tuple):                # NoiseGrid(t, W) on its own time grid
+        grid_t = np.ascontiguousarray(noise_grid[0], dtype=np.float64)
+        noise_grid = noise_grid[1]
+        if grid_t.ndim != 1 or grid_t.size != noise_grid.shape[0]:
+            raise ValueError("noise_grid=(t, W): t must be 1-d with one entry per row of W")
+        keep.append(grid_t)
     nz = noise_increments if noise_increments is not None else noise_grid
     if nz is not None:
         noise_mode = capi.NOISE_SUPPLIED_DW if noise_increments is not None else capi.NOISE_SUPPLIED_GRID
@@ -479,7 +491,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
                  save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=lo, seed=seed,
                  p_batch=p_batch, u0_batch=u0_batch, noise=noise_ptr, noise_mode=noise_mode, noise_mem=noise_mem,
                  out_mem=capi.MEM_DEVICE if ea.output == "device" else capi.MEM_HOST, want_paths=paths,
-                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj, save_idxs=save_idxs)
+                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj, save_idxs=save_idxs, noise_t=grid_t)
     d = m.desc
     skey = (d.alg, d.t0, d.tf, d.dt, tuple(d.lags[i] for i in range(d.n_lag)), d.order_discontinuity_t0,
             d.constant_lags_declared, d.save_start, d.save_end, d.save_everystep, m.keep[0].tobytes(), m.keep[1].tobytes())
@@ -492,7 +504,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     n_save, n_steps, save_t = _sched_cache["n_save"], _sched_cache["n_steps"], _sched_cache["save_t"].copy()
     if nz is not None:
         need = n_steps + (1 if noise_mode == capi.NOISE_SUPPLIED_GRID else 0)
-        if nz.shape[0] < need:
+        if grid_t is None and nz.shape[0] < need:
             raise ValueError(f"supplied noise has {nz.shape[0]} rows, the schedule needs {need}")
 
     n_saved = model.n_state if save_idxs is None else len(np.atleast_1d(save_idxs))

@@ -127,6 +127,38 @@ def test_noise_grid_mode():
     assert cases.scaled_err(sim.out, ref) < TOL
 
 
+@pytest.mark.parametrize("on_device", [False, True])
+def test_noise_grid_on_its_own_time_grid(on_device):
+    """NoiseGrid(t, W) whose grid is unrelated to the step grid (irregular spacing, a few shared nodes, last node a few
+    ulps off tf): W is interpolated at the step ends on the device; C3-shaped problem (clipped steps at the lag multiples),
+    two waves."""
+    import sdde_oracle as O
+    case = cases.c3(T=40.0)
+    sch = case.oracle_schedule()
+    n = 300
+    rng = np.random.default_rng(77)
+    gaps = rng.uniform(0.004, 0.09, size=1200)
+    ts = np.concatenate([[0.0], np.cumsum(gaps)])
+    ts = ts[ts < 40.0]
+    ts = np.unique(np.concatenate([ts, [0.05, 0.1, 17.02, 20.0], [40.0 * (1 + 3e-16)]]))
+    Wg = np.cumsum(np.sqrt(np.diff(ts, prepend=ts[0]))[:, None, None] * rng.standard_normal((ts.size, 1, n)), axis=0)
+    Wn = O.noise_grid_on_nodes(ts, Wg, sch.t)
+    dW = O.noise_grid_increments(Wn)
+    ref, _ = case.oracle(dW)
+    W_in = Wg
+    if on_device:
+        import torch
+        W_in = torch.from_numpy(Wg).cuda()
+    sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0, wave_traj=256), trajectories=n,
+                  noise_grid=(ts, W_in), **case.solve_kwargs())
+    assert sim.timing["waves"] == 2
+    assert cases.scaled_err(sim.out, ref) < TOL
+    short = ts[ts < 30.0]
+    with pytest.raises(S.SddeError):
+        S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0), trajectories=n,
+                noise_grid=(short, Wg[:short.size]), **case.solve_kwargs())
+
+
 def test_per_trajectory_params_and_u0():
     case = cases.c1(T=5.0)
     n = 700

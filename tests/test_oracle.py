@@ -206,3 +206,14 @@ def test_oracle_quantile_definition_known_answers():
     x = rng.standard_normal(1001)
     for p in (0.05, 0.3, 0.95):
         assert abs(O.julia_quantile(x, p) - np.quantile(x, p)) < 1e-14      # numpy 'linear' = the same type-7 definition
+
+
+def test_oracle_noise_grid_interpolation_known_answers():
+    """NoiseGrid lookups: exact nodes return the stored row, interior times the linear interpolant, the last node snaps."""
+    ts = np.array([0.0, 0.5, 2.0])
+    W = np.array([0.0, 1.0, 4.0]).reshape(3, 1, 1)
+    got = O.noise_grid_on_nodes(ts, W, [0.0, 0.25, 0.5, 1.25, 2.0 - 2e-16])[:, 0, 0]
+    assert np.array_equal(got, [0.0, 0.5, 1.0, 2.5, 4.0])
+    assert np.array_equal(O.noise_grid_increments(W)[:, 0, 0], [1.0, 3.0])
+    with pytest.raises(ValueError):
+        O.noise_grid_on_nodes(ts, W, [2.5])
