@@ -1097,7 +1097,8 @@ int sdde_b200_quantiles(sdde_ctx *c, const double *paths, int32_t mem, int64_t n
     for (int r = 0; r < R; ++r) ranks.k[r] = plan.ranks[(size_t)r];
     const size_t smem = (size_t)R * sdde::QS_BINS * sizeof(unsigned int);
     CU_CHECK(c->qs_cand.reserve((size_t)n_rows * R * sdde::QS_CAP * 8));
-    CU_CHECK(cudaFuncSetAttribute(sdde::qs_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int pass = 0; pass < sdde::QS_PASSES; ++pass)
+        CU_CHECK(cudaFuncSetAttribute(sdde::qs_stream_fn(pass), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // enough CTAs to fill the machine, but no slice shorter than 8192 values
     int64_t split = (8 * (int64_t)c->sm_count + n_rows - 1) / n_rows;
     split = std::max<int64_t>(1, std::min<int64_t>(split, (n_traj + 8191) / 8192));
@@ -1106,8 +1107,8 @@ int sdde_b200_quantiles(sdde_ctx *c, const double *paths, int32_t mem, int64_t n
     sdde::qs_init_kernel<<<(unsigned)n_rows, 32, 0, c->compute>>>((sdde::QsRow *)c->qs_rows.p, R, ranks);
     for (int pass = 0; pass < sdde::QS_PASSES; ++pass) {
         CU_CHECK(cudaMemsetAsync(c->qs_hist.p, 0, hist_bytes, c->compute));
-        sdde::qs_stream_kernel<<<dim3((unsigned)split, (unsigned)n_rows), sdde::QS_THREADS, smem, c->compute>>>(
-            src, pitch, n_traj, R, pass, (sdde::QsRow *)c->qs_rows.p, (unsigned int *)c->qs_hist.p, (unsigned long long *)c->qs_cand.p);
+        sdde::qs_stream_fn(pass)<<<dim3((unsigned)split, (unsigned)n_rows), sdde::QS_THREADS, smem, c->compute>>>(
+            src, pitch, n_traj, R, (sdde::QsRow *)c->qs_rows.p, (unsigned int *)c->qs_hist.p, (unsigned long long *)c->qs_cand.p);
         sdde::qs_scan_kernel<<<(unsigned)n_rows, 32 * R, 0, c->compute>>>((sdde::QsRow *)c->qs_rows.p, (const unsigned int *)c->qs_hist.p,
                                                                           (const unsigned long long *)c->qs_cand.p, R, pass);
     }

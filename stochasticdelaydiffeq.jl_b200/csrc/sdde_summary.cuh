@@ -3,9 +3,9 @@
 // Device half of sdde_b200_quantiles: for every saved row out[k][j][0..n_traj) select a handful of order statistics
 // (the neighbours Statistics.quantile / Statistics.median need, see summary.hpp) WITHOUT sorting the row:
 // most-significant-digit radix selection on the order-preserving 64-bit image of the doubles, 11 bits per pass
-// (6 passes).  Every pass streams the rows once, coalesced, builds per-CTA histograms in shared memory with
-// warp-aggregated atomics (the saved states of one time point share sign, exponent and leading mantissa bits, so
-// un-aggregated atomics would serialise on one bin), and a small scan kernel narrows every rank to one bin.
+// (at most 6 passes).  Every pass streams the rows once, coalesced, builds per-CTA histograms in shared memory
+// (the saved states of one time point share sign, exponent and leading mantissa bits, so
+// per-thread runs of one bin are accumulated in a register first), and a small scan kernel narrows every rank to one bin.
 // Ranks whose selected prefixes still coincide share one histogram ("leaders"), so median + two quantiles cost
 // three histograms in the early passes, not six.  HBM-bound: 6 x 8 B per saved value.
 #pragma once
@@ -53,13 +53,16 @@ __global__ void qs_init_kernel(QsRow *rows, int n_rank, QsRanks ranks) {
 }
 
 // One streaming pass over the rows.  grid (n_split, n_rows); dynamic shared memory n_rank * QS_BINS counters.
-//   row in HIST mode   : histogram of digit `pass` of the values that share a leader's prefix
+//   row in HIST mode   : histogram of digit PASS of the values that share a leader's prefix
 //   row in GATHER mode : append those values' keys to the leader's candidate list (they are few)
 //   row DONE           : nothing
 // From the second pass on almost no value belongs to any leader, so the inner loop first looks the value's PREVIOUS
-// digit up in a 2048-entry table of "leaders that chose this digit" and only then compares whole prefixes.
+// digit up in a 2048-entry table of "leaders that chose this digit" and only then compares whole prefixes.  Histogram
+// increments go through a thread-private run (bin, count): the saved states of one time point share sign, exponent and
+// leading mantissa bits, so in the first pass a thread sees one bin for its whole slice and issues one atomic at the end.
+template <int PASS>
 __global__ void __launch_bounds__(QS_THREADS, 3) qs_stream_kernel(const double *__restrict__ paths, long long pitch, long long n,
-                                                                  int n_rank, int pass, QsRow *__restrict__ rows,
+                                                                  int n_rank, QsRow *__restrict__ rows,
                                                                   unsigned int *__restrict__ ghist,
                                                                   unsigned long long *__restrict__ cand) {
     extern __shared__ unsigned int sh[];
@@ -67,6 +70,8 @@ __global__ void __launch_bounds__(QS_THREADS, 3) qs_stream_kernel(const double *
     __shared__ int s_slot[QS_MAX_RANK];
     __shared__ int s_nlead;
     __shared__ unsigned short s_tab[QS_BINS];
+    constexpr int width = PASS < QS_PASSES - 1 ? QS_BITS : 64 - QS_BITS * (QS_PASSES - 1);
+    constexpr int shift = PASS < QS_PASSES - 1 ? 64 - QS_BITS * (PASS + 1) : 0;
     const int row = blockIdx.y;
     QsRow &q = rows[row];
     const int mode = q.mode;
@@ -86,81 +91,78 @@ __global__ void __launch_bounds__(QS_THREADS, 3) qs_stream_kernel(const double *
     __syncthreads();
     const int nlead = s_nlead;
     const bool gather = mode == QS_MODE_GATHER;
-    // a gathering row has fixed digits 0..pass-1, a histogramming row too: the head of a key is everything above digit `pass`
-    const int width = qs_width(pass), shift = qs_shift(pass), bins = 1 << width;
     if (!gather) {
         for (int i = threadIdx.x; i < nlead * QS_BINS; i += QS_THREADS) sh[i] = 0u;
         __syncthreads();
     }
 
     const double *src = paths + (long long)row * pitch;
-    const long long chunk = 32ll * QS_UNROLL;
-    const long long per = ((n + gridDim.x - 1) / gridDim.x + chunk - 1) / chunk * chunk;    // warp-uniform trip counts
+    const long long chunk = (long long)QS_THREADS * QS_UNROLL;
+    const long long per = ((n + gridDim.x - 1) / gridDim.x + chunk - 1) / chunk * chunk;
     const long long lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned long long nan_seen = 0ull;
-    unsigned run_bin = 0u, run_cnt = 0u;          // warp-uniform run of identical (leader, digit) hits, flushed on change
-    for (long long base = lo + (long long)(threadIdx.x >> 5) * chunk; base < hi; base += (QS_THREADS / 32) * chunk) {
+    unsigned nan_seen = 0u;
+    unsigned run_bin = 0u, run_cnt = 0u;          // thread-private run of identical (leader, digit) hits
+    for (long long base = lo + threadIdx.x; base < hi; base += chunk) {
         double x[QS_UNROLL];
 #pragma unroll
         for (int j = 0; j < QS_UNROLL; ++j) {
-            const long long i = base + 32 * j + lane;
+            const long long i = base + (long long)j * QS_THREADS;
             x[j] = i < hi ? __ldg(src + i) : 0.0;
         }
 #pragma unroll
         for (int j = 0; j < QS_UNROLL; ++j) {
-            const bool valid = base + 32 * j + lane < hi;
+            if (base + (long long)j * QS_THREADS >= hi) break;
             const unsigned long long key = qs_key(x[j]);
-            const unsigned digit = (unsigned)(key >> shift) & (unsigned)(bins - 1);
+            const unsigned digit = (unsigned)(key >> shift) & (unsigned)((1 << width) - 1);
             unsigned mine = 1u;                        // leaders this value may belong to
             unsigned long long head = 0ull;
-            if (pass == 0) {
-                if (valid && x[j] != x[j]) ++nan_seen;
-                if (!valid) mine = 0u;
+            if constexpr (PASS == 0) {
+                nan_seen += x[j] != x[j];
             } else {
                 head = key >> (shift + width);
-                mine = valid ? (unsigned)s_tab[(unsigned)head & (QS_BINS - 1)] : 0u;
+                mine = (unsigned)s_tab[(unsigned)head & (QS_BINS - 1)];
             }
-            unsigned todo = __reduce_or_sync(0xffffffffu, mine);
-            while (todo) {
-                const int l = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const bool hit = ((mine >> l) & 1u) && head == s_prefix[l];
-                const unsigned hits = __ballot_sync(0xffffffffu, hit);
-                if (hits == 0u) continue;
+            while (mine) {
+                const int l = __ffs(mine) - 1;
+                mine &= mine - 1;
+                if (head != s_prefix[l]) continue;
                 if (gather) {
-                    if (hit) {
-                        const unsigned pos = atomicAdd(&q.n_cand[s_slot[l]], 1u);
-                        if (pos < (unsigned)QS_CAP) cand[((long long)row * n_rank + s_slot[l]) * QS_CAP + pos] = key;
-                    }
-                    continue;
-                }
-                // the saved states of one time point share their leading bits: one atomic per warp when all digits agree
-                const unsigned first = __shfl_sync(0xffffffffu, digit, __ffs(hits) - 1);
-                if (__ballot_sync(0xffffffffu, hit && digit != first) == 0u) {
-                    const unsigned bin = (unsigned)l * QS_BINS + first;
+                    const unsigned pos = atomicAdd(&q.n_cand[s_slot[l]], 1u);
+                    if (pos < (unsigned)QS_CAP) cand[((long long)row * n_rank + s_slot[l]) * QS_CAP + pos] = key;
+                } else {
+                    const unsigned bin = (unsigned)l * QS_BINS + digit;
                     if (bin != run_bin) {
-                        if (lane == 0 && run_cnt) atomicAdd(&sh[run_bin], run_cnt);
+                        if (run_cnt) atomicAdd(&sh[run_bin], run_cnt);
                         run_bin = bin; run_cnt = 0u;
                     }
-                    run_cnt += (unsigned)__popc(hits);
-                } else if (hit) {
-                    atomicAdd(&sh[l * QS_BINS + digit], 1u);
+                    ++run_cnt;
                 }
             }
         }
     }
     if (gather) return;
-    if (lane == 0 && run_cnt) atomicAdd(&sh[run_bin], run_cnt);
+    if (run_cnt) atomicAdd(&sh[run_bin], run_cnt);
     __syncthreads();
     for (int i = threadIdx.x; i < nlead * QS_BINS; i += QS_THREADS) {
         const unsigned v = sh[i];
         if (v) atomicAdd(&ghist[((long long)row * n_rank + s_slot[i >> QS_BITS]) * QS_BINS + (i & (QS_BINS - 1))], v);
     }
-    if (pass == 0) {
+    if (PASS == 0) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nan_seen += __shfl_xor_sync(0xffffffffu, nan_seen, o);
-        if (lane == 0 && nan_seen) atomicAdd(&q.n_nan, nan_seen);
+        if ((threadIdx.x & 31) == 0 && nan_seen) atomicAdd(&q.n_nan, (unsigned long long)nan_seen);
+    }
+}
+
+typedef void (*QsStreamFn)(const double *, long long, long long, int, QsRow *, unsigned int *, unsigned long long *);
+inline QsStreamFn qs_stream_fn(int pass) {
+    switch (pass) {
+        case 0: return qs_stream_kernel<0>;
+        case 1: return qs_stream_kernel<1>;
+        case 2: return qs_stream_kernel<2>;
+        case 3: return qs_stream_kernel<3>;
+        case 4: return qs_stream_kernel<4>;
+        default: return qs_stream_kernel<5>;
     }
 }
 
