@@ -273,7 +273,8 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        _, cpu_baseline, _ = cpu_reference_run(1, 0)
+        # about 10-15 s of CPU work: 15 000 trajectories per core x 10 000 steps in one pass (plus a short warm-up pass)
+        _, cpu_baseline, _ = cpu_reference_run(1, 0, sample_paths=(os.cpu_count() or 1) * 15000)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
