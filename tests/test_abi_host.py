@@ -226,3 +226,34 @@ def test_randomised_schedules_equal_oracle_bitwise():
             a, b = getattr(s, k), getattr(o, k)
             assert a.shape == b.shape and np.array_equal(a, b), (trial, k, t0, T, dt, lags, alg, order0, saveat)
         assert list(s.tstops_hit) == o.tstops_hit
+
+
+def test_randomised_schedules_with_explicit_saveat_tstops_and_flags():
+    """Explicit saveat vectors (with and without the end points), user tstops, save_start/save_end overrides and
+    undeclared lags: product schedule == oracle replay, bit for bit, on 80 random problems."""
+    rng = np.random.default_rng(77)
+    for trial in range(80):
+        t0 = float(rng.choice([0.0, 1.0]))
+        T = float(rng.choice([2.0, 5.5, 12.0]))
+        tf = t0 + T
+        dt = float(rng.choice([0.01, 0.04, 0.1, 2.0 ** -4]))
+        lag = float(rng.choice([0.5, 1.0, 1.7, 0.33]))
+        alg = int(rng.choice([0, 1, 4]))
+        declared = bool(rng.integers(0, 2))
+        npts = int(rng.integers(1, 9))
+        sv_user = sorted(set(float(np.round(x, 3)) for x in rng.uniform(t0, tf, size=npts)))
+        if rng.integers(0, 2):
+            sv_user = [t0] + sv_user
+        if rng.integers(0, 2):
+            sv_user = sv_user + [tf]
+        tst = sorted(set(float(np.round(x, 2)) for x in rng.uniform(t0, tf, size=int(rng.integers(0, 4)))))
+        prob = S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, (t0, tf), (-1.0, 0.5, 0.2),
+                             constant_lags=(lag,) if declared else (), lags=(lag,))
+        s = S.schedule(prob, cases.ALG_MAP[alg], dt=dt, saveat=sv_user, tstops=tst)
+        sv, ss, se = O.expand_saveat(sv_user, t0, tf)
+        o = O.build_schedule(t0, tf, dt, [lag], alg, constant_lags_declared=declared, saveat_times=sv, save_start=ss, save_end=se,
+                             save_everystep=False, tstops=tst)
+        for k in ["t", "dt", "sqdt", "lk_mode", "lk_idx", "lk_theta", "save_t", "save_step", "save_theta", "save_exact"]:
+            a, b = getattr(s, k), getattr(o, k)
+            assert a.shape == b.shape and np.array_equal(a, b), (trial, k, t0, tf, dt, lag, alg, declared, sv_user, tst)
+        assert list(s.tstops_hit) == o.tstops_hit
