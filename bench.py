@@ -215,6 +215,19 @@ def main():
     # one pass with ensemble moments: exercises the path's only collective (NCCL all-gather + Chan merge)
     simm = one_pass(0, ea_dev, out_dev, True)
     mean_end = float(simm.moments[-1, 0, 1])
+    # the same passes WITH the ensemble mean/variance reduction inside the timed region (moment kernels over the 4 GB of
+    # saved paths + the NCCL all-gather and Chan merge of the triples when N > 1): reported beside `value`
+    barrier_sync()
+    t0m = time.perf_counter()
+    Km = max(1, min(K, 5))
+    for i in range(Km):
+        simm = one_pass(W + i, ea_dev, out_dev, True)
+    barrier_sync()
+    elm = torch.tensor([time.perf_counter() - t0m], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elm, op=dist.ReduceOp.MAX)
+    with_moments = {"value": n_total * n_steps * Km / float(elm[0]), "unit": UNIT, "ms_per_step": float(elm[0]) / Km * 1e3, "steps": Km,
+                    "merge": "NCCL all_gather of (count, mean, M2) + Chan merge" if world > 1 else "single GPU: no collective"}
 
     # ---- end-to-end arm: host buffers, pinned, D2H inside the timed region ----
     e2e = None
@@ -282,7 +295,7 @@ def main():
             "config": dict(WORKLOAD, trajectories_per_gpu=n_traj, trajectories_total=n_total, n_steps=n_steps, n_save=n_save,
                            parallelism=f"trajectory-shard x{world}", ring_slots=timing["ring_slots"],
                            ensemble_mean_at_tf=mean_end),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "e2e": e2e, "with_moments": with_moments, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernel_ms_per_step_max_over_ranks": kms_max}
     print(json.dumps(line))
     if world > 1:

@@ -84,6 +84,7 @@ struct sdde_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
     DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
+    DevBuf mom_part;                 // per-slice moment triples of one wave (moments_kernel -> merge_moments_kernel)
     DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
     PinnedBuf h_status, h_mom;
     DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
@@ -112,40 +113,45 @@ struct sdde_ctx {
 // ------------------------------------------------------------------------------------------------
 namespace sdde {
 
-// (count, mean, M2) of one row of `out` per block: deterministic two-pass reduction.
-// Device side of [EXT] SciMLBase.EnsembleAnalysis.timeseries_steps_meanvar.
+// (count, mean, M2) of one slice of one row of `out` per block, in ONE read of the data: sums of (x - c) and (x - c)^2
+// about c = the slice's first value (a draw from the same distribution, so |c - mean| is a few standard deviations at most
+// and M2 = S2 - S1^2/n loses a few bits, not digits); fixed reduction order => deterministic.  grid (rows, n_split); the
+// slices of a row are Chan-merged in order by merge_moments_kernel.  Device side of
+// [EXT] SciMLBase.EnsembleAnalysis.timeseries_steps_meanvar.
 __global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__ out, long long pitch, long long off,
-                                                      long long n, double *__restrict__ mom) {
-    __shared__ double sh[8];
-    __shared__ double s_mean;
-    const double *row = out + (long long)blockIdx.x * pitch + off;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double s = 0.0;
-    for (long long i = threadIdx.x; i < n; i += 256) s += row[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sh[warp] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += sh[w];
-        s_mean = t / (double)n;
+                                                      long long n, double *__restrict__ part) {
+    __shared__ double sh1[8], sh2[8];
+    const long long rows = gridDim.x, row = blockIdx.x;       // rows on grid.x (save_everystep can exceed 65535 rows)
+    const double *rp = out + row * pitch + off;
+    const long long per = (n + gridDim.y - 1) / gridDim.y;
+    const long long lo = per * blockIdx.y, hi = lo + per < n ? lo + per : n;
+    double *dst = part + ((long long)blockIdx.y * rows + row) * 3;
+    if (hi <= lo) {
+        if (threadIdx.x == 0) { dst[0] = 0.0; dst[1] = 0.0; dst[2] = 0.0; }
+        return;
     }
-    __syncthreads();
-    const double mean = s_mean;
-    double q = 0.0;
-    for (long long i = threadIdx.x; i < n; i += 256) { const double d = row[i] - mean; q += d * d; }
+    const double c = rp[lo];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s1 = 0.0, s2 = 0.0;
+    long long i = lo + threadIdx.x;
+    for (; i + 3 * 256 < hi; i += 4 * 256) {              // four independent loads in flight per thread
+        const double d0 = rp[i] - c, d1 = rp[i + 256] - c, d2 = rp[i + 512] - c, d3 = rp[i + 768] - c;
+        s1 += (d0 + d1) + (d2 + d3);
+        s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    for (; i < hi; i += 256) { const double d = rp[i] - c; s1 += d; s2 += d * d; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    __syncthreads();
-    if (lane == 0) sh[warp] = q;
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) { sh1[warp] = s1; sh2[warp] = s2; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += sh[w];
-        mom[blockIdx.x * 3 + 0] = (double)n;
-        mom[blockIdx.x * 3 + 1] = mean;
-        mom[blockIdx.x * 3 + 2] = t;
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < 8; ++w) { t1 += sh1[w]; t2 += sh2[w]; }
+        const double cnt = (double)(hi - lo);
+        const double m2 = t2 - t1 * (t1 / cnt);
+        dst[0] = cnt;
+        dst[1] = c + t1 / cnt;
+        dst[2] = m2 > 0.0 || m2 != m2 ? m2 : 0.0;
     }
 }
 
@@ -521,7 +527,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
     c->h_status.release(); c->h_mom.release(); c->gather.release();
-    c->noise_src.release(); c->noise_nodes.release();
+    c->noise_src.release(); c->noise_nodes.release(); c->mom_part.release();
     c->qs_rows.release(); c->qs_hist.release(); c->qs_paths.release(); c->qs_cand.release();
     c->user.clear();
     if (c->compute) cudaStreamDestroy(c->compute);
@@ -841,7 +847,19 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         ++launches;
         if (d->want_moments && rows > 0) {
             double *dm = (double *)c->mom.p + (size_t)w * rows * 3;
-            sdde::moments_kernel<<<(unsigned)rows, 256, 0, c->compute>>>(A.out, A.out_pitch, A.out_off, nt, dm);
+            // enough slices per row to fill the machine, none shorter than 16384 values
+            int64_t msplit = (4 * (int64_t)c->sm_count + rows - 1) / rows;
+            msplit = std::max<int64_t>(1, std::min<int64_t>(msplit, (nt + 16383) / 16384));
+            if (msplit == 1) {
+                sdde::moments_kernel<<<dim3((unsigned)rows, 1), 256, 0, c->compute>>>(A.out, A.out_pitch, A.out_off, nt, dm);
+            } else {
+                CU_CHECK(c->mom_part.reserve((size_t)msplit * rows * 3 * 8));
+                sdde::moments_kernel<<<dim3((unsigned)rows, (unsigned)msplit), 256, 0, c->compute>>>(A.out, A.out_pitch, A.out_off, nt,
+                                                                                                   (double *)c->mom_part.p);
+                sdde::merge_moments_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c->compute>>>(
+                    (const double *)c->mom_part.p, rows * 3, (int)msplit, rows, dm);
+                ++launches;
+            }
             CU_CHECK(cudaGetLastError());
             ++launches;
         }
@@ -1102,12 +1120,11 @@ int sdde_b200_quantiles(sdde_ctx *c, const double *paths, int32_t mem, int64_t n
     // enough CTAs to fill the machine, but no slice shorter than 8192 values
     int64_t split = (8 * (int64_t)c->sm_count + n_rows - 1) / n_rows;
     split = std::max<int64_t>(1, std::min<int64_t>(split, (n_traj + 8191) / 8192));
-    if (n_rows > 65535) return fail(SDDE_ERR_UNSUPPORTED, "more than 65535 rows per call");
     CU_CHECK(cudaEventRecord(c->ev_k0, c->compute));
     sdde::qs_init_kernel<<<(unsigned)n_rows, 32, 0, c->compute>>>((sdde::QsRow *)c->qs_rows.p, R, ranks);
     for (int pass = 0; pass < sdde::QS_PASSES; ++pass) {
         CU_CHECK(cudaMemsetAsync(c->qs_hist.p, 0, hist_bytes, c->compute));
-        sdde::qs_stream_fn(pass)<<<dim3((unsigned)split, (unsigned)n_rows), sdde::QS_THREADS, smem, c->compute>>>(
+        sdde::qs_stream_fn(pass)<<<dim3((unsigned)n_rows, (unsigned)split), sdde::QS_THREADS, smem, c->compute>>>(
             src, pitch, n_traj, R, (sdde::QsRow *)c->qs_rows.p, (unsigned int *)c->qs_hist.p, (unsigned long long *)c->qs_cand.p);
         sdde::qs_scan_kernel<<<(unsigned)n_rows, 32 * R, 0, c->compute>>>((sdde::QsRow *)c->qs_rows.p, (const unsigned int *)c->qs_hist.p,
                                                                           (const unsigned long long *)c->qs_cand.p, R, pass);

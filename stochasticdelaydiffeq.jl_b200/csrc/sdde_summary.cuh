@@ -52,7 +52,7 @@ __global__ void qs_init_kernel(QsRow *rows, int n_rank, QsRanks ranks) {
     if (threadIdx.x == 0) { q.n_nan = 0ull; q.mode = QS_MODE_HIST; }
 }
 
-// One streaming pass over the rows.  grid (n_split, n_rows); dynamic shared memory n_rank * QS_BINS counters.
+// One streaming pass over the rows.  grid (n_rows, n_split); dynamic shared memory n_rank * QS_BINS counters.
 //   row in HIST mode   : histogram of digit PASS of the values that share a leader's prefix
 //   row in GATHER mode : append those values' keys to the leader's candidate list (they are few)
 //   row DONE           : nothing
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(QS_THREADS, 3) qs_stream_kernel(const double *
     __shared__ unsigned short s_tab[QS_BINS];
     constexpr int width = PASS < QS_PASSES - 1 ? QS_BITS : 64 - QS_BITS * (QS_PASSES - 1);
     constexpr int shift = PASS < QS_PASSES - 1 ? 64 - QS_BITS * (PASS + 1) : 0;
-    const int row = blockIdx.y;
+    const int row = blockIdx.x;                 // rows on grid.x (may exceed 65535), slices of a row on grid.y
     QsRow &q = rows[row];
     const int mode = q.mode;
     if (mode == QS_MODE_DONE) return;
@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(QS_THREADS, 3) qs_stream_kernel(const double *
 
     const double *src = paths + (long long)row * pitch;
     const long long chunk = (long long)QS_THREADS * QS_UNROLL;
-    const long long per = ((n + gridDim.x - 1) / gridDim.x + chunk - 1) / chunk * chunk;
-    const long long lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
+    const long long per = ((n + gridDim.y - 1) / gridDim.y + chunk - 1) / chunk * chunk;
+    const long long lo = per * blockIdx.y, hi = lo + per < n ? lo + per : n;
     unsigned nan_seen = 0u;
     unsigned run_bin = 0u, run_cnt = 0u;          // thread-private run of identical (leader, digit) hits
     for (long long base = lo + threadIdx.x; base < hi; base += chunk) {
