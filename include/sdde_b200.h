@@ -174,7 +174,9 @@ typedef struct sdde_timing {
     int32_t block_threads;
     int32_t traj_per_thread;
     int32_t moment_merge;      /* sdde_b200_solve_multi: 0 = none, 1 = host Chan merge, 2 = NCCL all-gather + device merge */
-    int32_t reserved;
+    int32_t n_unstable;        /* trajectories of this call that saw a non-finite state (counted on the device, so a caller
+                                  that passes status = NULL -- e.g. a moments-only run of 10^8 trajectories -- still learns
+                                  it without a byte per trajectory crossing PCIe) */
     int64_t ring_bytes;
     char kernel_name[128];
 } sdde_timing;

@@ -58,7 +58,7 @@ class SddeTiming(C.Structure):
         ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("n_steps", C.c_int64), ("n_save", C.c_int64),
         ("launches", C.c_int32), ("waves", C.c_int32), ("ring_slots", C.c_int32), ("regs_per_thread", C.c_int32),
-        ("block_threads", C.c_int32), ("traj_per_thread", C.c_int32), ("moment_merge", C.c_int32), ("reserved", C.c_int32),
+        ("block_threads", C.c_int32), ("traj_per_thread", C.c_int32), ("moment_merge", C.c_int32), ("n_unstable", C.c_int32),
         ("ring_bytes", C.c_int64),
         ("kernel_name", C.c_char * 128),
     ]

@@ -86,7 +86,7 @@ struct sdde_ctx {
     DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
     DevBuf mom_part;                 // per-slice moment triples of one wave (moments_kernel -> merge_moments_kernel)
     DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
-    PinnedBuf h_status, h_mom;
+    PinnedBuf h_status, h_mom, h_count;
     DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
     DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
     bool keep_moments_on_device = false;   // set by solve_multi: leave the wave-merged triples in `mom` for the all-gather
@@ -153,6 +153,15 @@ __global__ void __launch_bounds__(256) moments_kernel(const double *__restrict__
         dst[1] = c + t1 / cnt;
         dst[2] = m2 > 0.0 || m2 != m2 ? m2 : 0.0;
     }
+}
+
+// number of non-zero status bytes (trajectories that saw a non-finite state)
+__global__ void __launch_bounds__(256) count_status_kernel(const unsigned char *__restrict__ st, long long n, unsigned int *__restrict__ cnt) {
+    unsigned int c = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) c += st[i] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, c);
 }
 
 // Chan merge of `parts` arrays of (count, mean, M2) triples, in order: dst[i] = merge(src[0][i], src[1][i], ...).
@@ -526,7 +535,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     cudaDeviceSynchronize();
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
-    c->h_status.release(); c->h_mom.release(); c->gather.release();
+    c->h_status.release(); c->h_mom.release(); c->h_count.release(); c->gather.release();
     c->noise_src.release(); c->noise_nodes.release(); c->mom_part.release();
     c->qs_rows.release(); c->qs_hist.release(); c->qs_paths.release(); c->qs_cand.release();
     c->user.clear();
@@ -747,7 +756,11 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     }
     if (d->u0_stride != 0) CU_CHECK(c->u0.reserve((size_t)NS * pitch * 8));
     if (d->param_stride != 0) CU_CHECK(c->ptraj.reserve((size_t)std::max(1, K.n_param) * pitch * 8));
-    if (status) { CU_CHECK(c->status.reserve((size_t)NT + (size_t)pitch)); CU_CHECK(c->h_status.reserve((size_t)NT)); }   // all waves: ONE D2H at the end
+    const bool track = status != nullptr || tm != nullptr;     // status bytes live on the device either way; D2H only on request
+    if (track) CU_CHECK(c->status.reserve((size_t)NT + (size_t)pitch + 16));   // all waves + a 4-byte counter behind them
+    if (status) CU_CHECK(c->h_status.reserve((size_t)NT));
+    CU_CHECK(c->h_count.reserve(16));
+    unsigned int *d_count = track ? (unsigned int *)((unsigned char *)c->status.p + (((size_t)NT + (size_t)pitch + 3) & ~(size_t)3)) : nullptr;
     if (d->want_moments) CU_CHECK(c->mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves));
     if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
 
@@ -821,7 +834,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
                 A.noise = (const double *)c->noise.p; A.noise_pitch = pitch; A.noise_off = 0;
             }
         }
-        A.status = status ? (unsigned char *)c->status.p + off : nullptr;
+        A.status = track ? (unsigned char *)c->status.p + off : nullptr;
         A.n_traj = nt;
         A.traj_gid0 = d->traj_offset + off;
         if (out_dev) {
@@ -878,6 +891,15 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
     // Status bytes leave in ONE copy after the last wave: a small D2H per wave on the compute stream would queue behind the
     // wave's path copy in the D2H copy engine and stall the next wave's kernel until that copy ends (no overlap at all).
+    if (track) {
+        CU_CHECK(cudaMemsetAsync(d_count, 0, 4, c->compute));
+        sdde::count_status_kernel<<<(unsigned)std::min<int64_t>((NT + 255) / 256, 4 * (int64_t)c->sm_count), 256, 0, c->compute>>>(
+            (const unsigned char *)c->status.p, NT, d_count);
+        CU_CHECK(cudaGetLastError());
+        ++launches;
+        CU_CHECK(cudaMemcpyAsync(c->h_count.p, d_count, 4, cudaMemcpyDeviceToHost, c->compute));
+        d2h += 4;
+    }
     if (status) {
         CU_CHECK(cudaMemcpyAsync(c->h_status.p, c->status.p, (size_t)NT, cudaMemcpyDeviceToHost, c->compute));
         d2h += NT;
@@ -923,6 +945,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         tm->kernel_ms = kernel_ms;
         if (cudaEventElapsedTime(&ms, c->ev_c0, c->ev_c1) == cudaSuccess) tm->d2h_ms = ms;
         tm->h2d_bytes = h2d; tm->d2h_bytes = d2h; tm->launches = launches;
+        tm->n_unstable = (int32_t)std::min<unsigned int>(*(const unsigned int *)c->h_count.p, 0x7fffffffu);
         tm->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     }
     return SDDE_OK;

@@ -531,7 +531,9 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
                 raise ValueError("out must be a C-contiguous float64 array")
             out_ptr = capi.np_ptr(out_arr).value
     mom = np.zeros((n_save, n_saved, 3), dtype=np.float64) if moments else None
-    status = np.zeros(n_traj, dtype=np.uint8)
+    # per-trajectory return codes only make sense with per-trajectory solutions; a moments-only run gets the count
+    status = np.empty(n_traj, dtype=np.uint8) if paths else None
+    status_ptr = capi.np_ptr(status).value if paths else None
     tm = capi.SddeTiming()
     if ea.devices and len(ea.devices) > 1:
         if ea.output != "host":
@@ -540,11 +542,12 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
         tms = (capi.SddeTiming * len(ea.devices))()
         capi.check(capi.lib().sdde_b200_solve_multi(hs, len(ea.devices), C.byref(m.desc), out_ptr,
                                                     capi.np_ptr(mom).value if moments else None,
-                                                    capi.np_ptr(status).value, C.cast(tms, C.c_void_p)))
+                                                    status_ptr, C.cast(tms, C.c_void_p)))
         tm = tms[0]
+        tm.n_unstable = sum(t.n_unstable for t in tms)
     else:
         capi.check(capi.lib().sdde_b200_solve(ctx.handle, C.byref(m.desc), out_ptr,
-                                              capi.np_ptr(mom).value if moments else None, capi.np_ptr(status).value,
+                                              capi.np_ptr(mom).value if moments else None, status_ptr,
                                               C.byref(tm)))
     if moments and ea.distributed and world > 1:
         mom = _allgather_merge_moments(mom, device)
@@ -553,6 +556,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     sim = EnsembleSolution(save_t, out_arr, status, mom, base.scalar_state and n_saved == 1, time.perf_counter() - t0w, tm.as_dict(),
                            traj_offset=lo, n_total=n_total)
     sim.seed = seed
+    sim.n_unstable = int(tm.n_unstable)          # trajectories that saw a non-finite state (ReturnCode.Unstable)
     if single:
         return sim[0] if paths else sim
     return sim

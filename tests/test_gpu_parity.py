@@ -181,7 +181,18 @@ def test_unstable_trajectories_flagged():
     case = cases.c1(T=10.0).with_(p=np.array([300.0, 0.5, 0.2]))   # explicit Euler blows up -> Inf/NaN
     sim, ref, st = run_case(case, 64)
     assert np.all(sim.status == 1) and np.all(st == 1)
-    assert sim.retcodes[0] == "Unstable"
+    assert sim.retcodes[0] == "Unstable" and sim.n_unstable == 64
+    # a moments-only run carries no per-trajectory array, the count comes from the device; mixed stable/unstable ensemble
+    n = 3000
+    pb = np.tile(np.array([[-1.0], [0.5], [0.2]]), (1, n))
+    pb[0, ::3] = 300.0
+    dW = cases.increments(case.oracle_schedule(), 1, n)
+    good = cases.c1(T=10.0)
+    m = S.solve(S.EnsembleProblem(good.problem(), p_batch=pb), S.EM(), S.EnsembleB200(device=0, wave_traj=1024), trajectories=n,
+                noise_increments=dW, paths=False, moments=True, **good.solve_kwargs())
+    assert m.status is None and m.n_unstable == 1000 and m.timing["waves"] == 3
+    stable = S.solve(S.EnsembleProblem(good.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, seed=1, **good.solve_kwargs())
+    assert stable.n_unstable == 0 and int(stable.status.sum()) == 0
 
 
 def test_c4_cooperative_lanes_kernel_matches_oracle_and_thread_kernel():
