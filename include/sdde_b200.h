@@ -193,7 +193,9 @@ SDDE_API void sdde_b200_destroy(sdde_ctx *ctx);
 SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value);  /* "wave_traj" (0 = auto), "batch" (0 = compiled-in
                                                                                     prefetch depth), "mem_limit" (bytes the device workspaces may use, 0 = 80 % of free memory),
                                                                                     "chunk_steps" (schedule records staged per
-                                                                                    shared-memory refill, 1..1024) */
+                                                                                    shared-memory refill, 1..1024), "ramp_start" (trajectories of the first wave when the
+                                                                                    paths leave over PCIe; later waves grow x1.5; default 2^16, measured best on C2),
+                                                                                    "nccl", "jit_linsys" (0/1) */
 
 /* Host only: builds the step/lookup/save schedule for a descriptor (no GPU needed). */
 SDDE_API int sdde_b200_schedule(const sdde_desc *d, sdde_schedule *out);

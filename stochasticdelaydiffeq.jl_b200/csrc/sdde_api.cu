@@ -97,6 +97,7 @@ struct sdde_ctx {
     int64_t opt_wave_traj = 0;     // 0 = auto
     int64_t opt_batch = 0;         // 0 = compiled-in depth
     int64_t opt_chunk_steps = 128;
+    int64_t opt_ramp_start = (int64_t)1 << 16;   // trajectories of the first wave when paths leave over PCIe (host output)
     int64_t opt_mem_limit = 0;     // bytes the workspaces may use (0 = 80 % of the free device memory)
     sdde::UserModels user;
     int sm_count = 148;
@@ -556,6 +557,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "nccl")) c->opt_nccl = value;
     else if (!strcmp(key, "jit_linsys")) c->opt_jit_linsys = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
+    else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
     return SDDE_OK;
@@ -710,7 +712,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     std::vector<int64_t> wave_off, wave_cnt;
     {
         const bool ramp = c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > wave;
-        int64_t cur = ramp ? std::max<int64_t>(per_block, (((int64_t)1 << 16) / per_block) * per_block) : wave;
+        int64_t cur = ramp ? std::max<int64_t>(per_block, (c->opt_ramp_start / per_block) * per_block) : wave;
         for (int64_t off = 0; off < NT;) {
             const int64_t cnt = std::min(std::min(cur, wave), NT - off);
             wave_off.push_back(off); wave_cnt.push_back(cnt);
