@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 from dataclasses import dataclass
 
@@ -457,8 +458,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
 
     device = ea.device if ea.device is not None else (ea.devices[0] if ea.devices else _default_device())
     ctx = capi.get_context(device)
-    if ea.wave_traj:
-        ctx.set_option("wave_traj", ea.wave_traj)
+    ctx.set_option("wave_traj", int(ea.wave_traj or 0))     # per solve: a forced wave size must not leak into later solves
     model = _resolve_model(base, ctx)
     if seed == 0:
         seed = base.seed if base.seed != 0 else int(np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0])  # src/solve.jl:302

@@ -159,6 +159,29 @@ def test_noise_grid_on_its_own_time_grid(on_device):
                 noise_grid=(short, Wg[:short.size]), **case.solve_kwargs())
 
 
+def test_page_locked_host_output_is_written_by_the_kernel_itself():
+    """Host `out` in page-locked memory: the kernel stores the paths straight into it (one wave, no staging copy);
+    pageable `out` and the option switched off take the staged path; all three agree bit for bit."""
+    case = cases.c2(T=40.0)
+    n = 70_000
+    kw = dict(trajectories=n, seed=21, **case.solve_kwargs())
+    prob = S.EnsembleProblem(case.problem())
+    n_save = len(case.oracle_schedule().save_t)
+    pinned = S.pinned_empty((n_save, 1, n))
+    a = S.solve(prob, S.EM(), S.EnsembleB200(device=0), out=pinned, **kw)
+    b = S.solve(prob, S.EM(), S.EnsembleB200(device=0), **kw)                      # pageable numpy output
+    ctx = S.get_context(0)
+    ctx.set_option("zero_copy", 0)
+    try:
+        c = S.solve(prob, S.EM(), S.EnsembleB200(device=0), out=S.pinned_empty((n_save, 1, n)), **kw)
+    finally:
+        ctx.set_option("zero_copy", 1)
+    assert "mapped host out" in a.timing["kernel_name"]
+    assert "mapped host out" not in b.timing["kernel_name"] and "mapped host out" not in c.timing["kernel_name"]
+    assert a.timing["d2h_bytes"] >= n_save * n * 8 and c.timing["d2h_bytes"] >= n_save * n * 8
+    assert np.array_equal(a.out, b.out) and np.array_equal(a.out, c.out) and np.array_equal(a.status, b.status)
+
+
 def test_per_trajectory_params_and_u0():
     case = cases.c1(T=5.0)
     n = 700
