@@ -1,11 +1,10 @@
-// sdde_api.cu -- C ABI of libsdde_b200.so (see include/sdde_b200.h): descriptor validation, host schedule,
-// wave loop over trajectories, launches of the sm_100a step kernels, moments, D2H of the saved paths.
+// sdde_api.cu -- core of the C ABI of libsdde_b200.so (see include/sdde_b200.h): descriptor validation, host schedule,
+// wave loop over trajectories, launches of the sm_100a step kernels, moments, output of the saved paths.
+// (sdde_multi.cu: several GPUs from one process; sdde_summary_api.cu: order statistics; sdde_tools.cu: test hooks.)
 //
 // Replaces the ensemble dispatch [EXT] SciMLBase.__solve(::AbstractEnsembleProblem, alg, ensemblealg; trajectories)
 // -> per trajectory DiffEqBase.__solve (/root/reference/src/solve.jl:1-9) for the fixed-step constant-lag case.
 // No CPU fallback: every compute entry point needs a CUDA device.
-#include <cuda_runtime.h>
-
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -13,24 +12,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
-#include <thread>
-#include <string>
-#include <vector>
 
-#include "../../include/sdde_b200.h"
-#include "schedule.hpp"
+#include "sdde_internal.cuh"
 #include "sdde_dispatch.cuh"
-#include "user_model.hpp"
-#include "nccl_dyn.hpp"
-#include "summary.hpp"
-#include "sdde_summary.cuh"
 
 namespace {
-
 thread_local std::string g_last_error;
+}
 
-int fail(int code, const char *fmt, ...) {
+int sdde_fail(int code, const char *fmt, ...) {
     char buf[2048];
     va_list ap;
     va_start(ap, fmt);
@@ -39,79 +29,11 @@ int fail(int code, const char *fmt, ...) {
     g_last_error = buf;
     return code;
 }
-
-#define CU_CHECK(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-            return fail(SDDE_ERR_CUDA - (int)_e, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
-                        __FILE__, __LINE__);                                                             \
-    } while (0)
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct PinnedBuf {       // page-locked host staging (small D2H results: status bytes, moment triples)
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-}  // namespace
-
-struct sdde_ctx {
-    int device = 0;
-    cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
-    cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
-    DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
-    DevBuf mom_part;                 // per-slice moment triples of one wave (moments_kernel -> merge_moments_kernel)
-    DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
-    PinnedBuf h_status, h_mom, h_count;
-    DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
-    DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
-    bool keep_moments_on_device = false;   // set by solve_multi: leave the wave-merged triples in `mom` for the all-gather
-    int64_t opt_jit_linsys = 1;    // specialise the linear delay system's constants with NVRTC (zeros vanish, no LDCU per entry)
-    std::vector<std::pair<std::string, int>> linsys_jit;   // (shape + parameter bytes) -> user model id
-    int64_t opt_nccl = 1;          // solve_multi: 1 = merge moments with an NCCL all-gather + device merge, 0 = on the host
-    std::mutex mu;
-    int64_t opt_wave_traj = 0;     // 0 = auto
-    int64_t opt_batch = 0;         // 0 = compiled-in depth
-    int64_t opt_chunk_steps = 128;
-    int64_t opt_zero_copy = 1;     // page-locked host `out`: the step kernel stores the saved paths straight into it over PCIe
-    int64_t opt_ramp_start = (int64_t)1 << 16;   // trajectories of the first wave when paths leave over PCIe (host output)
-    int64_t opt_mem_limit = 0;     // bytes the workspaces may use (0 = 80 % of the free device memory)
-    sdde::UserModels user;
-    int sm_count = 148;
-    // schedule cache: repeated solves of the same problem shape (ensemble sweeps, benchmarks) reuse the host schedule
-    // and the packed device tables instead of replaying the time stepping and re-uploading them
-    std::string sched_key, table_key;
-    size_t mem_free_cached = 0;     // cudaMemGetInfo costs up to ~1.5 ms: refreshed only when the problem shape changes
-    std::string mem_key;
-    sdde::Schedule sched;
-};
+const std::string &sdde_last_error_string() { return g_last_error; }
+#define fail sdde_fail
 
 // ------------------------------------------------------------------------------------------------
-// small kernels owned by the API layer
+// small kernels owned by the solve path
 // ------------------------------------------------------------------------------------------------
 namespace sdde {
 
@@ -186,38 +108,6 @@ __global__ void merge_moments_kernel(const double *__restrict__ src, long long p
     dst[3 * i] = cnt; dst[3 * i + 1] = mean; dst[3 * i + 2] = m2;
 }
 
-// test hook: the normals the step kernels would draw, laid out [n][c][traj]
-__global__ void philox_dump_kernel(double *out, long long n_traj, long long traj_off, long long n_steps, int nc, u32 k0,
-                                   u32 k1) {
-    __shared__ double2 ltab[SDDE_RNG_TAB_ENTRIES];
-    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += blockDim.x) ltab[i] = RNG_TAB[i];
-    __syncthreads();
-    u32 rk[20];
-    philox_round_keys(k0, k1, rk);
-    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tr >= n_traj) return;
-    const long long nq = n_steps * nc;
-    for (long long call = 0; call * 4 < nq; ++call) {
-        double z[4];
-        philox_normal_quad((u64)(traj_off + tr), (u64)call, rk, ltab, z);
-        for (int i = 0; i < 4; ++i)
-            if (4 * call + i < nq) out[(4 * call + i) * n_traj + tr] = z[i];
-    }
-}
-
-// FP64 FMA throughput micro-benchmark: 8 independent chains per thread
-__global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, double a, double b) {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-        }
-    }
-    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-}
-
 // W on an arbitrary NoiseGrid -> W on the schedule's nodes (rows (k, c) of dst), linear in time; see plan_noise_grid.
 __global__ void __launch_bounds__(256) noise_regrid_kernel(const double *__restrict__ src, long long spitch, long long soff,
                                                            const GridNode *__restrict__ nodes, int nc, long long nt,
@@ -230,12 +120,12 @@ __global__ void __launch_bounds__(256) noise_regrid_kernel(const double *__restr
         dst[row * dpitch + tr] = g.lo == g.hi ? hi[tr] : (1.0 - g.theta) * lo[tr] + g.theta * hi[tr];
 }
 
-__global__ void __launch_bounds__(256) copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long n) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
-}
-
 }  // namespace sdde
+
+cudaError_t sdde_launch_merge_moments(cudaStream_t stream, const double *src, long long part_stride, int parts, long long n, double *dst) {
+    sdde::merge_moments_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(src, part_stride, parts, n, dst);
+    return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------------------------------
 // descriptor -> schedule input / kernel selection
@@ -478,6 +368,20 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
 }
 
 }  // namespace
+
+int sdde_check_desc(const sdde_desc *d) { return check_desc(d); }
+
+int sdde_plan_sizes(sdde_ctx *ctx, const sdde_desc *d, int64_t *rows, int64_t *noise_rows) {
+    sdde::KernelInfo K;
+    int rc = select_kernel(ctx, d, K);
+    if (rc) return rc;
+    sdde::Schedule S;
+    rc = make_schedule(d, S);
+    if (rc) return rc;
+    *rows = (int64_t)S.save_t.size() * (d->n_save_idxs > 0 ? d->n_save_idxs : d->n_state);
+    *noise_rows = (S.n_steps() + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * (int64_t)K.n_chan;
+    return SDDE_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
@@ -968,140 +872,6 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     return SDDE_OK;
 }
 
-namespace {
-
-// NCCL communicators of a device group, created once per device list (ncclCommInitAll) and kept for the process.
-struct NcclGroup {
-    std::vector<int> devices;
-    std::vector<ncclComm_t> comms;
-};
-std::mutex g_nccl_mu;
-std::vector<NcclGroup *> g_nccl_groups;
-
-NcclGroup *nccl_group_for(const std::vector<int> &devices, std::string &err) {
-    const sdde::NcclApi &N = sdde::nccl_api();
-    if (!N.ok) { err = N.why; return nullptr; }
-    std::lock_guard<std::mutex> lk(g_nccl_mu);
-    for (NcclGroup *g : g_nccl_groups)
-        if (g->devices == devices) return g;
-    NcclGroup *g = new NcclGroup();
-    g->devices = devices;
-    g->comms.assign(devices.size(), nullptr);
-    ncclResult_t r = N.CommInitAll(g->comms.data(), (int)devices.size(), devices.data());
-    if (r != ncclSuccess) { err = std::string("ncclCommInitAll: ") + N.GetErrorString(r); delete g; return nullptr; }
-    g_nccl_groups.push_back(g);
-    return g;
-}
-
-}  // namespace
-
-int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const sdde_desc *d, double *out, double *moments, uint8_t *status,
-                          sdde_timing *tm) {
-    if (!ctxs || n_ctx < 1) return fail(SDDE_ERR_BAD_DESC, "no contexts");
-    for (int r = 0; r < n_ctx; ++r) if (!ctxs[r]) return fail(SDDE_ERR_BAD_DESC, "context %d is NULL", r);
-    int rc = check_desc(d);
-    if (rc) return rc;
-    if (d->noise_t) return fail(SDDE_ERR_UNSUPPORTED, "sdde_b200_solve_multi takes supplied noise on the schedule's own nodes only");
-    if (d->out_mem != SDDE_MEM_HOST || (d->noise_mode != SDDE_NOISE_PHILOX && d->noise_mem != SDDE_MEM_HOST))
-        return fail(SDDE_ERR_UNSUPPORTED, "sdde_b200_solve_multi takes host buffers only");
-    if (d->model_id >= SDDE_MODEL_USER_BASE) return fail(SDDE_ERR_UNSUPPORTED, "user models are compiled per context: use one context per call");
-    if (n_ctx == 1) return sdde_b200_solve(ctxs[0], d, out, moments, status, tm);
-    // trajectory-independent sizes
-    sdde::KernelInfo K;
-    rc = select_kernel(ctxs[0], d, K);
-    if (rc) return rc;
-    sdde::Schedule S;
-    rc = make_schedule(d, S);
-    if (rc) return rc;
-    const int64_t rows = (int64_t)S.save_t.size() * (d->n_save_idxs > 0 ? d->n_save_idxs : d->n_state), NT = d->n_traj;
-    const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;
-    const int64_t per = (NT + n_ctx - 1) / n_ctx;
-    const int64_t noise_rows = (S.n_steps() + (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID ? 1 : 0)) * (int64_t)K.n_chan;
-
-    // The path's single collective: all-gather of the per-GPU moment triples over NCCL + device merge in rank order.
-    NcclGroup *grp = nullptr;
-    std::string nccl_why;
-    if (d->want_moments && rows > 0 && ctxs[0]->opt_nccl && (int64_t)(n_ctx - 1) * per < NT /* every GPU has work */) {
-        std::vector<int> devs;
-        for (int r = 0; r < n_ctx; ++r) devs.push_back(ctxs[r]->device);
-        bool distinct = true;
-        for (int r = 0; r < n_ctx && distinct; ++r) for (int q = 0; q < r; ++q) if (devs[q] == devs[r]) distinct = false;
-        if (distinct) grp = nccl_group_for(devs, nccl_why);
-    }
-    for (int r = 0; r < n_ctx; ++r) ctxs[r]->keep_moments_on_device = (grp != nullptr);
-
-    std::vector<int> rcs((size_t)n_ctx, 0);
-    std::vector<std::string> errs((size_t)n_ctx);
-    std::vector<std::vector<double>> moms((size_t)n_ctx);
-    std::vector<std::thread> th;
-    for (int r = 0; r < n_ctx; ++r) {
-        th.emplace_back([&, r]() {
-            const int64_t lo = std::min(NT, (int64_t)r * per), hi = std::min(NT, lo + per), n = hi - lo;
-            if (n == 0) return;
-            sdde_desc dr = *d;
-            dr.n_traj = n; dr.traj_offset = d->traj_offset + lo; dr.out_pitch = OP;
-            // per-trajectory inputs are [row][stride] arrays: the slice of this GPU starts at column lo.  params/u0 keep
-            // their stride; supplied noise is re-packed densely (its row pitch is n_traj by definition).
-            std::vector<double> nz;
-            if (d->param_stride) dr.params = d->params + lo;
-            if (d->u0_stride) dr.u0 = d->u0 + lo;
-            if (d->noise_mode != SDDE_NOISE_PHILOX) {
-                nz.resize((size_t)std::max<int64_t>(1, noise_rows * n));
-                for (int64_t k = 0; k < noise_rows; ++k) memcpy(nz.data() + k * n, d->noise + k * NT + lo, (size_t)n * 8);
-                dr.noise = nz.data();
-            }
-            if (d->want_moments) moms[(size_t)r].assign((size_t)std::max<int64_t>(1, rows * 3), 0.0);
-            rcs[(size_t)r] = sdde_b200_solve(ctxs[r], &dr, d->want_paths ? out + lo : nullptr,
-                                             d->want_moments ? moms[(size_t)r].data() : nullptr,
-                                             status ? status + lo : nullptr, tm ? tm + r : nullptr);
-            if (rcs[(size_t)r]) errs[(size_t)r] = g_last_error;     // thread-local -> hand to the caller's thread
-        });
-    }
-    for (auto &t : th) t.join();
-    for (int r = 0; r < n_ctx; ++r) ctxs[r]->keep_moments_on_device = false;
-    for (int r = 0; r < n_ctx; ++r)
-        if (rcs[(size_t)r]) return fail(rcs[(size_t)r], "GPU %d: %s", r, errs[(size_t)r].c_str());
-    int merge_kind = 0;
-    if (d->want_moments && rows > 0 && grp) {
-        const sdde::NcclApi &N = sdde::nccl_api();
-        const size_t cnt = (size_t)rows * 3;
-        for (int r = 0; r < n_ctx; ++r) {
-            CU_CHECK(cudaSetDevice(ctxs[r]->device));
-            CU_CHECK(ctxs[r]->gather.reserve(cnt * 8 * (size_t)n_ctx));
-        }
-        ncclResult_t nr = N.GroupStart();
-        for (int r = 0; r < n_ctx && nr == ncclSuccess; ++r) {
-            CU_CHECK(cudaSetDevice(ctxs[r]->device));
-            nr = N.AllGather(ctxs[r]->mom.p, ctxs[r]->gather.p, cnt, ncclDouble, grp->comms[(size_t)r], ctxs[r]->compute);
-        }
-        const ncclResult_t ne = N.GroupEnd();
-        if (nr == ncclSuccess) nr = ne;
-        if (nr != ncclSuccess) return fail(SDDE_ERR_NCCL - (int)nr, "NCCL all-gather of the moment triples failed: %s", N.GetErrorString(nr));
-        // every GPU now holds all partial triples; merge in rank order on GPU 0 and read the result back
-        sdde_ctx *c0 = ctxs[0];
-        CU_CHECK(cudaSetDevice(c0->device));
-        sdde::merge_moments_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c0->compute>>>(
-            (const double *)c0->gather.p, (long long)cnt, n_ctx, rows, (double *)c0->gather.p);
-        CU_CHECK(cudaGetLastError());
-        CU_CHECK(cudaMemcpyAsync(moments, c0->gather.p, cnt * 8, cudaMemcpyDeviceToHost, c0->compute));
-        for (int r = 0; r < n_ctx; ++r) {
-            CU_CHECK(cudaSetDevice(ctxs[r]->device));
-            CU_CHECK(cudaStreamSynchronize(ctxs[r]->compute));
-        }
-        merge_kind = 2;
-    } else if (d->want_moments) {
-        bool first = true;
-        for (int r = 0; r < n_ctx; ++r) {
-            if (moms[(size_t)r].empty()) continue;
-            if (first) { memcpy(moments, moms[(size_t)r].data(), (size_t)rows * 3 * 8); first = false; }
-            else sdde_b200_merge_moments(moments, moms[(size_t)r].data(), rows);
-        }
-        merge_kind = 1;
-    }
-    if (tm) for (int r = 0; r < n_ctx; ++r) tm[r].moment_merge = merge_kind;
-    return SDDE_OK;
-}
-
 int sdde_b200_compile_model(sdde_ctx *c, const char *source, int32_t *model_id) {
     if (!c || !source || !model_id) return fail(SDDE_ERR_BAD_DESC, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1112,138 +882,5 @@ int sdde_b200_compile_model(sdde_ctx *c, const char *source, int32_t *model_id) 
     *model_id = id;
     return SDDE_OK;
 }
-
-int sdde_b200_philox_normals(sdde_ctx *c, uint64_t seed, int64_t traj_offset, int64_t n_traj, int64_t n_steps, int32_t n_noise,
-                             double *out_host) {
-    if (!c || !out_host || n_traj <= 0 || n_steps <= 0 || n_noise <= 0) return fail(SDDE_ERR_BAD_DESC, "bad arguments");
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU_CHECK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)n_steps * n_noise * n_traj * 8;
-    CU_CHECK(c->out[0].reserve(bytes));
-    sdde::philox_dump_kernel<<<(unsigned)((n_traj + 127) / 128), 128, 0, c->compute>>>(
-        (double *)c->out[0].p, n_traj, traj_offset, n_steps, n_noise, (sdde::u32)(seed & 0xffffffffu), (sdde::u32)(seed >> 32));
-    CU_CHECK(cudaGetLastError());
-    CU_CHECK(cudaMemcpyAsync(out_host, c->out[0].p, bytes, cudaMemcpyDeviceToHost, c->compute));
-    CU_CHECK(cudaStreamSynchronize(c->compute));
-    return SDDE_OK;
-}
-
-int sdde_b200_quantiles(sdde_ctx *c, const double *paths, int32_t mem, int64_t n_rows, int64_t n_traj, int64_t pitch,
-                        const double *probs, int32_t n_prob, int32_t want_median, double *result, double *kernel_ms) {
-    if (!c || !paths || !result || n_rows <= 0 || n_traj <= 0 || pitch < n_traj || n_prob < 0 || (n_prob > 0 && !probs) ||
-        (n_prob == 0 && !want_median))
-        return fail(SDDE_ERR_BAD_DESC, "bad arguments");
-    if (mem != SDDE_MEM_HOST && mem != SDDE_MEM_DEVICE) return fail(SDDE_ERR_BAD_DESC, "mem must be SDDE_MEM_HOST or SDDE_MEM_DEVICE");
-    if (n_traj >= ((int64_t)1 << 32)) return fail(SDDE_ERR_UNSUPPORTED, "rows longer than 2^32 - 1 values");
-    sdde::QuantilePlan plan;
-    const std::string perr = sdde::plan_quantiles(n_traj, probs, n_prob, want_median != 0, plan);
-    if (!perr.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", perr.c_str());
-    const int R = (int)plan.ranks.size();
-    if (R > sdde::QS_MAX_RANK) return fail(SDDE_ERR_UNSUPPORTED, "at most %d distinct order statistics per call", sdde::QS_MAX_RANK);
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU_CHECK(cudaSetDevice(c->device));
-    const double *src = paths;
-    if (mem == SDDE_MEM_HOST) {
-        CU_CHECK(c->qs_paths.reserve((size_t)n_rows * pitch * 8));
-        CU_CHECK(cudaMemcpyAsync(c->qs_paths.p, paths, (size_t)n_rows * pitch * 8, cudaMemcpyHostToDevice, c->compute));
-        src = (const double *)c->qs_paths.p;
-    }
-    const size_t hist_bytes = (size_t)n_rows * R * sdde::QS_BINS * sizeof(unsigned int);
-    CU_CHECK(c->qs_rows.reserve((size_t)n_rows * sizeof(sdde::QsRow)));
-    CU_CHECK(c->qs_hist.reserve(hist_bytes));
-    sdde::QsRanks ranks{};
-    for (int r = 0; r < R; ++r) ranks.k[r] = plan.ranks[(size_t)r];
-    const size_t smem = (size_t)R * sdde::QS_BINS * sizeof(unsigned int);
-    CU_CHECK(c->qs_cand.reserve((size_t)n_rows * R * sdde::QS_CAP * 8));
-    for (int pass = 0; pass < sdde::QS_PASSES; ++pass)
-        CU_CHECK(cudaFuncSetAttribute(sdde::qs_stream_fn(pass), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // enough CTAs to fill the machine, but no slice shorter than 8192 values
-    int64_t split = (8 * (int64_t)c->sm_count + n_rows - 1) / n_rows;
-    split = std::max<int64_t>(1, std::min<int64_t>(split, (n_traj + 8191) / 8192));
-    CU_CHECK(cudaEventRecord(c->ev_k0, c->compute));
-    sdde::qs_init_kernel<<<(unsigned)n_rows, 32, 0, c->compute>>>((sdde::QsRow *)c->qs_rows.p, R, ranks);
-    for (int pass = 0; pass < sdde::QS_PASSES; ++pass) {
-        CU_CHECK(cudaMemsetAsync(c->qs_hist.p, 0, hist_bytes, c->compute));
-        sdde::qs_stream_fn(pass)<<<dim3((unsigned)n_rows, (unsigned)split), sdde::QS_THREADS, smem, c->compute>>>(
-            src, pitch, n_traj, R, (sdde::QsRow *)c->qs_rows.p, (unsigned int *)c->qs_hist.p, (unsigned long long *)c->qs_cand.p);
-        sdde::qs_scan_kernel<<<(unsigned)n_rows, 32 * R, 0, c->compute>>>((sdde::QsRow *)c->qs_rows.p, (const unsigned int *)c->qs_hist.p,
-                                                                          (const unsigned long long *)c->qs_cand.p, R, pass);
-    }
-    CU_CHECK(cudaGetLastError());
-    CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
-    std::vector<sdde::QsRow> rows((size_t)n_rows);
-    CU_CHECK(cudaMemcpyAsync(rows.data(), c->qs_rows.p, (size_t)n_rows * sizeof(sdde::QsRow), cudaMemcpyDeviceToHost, c->compute));
-    CU_CHECK(cudaStreamSynchronize(c->compute));
-    if (kernel_ms) { float ms = 0.f; CU_CHECK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1)); *kernel_ms = ms; }
-    const int ncol = (int)plan.items.size();
-    for (int64_t i = 0; i < n_rows; ++i) {
-        const sdde::QsRow &q = rows[(size_t)i];
-        double v[sdde::QS_MAX_RANK];
-        for (int r = 0; r < R; ++r) {
-            const unsigned long long key = q.prefix[r];
-            const unsigned long long b = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
-            std::memcpy(&v[r], &b, 8);
-        }
-        for (int j = 0; j < ncol; ++j) {
-            const sdde::QuantileItem &it = plan.items[(size_t)j];
-            result[i * ncol + j] = q.n_nan ? std::nan("") : sdde::combine_quantile(it, v[it.ia], v[it.ib]);
-        }
-    }
-    return SDDE_OK;
-}
-
-int sdde_b200_dfma_peak(sdde_ctx *c, double *tflops) {
-    if (!c || !tflops) return fail(SDDE_ERR_BAD_DESC, "NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU_CHECK(cudaSetDevice(c->device));
-    const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
-    CU_CHECK(c->out[0].reserve((size_t)blocks * threads * 8));
-    double best = 0.0;
-    for (int rep = 0; rep < 6; ++rep) {
-        CU_CHECK(cudaEventRecord(c->ev_k0, c->compute));
-        sdde::dfma_kernel<<<blocks, threads, 0, c->compute>>>((double *)c->out[0].p, iters, 0.999999, 1e-9);
-        CU_CHECK(cudaGetLastError());
-        CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
-        CU_CHECK(cudaStreamSynchronize(c->compute));
-        float ms = 0.f;
-        CU_CHECK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
-        const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
-        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
-    }
-    *tflops = best;
-    return SDDE_OK;
-}
-
-int sdde_b200_hbm_peak(sdde_ctx *c, double *gbs) {
-    if (!c || !gbs) return fail(SDDE_ERR_BAD_DESC, "NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
-    CU_CHECK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)1 << 30;
-    CU_CHECK(c->out[0].reserve(bytes));
-    CU_CHECK(c->out[1].reserve(bytes));
-    double best = 0.0;
-    for (int rep = 0; rep < 6; ++rep) {
-        CU_CHECK(cudaEventRecord(c->ev_k0, c->compute));
-        sdde::copy_kernel<<<c->sm_count * 16, 256, 0, c->compute>>>((const uint4 *)c->out[0].p, (uint4 *)c->out[1].p, (long long)(bytes / 16));
-        CU_CHECK(cudaGetLastError());
-        CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
-        CU_CHECK(cudaStreamSynchronize(c->compute));
-        float ms = 0.f;
-        CU_CHECK(cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1));
-        if (rep > 0) best = std::max(best, 2.0 * (double)bytes / (ms * 1e-3) / 1e9);
-    }
-    *gbs = best;
-    return SDDE_OK;
-}
-
-void *sdde_b200_alloc_pinned(int64_t bytes) {
-    void *p = nullptr;
-    if (bytes <= 0) return nullptr;
-    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault);
-    if (e != cudaSuccess) { cudaGetLastError(); fail(SDDE_ERR_CUDA - (int)e, "cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); return nullptr; }
-    return p;
-}
-
-void sdde_b200_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"
