@@ -329,7 +329,7 @@ def timepoint_meanvar(sim, t):
     return mean[k], var[k]
 
 
-def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=None):
+def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=None, local=False):
     """[EXT] SciMLBase.EnsembleAnalysis.timeseries_steps_quantile (and _median): per saved time point and state, the
     quantile(s) ``q`` across this solution's trajectories -- Statistics.quantile's definition, selected exactly on the
     device (sdde_b200_quantiles; the paths stay in HBM when the solve ran with ``output='device'``).
@@ -338,6 +338,10 @@ def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=
     appended as the last entry of the last axis."""
     if sim.out is None:
         raise ValueError("solve(..., paths=True) first: order statistics need the saved paths")
+    if sim.n_total is not None and sim.n_total != sim.out.shape[2] and not local:
+        raise NotImplementedError("this solution holds one rank's shard of a distributed ensemble: order statistics over "
+                                  "all ranks need a distributed selection (DESIGN.md section 8); pass local=True for the "
+                                  "quantiles of this rank's trajectories only")
     probs = np.atleast_1d(np.asarray(q, dtype=np.float64)) if q is not None else np.zeros(0)
     out = sim.out
     n_save, n_state, n_traj = out.shape
