@@ -686,7 +686,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
 
     int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
     if (chunk >= 8) chunk -= chunk % 8;   // batches (B <= 8) never straddle a chunk; step index of a batch start stays even
-    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 1) * K.rec_size;
+    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 8) * K.rec_size;   // + look-ahead records (next step / next batch prefetch)
     int batch = K.batch;
     if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
     if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step

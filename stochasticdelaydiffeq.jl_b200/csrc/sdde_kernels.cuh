@@ -403,6 +403,20 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         for (int j = 0; j < NS; ++j)
 #pragma unroll
             for (int tt = 0; tt < TPT; ++tt) st.carry[l][j][tt] = xhi[BW - 1][l][j][tt];
+    // batched path: pull the NEXT batch's nodes towards L1/L2 now; this batch's generator and recurrence work (about a
+    // thousand cycles per warp) covers the HBM latency that the first use of a freshly loaded node otherwise exposes
+    if (BW > 1 && prefetch_next) {
+#pragma unroll
+        for (int k = 0; k < BW; ++k)
+#pragma unroll
+            for (int l = 0; l < NLK; ++l) {
+                const char *phi = ringb + recs[BW + k].lk[l].off_hi;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(phi + j * jstride));
+                }
+            }
+    }
     // step-by-step path (multi-state models): pull the NEXT step's upper nodes towards L1 while this step computes
     // (they were written at least one step ago; recs[BW] is staged by the caller when prefetch_next is set)
     if (BW == 1 && prefetch_next) {
@@ -639,7 +653,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(c
     const bool batched = (B > 1) && (a.batch >= B);   // host: batch = min(B, min_gap + 1); chunk_steps % B == 0
     for (int n0 = 0; n0 < a.n_steps; n0 += a.chunk_steps) {
         const int cnt = (a.n_steps - n0 < a.chunk_steps) ? (a.n_steps - n0) : a.chunk_steps;
-        const int nrec = (a.n_steps - n0 > cnt) ? cnt + 1 : cnt;      // one record of look-ahead for the prefetch
+        const int nrec = (a.n_steps - n0 - cnt >= B) ? cnt + B : ((a.n_steps - n0 > cnt) ? cnt + 1 : cnt);   // look-ahead records
         __syncthreads();
         {   // stage this chunk of the schedule in shared memory
             const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
@@ -651,7 +665,8 @@ __global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(c
         int nb = 0;
         if (batched) {
             for (; nb + B <= cnt; nb += B)
-                run_batch<M, ALG, NOISE, PTRAJ, TPT, B>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, false);
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, B>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec,
+                                                        nb + 2 * B <= nrec /* next batch's records staged: prefetch its nodes */);
         }
         const bool pf = (B == 1) && a.prefetch;
         for (; nb < cnt; ++nb)
