@@ -48,7 +48,7 @@ Base.@kwdef mutable struct SddeDesc
 end
 
 alg_id(::EM{true}) = Int32(0); alg_id(::EM{false}) = Int32(1)
-alg_id(a::RKMil) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(2) : Int32(3)
+alg_id(a::Union{RKMil, RKMilCommute}) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(2) : Int32(3)   # diagonal noise: same update
 alg_id(::EulerHeun) = Int32(4)
 
 last_error() = unsafe_string(ccall((:sdde_b200_last_error, libsdde), Cstring, ()))
@@ -62,7 +62,7 @@ function context(dev)
     end
 end
 
-function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM, RKMil, EulerHeun}, ea::EnsembleB200;
+function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM, RKMil, RKMilCommute, EulerHeun}, ea::EnsembleB200;
         trajectories, dt, saveat = Float64[], adaptive = false, seed = UInt64(0), moments = false, kwargs...)
     prob = ep.prob
     prob isa SciMLBase.AbstractSDDEProblem || error("EnsembleB200 handles SDDEProblems only")

@@ -44,6 +44,13 @@ class RKMil:
 
 
 @dataclass(frozen=True)
+class RKMilCommute(RKMil):
+    """Milstein for commutative noise ([EXT] StochasticDiffEq RKMilCommute; reference smoke test test/test_prob_sol.jl:44-49).
+    On this path only diagonal noise is supported, where its update ``K + L dW + Dg (dW^2/2 [- dt/2])`` is the RKMil
+    update written with the iterated integral J: the same kernel serves both (they differ by rounding only)."""
+
+
+@dataclass(frozen=True)
 class EulerHeun:
     """Euler-Heun (Stratonovich), fixed step: second drift/diffusion evaluation at t + dt, i.e. a second set of
     delayed-state lookups per step ([EXT] StochasticDiffEq EulerHeun; reference smoke test test/test_prob_sol.jl:34)."""

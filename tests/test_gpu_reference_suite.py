@@ -20,7 +20,8 @@ PADD = [1.0, -4.0, -2.0, 10.0, -0.0, -0.0, 0.1]
 
 
 @pytest.mark.parametrize("alg,kw", [(S.EM(), {}), (S.EM(False), {}), (S.EulerHeun(), {}), (S.RKMil(), {"adaptive": False}),
-                                    (S.RKMil("Stratonovich"), {"adaptive": False})])
+                                    (S.RKMil("Stratonovich"), {"adaptive": False}), (S.RKMilCommute(), {"adaptive": False}),
+                                    (S.RKMilCommute("Stratonovich"), {"adaptive": False})])
 @pytest.mark.parametrize("p", [PMUL, PADD])
 def test_prob_sol_smoke(alg, kw, p):
     # test/test_prob_sol.jl:15-43: h(p,t) = 1 + t, u0 = [1.0], tspan = (0, 0.1), dt = 0.01, constant_lags = (p[1],)
