@@ -426,6 +426,22 @@ def _default_device():
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _choose_seed(seed: int, prob_seed: int, across_ranks: bool) -> int:
+    """seed keyword, else prob.seed, else a drawn one (src/solve.jl:302).  A drawn seed must be the SAME on every rank of a
+    distributed solve -- the Philox streams are keyed by (seed, global trajectory id) -- so rank 0's draw is broadcast."""
+    if seed != 0:
+        return int(seed)
+    if prob_seed != 0:
+        return int(prob_seed)
+    seed = int(np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0]) or 1
+    if across_ranks:
+        import torch.distributed as dist
+        box = [seed]
+        dist.broadcast_object_list(box, src=0)
+        seed = int(box[0])
+    return seed
+
+
 def shard_range(n_total: int, rank: int, world: int):
     """Contiguous global-id range of rank r: [r*ceil(N/R), min(N, (r+1)*ceil(N/R)))  (SURVEY.md section 8(e))."""
     per = -(-n_total // world)
@@ -464,8 +480,9 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     ctx = capi.get_context(device)
     ctx.set_option("wave_traj", int(ea.wave_traj or 0))     # per solve: a forced wave size must not leak into later solves
     model = _resolve_model(base, ctx)
-    if seed == 0:
-        seed = base.seed if base.seed != 0 else int(np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0])  # src/solve.jl:302
+    if not paths and not moments:
+        raise ValueError("nothing to return: ask for paths, moments or both")
+    seed = _choose_seed(seed, base.seed, ea.distributed and world > 1)
     p_batch, u0_batch = eprob.batches(n_traj, lo)
 
     t0w = time.perf_counter()

@@ -21,7 +21,9 @@ def _worker(rank, world, port, q):
     lo, hi = S.shard_range(1001, rank, world)
     local = O.moments(x[..., lo:hi])
     merged = _allgather_merge_moments(local, 0)
-    q.put((rank, lo, hi, merged, O.moments(x)))
+    from sdde_b200.ensemble import _choose_seed
+    seeds = (_choose_seed(0, 0, True), _choose_seed(0, 0, True), _choose_seed(7, 0, True), _choose_seed(0, 9, True))
+    q.put((rank, lo, hi, merged, O.moments(x), seeds))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -39,7 +41,9 @@ def test_world2_moment_merge_gloo():
         assert p.exitcode == 0
     res.sort(key=lambda r: r[0])
     assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 501, 501, 1001)
-    for _, _, _, merged, full in res:
+    # a drawn seed is agreed on across ranks (and differs from draw to draw); explicit seeds pass through
+    assert res[0][5] == res[1][5] and res[0][5][0] != res[0][5][1] and res[0][5][2:] == (7, 9)
+    for _, _, _, merged, full, _ in res:
         assert np.allclose(merged[..., 0], 1001)
         assert np.allclose(merged, full, rtol=1e-12)
     assert np.array_equal(res[0][3], res[1][3])       # every rank ends with identical moments
