@@ -234,6 +234,25 @@ SDDE_API int sdde_b200_merge_moments(double *a, const double *b, int64_t n);
 SDDE_API int sdde_b200_quantiles(sdde_ctx *ctx, const double *paths, int32_t mem, int64_t n_rows, int64_t n_traj, int64_t pitch,
                                  const double *probs, int32_t n_prob, int32_t want_median, double *result, double *kernel_ms);
 
+/* The same selection in phases, for an ensemble whose trajectories are sharded over several processes / GPUs (one
+ * context each, e.g. under torchrun): every rank histograms ITS columns of the rows, the caller sums the histograms over
+ * the ranks (ncclAllReduce / torch.distributed.all_reduce on `d_hist`), every rank applies the same bin decisions, and
+ * after QS passes = 6 rounds every rank holds the order statistics of the WHOLE ensemble (exact).
+ *   sdde_b200_qsel_ranks   host only: how many distinct order statistics (n_rank) the request needs for n_total values
+ *   sdde_b200_qsel_begin   paths = this rank's [n_rows][pitch] block (n_local columns used, may be 0); d_hist = a device
+ *                          buffer of n_rows * n_rank * 2048 uint32 owned by the caller
+ *   sdde_b200_qsel_local   pass p: zero d_hist, add this rank's histograms, synchronise          -> caller all-reduces d_hist
+ *   sdde_b200_qsel_apply   pass p: narrow every rank's prefix by one digit from the summed histograms
+ *   sdde_b200_qsel_nan     set = 0: counts[n_rows] <- NaNs seen by this rank; set = 1: install the summed counts
+ *   sdde_b200_qsel_end     result [n_rows][n_prob + (want_median != 0)], host memory; closes the selection          */
+SDDE_API int sdde_b200_qsel_ranks(int64_t n_total, const double *probs, int32_t n_prob, int32_t want_median, int32_t *n_rank);
+SDDE_API int sdde_b200_qsel_begin(sdde_ctx *ctx, const double *paths, int32_t mem, int64_t n_rows, int64_t n_local, int64_t pitch,
+                                  int64_t n_total, const double *probs, int32_t n_prob, int32_t want_median, uint32_t *d_hist);
+SDDE_API int sdde_b200_qsel_local(sdde_ctx *ctx, int32_t pass);
+SDDE_API int sdde_b200_qsel_apply(sdde_ctx *ctx, int32_t pass);
+SDDE_API int sdde_b200_qsel_nan(sdde_ctx *ctx, int64_t *counts, int32_t set);
+SDDE_API int sdde_b200_qsel_end(sdde_ctx *ctx, double *result);
+
 /* Register a user model from CUDA C++ source (NVRTC, sm_100a).  The source must define
  *   struct UserModel { static constexpr int NS, NL, NW, NP; static constexpr bool DIAG;
  *                      template<class P> __device__ static void f(double*du,const double*u,const double(*ul)[NS],const P&p,double t);

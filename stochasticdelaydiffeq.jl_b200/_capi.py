@@ -75,6 +75,8 @@ EXPORTS = [
     "sdde_b200_set_option", "sdde_b200_schedule", "sdde_b200_schedule_free", "sdde_b200_solve", "sdde_b200_solve_multi",
     "sdde_b200_merge_moments", "sdde_b200_compile_model", "sdde_b200_philox_normals", "sdde_b200_dfma_peak",
     "sdde_b200_hbm_peak", "sdde_b200_alloc_pinned", "sdde_b200_free_pinned", "sdde_b200_quantiles",
+    "sdde_b200_qsel_ranks", "sdde_b200_qsel_begin", "sdde_b200_qsel_local", "sdde_b200_qsel_apply", "sdde_b200_qsel_nan",
+    "sdde_b200_qsel_end",
 ]
 
 LIB_PATH = os.environ.get("SDDE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdde_b200.so")
@@ -93,6 +95,19 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if "SDDE_B200_NCCL_LIB" not in os.environ:
+        # the library resolves libnccl at run time (sdde_b200_solve_multi); a process gets ONE libnccl (shared by SONAME),
+        # so point it at the copy PyTorch ships -- a later `import torch` then finds the NCCL it was built against
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for d in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(d, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["SDDE_B200_NCCL_LIB"] = cand
+                    break
+        except Exception:
+            pass
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback for this path)")
@@ -115,6 +130,13 @@ def lib():
     L.sdde_b200_philox_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
     L.sdde_b200_quantiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, _dp]
+    L.sdde_b200_qsel_ranks.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    L.sdde_b200_qsel_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_void_p]
+    L.sdde_b200_qsel_local.argtypes = [C.c_void_p, C.c_int32]
+    L.sdde_b200_qsel_apply.argtypes = [C.c_void_p, C.c_int32]
+    L.sdde_b200_qsel_nan.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.sdde_b200_qsel_end.argtypes = [C.c_void_p, C.c_void_p]
     L.sdde_b200_dfma_peak.argtypes = [C.c_void_p, _dp]
     L.sdde_b200_hbm_peak.argtypes = [C.c_void_p, _dp]
     L.sdde_b200_alloc_pinned.argtypes = [C.c_int64]

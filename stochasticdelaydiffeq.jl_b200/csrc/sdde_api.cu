@@ -443,6 +443,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
     c->h_status.release(); c->h_mom.release(); c->h_count.release(); c->gather.release();
     c->noise_src.release(); c->noise_nodes.release(); c->mom_part.release();
+    sdde_qsel_free(c->qsel); c->qsel = nullptr;
     c->qs_rows.release(); c->qs_hist.release(); c->qs_paths.release(); c->qs_cand.release();
     c->user.clear();
     if (c->compute) cudaStreamDestroy(c->compute);

@@ -53,6 +53,9 @@ struct PinnedBuf {       // page-locked host staging (small D2H results: status 
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+struct sdde_qsel;
+void sdde_qsel_free(struct sdde_qsel *q);
+
 struct sdde_ctx {
     int device = 0;
     cudaStream_t compute = nullptr, copy_in = nullptr, copy_out = nullptr;
@@ -63,6 +66,7 @@ struct sdde_ctx {
     DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
     PinnedBuf h_status, h_mom, h_count;
     DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
+    struct sdde_qsel *qsel = nullptr;   // the active order-statistics selection (sdde_summary_api.cu), freed by sdde_qsel_free
     DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
     bool keep_moments_on_device = false;   // set by solve_multi: leave the wave-merged triples in `mom` for the all-gather
     int64_t opt_jit_linsys = 1;    // specialise the linear delay system's constants with NVRTC (zeros vanish, no LDCU per entry)

@@ -171,7 +171,7 @@ inline QsStreamFn qs_stream_fn(int pass) {
 //                switch the row to GATHER for the next streaming pass
 //   GATHER mode: the leader's candidate list holds every value with the rank's prefix: pick the k-th by counting
 __global__ void __launch_bounds__(32 * QS_MAX_RANK) qs_scan_kernel(QsRow *__restrict__ rows, const unsigned int *__restrict__ ghist,
-                                                                   const unsigned long long *__restrict__ cand, int n_rank, int pass) {
+                                                                   const unsigned long long *__restrict__ cand, int n_rank, int pass, int allow_gather) {
     __shared__ unsigned long long s_cand[QS_CAP];
     __shared__ int s_big;
     const int row = blockIdx.x, r = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(32 * QS_MAX_RANK) qs_scan_kernel(QsRow *__rest
             q.n_cand[a] = 0u;
         }
         if (pass == QS_PASSES - 1) q.mode = QS_MODE_DONE;
-        else if (!s_big && pass < QS_PASSES - 2) q.mode = QS_MODE_GATHER;
+        else if (allow_gather && !s_big && pass < QS_PASSES - 2) q.mode = QS_MODE_GATHER;
     }
 }
 

@@ -335,13 +335,10 @@ def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=
     device (sdde_b200_quantiles; the paths stay in HBM when the solve ran with ``output='device'``).
 
     -> array [n_save, n_state, len(q)] (``[n_save, n_state]`` for a scalar q); with ``median=True`` the median is
-    appended as the last entry of the last axis."""
+    appended as the last entry of the last axis.  A solution that holds one rank's shard of a distributed solve yields the
+    statistics of the WHOLE ensemble (collective: every rank must call; ``local=True`` restricts to this rank's paths)."""
     if sim.out is None:
         raise ValueError("solve(..., paths=True) first: order statistics need the saved paths")
-    if sim.n_total is not None and sim.n_total != sim.out.shape[2] and not local:
-        raise NotImplementedError("this solution holds one rank's shard of a distributed ensemble: order statistics over "
-                                  "all ranks need a distributed selection (DESIGN.md section 8); pass local=True for the "
-                                  "quantiles of this rank's trajectories only")
     probs = np.atleast_1d(np.asarray(q, dtype=np.float64)) if q is not None else np.zeros(0)
     out = sim.out
     n_save, n_state, n_traj = out.shape
@@ -356,6 +353,11 @@ def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=
     ctx = capi.get_context(dev)
     ncol = probs.size + (1 if median else 0)
     res = np.empty((n_save * n_state, ncol), dtype=np.float64)
+    if sim.n_total is not None and sim.n_total != n_traj and not local:
+        # one rank's shard of a distributed ensemble: selection over ALL ranks (histograms all-reduced over NCCL)
+        _quantiles_across_ranks(ctx, dev, ptr, on_dev, n_save * n_state, n_traj, sim.n_total, probs, median, res)
+        res = res.reshape(n_save, n_state, ncol)
+        return res[..., 0] if (np.isscalar(q) and not median) else res
     ms = C.c_double(0.0)
     capi.check(capi.lib().sdde_b200_quantiles(ctx.handle, ptr, capi.MEM_DEVICE if on_dev else capi.MEM_HOST, n_save * n_state,
                                               n_traj, n_traj, capi.np_ptr(probs).value if probs.size else None, probs.size,
@@ -365,6 +367,34 @@ def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=
     if np.isscalar(q) and not median:
         return res[..., 0]
     return res
+
+
+def _quantiles_across_ranks(ctx, dev, ptr, on_dev, n_rows, n_local, n_total, probs, median, res):
+    """Exact order statistics of an ensemble sharded over the ranks of the torch.distributed group: per digit pass every
+    rank histograms its own trajectories on its GPU, the histograms are summed with one all-reduce (NCCL over NVLink), and
+    every rank narrows the same bins -- no path ever leaves its GPU."""
+    import torch
+    import torch.distributed as dist
+    L = capi.lib()
+    n_rank = C.c_int32(0)
+    pp = capi.np_ptr(probs).value if probs.size else None
+    capi.check(L.sdde_b200_qsel_ranks(n_total, pp, probs.size, 1 if median else 0, C.byref(n_rank)))
+    tdev = torch.device(f"cuda:{dev}")
+    hist = torch.empty(n_rows * n_rank.value * 2048, dtype=torch.int32, device=tdev)
+    capi.check(L.sdde_b200_qsel_begin(ctx.handle, ptr if n_local else None, capi.MEM_DEVICE if on_dev else capi.MEM_HOST, n_rows,
+                                      n_local, max(n_local, 1), n_total, pp, probs.size, 1 if median else 0, hist.data_ptr()))
+    for p in range(6):
+        capi.check(L.sdde_b200_qsel_local(ctx.handle, p))
+        dist.all_reduce(hist)                       # counts per (row, rank, digit) over the whole ensemble
+        torch.cuda.synchronize(tdev)
+        capi.check(L.sdde_b200_qsel_apply(ctx.handle, p))
+    nan = np.zeros(n_rows, dtype=np.int64)
+    capi.check(L.sdde_b200_qsel_nan(ctx.handle, capi.np_ptr(nan).value, 0))
+    t = torch.from_numpy(nan).to(tdev)
+    dist.all_reduce(t)
+    nan = t.cpu().numpy()
+    capi.check(L.sdde_b200_qsel_nan(ctx.handle, capi.np_ptr(nan).value, 1))
+    capi.check(L.sdde_b200_qsel_end(ctx.handle, capi.np_ptr(res).value))
 
 
 def timeseries_steps_median(sim: EnsembleSolution):
@@ -386,7 +416,7 @@ class EnsembleSummary:
         r = timeseries_steps_quantile(sim, list(quantiles), median=True)
         self.qlow, self.qhigh, self.med = r[..., 0], r[..., 1], r[..., 2]
         self.t = sim.t
-        self.num_monte = len(sim)
+        self.num_monte = sim.n_total or len(sim)
         self.elapsedTime = sim.elapsedTime
         self.converged = sim.converged
 
