@@ -534,6 +534,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (d->want_moments && !moments) return fail(SDDE_ERR_BAD_DESC, "want_moments set but moments is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     CU_CHECK(cudaSetDevice(c->device));
+    cudaGetLastError();        // a failed earlier call must not leak its (non-sticky) error into this one
 
     sdde::KernelInfo K;
     rc = select_kernel(c, d, K);
@@ -687,7 +688,13 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
 
     int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
     if (chunk >= 8) chunk -= chunk % 8;   // batches (B <= 8) never straddle a chunk; step index of a batch start stays even
-    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 8) * K.rec_size;   // + look-ahead records (next step / next batch prefetch)
+    // schedule records staged per refill (+ look-ahead records for the next step / next batch prefetch) must fit in shared
+    // memory beside the generator tables: 200 KB at most, so that one more CTA's static share still fits
+    const size_t smem_cap = 200 * 1024;
+    while (chunk > 8 && (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 8) * K.rec_size > smem_cap) chunk = ((chunk / 2) / 8) * 8;
+    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 8) * K.rec_size;
+    if (smem > 48 * 1024)      // above the default limit the kernel has to opt in (built-in kernels and NVRTC kernel handles alike)
+        CU_CHECK(cudaFuncSetAttribute(K.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int batch = K.batch;
     if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
     if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step

@@ -1,0 +1,102 @@
+"""-m gpu: randomised parity sweep.  Random combinations of model, algorithm, lag(s), step size, time span, discontinuity
+order, saveat form, user tstops, affine history, per-trajectory parameters / initial states, noise source (increments or
+NoiseGrid), forced wave sizes and schedule-chunk sizes -- every one compared path by path with the oracle under shared
+noise (1e-12).  Exercises the table packing (carried nodes, ring size, clipped steps, records at chunk boundaries, the
+next-batch prefetch), the step-by-step fallback for short lags, and the wave loop, in combinations the named tests miss."""
+import numpy as np
+import pytest
+
+import cases
+import sdde_b200 as S
+import sdde_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _random_case(rng):
+    kind = rng.choice(["linear1", "mg", "hayes", "scalar_add", "c4", "sir"], p=[0.3, 0.25, 0.15, 0.1, 0.1, 0.1])
+    dt = float(rng.choice([0.01, 0.02, 0.05, 2.0 ** -5, 0.013]))
+    T = float(rng.choice([1.5, 4.0, 7.3]))
+    order0 = int(rng.choice([0, 0, 1, 2]))
+    if kind == "linear1":
+        lag = float(rng.choice([0.05, 0.3, 1.0, 0.777, 2.5 * dt, 1.0 * dt]))
+        c = cases.c1(T=T).with_(lags=[lag], dt=dt, alg=int(rng.choice([0, 1, 2, 3, 4])), order0=order0,
+                                h0=[float(rng.uniform(0.5, 1.5))], h1=[float(rng.choice([0.0, 0.3]))])
+    elif kind == "mg":
+        lag = float(rng.choice([0.5, 1.7, 17.0 / 8, 3.01]))
+        c = cases.c2(T=T, tau=lag).with_(dt=dt, alg=int(rng.choice([0, 1, 2, 3, 4])), order0=order0)
+    elif kind == "hayes":
+        c = cases.hayes(T=min(T, 3.0), dt=dt, alg=int(rng.choice([0, 2, 3, 4])), beta=float(rng.choice([0.0, -1.2])))
+        c = c.with_(order0=order0)
+    elif kind == "scalar_add":
+        c = cases.scalar_add(T=T).with_(dt=dt, alg=int(rng.choice([0, 1, 4])), order0=order0)
+    elif kind == "c4":
+        c = cases.c4(T=min(T, 4.0)).with_(dt=dt, alg=int(rng.choice([0, 1, 4])), order0=order0,
+                                         lags=[float(rng.choice([0.5, 1.0])), float(rng.choice([1.3, 2.5]))])
+    else:
+        c = cases.sir(T=min(T, 4.0), dt=0.02).with_(alg=int(rng.choice([0, 1, 4])))
+    if c.alg in (2, 3, 4) and c.dt > min(c.lags):
+        c = c.with_(dt=min(c.lags) / 2)                       # src/solve.jl:581-585 guard
+    t0, tf = c.tspan
+    form = rng.choice(["number", "list", "everystep"])
+    if form == "number":
+        c = c.with_(saveat=float(rng.choice([0.1, 0.25, 0.5])))
+    elif form == "list":
+        pts = sorted(set(float(np.round(x, 3)) for x in rng.uniform(t0, tf, size=int(rng.integers(1, 6)))))
+        c = c.with_(saveat=([t0] if rng.integers(0, 2) else []) + pts + ([tf] if rng.integers(0, 2) else []))
+    else:
+        c = c.with_(saveat=None)
+    return c
+
+
+@pytest.mark.parametrize("seed", list(range(64)))
+def test_random_configuration_matches_oracle(seed):
+    rng = np.random.default_rng(9000 + seed)
+    c = _random_case(rng)
+    n = int(rng.choice([97, 256, 1000, 1537]))
+    tst = sorted(set(float(np.round(x, 2)) for x in rng.uniform(c.tspan[0], c.tspan[1], size=int(rng.integers(0, 3)))))
+    tst = [x for x in tst if c.tspan[0] < x < c.tspan[1]]
+    if c.alg in (2, 3, 4):
+        tst = []                                              # extra stops could make a step longer than the smallest lag
+    sv, ss, se = O.expand_saveat(c.saveat, *c.tspan)
+    sch = O.build_schedule(c.tspan[0], c.tspan[1], c.dt, c.lags, c.alg, order_discontinuity_t0=c.order0,
+                           constant_lags_declared=c.declared, saveat_times=sv, save_start=ss, save_end=se,
+                           save_everystep=c.saveat is None, tstops=tst)
+    nchan = c.model.n_chan
+    dW = cases.increments(sch, nchan, n, key=555 + seed)
+    ptraj = bool(rng.integers(0, 2))
+    pb = ub = None
+    if ptraj:
+        pb = np.repeat(np.asarray(c.p, float)[:, None], n, axis=1) * (1.0 + 0.05 * rng.random((len(c.p), n)))
+        ub = np.repeat(np.asarray(c.u0, float)[:, None], n, axis=1) * (1.0 + 0.05 * rng.random((len(c.u0), n)))
+    ref, st = O.solve_ensemble(c.omodel, pb if ptraj else c.p, ub if ptraj else c.u0, c.h0, c.h1, c.lags, sch, c.alg, dW)
+    kw = dict(dt=c.dt, saveat=c.saveat, tstops=tst)
+    if c.alg in (2, 3):
+        kw["adaptive"] = False
+    noise = {}
+    if rng.integers(0, 2):
+        noise["noise_increments"] = dW
+    else:
+        noise["noise_grid"] = np.concatenate([np.zeros((1, nchan, n)), np.cumsum(dW, axis=0)], axis=0)
+        cur = np.zeros((nchan, n)); dWg = np.empty_like(dW)
+        for k in range(sch.n_steps):
+            dWg[k] = noise["noise_grid"][k + 1] - cur
+            cur = cur + dWg[k]
+        ref, st = O.solve_ensemble(c.omodel, pb if ptraj else c.p, ub if ptraj else c.u0, c.h0, c.h1, c.lags, sch, c.alg, dWg)
+    wave = int(rng.choice([0, 0, 128, 512]))
+    ctx = S.get_context(0)
+    ctx.set_option("chunk_steps", int(rng.choice([128, 8, 24, 1024])))
+    try:
+        sim = S.solve(S.EnsembleProblem(c.problem(), p_batch=pb, u0_batch=ub), cases.ALG_MAP[c.alg],
+                      S.EnsembleB200(device=0, wave_traj=wave or None), trajectories=n, **kw, **noise)
+    finally:
+        ctx.set_option("chunk_steps", 128)
+    what = (c.name, c.alg, c.lags, c.dt, c.tspan, c.order0, c.saveat if not isinstance(c.saveat, list) else "list", tst, n, ptraj, wave,
+            list(noise)[0], sim.timing["kernel_name"])
+    assert sim.out.shape == ref.shape, what
+    assert np.array_equal(sim.t, sch.save_t), what
+    ok = np.isfinite(ref).all(axis=(0, 1))
+    assert ok.any(), what
+    assert cases.scaled_err(sim.out[:, :, ok], ref[:, :, ok]) < TOL, what
+    assert np.array_equal(sim.status, st), what

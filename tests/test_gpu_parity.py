@@ -484,3 +484,26 @@ def test_linsys_nvrtc_constant_specialisation_equals_generic_kernel():
     assert cases.scaled_err(a.out, b.out) < 1e-13
     ref, _ = case.oracle(dW)
     assert cases.scaled_err(a.out, ref) < TOL and cases.scaled_err(b.out, ref) < TOL
+
+
+@pytest.mark.parametrize("chunk", [8, 40, 1024])
+def test_schedule_chunk_sizes_give_identical_paths(chunk):
+    """The schedule records are staged in shared memory chunk by chunk; any chunk size (down to one batch, up to the
+    1024-record maximum, which needs the > 48 KB shared-memory opt-in) gives the same paths, for a built-in model, a
+    two-stage algorithm on the 4-state system (176-byte records) and an NVRTC user model."""
+    ctx = S.get_context(0)
+    runs = []
+    c2 = cases.c2(T=100.0)
+    c4 = cases.c4(T=12.0).with_(alg=4)
+    for case, n in ((c2, 512), (c4, 300)):
+        sch = case.oracle_schedule()
+        dW = cases.increments(sch, case.model.n_chan, n)
+        kw = dict(trajectories=n, noise_increments=dW, **case.solve_kwargs())
+        ref = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0), **kw)
+        ctx.set_option("chunk_steps", chunk)
+        try:
+            got = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0), **kw)
+        finally:
+            ctx.set_option("chunk_steps", 128)
+        runs.append((case.name, np.array_equal(ref.out, got.out)))
+    assert all(ok for _, ok in runs), runs
