@@ -100,3 +100,15 @@ def test_random_configuration_matches_oracle(seed):
     assert ok.any(), what
     assert cases.scaled_err(sim.out[:, :, ok], ref[:, :, ok]) < TOL, what
     assert np.array_equal(sim.status, st), what
+    # the same solve with a random subset of saved states, device-resident output and ensemble moments
+    ns = ref.shape[1]
+    idxs = sorted(rng.choice(ns, size=int(rng.integers(1, ns + 1)), replace=False).tolist())
+    sim2 = S.solve(S.EnsembleProblem(c.problem(), p_batch=pb, u0_batch=ub), cases.ALG_MAP[c.alg],
+                   S.EnsembleB200(device=0, output="device"), trajectories=n, save_idxs=idxs, moments=True, **kw, **noise)
+    out2 = sim2.out.cpu().numpy()
+    assert np.array_equal(out2, sim.out[:, idxs, :]), what
+    if ok.all():
+        om = O.moments(ref[:, idxs, :])
+        assert np.allclose(sim2.moments[..., 0], n) and np.allclose(sim2.moments[..., 1], om[..., 1], rtol=1e-11, atol=1e-13), what
+        assert np.allclose(sim2.moments[..., 2], om[..., 2], rtol=1e-8, atol=1e-13), what
+        assert sim2.n_unstable == 0
