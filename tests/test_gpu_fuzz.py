@@ -112,3 +112,26 @@ def test_random_configuration_matches_oracle(seed):
         assert np.allclose(sim2.moments[..., 0], n) and np.allclose(sim2.moments[..., 1], om[..., 1], rtol=1e-11, atol=1e-13), what
         assert np.allclose(sim2.moments[..., 2], om[..., 2], rtol=1e-8, atol=1e-13), what
         assert sim2.n_unstable == 0
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_configuration_philox_paths_do_not_depend_on_the_launch_geometry(seed):
+    """In-kernel Philox noise: the paths of a random configuration are the same bit for bit whatever the wave size, the
+    schedule-chunk size and the output residency (counter = global trajectory id, key = seed)."""
+    rng = np.random.default_rng(7000 + seed)
+    c = _random_case(rng)
+    n = int(rng.choice([300, 1000, 2049]))
+    kw = dict(dt=c.dt, saveat=c.saveat, trajectories=n, seed=1234 + seed)
+    if c.alg in (2, 3):
+        kw["adaptive"] = False
+    prob = S.EnsembleProblem(c.problem())
+    base = S.solve(prob, cases.ALG_MAP[c.alg], S.EnsembleB200(device=0), **kw)
+    ctx = S.get_context(0)
+    ctx.set_option("chunk_steps", int(rng.choice([8, 16, 1024])))
+    try:
+        other = S.solve(prob, cases.ALG_MAP[c.alg], S.EnsembleB200(device=0, wave_traj=int(rng.choice([128, 256, 1024])), output="device"), **kw)
+    finally:
+        ctx.set_option("chunk_steps", 128)
+    what = (c.name, c.alg, c.lags, c.dt, c.tspan, n, base.timing["kernel_name"], other.timing["waves"])
+    assert np.array_equal(base.out, other.out.cpu().numpy(), equal_nan=True), what
+    assert np.array_equal(base.status, other.status), what
