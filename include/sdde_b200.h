@@ -222,6 +222,11 @@ SDDE_API int sdde_b200_solve_multi(sdde_ctx *const *ctxs, int32_t n_ctx, const s
 /* Merge two (count, mean, M2) arrays of n triples: a <- merge(a, b)  (Chan et al.); host only. */
 SDDE_API int sdde_b200_merge_moments(double *a, const double *b, int64_t n);
 
+/* (count, mean, M2) across trajectories of saved rows that already exist (e.g. a device-resident `out` of an earlier solve that
+ * did not ask for moments): the same one-read kernels sdde_b200_solve uses; [EXT] EnsembleAnalysis.timeseries_steps_meanvar.
+ *   paths [n_rows][pitch] host or device (`mem`), first n_traj values per row; moments [n_rows][3] host memory. */
+SDDE_API int sdde_b200_moments(sdde_ctx *ctx, const double *paths, int32_t mem, int64_t n_rows, int64_t n_traj, int64_t pitch, double *moments);
+
 /* Order statistics across trajectories of saved rows, on the device: the reference side computes them with
  * [EXT] SciMLBase EnsembleSummary -> EnsembleAnalysis.timeseries_steps_quantile / timeseries_steps_median ->
  * Statistics.quantile(v, p) (alpha = beta = 1) / Statistics.median(v) on the per-time-point vectors of a solved ensemble.

@@ -76,7 +76,7 @@ EXPORTS = [
     "sdde_b200_merge_moments", "sdde_b200_compile_model", "sdde_b200_philox_normals", "sdde_b200_dfma_peak",
     "sdde_b200_hbm_peak", "sdde_b200_alloc_pinned", "sdde_b200_free_pinned", "sdde_b200_quantiles",
     "sdde_b200_qsel_ranks", "sdde_b200_qsel_begin", "sdde_b200_qsel_local", "sdde_b200_qsel_apply", "sdde_b200_qsel_nan",
-    "sdde_b200_qsel_end",
+    "sdde_b200_qsel_end", "sdde_b200_moments",
 ]
 
 LIB_PATH = os.environ.get("SDDE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdde_b200.so")
@@ -137,6 +137,7 @@ def lib():
     L.sdde_b200_qsel_apply.argtypes = [C.c_void_p, C.c_int32]
     L.sdde_b200_qsel_nan.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.sdde_b200_qsel_end.argtypes = [C.c_void_p, C.c_void_p]
+    L.sdde_b200_moments.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
     L.sdde_b200_dfma_peak.argtypes = [C.c_void_p, _dp]
     L.sdde_b200_hbm_peak.argtypes = [C.c_void_p, _dp]
     L.sdde_b200_alloc_pinned.argtypes = [C.c_int64]

@@ -522,6 +522,30 @@ int sdde_b200_merge_moments(double *a, const double *b, int64_t n) {
     return SDDE_OK;
 }
 
+int sdde_b200_moments(sdde_ctx *c, const double *paths, int32_t mem, int64_t n_rows, int64_t n_traj, int64_t pitch, double *moments) {
+    if (!c || !paths || !moments || n_rows <= 0 || n_traj <= 0 || pitch < n_traj) return fail(SDDE_ERR_BAD_DESC, "bad arguments");
+    if (mem != SDDE_MEM_HOST && mem != SDDE_MEM_DEVICE) return fail(SDDE_ERR_BAD_DESC, "mem must be SDDE_MEM_HOST or SDDE_MEM_DEVICE");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_CHECK(cudaSetDevice(c->device));
+    const double *src = paths;
+    if (mem == SDDE_MEM_HOST) {
+        CU_CHECK(c->qs_paths.reserve((size_t)n_rows * pitch * 8));
+        CU_CHECK(cudaMemcpyAsync(c->qs_paths.p, paths, (size_t)n_rows * pitch * 8, cudaMemcpyHostToDevice, c->compute));
+        src = (const double *)c->qs_paths.p;
+    }
+    int64_t msplit = (4 * (int64_t)c->sm_count + n_rows - 1) / n_rows;
+    msplit = std::max<int64_t>(1, std::min<int64_t>(msplit, (n_traj + 16383) / 16384));
+    CU_CHECK(c->mom.reserve((size_t)n_rows * 3 * 8));
+    CU_CHECK(c->mom_part.reserve((size_t)msplit * n_rows * 3 * 8));
+    sdde::moments_kernel<<<dim3((unsigned)n_rows, (unsigned)msplit), 256, 0, c->compute>>>(src, pitch, 0, n_traj, (double *)c->mom_part.p);
+    sdde::merge_moments_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, c->compute>>>((const double *)c->mom_part.p, n_rows * 3, (int)msplit,
+                                                                                       n_rows, (double *)c->mom.p);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(moments, c->mom.p, (size_t)n_rows * 3 * 8, cudaMemcpyDeviceToHost, c->compute));
+    CU_CHECK(cudaStreamSynchronize(c->compute));
+    return SDDE_OK;
+}
+
 int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm) {
     const auto wall0 = std::chrono::steady_clock::now();
     static const bool dbg = getenv("SDDE_DEBUG_TIMING") != nullptr;

@@ -401,6 +401,26 @@ def timeseries_steps_median(sim: EnsembleSolution):
     return timeseries_steps_quantile(sim, None, median=True)[..., 0]
 
 
+def _moments_of_paths(sim: EnsembleSolution) -> np.ndarray:
+    """(count, mean, M2) per (save point, state) of a solution that was solved without ``moments=True`` (device kernels;
+    a shard of a distributed solve is merged over the ranks like the solve itself does)."""
+    if sim.out is None:
+        raise ValueError("no saved paths")
+    out = sim.out
+    n_save, n_state, n_traj = out.shape
+    on_dev = hasattr(out, "data_ptr")
+    dev = out.device.index if on_dev else _default_device()
+    if not on_dev:
+        out = np.ascontiguousarray(out, dtype=np.float64)
+    mom = np.zeros((n_save, n_state, 3), dtype=np.float64)
+    capi.check(capi.lib().sdde_b200_moments(capi.get_context(dev).handle, out.data_ptr() if on_dev else capi.np_ptr(out).value,
+                                            capi.MEM_DEVICE if on_dev else capi.MEM_HOST, n_save * n_state, n_traj, n_traj,
+                                            capi.np_ptr(mom).value))
+    if sim.n_total is not None and sim.n_total != n_traj:
+        mom = _allgather_merge_moments(mom, dev)
+    return mom
+
+
 class EnsembleSummary:
     """[EXT] SciMLBase.EnsembleSummary(sim; quantiles=[0.05, 0.95]): mean ``u``, variance ``v``, median ``med`` and the
     two quantile bands ``qlow``/``qhigh`` per saved time point, all computed on the device."""
@@ -408,11 +428,9 @@ class EnsembleSummary:
     def __init__(self, sim: EnsembleSolution, quantiles=(0.05, 0.95)):
         if len(quantiles) != 2:
             raise ValueError("quantiles must be (low, high)")
-        if sim.moments is not None:
-            self.u, self.v = timeseries_steps_meanvar(sim)
-        else:
-            o = sim.out.cpu().numpy() if hasattr(sim.out, "data_ptr") else sim.out
-            self.u, self.v = o.mean(axis=2), o.var(axis=2, ddof=1)
+        if sim.moments is None:
+            sim.moments = _moments_of_paths(sim)        # on the device, from the saved paths
+        self.u, self.v = timeseries_steps_meanvar(sim)
         r = timeseries_steps_quantile(sim, list(quantiles), median=True)
         self.qlow, self.qhigh, self.med = r[..., 0], r[..., 1], r[..., 2]
         self.t = sim.t

@@ -92,3 +92,17 @@ def test_quantiles_full_size_row_properties():
         not_above = (xs <= v).sum(dim=1).cpu().numpy()
         h = (n - 1) * p
         assert np.all(below <= np.floor(h) + 1) and np.all(not_above >= np.floor(h)), (p, below, not_above)
+
+
+def test_summary_of_a_solution_solved_without_moments():
+    """EnsembleSummary computes the missing mean/variance from the saved paths on the device (sdde_b200_moments), for
+    device-resident and host-resident paths alike."""
+    case = cases.c1(T=5.0)
+    kw = dict(trajectories=30_001, seed=3, **case.solve_kwargs())
+    for output in ("device", "host"):
+        sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(output=output), **kw)
+        assert sim.moments is None
+        summ = S.EnsembleSummary(sim)
+        paths = sim.out.cpu().numpy() if output == "device" else sim.out
+        assert np.allclose(summ.u, paths.mean(axis=2), rtol=1e-12) and np.allclose(summ.v, paths.var(axis=2, ddof=1), rtol=1e-9)
+        assert sim.moments is not None and np.all(sim.moments[..., 0] == 30_001)
