@@ -62,12 +62,29 @@ function context(dev)
     end
 end
 
+"""
+    pinned_array(dims...) -> Array{Float64}
+
+Page-locked host memory from the library (`sdde_b200_alloc_pinned`), wrapped as a Julia array and freed by a finalizer.
+With a page-locked `out` the step kernel writes the saved paths straight into it over PCIe (no staging copy).
+"""
+function pinned_array(dims::Int...)
+    ptr = ccall((:sdde_b200_alloc_pinned, libsdde), Ptr{Float64}, (Int64,), 8 * prod(dims))
+    ptr == C_NULL && error("libsdde_b200: " * last_error())
+    a = unsafe_wrap(Array, ptr, dims; own = false)
+    finalizer(_ -> ccall((:sdde_b200_free_pinned, libsdde), Cvoid, (Ptr{Float64},), ptr), a)
+    return a
+end
+
 function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM, RKMil, RKMilCommute, EulerHeun}, ea::EnsembleB200;
-        trajectories, dt, saveat = Float64[], adaptive = false, seed = UInt64(0), moments = false, kwargs...)
+        trajectories, dt, saveat = Float64[], tstops = Float64[], adaptive = false, seed = UInt64(0), moments = false,
+        save_idxs = nothing, noise_increments = nothing, pinned = true, kwargs...)
     prob = ep.prob
     prob isa SciMLBase.AbstractSDDEProblem || error("EnsembleB200 handles SDDEProblems only")
     adaptive && error("EnsembleB200 is a fixed-step path: pass adaptive=false")          # src/solve.jl:40
     isempty(kwargs) || error("unsupported keyword(s) on the EnsembleB200 path: $(keys(kwargs))")
+    (ep.output_func === SciMLBase.DEFAULT_OUTPUT_FUNC && ep.reduction === SciMLBase.DEFAULT_REDUCTION) ||
+        error("output_func / reduction run on the host in SciML; on this path use saveat + moments")
     m = prob.f.f::B200Model
     t0, tf = prob.tspan
     # saveat expansion exactly as tstop_saveat_disc_handling does it (src/solve.jl:659-677)
@@ -75,24 +92,47 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM,
          Float64[t for t in saveat if t0 < t < tf]
     save_start = saveat isa Number || isempty(saveat) || t0 in saveat
     save_end = saveat isa Number || isempty(saveat) || tf in saveat
-    # affine history h(p,t) = c0 + c1 t (checked)
-    h1 = prob.h(prob.p, t0 - 1.0); h2 = prob.h(prob.p, t0 - 2.0)
+    ts_user = collect(Float64, tstops)
+    # affine history h(p,t) = c0 + c1 t (checked at a third point)
+    h1 = prob.h(prob.p, t0 - 1.0); h2 = prob.h(prob.p, t0 - 2.0); h3 = prob.h(prob.p, t0 - 3.5)
     c1 = collect(Float64, h1 .- h2); c0 = collect(Float64, h1 .- c1 .* (t0 - 1.0))
-    p = collect(Float64, prob.p); u0 = collect(Float64, prob.u0 isa Number ? [prob.u0] : prob.u0)
+    all(isapprox.(c0 .+ c1 .* (t0 - 3.5), h3; rtol = 1e-13, atol = 1e-13)) ||
+        error("only affine history functions cross the C ABI for built-in models (user models may define h in CUDA source)")
+    # EnsembleProblem.prob_func: a trajectory may differ in p and u0 (called on the host for every i, like the reference)
+    per_traj = ep.prob_func !== SciMLBase.DEFAULT_PROB_FUNC
+    if per_traj
+        P = Array{Float64, 2}(undef, trajectories, m.n_param)           # == C layout [n_param][n_traj]
+        U0 = Array{Float64, 2}(undef, trajectories, m.n_state)
+        for i in 1:trajectories
+            q = ep.prob_func(deepcopy(prob), i, 1)
+            (q.tspan == prob.tspan && q.constant_lags == prob.constant_lags) || error("prob_func may change p and u0 only on this path")
+            P[i, :] .= q.p; U0[i, :] .= q.u0
+        end
+        p, u0 = P, U0
+    else
+        p = collect(Float64, prob.p); u0 = collect(Float64, prob.u0 isa Number ? [prob.u0] : prob.u0)
+    end
+    idxs = save_idxs === nothing ? Int32[] : Int32[i - 1 for i in save_idxs]          # 0-based on the C side
+    n_saved = isempty(idxs) ? Int(m.n_state) : length(idxs)
+    nz = noise_increments === nothing ? Float64[] : noise_increments        # Array{Float64,3}(n_traj, n_chan, n_steps) == C [n][c][traj]
     d = SddeDesc(; struct_size = sizeof(SddeDesc), model_id = m.id, alg = alg_id(alg), n_state = m.n_state,
         n_noise = m.n_noise, n_lag = m.n_lag, n_param = m.n_param,
         order_discontinuity_t0 = prob.order_discontinuity_t0, constant_lags_declared = isempty(prob.constant_lags) ? 0 : 1,
         save_start, save_end, save_everystep = (isempty(sv) && !(saveat isa Number)) ? 1 : 0,
-        want_moments = moments ? 1 : 0, n_saveat = length(sv), t0, tf, dt,
+        want_moments = moments ? 1 : 0, n_saveat = length(sv), n_tstops = length(ts_user), t0, tf, dt,
         lags = ntuple(i -> i <= length(prob.constant_lags) ? Float64(prob.constant_lags[i]) : 0.0, 4),
         hist_c0 = ntuple(i -> i <= length(c0) ? c0[i] : 0.0, 8), hist_c1 = ntuple(i -> i <= length(c1) ? c1[i] : 0.0, 8),
-        params = pointer(p), u0 = pointer(u0), saveat = pointer(sv), n_traj = trajectories,
+        params = pointer(p), param_stride = per_traj ? trajectories : 0, u0 = pointer(u0), u0_stride = per_traj ? trajectories : 0,
+        saveat = pointer(sv), tstops = pointer(ts_user), n_traj = trajectories,
+        noise_mode = isempty(nz) ? 0 : 1, noise = isempty(nz) ? C_NULL : pointer(nz),
+        n_save_idxs = length(idxs), save_idxs = ntuple(i -> i <= length(idxs) ? idxs[i] : Int32(0), 8),
         seed = seed == 0 ? (prob.seed == 0 ? rand(UInt64) : prob.seed) : seed)                # src/solve.jl:302
     n_save = length(sv) + save_start + (save_end && (isempty(sv) || sv[end] != tf))
-    out = Array{Float64, 3}(undef, trajectories, m.n_state, n_save)      # == C layout [n_save][n_state][n_traj]
-    mom = zeros(Float64, 3, m.n_state, n_save)
+    # == C layout [n_save][n_saved][n_traj]; page-locked so that the kernel writes it directly
+    out = pinned ? pinned_array(trajectories, n_saved, n_save) : Array{Float64, 3}(undef, trajectories, n_saved, n_save)
+    mom = zeros(Float64, 3, n_saved, n_save)
     status = zeros(UInt8, trajectories)
-    rc = GC.@preserve p u0 sv out mom status ccall((:sdde_b200_solve, libsdde), Cint,
+    rc = GC.@preserve p u0 sv ts_user nz out mom status ccall((:sdde_b200_solve, libsdde), Cint,
         (Ptr{Cvoid}, Ref{SddeDesc}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Cvoid}),
         context(ea.device), d, out, moments ? pointer(mom) : C_NULL, status, C_NULL)
     rc == 0 || error("libsdde_b200 ($rc): " * last_error())
@@ -100,7 +140,8 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM,
     # lazy per-trajectory solutions: views into `out`, built with the reference's own build_solution
     sols = [SciMLBase.build_solution(prob, alg, ts, [view(out, i, :, k) for k in 1:n_save];
                 retcode = status[i] == 0 ? ReturnCode.Success : ReturnCode.Unstable) for i in 1:trajectories]
-    return SciMLBase.EnsembleSolution(sols, 0.0, true)
+    sim = SciMLBase.EnsembleSolution(sols, 0.0, true)
+    return moments ? (sim, mom) : sim          # mom[:, j, k] = (count, mean, M2) of state j at ts[k]
 end
 
 """
