@@ -20,7 +20,7 @@ run("C2 MG EM(false)", cases.c2(T=500.0, alg=1), 1_000_000, 16.4)
 run("C3 MG RKMil tau=17.02 order0=0 T=100", cases.c3(0), 1_000_000, 16 + 8 * 101 / 2002)
 run("C3 MG RKMil tau=17.02 order0=2 T=100", cases.c3(2), 1_000_000, 16 + 8 * 101 / 2001)
 run("C3 MG RKMil Strat", cases.c3(0, alg=3), 1_000_000, 16 + 8 * 101 / 2002)
-run("C4 linsys 4/2/2 EM T=20", cases.c4(), 1_000_000, 64 + 32 * 41 / 2003)
+run("C4 linsys 4/2/2 EM T=20", cases.c4(), 1_000_000, 96 + 32 * 41 / 2003)   # two delayed nodes read + one written per step
 run("C5 linear1 EM T=10 moments only", cases.c1(T=10.0, saveat=1.0), 4_000_000, 16 + 8 * 11 / 1001, moments=True, paths=False)
 run("hayes EM T=10 dt=2^-6", cases.hayes(T=10.0, dt=2.0**-6, saveat=1.0), 1_000_000, 16.1)
 run("sir EM T=20 dt=0.02", cases.sir(T=20.0, dt=0.02), 1_000_000, 48 + 24 * 21 / 1001)
