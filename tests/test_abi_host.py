@@ -257,3 +257,27 @@ def test_randomised_schedules_with_explicit_saveat_tstops_and_flags():
             a, b = getattr(s, k), getattr(o, k)
             assert a.shape == b.shape and np.array_equal(a, b), (trial, k, t0, tf, dt, lag, alg, declared, sv_user, tst)
         assert list(s.tstops_hit) == o.tstops_hit
+
+
+def test_order_statistic_planning_host_only():
+    """sdde_b200_qsel_ranks (no GPU): how many distinct order statistics a request needs -- Statistics.quantile brackets
+    each probability with two neighbours, exact hits and shared neighbours collapse, the median of an odd count is one."""
+    import ctypes as C
+    L = capi.lib()
+
+    def ranks(n, probs, median):
+        p = np.asarray(probs, dtype=np.float64)
+        out = C.c_int32(-1)
+        rc = L.sdde_b200_qsel_ranks(n, capi.np_ptr(p).value if p.size else None, p.size, 1 if median else 0, C.byref(out))
+        return rc, out.value
+
+    assert ranks(1, [0.3], True) == (0, 1)                     # a single trajectory: every statistic is that value
+    assert ranks(5, [], True) == (0, 1)                        # odd count: the middle one
+    assert ranks(4, [], True) == (0, 2)                        # even count: the two central ones
+    assert ranks(5, [0.5], False) == (0, 2)                    # h = 3 exactly: v[3] and v[4] (gamma = 0)
+    assert ranks(1001, [0.05, 0.95], True) == (0, 5)           # 2 + 2 + 1
+    assert ranks(10, [0.0, 1.0], False) == (0, 4)              # clamped to [1, n-1]: (1,2) and (9,10)
+    rc, _ = ranks(10, [1.5], False)
+    assert rc == -1 and b"[0, 1]" in L.sdde_b200_last_error()
+    rc, _ = ranks(1000, list(np.linspace(0.01, 0.99, 14)), False)
+    assert rc == -2 and b"distinct order statistics" in L.sdde_b200_last_error()
