@@ -103,13 +103,16 @@ struct KArgs {
 #ifndef SDDE_MIN_BLOCKS
 #define SDDE_MIN_BLOCKS 4
 #endif
+#ifndef SDDE_TUNE_MULTI_MIN_NS
+#define SDDE_TUNE_MULTI_MIN_NS 4
+#endif
 template <class M> struct Tune {
-    static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : (M::NS >= 4 ? SDDE_TUNE_TPT_MULTI : 1);
+    static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : (M::NS >= SDDE_TUNE_MULTI_MIN_NS ? SDDE_TUNE_TPT_MULTI : 1);
     static constexpr int FOOT = M::NS * M::NL * TPT;              // doubles per prefetched step (one node set)
     static constexpr int B = (M::NS == 1 && M::NL == 1) ? SDDE_TUNE_B_SCALAR : (FOOT <= SDDE_TUNE_FOOT_B2 ? 2 : 1);
     // resident CTAs per SM the register allocation aims for: scalar models 5 (<= 102 registers); multi-state models
     // with two trajectories per thread need the registers more than the occupancy (measured, profiles/README.md)
-    static constexpr int MINB = (M::NS >= 4 && TPT > 1) ? 3 : SDDE_MIN_BLOCKS;
+    static constexpr int MINB = (M::NS >= SDDE_TUNE_MULTI_MIN_NS && TPT > 1) ? 3 : SDDE_MIN_BLOCKS;
 };
 
 // ------------------------------------------------------------------------------------------------
