@@ -335,6 +335,14 @@ def test_full_size_properties_c2():
     out = np.empty((501, 1, 4096))
     capi.check(capi.lib().sdde_b200_solve(S.get_context(0).handle, C.byref(m.desc), capi.np_ptr(out), None, None, None))
     assert np.array_equal(out, sl)
+    # the same rows against the ORACLE fed with its own restatement of the in-kernel Philox normal stream: per-path parity
+    # with in-kernel noise over the full 10 000 steps of the bench configuration (512 paths of the middle of the ensemble)
+    import sdde_oracle as O
+    sch = case.oracle_schedule()
+    ids = np.arange(500_000, 500_512, dtype=np.uint64)
+    z = O.philox_normals(ids, sch.n_steps, 1, 20261019)
+    ref, _ = case.oracle(z * sch.sqdt[:, None, None])
+    assert cases.relerr(sl[:, :, :512], ref) < 1e-11
     mean = sim.out.mean(dim=2).cpu().numpy()
     assert np.allclose(sim.moments[..., 1], mean, rtol=1e-12)
     var = sim.out.var(dim=2, unbiased=True).cpu().numpy()
