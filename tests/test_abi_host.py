@@ -281,3 +281,34 @@ def test_order_statistic_planning_host_only():
     assert rc == -1 and b"[0, 1]" in L.sdde_b200_last_error()
     rc, _ = ranks(1000, list(np.linspace(0.01, 0.99, 14)), False)
     assert rc == -2 and b"distinct order statistics" in L.sdde_b200_last_error()
+
+
+def test_problem_surface_argument_checks_without_gpu():
+    """Host-side mirror of the SciML surface: what is outside the path is refused with a clear error before any GPU work."""
+    um_h = S.UserModel("struct UserModel {};", 2, 2, 2, 2, True, history=True)
+    um = S.UserModel("struct UserModel {};", 2, 1, 2, 3, True)
+    with pytest.raises(ValueError):                       # a model with its own h must be given that h
+        S.SDDEProblem(um_h.f, um_h.g, [1.0, 0.5], 1.0, (0.0, 1.0), [1.0, 0.1], constant_lags=(0.5, 1.0))
+    with pytest.raises(AttributeError):
+        um.h
+    with pytest.raises(ValueError):                       # h of another model
+        S.SDDEProblem(um.f, um.g, [1.0, 0.5], um_h.h, (0.0, 1.0), [1.0, 0.1, 0.2], constant_lags=(0.5,))
+    with pytest.raises(TypeError):                        # Python callables cannot cross the C ABI as f, g
+        S.SDDEProblem(lambda *a: 0, lambda *a: 0, 1.0, 1.0, (0.0, 1.0))
+    with pytest.raises(ValueError):
+        S.SDDEProblem(S.linear1.f, S.hayes.g, 1.0, 1.0, (0.0, 1.0), (1.0, 1.0, 1.0), constant_lags=(1.0,))
+    with pytest.raises(NotImplementedError):
+        S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, (0.0, 1.0), (1.0, 1.0, 1.0), constant_lags=(1.0,), dependent_lags=(lambda u, p, t: 1.0,))
+    with pytest.raises(NotImplementedError):
+        S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, (0.0, 1.0), (1.0, 1.0, 1.0), constant_lags=(1.0,), neutral=True)
+    prob = S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, (0.0, 1.0), (1.0, 1.0, 1.0), constant_lags=(1.0,))
+    with pytest.raises(NotImplementedError):
+        S.EnsembleProblem(prob, output_func=lambda sol, i: (sol, False))
+    with pytest.raises(NotImplementedError):              # non-affine Python history for a built-in model
+        S.schedule(S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, lambda p, t: np.cos(t), (0.0, 1.0), (1.0, 1.0, 1.0),
+                                 constant_lags=(1.0,)), S.EM(), dt=0.1)
+    with pytest.raises(NotImplementedError):              # RKMil is adaptive by default in the reference
+        S.schedule(prob, S.RKMil(), dt=0.1)
+    assert S.RKMilCommute().alg_id == S.RKMil().alg_id and S.RKMilCommute("Stratonovich").alg_id == S.RKMil("Stratonovich").alg_id
+    with pytest.raises(ValueError):
+        S.RKMil("Foo")
