@@ -1,8 +1,8 @@
 """Throughput of every BASELINE.json config on one GPU (Philox noise, device-resident output)."""
 import sys, os, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
-import sdde_b200 as S, cases
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))]
+import sdde_b200 as S, _problems as cases
 
 def run(name, case, n, bytes_per_step, reps=3, **extra):
     for r in range(reps):

@@ -1,7 +1,7 @@
 """C4 throughput: thread-per-trajectory vs cooperative lanes.  python tools/probe_c4.py [n_traj]"""
 import sys, os
-sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")]
-import sdde_b200 as S, cases
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))]
+import sdde_b200 as S, _problems as cases
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000
 case = cases.c4()
 for lanes in (0, 4):

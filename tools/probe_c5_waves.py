@@ -1,7 +1,7 @@
 """C5 (10^8 scalar trajectories, moments only): wall time against the wave size.  python tools/probe_c5_waves.py"""
 import sys, os, time
-sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")]
-import sdde_b200 as S, cases
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))]
+import sdde_b200 as S, _problems as cases
 n = 100_000_000
 case = cases.c1(T=10.0, saveat=1.0)
 for wave in (0, 1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24):

@@ -1,7 +1,7 @@
 """SIR (3 states, 3x2 sparse noise; the reference's nondiagonal_sparse_noise test model) and the 2-state user-model shape."""
 import sys, os
-sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")]
-import sdde_b200 as S, cases
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))]
+import sdde_b200 as S, _problems as cases
 case = cases.sir(T=20.0, dt=0.02)
 best = 1e9
 for r in range(4):

@@ -1,8 +1,8 @@
 """Latency of small ensembles (BASELINE.json configs[0]: 10^4 paths, linear SDDE, dt=0.01, T=10)."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
-import sdde_b200 as S, cases
+sys.path[:0] = [os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))]
+import sdde_b200 as S, _problems as cases
 case = cases.c1(T=10.0, saveat=0.1)
 for n in (1, 100, 10_000, 100_000, 1_000_000):
     for r in range(3):

@@ -1,11 +1,10 @@
 """Small end-to-end workload for compute-sanitizer (memcheck / racecheck): every kernel family once, tiny sizes."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import sdde_b200 as S
-import cases
+import _problems as cases
 
 def run(case, n=777, **kw):
     return S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0), trajectories=n, seed=3,
@@ -17,8 +16,7 @@ for case in (cases.c1(T=3.0), cases.c2(T=40.0), cases.c3(T=40.0), cases.c3(order
     print(case.name, "ok", float(np.asarray(sim.out)[-1].mean()), flush=True)
 # supplied increments, per-trajectory parameters, several waves, device output, quantiles
 case = cases.c1(T=2.0)
-sch = case.oracle_schedule()
-dW = cases.increments(sch, 1, 300)
+dW = cases.increments(case, 300)
 sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, wave_traj=128), trajectories=300,
               noise_increments=dW, **case.solve_kwargs())
 simd = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), trajectories=5000, seed=9,
