@@ -229,6 +229,23 @@ def main():
     with_moments = {"value": n_total * n_steps * Km / float(elm[0]), "unit": UNIT, "ms_per_step": float(elm[0]) / Km * 1e3, "steps": Km,
                     "merge": "NCCL all_gather of (count, mean, M2) + Chan merge" if world > 1 else "single GPU: no collective"}
 
+    # ---- summary arm (extra, not the headline): the ensemble never leaves HBM, the host receives mean, variance, median and
+    #      5 % / 95 % bands per saved time point (EnsembleSummary: moment kernels + exact order statistics on the device) ----
+    e2e_summary = None
+    if world == 1:
+        for i in range(2):
+            S.EnsembleSummary(one_pass(i, ea_dev, out_dev, True))
+        barrier_sync()
+        t0s = time.perf_counter()
+        Ks = max(1, min(K, 5))
+        for i in range(Ks):
+            summ = S.EnsembleSummary(one_pass(W + i, ea_dev, out_dev, True))
+        barrier_sync()
+        els = time.perf_counter() - t0s
+        e2e_summary = {"value": n_total * n_steps * Ks / els, "unit": UNIT, "ms_per_step": els / Ks * 1e3, "steps": Ks,
+                       "d2h_bytes_per_step": int(summ.u.nbytes + summ.v.nbytes + summ.med.nbytes + summ.qlow.nbytes + summ.qhigh.nbytes),
+                       "what": "solve + mean/variance + median + 5%/95% quantile bands computed on the device, only the summary crosses PCIe"}
+
     # ---- end-to-end arm: host buffers, pinned, D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -295,7 +312,7 @@ def main():
             "config": dict(WORKLOAD, trajectories_per_gpu=n_traj, trajectories_total=n_total, n_steps=n_steps, n_save=n_save,
                            parallelism=f"trajectory-shard x{world}", ring_slots=timing["ring_slots"],
                            ensemble_mean_at_tf=mean_end),
-            "clocks": clocks, "e2e": e2e, "with_moments": with_moments, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "e2e": e2e, "with_moments": with_moments, "e2e_summary": e2e_summary, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernel_ms_per_step_max_over_ranks": kms_max}
     print(json.dumps(line))
     if world > 1:
