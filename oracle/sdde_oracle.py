@@ -708,9 +708,18 @@ def exact_mean_linear1(sched: Schedule, a, b, u0, h0, h1, lag):
 # EnsembleAnalysis.timeseries_steps_quantile / timeseries_steps_median -> [EXT] Statistics.quantile (alpha = beta = 1)
 # and Statistics.median.  Checker for sdde_b200_quantiles; a full sort per row, formulas restated from Statistics.jl.
 # ---------------------------------------------------------------------------------------------------
+def _julia_sort(v):
+    """sort(v) under Julia's isless for floats: a total order with -0.0 before +0.0 (numpy's sort leaves the order of the
+    two zeros unspecified); NaNs are handled by the callers."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    b = v.view(np.uint64)
+    key = np.where(b >> np.uint64(63) != 0, ~b, b | np.uint64(1 << 63))
+    return v[np.argsort(key, kind="stable")]
+
+
 def julia_quantile(v, p):
     """Statistics.quantile(v, p) for a float64 vector (sorted internally)."""
-    v = np.sort(np.asarray(v, dtype=np.float64))
+    v = _julia_sort(v)
     n = v.size
     if not 0.0 <= p <= 1.0:
         raise ValueError("input probability out of [0,1] range")
@@ -733,7 +742,7 @@ def julia_quantile(v, p):
 
 def julia_median(v):
     """Statistics.median(v): middle order statistic, or middle(a, b) = a/2 + b/2 of the two central ones."""
-    v = np.sort(np.asarray(v, dtype=np.float64))
+    v = _julia_sort(v)
     n = v.size
     if np.isnan(v).any():
         return np.nan

@@ -217,3 +217,11 @@ def test_oracle_noise_grid_interpolation_known_answers():
     assert np.array_equal(O.noise_grid_increments(W)[:, 0, 0], [1.0, 3.0])
     with pytest.raises(ValueError):
         O.noise_grid_on_nodes(ts, W, [2.5])
+
+
+def test_oracle_sort_is_julias_total_order():
+    v = np.array([0.0, -0.0, 1.0, -0.0, 0.0, -1.0])
+    s = O._julia_sort(v)
+    assert np.array_equal(np.signbit(s), [True, True, True, False, False, False]) and s[0] == -1.0 and s[-1] == 1.0
+    # the median of an odd count is an order statistic itself: [-1, -0, -0, +0, 1] -> -0.0
+    assert np.signbit(O.julia_median(np.array([0.0, -0.0, 1.0, -0.0, -1.0]))) and not np.signbit(O.julia_median(np.array([0.0, -0.0, 1.0, 0.0, -1.0])))
