@@ -312,3 +312,22 @@ def test_problem_surface_argument_checks_without_gpu():
     assert S.RKMilCommute().alg_id == S.RKMil().alg_id and S.RKMilCommute("Stratonovich").alg_id == S.RKMil("Stratonovich").alg_id
     with pytest.raises(ValueError):
         S.RKMil("Foo")
+
+
+def test_plain_c_program_drives_the_abi(tmp_path):
+    """tests/c/abi_smoke.c: a C99 program that includes only include/sdde_b200.h and links libsdde_b200.so -- the boundary
+    carries no Python, torch or C++ types.  Host-only entry points here; with a GPU the same program also solves."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"),
+                    "-o", exe, "-L", libdir, "-lsdde_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "C1 steps 1001 saves 11" in out                       # SURVEY.md K4
+    assert "C2 steps 2001 saves 101 ring 342" in out and "tstops 17 34 100" in out
+    assert "bad struct_size -> -1 (refused)" in out
