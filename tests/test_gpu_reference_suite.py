@@ -41,3 +41,21 @@ def test_nondiagonal_sparse_noise_runs():
     # S + I + R is conserved by the drift and by the noise columns (each column sums to zero)
     tot = sim.out.sum(axis=1)
     assert np.allclose(tot, 1000.0, rtol=1e-12)
+
+
+def test_plain_c_program_solves_on_the_gpu(tmp_path):
+    """tests/c/abi_smoke.c (C99, only include/sdde_b200.h): schedule + an 8-path C2 solve through the bare C ABI."""
+    import os
+    import shutil
+    import subprocess
+    from sdde_b200 import _capi as capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run([cc, "-std=c99", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"),
+                    "-o", exe, "-L", libdir, "-lsdde_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "solve -> 0, u(0) = 1.2" in out, out
