@@ -115,6 +115,9 @@ template <class M> struct Tune {
     static constexpr int MINB = (M::NS >= SDDE_TUNE_MULTI_MIN_NS && TPT > 1) ? 3 : SDDE_MIN_BLOCKS;
 };
 
+// occupancy target per (model, algorithm): the model's, unless a measured exception is specialised next to the model
+template <class M, int ALG> struct TuneK { static constexpr int MINB = Tune<M>::MINB; };
+
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) + Box-Muller in float64.
 // Stream layout: counter = (traj_id_lo, traj_id_hi, call_lo, call_hi), key = (seed_lo, seed_hi);
@@ -580,7 +583,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 }
 
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
-__global__ void __launch_bounds__(SDDE_BLOCK, Tune<M>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(SDDE_BLOCK, TuneK<M, ALG>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
     typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
