@@ -331,3 +331,47 @@ def test_plain_c_program_drives_the_abi(tmp_path):
     assert "C1 steps 1001 saves 11" in out
     assert "C2 steps 2001 saves 101 ring 342" in out and "tstops 17 34 100" in out
     assert "bad struct_size -> -1 (refused)" in out
+
+
+def test_schedule_structural_invariants_on_random_problems():
+    """Independent re-derivation, from the lookup tables alone, of the two numbers the kernels trust: `ring_slots` (no node
+    is overwritten while a later step may still read it) and `min_gap` (how many steps may be batched before a lookup could
+    touch a node of the same batch); plus monotone time, steps that tile the span, saves inside their step."""
+    rng = np.random.default_rng(4242)
+    for trial in range(150):
+        t0 = float(rng.choice([0.0, 0.5]))
+        T = float(rng.choice([1.0, 3.3, 8.0]))
+        dt = float(rng.choice([0.01, 0.03, 0.1, 2.0 ** -4]))
+        nl = int(rng.integers(1, 3))
+        lags = sorted(float(x) for x in rng.choice([0.05, 0.3, 0.31, 1.0, 1.7, 2.5], size=nl, replace=False))
+        alg = int(rng.choice([0, 1, 2, 4]))
+        if alg in (2, 4) and dt > min(lags):
+            dt = min(lags) / 2
+        model = S.linear1 if nl == 1 else S.linsys(2, 2, 1)
+        if alg == 2 and nl > 1:
+            alg = 0
+        u0 = [1.0] * model.n_state
+        prob = S.SDDEProblem(model.f, model.g, u0 if model.n_state > 1 else 1.0, S.ConstantHistory(u0), (t0, t0 + T),
+                             np.zeros(model.n_param), constant_lags=tuple(lags), order_discontinuity_t0=int(rng.choice([0, 1, 2])))
+        kw = dict(dt=dt, saveat=float(rng.choice([0.1, 0.37, 1.0])))
+        if alg == 2:
+            kw["adaptive"] = False
+        s = S.schedule(prob, cases.ALG_MAP[alg], **kw)
+        N = len(s.dt)
+        assert np.all(np.diff(s.t) > 0) and s.t[0] == t0 and s.t[-1] == t0 + T
+        assert np.all(s.dt > 0) and np.all(s.dt <= dt * (1 + 1e-12)) and abs(float(np.sum(s.dt)) - T) < 1e-9
+        need, gap = 1, 2 ** 31 - 1
+        for n in range(N):
+            for e in range(s.lk_mode.shape[1]):
+                mode, i = int(s.lk_mode[n, e]), int(s.lk_idx[n, e])
+                if mode == 1:                       # exact node i
+                    assert 0 <= i <= n and 0.0 <= s.lk_theta[n, e] <= 1.0
+                    need = max(need, n - i); gap = min(gap, n - i)
+                elif mode == 2:                     # between nodes i-1 and i
+                    assert 1 <= i <= n and 0.0 < s.lk_theta[n, e] < 1.0
+                    need = max(need, n - (i - 1)); gap = min(gap, n - i)
+        assert s.ring_slots == max(2, need + 1), (trial, s.ring_slots, need)
+        assert s.min_gap == gap, (trial, s.min_gap, gap)
+        k = s.save_step >= 0
+        assert np.all(s.save_t[k] <= s.t[s.save_step[k] + 1]) and np.all(s.save_t[k] >= s.t[s.save_step[k]])
+        assert np.all((s.save_theta >= 0) & (s.save_theta <= 1))
