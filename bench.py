@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--trajectories", type=int, default=WORKLOAD["trajectories_per_gpu"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the with-moments and summary arms (A/B timing runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +220,7 @@ def main():
     # saved paths + the NCCL all-gather and Chan merge of the triples when N > 1): reported beside `value`
     barrier_sync()
     t0m = time.perf_counter()
-    Km = max(1, min(K, 5))
+    Km = 1 if args.no_extras else max(1, min(K, 5))
     for i in range(Km):
         simm = one_pass(W + i, ea_dev, out_dev, True)
     barrier_sync()
@@ -232,7 +233,7 @@ def main():
     # ---- summary arm (extra, not the headline): the ensemble never leaves HBM, the host receives mean, variance, median and
     #      5 % / 95 % bands per saved time point (EnsembleSummary: moment kernels + exact order statistics on the device) ----
     e2e_summary = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         for i in range(2):
             S.EnsembleSummary(one_pass(i, ea_dev, out_dev, True))
         barrier_sync()

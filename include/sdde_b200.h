@@ -272,6 +272,9 @@ SDDE_API int sdde_b200_compile_model(sdde_ctx *ctx, const char *source, int32_t 
 /* Test hooks / micro-benchmarks. */
 SDDE_API int sdde_b200_philox_normals(sdde_ctx *ctx, uint64_t seed, int64_t traj_offset, int64_t n_traj,
                              int64_t n_steps, int32_t n_noise, double *out_host /* [n_steps][n_noise][n_traj] */);
+/* Host copy of the normal generator's lookup table (layout: csrc/sdde_rng_tables.cuh); needs no device.
+ * out may be NULL to query *n_entries (double2 entries; out needs 2 * n_entries doubles). */
+SDDE_API int sdde_b200_rng_table(double *out, int64_t cap_doubles, int64_t *n_entries);
 SDDE_API int sdde_b200_dfma_peak(sdde_ctx *ctx, double *tflops);       /* measured FP64 FMA throughput of this GPU */
 SDDE_API int sdde_b200_hbm_peak(sdde_ctx *ctx, double *gbs);           /* measured device copy bandwidth (read+write) */
 

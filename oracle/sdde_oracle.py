@@ -95,10 +95,7 @@ def expand_saveat(saveat, t0: float, tf: float):
 
     ``saveat`` may be ``None``/empty (=> no saveat; caller decides save_everystep), a number or a sequence.
     For a number ``s`` the reference pushes ``(t0+s):s:tf`` when ``(t0:s:tf)[end] == tf`` else
-    ``(t0+s):s:(tf-s)``.  Julia's float ranges are computed in twice precision from a rational lift of
-    (start, step); here the k-th element is ``t0 + k*s`` evaluated as ``(n0 + k*ns)/d`` when t0 and s are
-    both exactly representable multiples of 1/d for a power-of-ten d <= 1e6, else ``t0 + k*s`` in float64.
-    For the configs of BASELINE.json (s = 1.0, 0.5, 0.1 with t0 = 0) both agree with Julia.
+    ``(t0+s):s:(tf-s)`` (src/solve.jl:662-671); the ranges are Julia Float64 ranges, restated in ``_float_range``.
     """
     if saveat is None:
         return np.zeros(0), True, True
@@ -106,11 +103,11 @@ def expand_saveat(saveat, t0: float, tf: float):
         s = float(saveat)
         if s <= 0:
             raise ValueError("saveat must be positive")
-        pts = _float_range(t0, s, tf)          # t0:s:tf
-        if pts[-1] == tf:
-            sv = pts[1:]                        # (t0+s):s:tf
+        probe = _float_range(t0, s, tf)         # t0:s:tf
+        if len(probe) > 0 and probe[-1] == tf:
+            sv = _float_range(t0 + s, s, tf)
         else:
-            sv = np.array([x for x in pts[1:] if x <= tf - s])
+            sv = _float_range(t0 + s, s, tf - s)
         return np.asarray(sv, dtype=np.float64), True, True
     arr = np.asarray(list(saveat), dtype=np.float64)
     if arr.size == 0:
@@ -121,15 +118,67 @@ def expand_saveat(saveat, t0: float, tf: float):
     return interior, save_start, save_end
 
 
+def _rational_lift(x: float):
+    """[EXT] Base.rat(x) of julia/base/twiceprecision.jl (Julia 1.10): convergents of the continued fraction of x while
+    numerator and denominator stay <= 2^24 (= maxintfloat(Float32)); (c, d) = previous convergent on overflow."""
+    LIM = 1 << 24
+    y = x
+    a, b, c, d = 1, 0, 0, 1
+    while abs(y) <= float(LIM):
+        f = int(y)                      # trunc toward zero
+        y = y - f
+        a, c = f * a + c, a
+        b, d = f * b + d, b
+        if abs(a) > LIM or abs(b) > LIM:
+            return c, d
+        if b != 0 and float(a) / float(b) == x:
+            return a, b
+        y = 1.0 / y if y != 0.0 else float("inf")
+    return a, b
+
+
 def _float_range(a: float, s: float, b: float) -> np.ndarray:
-    """Elements of the Julia range ``a:s:b`` (see expand_saveat docstring)."""
-    for d in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
-        na, ns, nb = round(a * d), round(s * d), b * d
-        if na / d == a and ns / d == s and ns > 0:
-            n = int(math.floor((nb - na) / ns + 1e-9))
-            return np.array([(na + k * ns) / d for k in range(n + 1)], dtype=np.float64)
-    n = int(math.floor((b - a) / s + 1e-9))
-    return np.array([a + k * s for k in range(n + 1)], dtype=np.float64)
+    """Elements of the Julia range ``a:s:b`` for Float64 ([EXT] Base.:(start, step, stop), twiceprecision.jl; MED-HIGH
+    confidence, restated from knowledge of Julia 1.10 -- K-check: 0.1:0.1:0.5 == [0.1, 0.2, 0.3, 0.4, 0.5] exactly).
+
+    Rational branch: start, step, stop all equal their small-rational lifts -> integer numerators over a common
+    denominator, length by integer division, elements (n0 + k ns)/den rounded once (twice-precision evaluation).
+    Literal branch: length = round((b-a)/s) + 1 (minus one on overshoot), elements a + k s rounded once."""
+    from fractions import Fraction
+    if s == 0.0:
+        raise ValueError("range step cannot be zero")
+
+    def inside(p, x, q):
+        return (p <= x <= q) or (q <= x <= p)
+
+    sn, sd = _rational_lift(s)
+    if sd != 0 and sn / sd == s:
+        an, ad = _rational_lift(a)
+        bn, bd = _rational_lift(b)
+        if ad != 0 and bd != 0 and an / ad == a and bn / bd == b:
+            den = ad * (sd // math.gcd(ad, sd))
+            big = float(1 << 53)
+            if den != 0 and abs(a * den) <= big and abs(s * den) <= big and den % ad == 0 and den % sd == 0:
+                n0, ns = int(round(a * den)), int(round(s * den))
+                top, bot = den * bn - bd * n0, ns * bd
+                quo = abs(top) // abs(bot)
+                if (top < 0) != (bot < 0):
+                    quo = -quo                       # Julia's div truncates
+                n = max(0, quo + 1)
+                if inside(a, a + (n - 1) * s, b + s / 2) and not inside(a, a + n * s, b):
+                    return np.array([float(Fraction(n0 + k * ns, den)) for k in range(n)], dtype=np.float64)
+    lf = (b - a) / s
+    if lf < 0:
+        n = 0
+    elif lf == 0:
+        n = 1
+    else:
+        n = int(round(lf)) + 1
+        end = a + (n - 1) * s
+        if (a < b < end) or (a > b > end):
+            n -= 1
+    A, S_ = Fraction(a), Fraction(s)
+    return np.array([float(A + k * S_) for k in range(n)], dtype=np.float64)
 
 
 def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_lags_declared=True,

@@ -76,7 +76,7 @@ EXPORTS = [
     "sdde_b200_merge_moments", "sdde_b200_compile_model", "sdde_b200_philox_normals", "sdde_b200_dfma_peak",
     "sdde_b200_hbm_peak", "sdde_b200_alloc_pinned", "sdde_b200_free_pinned", "sdde_b200_quantiles",
     "sdde_b200_qsel_ranks", "sdde_b200_qsel_begin", "sdde_b200_qsel_local", "sdde_b200_qsel_apply", "sdde_b200_qsel_nan",
-    "sdde_b200_qsel_end", "sdde_b200_moments",
+    "sdde_b200_qsel_end", "sdde_b200_moments", "sdde_b200_rng_table",
 ]
 
 LIB_PATH = os.environ.get("SDDE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdde_b200.so")
@@ -138,6 +138,8 @@ def lib():
     L.sdde_b200_qsel_nan.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.sdde_b200_qsel_end.argtypes = [C.c_void_p, C.c_void_p]
     L.sdde_b200_moments.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    if hasattr(L, "sdde_b200_rng_table"):      # absent only in older builds loaded through SDDE_B200_LIB for A/B timing
+        L.sdde_b200_rng_table.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     L.sdde_b200_dfma_peak.argtypes = [C.c_void_p, _dp]
     L.sdde_b200_hbm_peak.argtypes = [C.c_void_p, _dp]
     L.sdde_b200_alloc_pinned.argtypes = [C.c_int64]
@@ -151,6 +153,15 @@ def lib():
 def check(rc):
     if rc != 0:
         raise SddeError(rc, lib().sdde_b200_last_error().decode(errors="replace"))
+
+
+def rng_table() -> np.ndarray:
+    """Host copy of the normal generator's lookup table, shape (n_entries, 2) (layout: csrc/sdde_rng_tables.cuh)."""
+    n = C.c_int64(0)
+    check(lib().sdde_b200_rng_table(None, 0, C.byref(n)))
+    out = np.empty((n.value, 2))
+    check(lib().sdde_b200_rng_table(np_ptr(out), out.size, C.byref(n)))
+    return out
 
 
 def np_ptr(a: np.ndarray):

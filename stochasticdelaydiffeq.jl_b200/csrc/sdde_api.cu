@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "rng_table.hpp"
 #include "sdde_internal.cuh"
 #include "sdde_dispatch.cuh"
 
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) count_status_kernel(const unsigned char *
 
 // Chan merge of `parts` arrays of (count, mean, M2) triples, in order: dst[i] = merge(src[0][i], src[1][i], ...).
 // One thread per triple; used across trajectory waves and, after the NCCL all-gather, across GPUs.
-__global__ void merge_moments_kernel(const double *__restrict__ src, long long part_stride, int parts, long long n, double *__restrict__ dst) {
+__global__ void merge_moments_kernel(const double *src, long long part_stride, int parts, long long n, double *dst) {   // dst may be src (in-place wave merge)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double cnt = src[3 * i], mean = src[3 * i + 1], m2 = src[3 * i + 2];
@@ -112,11 +113,11 @@ __global__ void merge_moments_kernel(const double *__restrict__ src, long long p
 __global__ void __launch_bounds__(256) noise_regrid_kernel(const double *__restrict__ src, long long spitch, long long soff,
                                                            const GridNode *__restrict__ nodes, int nc, long long nt,
                                                            double *__restrict__ dst, long long dpitch) {
-    const long long row = blockIdx.y;                       // k * nc + c
+    const long long row = blockIdx.x;                       // k * nc + c; rows on grid.x (grid.y is capped at 65535)
     const GridNode g = nodes[row / nc];
     const int c = (int)(row % nc);
     const double *lo = src + ((long long)g.lo * nc + c) * spitch + soff, *hi = src + ((long long)g.hi * nc + c) * spitch + soff;
-    for (long long tr = (long long)blockIdx.x * 256 + threadIdx.x; tr < nt; tr += (long long)gridDim.x * 256)
+    for (long long tr = (long long)blockIdx.y * 256 + threadIdx.x; tr < nt; tr += (long long)gridDim.y * 256)
         dst[row * dpitch + tr] = g.lo == g.hi ? hi[tr] : (1.0 - g.theta) * lo[tr] + g.theta * hi[tr];
 }
 
@@ -315,8 +316,8 @@ int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
     return SDDE_OK;
 }
 
-void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pitch, std::vector<unsigned char> &steps,
-                 std::vector<sdde::SaveRec> &saves) {
+void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pitch, int batch, int chunk,
+                 std::vector<unsigned char> &steps, std::vector<sdde::SaveRec> &saves) {
     const int64_t N = S.n_steps();
     const int L = S.n_lag;
     const int64_t R = S.ring_slots;
@@ -364,6 +365,46 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
         memcpy(rec + 32, &off_store, 8);
         const double inv_sq = 1.0 / S.sqdt[(size_t)n];
         memcpy(rec + 40, &inv_sq, 8);
+    }
+    // Mark the batches (of the size the kernel will run: `batch` steps, starting at multiples of `batch` inside every
+    // chunk) that qualify for the lean body of run_batch: every lookup of every step is a ring hit of ONE kind
+    // (all exact / all interpolating), nodes and stored slots are consecutive ring slots without a wrap, dt and theta are
+    // bitwise the same for all steps, at most 255 saves per step.  The mark and the packed save counts live in the
+    // batch's first record.
+    if (batch < 1) return;                                  // option "lean" = 0: every batch takes the general body
+    const int NLK = L * S.n_stage;
+    auto rd64 = [](const unsigned char *p) { long long v; memcpy(&v, p, 8); return v; };
+    for (int64_t c0 = 0; c0 < N; c0 += chunk) {
+        const int64_t cend = std::min<int64_t>(N, c0 + chunk);
+        for (int64_t n = c0; n + batch <= cend; n += batch) {
+            unsigned char *r0 = steps.data() + (size_t)n * k.rec_size;
+            int m0;
+            memcpy(&m0, r0 + 28, 4);
+            bool ok = true, all_exact = true, all_interp = true;
+            unsigned long long packed = 0;
+            for (int kk = 0; kk < batch && ok; ++kk) {
+                const unsigned char *r = steps.data() + (size_t)(n + kk) * k.rec_size;
+                ok = ok && memcmp(r + 8, r0 + 8, 16) == 0;                                   // dt, sqrt|dt|
+                ok = ok && rd64(r + 32) == rd64(r0 + 32) + kk * slot_bytes;                  // stored slots consecutive
+                ok = ok && nsave[(size_t)(n + kk)] <= 255;
+                packed |= (unsigned long long)(nsave[(size_t)(n + kk)] & 255) << (8 * kk);
+                for (int l = 0; l < NLK && ok; ++l) {
+                    const int mode = S.lk_mode[(size_t)(n + kk) * NLK + l];
+                    all_exact = all_exact && mode == sdde::LK_EXACT;
+                    all_interp = all_interp && mode == sdde::LK_INTERP;
+                    const unsigned char *lk = r + 48 + 32 * l, *lk0 = r0 + 48 + 32 * l;
+                    ok = ok && rd64(lk + 16) == rd64(lk0 + 16) + kk * slot_bytes;            // nodes consecutive
+                    if (mode == sdde::LK_INTERP)
+                        ok = ok && memcmp(lk, lk0, 8) == 0 && rd64(lk + 8) == rd64(lk + 16) - slot_bytes;   // one theta; lo just below hi
+                }
+            }
+            ok = ok && (all_exact || all_interp) && batch <= 8;
+            if (ok) {
+                m0 |= all_exact ? SDDE_MASK_FAST_EXACT : SDDE_MASK_FAST_INTERP;
+                memcpy(r0 + 28, &m0, 4);
+                memcpy(r0 + 48 + 24, &packed, 8);            // lk[0].pad
+            }
+        }
     }
 }
 
@@ -432,6 +473,13 @@ sdde_ctx *sdde_b200_create(int device) {
         ok = cudaEventCreateWithFlags(&c->ev_kdone[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { fail(SDDE_ERR_CUDA, "stream/event creation failed"); sdde_b200_destroy(c); return nullptr; }
+    const size_t tab_bytes = (size_t)sdde::rng_table_entries() * 16;
+    if (c->rng_tab.reserve(tab_bytes) != cudaSuccess ||
+        cudaMemcpy(c->rng_tab.p, sdde::rng_table_host(), tab_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(SDDE_ERR_CUDA, "upload of the normal generator's table failed");
+        sdde_b200_destroy(c);
+        return nullptr;
+    }
     return c;
 }
 
@@ -439,6 +487,7 @@ void sdde_b200_destroy(sdde_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    c->rng_tab.release();
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
     c->h_status.release(); c->h_mom.release(); c->h_count.release(); c->gather.release();
@@ -464,6 +513,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "jit_linsys")) c->opt_jit_linsys = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
     else if (!strcmp(key, "zero_copy")) c->opt_zero_copy = value != 0;
+    else if (!strcmp(key, "lean")) { c->opt_lean = value != 0; c->table_key.clear(); }
     else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
@@ -546,7 +596,27 @@ int sdde_b200_moments(sdde_ctx *c, const double *paths, int32_t mem, int64_t n_r
     return SDDE_OK;
 }
 
+static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm);
+
 int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm) {
+    int rc = solve_once(c, d, out, moments, status, tm);
+    if (rc == SDDE_ERR_CUDA - (int)cudaErrorMemoryAllocation && c) {
+        // The wave size was planned from a cached cudaMemGetInfo (it costs ~1.5 ms per call) and other allocators share the
+        // device (torch, other contexts, this context's summary workspaces): drop our reusable workspaces, forget the cached
+        // budget and plan once more from a fresh reading -- the wave shrinks instead of the solve failing.
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            cudaSetDevice(c->device);
+            cudaGetLastError();
+            c->ring.release(); c->out[0].release(); c->out[1].release(); c->noise.release(); c->noise_src.release();
+            c->mem_key.clear(); c->mem_free_cached = 0;
+        }
+        rc = solve_once(c, d, out, moments, status, tm);
+    }
+    return rc;
+}
+
+static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *moments, uint8_t *status, sdde_timing *tm) {
     const auto wall0 = std::chrono::steady_clock::now();
     static const bool dbg = getenv("SDDE_DEBUG_TIMING") != nullptr;
     auto lap = [&](const char *what) { if (dbg) fprintf(stderr, "[sdde timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count()); };
@@ -582,7 +652,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (d->out_pitch != 0 && d->out_pitch < NT) return fail(SDDE_ERR_BAD_DESC, "out_pitch < n_traj");
     if (N >= (int64_t)1 << 30) return fail(SDDE_ERR_UNSUPPORTED, "more than 2^30 steps");
     if (tm) {
-        tm->n_steps = N; tm->n_save = n_save; tm->ring_slots = S.ring_slots; tm->block_threads = SDDE_BLOCK;
+        tm->n_steps = N; tm->n_save = n_save; tm->ring_slots = S.ring_slots; tm->block_threads = K.block;
         tm->traj_per_thread = K.tpt;
         if (K.lanes > 1) snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_coop_kernel<%s,alg%d,noise%d,lanes%d>", K.name, d->alg, d->noise_mode, K.lanes);
         else snprintf(tm->kernel_name, sizeof(tm->kernel_name), "sdde_solve_kernel<%s,alg%d,noise%d,ptraj%d,tpt%d,B%d>", K.name,
@@ -601,7 +671,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     int64_t h2d = 0, d2h = 0;
 
     // ---- wave geometry ----
-    const int64_t per_block = (int64_t)SDDE_BLOCK * K.tpt / K.lanes;
+    const int64_t per_block = (int64_t)K.block * K.tpt / K.lanes;
     size_t free_b = 0, total_b = 0;
     {
         std::string mkey = skey;
@@ -646,36 +716,55 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     int64_t wave = c->opt_wave_traj > 0 ? c->opt_wave_traj : ((int64_t)1 << 20);
     if (c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > ((int64_t)1 << 19)) wave = (int64_t)1 << 19;  // pipeline D2H (PCIe-bound: few, wide waves)
     const int64_t mem_cap = (int64_t)((double)free_b * 0.80 / bytes_per_traj);
-    wave = std::min(wave, std::max<int64_t>(per_block, mem_cap));
-    wave = std::max<int64_t>(per_block, (wave / per_block) * per_block);
-    wave = std::min(wave, ((NT + per_block - 1) / per_block) * per_block);
-    const int64_t pitch = wave;   // multiple of per_block => every thread of the grid owns in-bounds ring columns
+    // a wave is a whole number of warps (wq trajectories); the ring / staging pitch is rounded up to whole CTAs, so every
+    // thread of the grid owns in-bounds columns (threads past the wave's last trajectory recompute it and store nothing)
+    const int64_t wq = (int64_t)128 * K.tpt / K.lanes;
+    wave = std::min(wave, std::max<int64_t>(wq, mem_cap));
+    wave = std::max<int64_t>(wq, (wave / wq) * wq);
+    wave = std::min(wave, ((NT + wq - 1) / wq) * wq);
+    const int64_t pitch = ((wave + per_block - 1) / per_block) * per_block;
     // Wave list.  When the saved paths leave over PCIe (host output) the first waves are small and grow geometrically,
     // so that the D2H stream starts after a few milliseconds instead of after a whole 2^19-trajectory wave
     // and then never idles (measured on C2: D2H engine busy from 4 ms to the end).
     std::vector<int64_t> wave_off, wave_cnt;
     {
         const bool ramp = c->opt_wave_traj <= 0 && d->want_paths && !out_dev && NT > wave;
-        int64_t cur = ramp ? std::max<int64_t>(per_block, (c->opt_ramp_start / per_block) * per_block) : wave;
+        int64_t cur = ramp ? std::max<int64_t>(wq, (c->opt_ramp_start / wq) * wq) : wave;
         for (int64_t off = 0; off < NT;) {
             const int64_t cnt = std::min(std::min(cur, wave), NT - off);
             wave_off.push_back(off); wave_cnt.push_back(cnt);
             off += cnt;
-            if (ramp) cur = std::min(wave, std::max<int64_t>(per_block, (cur * 3 / 2 / per_block) * per_block));   // x1.5: a wave's kernel must end before the previous wave's copy does (kernel ~25, PCIe ~14 trajectories/us on C2)
+            if (ramp) cur = std::min(wave, std::max<int64_t>(wq, (cur * 3 / 2 / wq) * wq));   // x1.5: a wave's kernel must end before the previous wave's copy does (kernel ~25, PCIe ~14 trajectories/us on C2)
         }
     }
     const int n_waves = (int)wave_off.size();
+
+    int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
+    if (chunk >= 8) chunk -= chunk % 8;   // batches (B <= 8) never straddle a chunk; step index of a batch start stays even
+    // schedule records staged per refill (+ look-ahead records for the next step / next batch prefetch) must fit in shared
+    // memory beside the generator's table (in-kernel normals only): the SM's 227 KB, less 1 KB per CTA the system reserves,
+    // shared by the CTAs the kernel was compiled to keep resident
+    const size_t tab_bytes = d->noise_mode == SDDE_NOISE_PHILOX ? (size_t)SDDE_RNG_SMEM_BYTES : 0;
+    const size_t smem_cap = (size_t)(227 * 1024) / (size_t)std::max(1, K.min_ctas) - 2048;
+    while (chunk > 8 && tab_bytes + (size_t)(chunk + 8) * K.rec_size > smem_cap) chunk = ((chunk / 2) / 8) * 8;
+    const size_t smem = tab_bytes + (size_t)(chunk + 8) * K.rec_size;
+    if (smem > 48 * 1024)      // above the default limit the kernel has to opt in (built-in kernels and NVRTC kernel handles alike)
+        CU_CHECK(cudaFuncSetAttribute(K.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int batch = K.batch;
+    if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
+    if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step
+    if (batch < K.batch && K.batch > 1) batch = 1;          // the kernel runs its compiled depth or step by step
 
     // ---- schedule tables -> device (byte offsets depend on the wave pitch) ----
     std::vector<unsigned char> h_steps;
     std::vector<sdde::SaveRec> h_saves;
     {
         std::string tkey = skey;
-        const int64_t tk[] = {pitch, (int64_t)K.rec_size, (int64_t)K.n_state};
+        const int64_t tk[] = {pitch, (int64_t)K.rec_size, (int64_t)K.n_state, (int64_t)batch, (int64_t)chunk, (int64_t)c->opt_lean};
         tkey.append((const char *)tk, sizeof(tk));
         if (tkey != c->table_key) {
             c->table_key.clear();
-            pack_tables(S, K, pitch, h_steps, h_saves);
+            pack_tables(S, K, pitch, c->opt_lean ? batch : 0, chunk, h_steps, h_saves);
             CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
             CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
             if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
@@ -710,25 +799,14 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
     if (d->want_moments) CU_CHECK(c->mom.reserve((size_t)std::max<int64_t>(1, rows) * 3 * 8 * n_waves));
     if (tm) { tm->waves = n_waves; tm->ring_bytes = (int64_t)S.ring_slots * NS * pitch * 8; }
 
-    int chunk = (int)std::min<int64_t>(c->opt_chunk_steps, std::max<int64_t>(1, N));
-    if (chunk >= 8) chunk -= chunk % 8;   // batches (B <= 8) never straddle a chunk; step index of a batch start stays even
-    // schedule records staged per refill (+ look-ahead records for the next step / next batch prefetch) must fit in shared
-    // memory beside the generator tables: 200 KB at most, so that one more CTA's static share still fits
-    const size_t smem_cap = 200 * 1024;
-    while (chunk > 8 && (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 8) * K.rec_size > smem_cap) chunk = ((chunk / 2) / 8) * 8;
-    const size_t smem = (size_t)SDDE_RNG_SMEM_BYTES + (size_t)(chunk + 8) * K.rec_size;
-    if (smem > 48 * 1024)      // above the default limit the kernel has to opt in (built-in kernels and NVRTC kernel handles alike)
-        CU_CHECK(cudaFuncSetAttribute(K.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int batch = K.batch;
-    if (c->opt_batch > 0) batch = (int)std::min<int64_t>(batch, c->opt_batch);
-    if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step
-
     sdde::KArgs A;
     memset(&A, 0, sizeof(A));
     A.steps = (const unsigned char *)c->steps.p;
     A.saves = (const sdde::SaveRec *)c->saves.p;
     A.ring = (double *)c->ring.p;
     A.ring_pitch = pitch;
+    A.slot_bytes = (long long)NS * pitch * 8;
+    A.rng_tab = (const double2 *)c->rng_tab.p;
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
     A.n_saved = NSAVED;
@@ -779,7 +857,7 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
             else { A.noise = d->noise; A.noise_pitch = NT; A.noise_off = off; }
             if (regrid) {
                 const unsigned gx = (unsigned)std::min<int64_t>((nt + 255) / 256, 1024);
-                sdde::noise_regrid_kernel<<<dim3(gx, (unsigned)noise_rows), 256, 0, c->compute>>>(
+                sdde::noise_regrid_kernel<<<dim3((unsigned)noise_rows, gx), 256, 0, c->compute>>>(
                     A.noise, A.noise_pitch, A.noise_off, (const sdde::GridNode *)c->noise_nodes.p, NC, nt, (double *)c->noise.p, pitch);
                 CU_CHECK(cudaGetLastError());
                 ++launches;
@@ -805,10 +883,10 @@ int sdde_b200_solve(sdde_ctx *c, const sdde_desc *d, double *out, double *moment
         dbg_mark(c->compute);
         if (K.is_user) {
             std::string err;
-            if (!c->user.launch(K, grid, SDDE_BLOCK, smem, c->compute, &A, sizeof(A), err)) return fail(SDDE_ERR_CUDA, "%s", err.c_str());
+            if (!c->user.launch(K, grid, (unsigned)K.block, smem, c->compute, &A, sizeof(A), err)) return fail(SDDE_ERR_CUDA, "%s", err.c_str());
         } else {
             void *args[] = {(void *)&A};
-            CU_CHECK(cudaLaunchKernel(K.fn, dim3(grid), dim3(SDDE_BLOCK), args, smem, c->compute));
+            CU_CHECK(cudaLaunchKernel(K.fn, dim3(grid), dim3((unsigned)K.block), args, smem, c->compute));
         }
         ++launches;
         if (d->want_moments && rows > 0) {

@@ -15,16 +15,18 @@
 namespace sdde {
 
 template <class M, int ALG, int NOISE>
-__global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(SDDE_BLOCK_COOP) sdde_coop_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NW = M::NW, LPT = NS;
     static_assert(!M::DIAG && M::HAS_ROWS, "cooperative kernel needs a row-wise model with a noise matrix");
     static_assert(LPT == 4 || LPT == 8, "lanes per trajectory must be 4 or 8");
     typedef StepRec<NL> Rec;
+    constexpr int SDDE_BLOCK = SDDE_BLOCK_COOP;
+    constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
-    Rec *srec = reinterpret_cast<Rec *>(smem_raw + SDDE_RNG_SMEM_BYTES);
+    Rec *srec = reinterpret_cast<Rec *>(smem_raw + TAB_BYTES);
     if (NOISE == K_NOISE_PHILOX) {
-        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += SDDE_BLOCK) ltab[i] = RNG_TAB[i];
+        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += SDDE_BLOCK) ltab[i] = a.rng_tab[i];
     }
     const int j = threadIdx.x % LPT;                                                        // my state component
     const long long tr = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) / LPT;          // wave-local trajectory
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK) sdde_coop_kernel(const __grid_cons
         __syncthreads();
         {
             const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
-            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + SDDE_RNG_SMEM_BYTES);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + TAB_BYTES);
             const int nvec = cnt * (int)(sizeof(Rec) / 16);
             for (int i = threadIdx.x; i < nvec; i += SDDE_BLOCK) dst[i] = src[i];
         }

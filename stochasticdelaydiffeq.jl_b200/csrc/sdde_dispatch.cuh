@@ -8,6 +8,8 @@ namespace sdde {
 
 struct KernelInfo {
     const void *fn = nullptr;   // __global__ entry for cudaLaunchKernel
+    int block = 128;            // threads per CTA
+    int min_ctas = 1;           // CTAs per SM the kernel was compiled for (__launch_bounds__): shared-memory budget
     int tpt = 1;                // trajectories per thread
     int batch = 1;              // prefetch depth B compiled into the kernel
     int rec_size = 0;           // sizeof(StepRec<NL>)
@@ -24,6 +26,8 @@ inline KernelInfo make_info(const char *name) {
     KernelInfo k;
     constexpr int BB = (alg_stages(ALG) > 1 && Tune<M>::B > 1) ? Tune<M>::B / 2 : Tune<M>::B;   // two lookup sets per step
     k.fn = (const void *)&sdde_solve_kernel<M, ALG, NOISE, PT, Tune<M>::TPT, BB>;
+    k.block = Tune<M>::BLOCK;
+    k.min_ctas = TuneK<M, ALG>::MINB;
     k.tpt = Tune<M>::TPT;
     k.batch = BB;
     k.n_stage = alg_stages(ALG);
@@ -38,6 +42,7 @@ template <class M, int ALG, int NOISE>
 inline KernelInfo make_coop_info(const char *name) {
     KernelInfo k;
     k.fn = (const void *)&sdde_coop_kernel<M, ALG, NOISE>;
+    k.block = SDDE_BLOCK_COOP;
     k.tpt = 1; k.batch = 1; k.lanes = M::NS;
     k.rec_size = (int)sizeof(StepRec<M::NL>);
     k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = M::NW; k.n_param = M::NP;

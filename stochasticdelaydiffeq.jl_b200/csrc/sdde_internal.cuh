@@ -62,6 +62,7 @@ struct sdde_ctx {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
     cudaEvent_t ev_kdone[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_in = nullptr;
     DevBuf ring, out[2], steps, saves, noise, u0, ptraj, status, mom;
+    DevBuf rng_tab;                  // the normal generator's table (rng_table.cpp), uploaded once at creation
     DevBuf mom_part;                 // per-slice moment triples of one wave (moments_kernel -> merge_moments_kernel)
     DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
     PinnedBuf h_status, h_mom, h_count;
@@ -76,6 +77,7 @@ struct sdde_ctx {
     int64_t opt_wave_traj = 0;     // 0 = auto
     int64_t opt_batch = 0;         // 0 = compiled-in depth
     int64_t opt_chunk_steps = 128;
+    int64_t opt_lean = 1;          // mark uniform batches for the lean body of run_batch (0: general body everywhere; A/B and tests)
     int64_t opt_zero_copy = 1;     // page-locked host `out`: the step kernel stores the saved paths straight into it over PCIe
     int64_t opt_ramp_start = (int64_t)1 << 16;   // trajectories of the first wave when paths leave over PCIe (host output)
     int64_t opt_mem_limit = 0;     // bytes the workspaces may use (0 = 80 % of the free device memory)

@@ -35,10 +35,23 @@ __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULE
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
-#ifndef SDDE_BLOCK
-#define SDDE_BLOCK 128
+// CTA sizes.  Every CTA that draws in-kernel normals stages the generator's table (72 or 104 KB, sdde_rng_tables.cuh) in
+// shared memory, so the step kernels run FEW, LARGE CTAs per SM: scalar models 2 x 256 threads (SDDE_RNG_HALF = 0) or
+// 1 x 512 threads, multi-state models 1 x 384 threads (168 registers per thread); the cooperative-lanes kernel 128.
+#ifndef SDDE_BLOCK_SCALAR
+#define SDDE_BLOCK_SCALAR (SDDE_RNG_HALF ? 512 : 256)
 #endif
-#define SDDE_RNG_SMEM_BYTES (SDDE_RNG_TAB_ENTRIES * 16)   // 12 KB: log + cos/sin tables of the normal generator
+#ifndef SDDE_BLOCK_MULTI
+#define SDDE_BLOCK_MULTI 384
+#endif
+#define SDDE_BLOCK_COOP 128
+#define SDDE_RNG_SMEM_BYTES (SDDE_RNG_TAB_ENTRIES * 16)   // log + cos/sin tables of the normal generator
+// first record of a batch whose steps the kernel may run through the lean body (pack_tables decides):
+#define SDDE_MASK_FAST_EXACT (1 << 24)    // every lookup of every step hits a ring node exactly; slots, dt uniform / contiguous
+#define SDDE_MASK_FAST_INTERP (1 << 25)   // every lookup interpolates between consecutive nodes with ONE theta per lag
+#ifndef SDDE_PHILOX_ROUNDS
+#define SDDE_PHILOX_ROUNDS 10
+#endif
 
 struct SaveRec {
     int step;       // step whose end produces this save (-1: initial condition)
@@ -75,6 +88,8 @@ struct KArgs {
     long long ring_pitch, out_pitch, out_off, noise_pitch, noise_off, u0_pitch, p_pitch;
     long long n_traj;        // valid trajectories of this wave
     long long traj_gid0;     // global id of the wave's first trajectory
+    const double2 *rng_tab;  // generator table in global memory (sdde_rng_tables.cuh), staged per CTA
+    long long slot_bytes;    // one ring slot = NS * ring_pitch * 8 bytes
     int n_steps, n_saves, ring_slots, chunk_steps, batch, noise_kind;
     int out_vec_ok;          // out rows are 16-byte aligned for double2 stores
     int n_saved;             // states saved per save point (save_idxs)
@@ -110,16 +125,20 @@ template <class M> struct Tune {
     static constexpr int TPT = (M::NS == 1) ? SDDE_TUNE_TPT_SCALAR : (M::NS >= SDDE_TUNE_MULTI_MIN_NS ? SDDE_TUNE_TPT_MULTI : 1);
     static constexpr int FOOT = M::NS * M::NL * TPT;              // doubles per prefetched step (one node set)
     static constexpr int B = (M::NS == 1 && M::NL == 1) ? SDDE_TUNE_B_SCALAR : (FOOT <= SDDE_TUNE_FOOT_B2 ? 2 : 1);
-    // resident CTAs per SM the register allocation aims for: scalar models 5 (<= 102 registers); multi-state models
-    // with two trajectories per thread need the registers more than the occupancy (measured, profiles/README.md)
-    static constexpr int MINB = (M::NS >= SDDE_TUNE_MULTI_MIN_NS && TPT > 1) ? 3 : SDDE_MIN_BLOCKS;
+    // threads per CTA and resident CTAs per SM the register allocation aims for: 512 threads per SM with 128 registers
+    // for the small models, 384 threads with 168 registers for multi-state models with two trajectories per thread
+    // (they need the registers more than the occupancy: measured, profiles/README.md)
+    static constexpr bool WIDE = (M::NS >= SDDE_TUNE_MULTI_MIN_NS && TPT > 1);
+    static constexpr int BLOCK = WIDE ? SDDE_BLOCK_MULTI : SDDE_BLOCK_SCALAR;
+    static constexpr int MINB = WIDE ? 1 : 512 / SDDE_BLOCK_SCALAR;
 };
 
 // occupancy target per (model, algorithm): the model's, unless a measured exception is specialised next to the model
 template <class M, int ALG> struct TuneK { static constexpr int MINB = Tune<M>::MINB; };
 
 // ------------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011) + Box-Muller in float64.
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011; SDDE_PHILOX_ROUNDS = 7 is the paper's fastest Crush-resistant
+// variant, build-time option) + Box-Muller in float64.
 // Stream layout: counter = (traj_id_lo, traj_id_hi, call_lo, call_hi), key = (seed_lo, seed_hi);
 // normal number q = step*NC + channel of a trajectory is lane (q & 3) of call (q >> 2): four normals per call.
 // Replaces Xoroshiro128Plus + randn of /root/reference/src/solve.jl:313-336 (the bit stream is NOT reproduced,
@@ -127,7 +146,7 @@ template <class M, int ALG> struct TuneK { static constexpr int MINB = Tune<M>::
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, const u32 *__restrict__ rk, u32 (&o)[4]) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < SDDE_PHILOX_ROUNDS; ++r) {
         const u64 p0 = (u64)0xD2511F53u * c0;
         const u64 p1 = (u64)0xCD9E8D57u * c2;
         const u32 n0 = (u32)(p1 >> 32) ^ c1 ^ rk[2 * r];
@@ -160,15 +179,16 @@ __device__ __forceinline__ double rsqrt_approx(double x) {
 // smooth functional the mean over 2^24 equispaced directions is the trapezoidal rule of a smooth periodic function
 // (error beyond any power of 2^-24), so each z stays N(0,1) to far below float64 rounding; the radius keeps 40 bits
 // (tail truncated at 7.5 sigma, probability 5e-14 per draw; spacing of r at 6 sigma: 8e-5).
-// Evaluation: every argument range is known, so no special cases and no libm calls; both transcendental parts are
-// "table + short polynomial" with one shared-memory table (RNG_TAB, 12 KB, staged per CTA):
-//   -2 ln u  : u = 2^e' * M'; k = top 9 mantissa bits -> {1/c_k, -2 ln c'_k}; rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-10,
-//              log1p(rho) = rho + rho^2 (L2 + L3 rho + L4 rho^2 + L5 rho^3)            (truncation < 2^-62)
-//   sqrt     : MUFU.RSQ64H seed y, e = 1 - t y^2, y <- y (1 + e/2 + 3 e^2/8) (cubic step), r = t y   (<= 1 ulp)
-//   sin, cos : i = top 8 bits of the angle fraction -> {cos, sin}(pi/2 x_i); residual d = x - x_i, |d| <= 2^-9,
-//              sin(pi/2 d) = d (S1 + S3 d^2 + S5 d^4), cos(pi/2 d) = 1 + C2 d^2 + C4 d^4 (truncation < 2e-18), angle
-//              addition, exact quadrant rotation
-// 29 FP64 instructions per pair (the Taylor-only version needed 39).
+// Evaluation: every argument range is known, so no special cases and no libm calls; one shared-memory table
+// (sdde_rng_tables.cuh, staged per CTA):
+//   -2 ln u  : u = 2^e' * M'; k = top 9 mantissa bits -> {1/c_k, -2 ln c'_k}; rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-9,
+//              log1p(rho) = rho + rho^2 (L2 + L3 rho + L4 rho^2 + L5 rho^3)            (truncation < 2^-58)
+//   sqrt     : MUFU.RSQ64H seed y, r0 = t y, e = 1 - r0 y, r = r0 (1 + e/2 + 3 e^2/8) (cubic step)   (<= 1 ulp)
+//   sin, cos : the 2^23 angles of half a turn are alpha_i + beta_b with a 4096-entry and a 2048-entry table of exact
+//              {cos, sin}: ONE angle addition (mul, fma, mul, fma; <= 2 ulp absolute), the other half turn is a sign flip
+//              of the radius.  (Round 1 evaluated sin / cos of the residual angle by polynomials: 11 FP64 instructions
+//              and ~18 integer / select instructions instead of 4 and 5.)
+// 21 FP64 instructions per pair (round 1: 29; the Taylor-only version 39).
 __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const double2 *__restrict__ tab, double &z0, double &z1) {
     // ---- radius ----
     const double X = __hiloint2double((int)(0x3FF00000u | ((wb & 0xFFu) << 12) | (wa >> 20)), (int)(wa << 12));   // 1 + m 2^-40
@@ -178,13 +198,13 @@ __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const dou
     const int n = 1023 - (hi >> 20) - ((hi >> 19) & 1);                                      // -e' in [0, 41]
     const double M = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(U));    // mantissa in [1,2)
     const double2 te = tab[k];
-    // ---- angle: table lookup issued early ----
-    const u32 q = wb >> 30;
-    const u32 f = (wb >> 8) & 0x3FFFFFu;                                                     // 22-bit fraction
-    const double2 cs = tab[512 + (f >> 14)];
-    const u32 flow = f & 0x3FFFu;
-    const double D = __hiloint2double((int)(0x3FF00000u | (flow >> 2)), (int)((flow & 3u) << 30));   // 1 + flow 2^-22
-    const double dl = D - 1.00195300579071044921875;                                         // (flow + 1/2) 2^-22 - 2^-9, exact
+    // ---- angle: table lookups issued early ----
+#if SDDE_RNG_HALF
+    const double2 ca = tab[SDDE_RNG_OFF_COARSE + ((wb >> 19) & 0xFFFu)];
+#else
+    const double2 ca = tab[SDDE_RNG_OFF_COARSE + ((wb >> 19) & 0x7FFu)];
+#endif
+    const double2 cb = tab[SDDE_RNG_OFF_FINE + ((wb >> 8) & 0x7FFu)];
     // ---- -2 ln u ----
     const double rho = fma(M, te.x, -1.0);
     const double dn = __hiloint2double(0x43300000, n) - 4503599627370496.0;                  // (double)n
@@ -196,23 +216,27 @@ __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const dou
     t = fma(-2.0, l1p, t);                                                                   // -2 ln u  > 0
     // ---- sqrt(t) ----
     const double y = rsqrt_approx(t);
-    const double e = fma(-t, y * y, 1.0);
-    const double y1 = fma(y * e, fma(e, 0.375, 0.5), y);
-    const double g = t * y1;
-    // ---- sin / cos of (pi/2) x = (pi/2)(x_i + d) ----
-    const double d2 = dl * dl;
-    const double sd = dl * fma(d2, fma(d2, RNG_SINR_C[2], RNG_SINR_C[1]), RNG_SINR_C[0]);
-    const double cd = fma(d2, fma(d2, RNG_COSR_C[1], RNG_COSR_C[0]), 1.0);
-    const double cp = fma(-cs.y, sd, cs.x * cd);
-    const double sn = fma(cs.x, sd, cs.y * cd);
+    const double r0 = t * y;
+    const double e = fma(-r0, y, 1.0);
+    const double g = fma(r0 * e, fma(e, 0.375, 0.5), r0);
+    // ---- cos / sin (alpha + beta) ----
+    const double cp = fma(ca.x, cb.x, -(ca.y * cb.y));
+    const double sn = fma(ca.y, cb.x, ca.x * cb.y);
+    const int ghi = __double2hiint(g), glo = __double2loint(g);
+#if SDDE_RNG_HALF
+    const double gs = __hiloint2double(ghi ^ (int)(wb & 0x80000000u), glo);                 // second half turn: (-c, -s)
+    z0 = gs * cp;
+    z1 = gs * sn;
+#else
     // quadrant rotation: q=0 (c,s), 1 (-s,c), 2 (-c,-s), 3 (s,-c); signs folded into the radius
+    const u32 q = wb >> 30;
     const bool odd = (q & 1u) != 0;
     const double cc = odd ? sn : cp, ss = odd ? cp : sn;
-    const int ghi = __double2hiint(g), glo = __double2loint(g);
     const double gc = __hiloint2double(ghi ^ (int)(((q + 1u) & 2u) << 30), glo);
     const double gs = __hiloint2double(ghi ^ (int)((q & 2u) << 30), glo);
     z0 = gc * cc;
     z1 = gs * ss;
+#endif
 }
 
 // normals 4*call .. 4*call+3 of trajectory gid
@@ -372,33 +396,70 @@ struct TrajState {
 // BW consecutive steps starting at global step index n (recs[0..BW)).  BW > 1: the delayed-state nodes of all BW
 // steps are loaded up front (the host guarantees they are older than the batch) and n*NC is even, so which half of
 // a Philox pair a step consumes is a compile-time fact.
-template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW>
+// FAST selects the lean body for batches pack_tables marked on their first record (SDDE_MASK_FAST_*): every lookup of
+// the batch is a ring hit of one kind, the nodes and the stored slots are consecutive ring slots without a wrap, dt and
+// theta are the same for all BW steps and no step saves more than 255 points.  The lean body reads only recs[0]
+// (five 128-bit shared-memory loads per batch instead of nine 64-bit loads per step), derives every address from two
+// bases and the slot stride, and has no prehistory / constant-u0 selects; K_FAST_EXACT also drops the blend arithmetic.
+enum { K_FAST_NONE = 0, K_FAST_EXACT = 1, K_FAST_INTERP = 2 };
+template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW, int FAST>
 __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL * alg_stages(ALG)> *recs, int n,
                                           char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec,
                                           bool prefetch_next) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NSTG = alg_stages(ALG), NLK = NL * NSTG;
     constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 4 == 0);   // batch start n*NC is then a multiple of 4 as well
+    constexpr bool LEAN = FAST != K_FAST_NONE;
     typedef StepRec<NLK> Rec;
     const long long jstride = a.ring_pitch * 8;
+    const long long slot = a.slot_bytes;
     // ---- all delayed-state loads of the batch, unconditionally (prehistory records point at slot 0) ----
     double xlo[BW][NLK][NS][TPT], xhi[BW][NLK][NS][TPT];
-#pragma unroll
-    for (int k = 0; k < BW; ++k) {
+    if constexpr (LEAN) {
 #pragma unroll
         for (int l = 0; l < NLK; ++l) {
-            const char *plo = ringb + recs[k].lk[l].off_lo, *phi = ringb + recs[k].lk[l].off_hi;
+            const char *phi = ringb + recs[0].lk[l].off_hi;
+            if (FAST == K_FAST_INTERP) {
+                const bool reuse = (recs[0].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1): already in registers
+                const char *plo = ringb + recs[0].lk[l].off_lo;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[0][l][j]);
+                    else {
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) xlo[0][l][j][tt] = st.carry[l][j][tt];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < BW; ++k)
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    ld_traj<TPT>(reinterpret_cast<const double *>(phi + k * slot + j * jstride), xhi[k][l][j]);
+                    if (FAST == K_FAST_INTERP && k > 0) {
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) xlo[k][l][j][tt] = xhi[k - 1][l][j][tt];
+                    }
+                }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < BW; ++k) {
+#pragma unroll
+            for (int l = 0; l < NLK; ++l) {
+                const char *plo = ringb + recs[k].lk[l].off_lo, *phi = ringb + recs[k].lk[l].off_hi;
 #ifdef SDDE_NO_CARRY
-            const bool reuse = false;
+                const bool reuse = false;
 #else
-            const bool reuse = (recs[k].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1): already in registers
+                const bool reuse = (recs[k].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1): already in registers
 #endif
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
-                ld_traj<TPT>(reinterpret_cast<const double *>(phi + j * jstride), xhi[k][l][j]);
-                if (reuse) {
+                for (int j = 0; j < NS; ++j) {
+                    if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
+                    ld_traj<TPT>(reinterpret_cast<const double *>(phi + j * jstride), xhi[k][l][j]);
+                    if (reuse) {
 #pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt) xlo[k][l][j][tt] = (k == 0) ? st.carry[l][j][tt] : xhi[k > 0 ? k - 1 : 0][l][j][tt];
+                        for (int tt = 0; tt < TPT; ++tt) xlo[k][l][j][tt] = (k == 0) ? st.carry[l][j][tt] : xhi[k > 0 ? k - 1 : 0][l][j][tt];
+                    }
                 }
             }
         }
@@ -438,7 +499,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
     double dwb[BW][TPT][NC];
 #pragma unroll
     for (int k = 0; k < BW; ++k) {
-        const double sq = recs[k].sqdt;
+        const double sq = recs[LEAN ? 0 : k].sqdt;
         if (NOISE == K_NOISE_PHILOX) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -496,44 +557,57 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         for (int j = 0; j < NS; ++j) useq[0][tt][j] = st.u[tt][j];
 #pragma unroll
     for (int k = 0; k < BW; ++k) {
-        const Rec &r = recs[k];
-        const double tn = r.t, dtn = r.dt, sq = r.sqdt, isq = r.inv_sqdt;
+        const Rec &r = recs[LEAN ? 0 : k];
+        const double tn = recs[k].t, dtn = r.dt, sq = r.sqdt, isq = r.inv_sqdt;
         // delayed states: [EXT] HistoryFunction regimes
         double ul[TPT][NSTG][NL][NS];
 #pragma unroll
         for (int l = 0; l < NLK; ++l) {
-            const double th = r.lk[l].theta;
-            const bool ring = (r.ring_mask & (1 << l)) != 0;
-            const double omt = 1.0 - th;
-#pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                const double hv = a.hist_c0[j] + a.hist_c1[j] * th;
-#pragma unroll
-                for (int tt = 0; tt < TPT; ++tt) {
-                    const double iv = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
-                    ul[tt][l / NL][l % NL][j] = ring ? iv : hv;
-                }
-            }
-            if constexpr (HasHist<M>::value) {
-                if (!ring) {                                    // prehistory record (warp-uniform: the schedule is shared)
-#pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt) {
-                        double hv[NS];
-                        if (PTRAJ) M::h(hv, st.preg[tt], th);
-                        else M::h(hv, ConstParams{a.p}, th);
-#pragma unroll
-                        for (int j = 0; j < NS; ++j) ul[tt][l / NL][l % NL][j] = hv[j];
-                    }
-                }
-            }
-            if (NSTG > 1 && (r.ring_mask & (0x10000 << l))) {   // second-stage lookup past the dense history: constant u0
+            if constexpr (FAST == K_FAST_EXACT) {
 #pragma unroll
                 for (int j = 0; j < NS; ++j)
 #pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) ul[tt][l / NL][l % NL][j] = xhi[k][l][j][tt];
+            } else if constexpr (FAST == K_FAST_INTERP) {
+                const double th = r.lk[l].theta, omt = 1.0 - th;
+#pragma unroll
+                for (int j = 0; j < NS; ++j)
+#pragma unroll
+                    for (int tt = 0; tt < TPT; ++tt) ul[tt][l / NL][l % NL][j] = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
+            } else {
+                const double th = r.lk[l].theta;
+                const bool ring = (r.ring_mask & (1 << l)) != 0;
+                const double omt = 1.0 - th;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const double hv = a.hist_c0[j] + a.hist_c1[j] * th;
+#pragma unroll
                     for (int tt = 0; tt < TPT; ++tt) {
-                        const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
-                        ul[tt][l / NL][l % NL][j] = a.u0 ? a.u0[j * a.u0_pitch + tr] : a.u0c[j];
+                        const double iv = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
+                        ul[tt][l / NL][l % NL][j] = ring ? iv : hv;
                     }
+                }
+                if constexpr (HasHist<M>::value) {
+                    if (!ring) {                                    // prehistory record (warp-uniform: the schedule is shared)
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) {
+                            double hv[NS];
+                            if (PTRAJ) M::h(hv, st.preg[tt], th);
+                            else M::h(hv, ConstParams{a.p}, th);
+#pragma unroll
+                            for (int j = 0; j < NS; ++j) ul[tt][l / NL][l % NL][j] = hv[j];
+                        }
+                    }
+                }
+                if (NSTG > 1 && (r.ring_mask & (0x10000 << l))) {   // second-stage lookup past the dense history: constant u0
+#pragma unroll
+                    for (int j = 0; j < NS; ++j)
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) {
+                            const long long tr = (tr0 + tt <= last) ? tr0 + tt : last;
+                            ul[tt][l / NL][l % NL][j] = a.u0 ? a.u0[j * a.u0_pitch + tr] : a.u0c[j];
+                        }
+                }
             }
         }
         double (&dw)[TPT][NC] = dwb[k];
@@ -546,54 +620,66 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
             for (int j = 0; j < NS; ++j) useq[k + 1][tt][j] = st.u[tt][j];
         }
         // dense history: node n+1 (the save_everystep push of src/integrators/interface.jl:406-417)
+        char *pst = ringb + (LEAN ? recs[0].off_store + k * slot : recs[k].off_store);
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
             double v[TPT];
 #pragma unroll
             for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
-            st_traj<TPT>(reinterpret_cast<double *>(ringb + r.off_store + j * jstride), v);
+            st_traj<TPT>(reinterpret_cast<double *>(pst + j * jstride), v);
         }
     }
+    // [EXT] check_error! (src/solve.jl:578) looks at u after every step; here once per batch: every algorithm of this path
+    // forms u_{n+1} = u_n + increments, so a non-finite u_n never turns finite again and nothing slips through between checks
+#pragma unroll
+    for (int tt = 0; tt < TPT; ++tt)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) st.bad[tt] = st.bad[tt] || !finite_d(st.u[tt][j]);
     // ---- savevalues! (src/integrators/interface.jl:357-430), after the batch ----
+    const unsigned long long packed = LEAN ? (unsigned long long)recs[0].lk[0].pad : ~0ull;   // lean: nsave of step k in byte k
+    if (packed != 0) {
 #pragma unroll
-    for (int k = 0; k < BW; ++k) {
-        for (int s = 0; s < recs[k].nsave; ++s) {
-            const SaveRec sr = a.saves[st.ks];
+        for (int k = 0; k < BW; ++k) {
+            const int ns = LEAN ? (int)((packed >> (8 * k)) & 255u) : recs[k].nsave;
+            for (int s = 0; s < ns; ++s) {
+                const SaveRec sr = a.saves[st.ks];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                double v[TPT];
+                for (int j = 0; j < NS; ++j) {
+                    double v[TPT];
 #pragma unroll
-                for (int tt = 0; tt < TPT; ++tt) {
-                    v[tt] = sr.exact ? useq[k + 1][tt][j] : ((1.0 - sr.theta) * useq[k][tt][j] + sr.theta * useq[k + 1][tt][j]);
-                    st.bad[tt] = st.bad[tt] || !finite_d(v[tt]);
-                }
-                if (a.out && a.save_row[j] >= 0) {
-                    double *op = a.out + ((long long)st.ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr0;
-                    if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
-                    else {
+                    for (int tt = 0; tt < TPT; ++tt) {
+                        v[tt] = sr.exact ? useq[k + 1][tt][j] : ((1.0 - sr.theta) * useq[k][tt][j] + sr.theta * useq[k + 1][tt][j]);
+                        st.bad[tt] = st.bad[tt] || !finite_d(v[tt]);
+                    }
+                    if (a.out && a.save_row[j] >= 0) {
+                        double *op = a.out + ((long long)st.ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr0;
+                        if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
+                        else {
 #pragma unroll
-                        for (int tt = 0; tt < TPT; ++tt)
-                            if (tr0 + tt <= last) op[tt] = v[tt];
+                            for (int tt = 0; tt < TPT; ++tt)
+                                if (tr0 + tt <= last) op[tt] = v[tt];
+                        }
                     }
                 }
+                ++st.ks;
             }
-            ++st.ks;
         }
     }
 }
 
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
-__global__ void __launch_bounds__(SDDE_BLOCK, TuneK<M, ALG>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
-    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP;
+__global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
+    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP, BLOCK = Tune<M>::BLOCK;
+    constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES : 0;   // supplied noise: no generator table
     typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *ltab = reinterpret_cast<double2 *>(smem_raw);                  // tables of the normal generator
-    Rec *srec = reinterpret_cast<Rec *>(smem_raw + SDDE_RNG_SMEM_BYTES);
+    Rec *srec = reinterpret_cast<Rec *>(smem_raw + TAB_BYTES);
     if (NOISE == K_NOISE_PHILOX) {
-        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += SDDE_BLOCK) ltab[i] = RNG_TAB[i];
+        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += BLOCK) ltab[i] = a.rng_tab[i];
     }
 
-    const long long tr0 = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) * TPT;  // wave-local trajectory index
+    const long long tr0 = ((long long)blockIdx.x * BLOCK + threadIdx.x) * TPT;  // wave-local trajectory index
     const long long last = a.n_traj - 1;
 
     // ---- per-trajectory "__init": state, parameters, noise state (src/solve.jl:137, 302-339) ----
@@ -663,21 +749,35 @@ __global__ void __launch_bounds__(SDDE_BLOCK, TuneK<M, ALG>::MINB) sdde_solve_ke
         __syncthreads();
         {   // stage this chunk of the schedule in shared memory
             const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
-            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + SDDE_RNG_SMEM_BYTES);
+            uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + TAB_BYTES);
             const int nvec = nrec * (int)(sizeof(Rec) / 16);
-            for (int i = threadIdx.x; i < nvec; i += SDDE_BLOCK) dst[i] = src[i];
+            for (int i = threadIdx.x; i < nvec; i += BLOCK) dst[i] = src[i];
         }
         __syncthreads();
         int nb = 0;
         if (batched) {
-            for (; nb + B <= cnt; nb += B)
-                run_batch<M, ALG, NOISE, PTRAJ, TPT, B>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec,
-                                                        nb + 2 * B <= nrec /* next batch's records staged: prefetch its nodes */);
+            for (; nb + B <= cnt; nb += B) {
+                const int fm = srec[nb].ring_mask;
+                const bool pfn = nb + 2 * B <= nrec;   // next batch's records staged: prefetch its nodes
+                if (fm & SDDE_MASK_FAST_EXACT)
+                    run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_EXACT>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+                else if (fm & SDDE_MASK_FAST_INTERP)
+                    run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_INTERP>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+                else
+                    run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_NONE>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+            }
         }
         const bool pf = (B == 1) && a.prefetch;
-        for (; nb < cnt; ++nb)
-            run_batch<M, ALG, NOISE, PTRAJ, TPT, 1>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec,
-                                                    pf && (nb + 1 < nrec));
+        for (; nb < cnt; ++nb) {
+            const int fm = (B == 1) ? srec[nb].ring_mask : 0;   // step-by-step kernels: the marks are per step
+            const bool pfn = pf && (nb + 1 < nrec);
+            if (fm & SDDE_MASK_FAST_EXACT)
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_EXACT>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+            else if (fm & SDDE_MASK_FAST_INTERP)
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_INTERP>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+            else
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_NONE>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+        }
     }
     // [EXT] check_error! (src/solve.jl:578): NaN/Inf -> ReturnCode.Unstable, reported per trajectory
     if (a.status) {

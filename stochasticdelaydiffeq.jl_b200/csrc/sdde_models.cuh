@@ -85,9 +85,6 @@ struct ModelMackeyGlassT {
 };
 typedef ModelMackeyGlassT<0> ModelMackeyGlass;
 typedef ModelMackeyGlassT<10> ModelMackeyGlass10;
-// C2, the bench kernel (split-step EM on Mackey-Glass n = 10): 3 CTAs per SM with 128 registers beat 4 CTAs with 118 by
-// 1-2.4 % in same-box A/B runs, in bursts and under the power cap; EM(false) and the bandwidth-bound scalar models lose with 3.
-template <> struct TuneK<ModelMackeyGlassT<10>, K_ALG_EM_SPLIT> { static constexpr int MINB = 3; };
 
 // n-state linear delay system with n x m noise: BASELINE.json configs[3]
 //   du = (A u + sum_l B_l u(t-tau_l) + c) dt + G(u) dW,  G_ij = M_ij u_i + N_ij

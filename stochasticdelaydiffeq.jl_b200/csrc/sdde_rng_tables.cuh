@@ -1,785 +1,31 @@
-// sdde_rng_tables.cuh -- GENERATED by tools/gen_rng_tables.py (mpmath, 200-bit); do not edit.
-// Tables and coefficients of the range-restricted log / sin / cos used by the in-kernel Box-Muller transform.
+// sdde_rng_tables.cuh -- layout and polynomial coefficients of the in-kernel Box-Muller transform (NVRTC-clean).
+//
+// The table itself is computed once per process on the host in extended precision (rng_table.cpp, checked against
+// mpmath by tests/test_abi_host.py), uploaded once per context and staged into shared memory by every CTA that draws
+// in-kernel normals.  Layout (double2 entries):
+//   [0, 512)              LOG   k = top 9 mantissa bits of u: {1/c_k, -2 ln c'_k}, c_k = 1 + (k+1/2)/512 (c_511 = 2),
+//                               c'_k = c_k (k < 256) or c_k/2
+//   [512, 2560)           FINE  b = low 11 bits of the 22-bit angle fraction: {cos, sin}(beta_b),
+//                               beta_b = (pi/2) ((b + 1/2) 2^-22 - 2^-12)                       (|beta_b| < 3.9e-4)
+//   [2560, 2560 + 4096)   COARSE  i = (h << 11) | a, a = top 11 bits of the fraction, h = low quadrant bit:
+//                               {cos, sin}(alpha_i), alpha_i = (pi/2) (h + (a + 1/2) 2^-11 - 1/2)   (half a turn)
+// so that the angle of a draw, theta = (pi/2)(q + (f + 1/2) 2^-22 - 1/2) with q = 2 s + h, is alpha + beta + s pi and
+// cos / sin follow from ONE angle addition (4 FP64 instructions) and a sign flip -- no polynomial, no quadrant selects.
+// SDDE_RNG_HALF = 0 stages only the h = 0 half of COARSE (72 KB instead of 104 KB per CTA) and rotates quadrants in registers.
 #pragma once
-namespace sdde {
-// residual angle d, |d| <= 2^-9: sin(pi/2 d) = d (S[0] + S[1] d^2 + S[2] d^4), cos(pi/2 d) = 1 + C[0] d^2 + C[1] d^4
-static __constant__ double RNG_SINR_C[3] = {1.5707963267948966, -0.6459640975062463, 0.07969262624616705};
-static __constant__ double RNG_COSR_C[2] = {-1.2337005501361697, 0.25366950790104803};
-// log1p(r) = r + r^2 (L[0] + L[1] r + L[2] r^2 + L[3] r^3), |r| <= 2^-10
-static __constant__ double RNG_LOG1P_C[4] = {-0.5, 0.3333333333333333, -0.25, 0.2};
-// one table, staged in shared memory by every CTA (12 KB):
-//   [0, 512)   k = top 9 mantissa bits of u: {1/c_k, -2 ln c'_k}, c_k = 1 + (k+1/2)/512 (c_511 = 2), c'_k = c_k (k<256) or c_k/2
-//   [512, 768) i = top 8 bits of the angle fraction: {cos, sin}(pi/2 x_i), x_i = (i+1/2)/256 - 1/2
-#define SDDE_RNG_TAB_ENTRIES 768
-static __constant__ double2 RNG_TAB[768] = {
-    {0.9990243902439024, -0.0019521719461109196},
-    {0.997078870496592, -0.005850808658210201},
-    {0.9951409135082604, -0.009741860469193132},
-    {0.9932104752667313, -0.013625356835013638},
-    {0.9912875121006777, -0.01750132704037084},
-    {0.9893719806763285, -0.02136980020003276},
-    {0.9874638379942141, -0.025230805260148405},
-    {0.9855630413859481, -0.02908437099954849},
-    {0.983669548511047, -0.03293052603103164},
-    {0.9817833173537871, -0.03676929880263881},
-    {0.9799043062200957, -0.04060071759891651},
-    {0.9780324737344794, -0.044424810542167584},
-    {0.9761677788369876, -0.048241605593688223},
-    {0.9743101807802094, -0.052051130554995974},
-    {0.9724596391263058, -0.05585341306904471},
-    {0.9706161137440759, -0.05964848062142749},
-    {0.9687795648060549, -0.06343636054156908},
-    {0.9669499527856469, -0.06721708000390664},
-    {0.9651272384542884, -0.07099066602906014},
-    {0.9633113828786454, -0.0747571454849896},
-    {0.9615023474178404, -0.07851654508814483},
-    {0.9597000937207123, -0.0822688914046005},
-    {0.9579045837231057, -0.08601421085118424},
-    {0.9561157796451915, -0.08975252969659125},
-    {0.9543336439888164, -0.09348387406249083},
-    {0.9525581395348838, -0.09720826992462005},
-    {0.9507892293407614, -0.10092574311387094},
-    {0.9490268767377201, -0.1046363193173631},
-    {0.9472710453283997, -0.10834002407951027},
-    {0.9455216989843028, -0.11203688280307511},
-    {0.943778801843318, -0.11572692075021367},
-    {0.9420423183072677, -0.11941016304351272},
-    {0.9403122130394858, -0.12308663466701478},
-    {0.9385884509624198, -0.12675636046723537},
-    {0.9368709972552608, -0.13041936515417082},
-    {0.9351598173515981, -0.13407567330229628},
-    {0.9334548769371012, -0.13772530935155436},
-    {0.9317561419472248, -0.14136829760833647},
-    {0.9300635785649409, -0.1450046622464538},
-    {0.928377153218495, -0.14863442730809875},
-    {0.9266968325791856, -0.15225761670480012},
-    {0.9250225835591689, -0.15587425421836765},
-    {0.9233543733092876, -0.15948436350182799},
-    {0.9216921692169217, -0.1630879680803539},
-    {0.9200359389038635, -0.16668509135218337},
-    {0.9183856502242153, -0.17027575658953206},
-    {0.9167412712623098, -0.17385998693949523},
-    {0.9151027703306523, -0.1774378054249443},
-    {0.9134701159678859, -0.18100923494541354},
-    {0.9118432769367765, -0.18457429827798022},
-    {0.9102222222222223, -0.18813301807813473},
-    {0.9086069210292813, -0.19168541688064633},
-    {0.9069973427812223, -0.19523151710041778},
-    {0.905393457117595, -0.19877134103333483},
-    {0.9037952338923213, -0.20230491085710636},
-    {0.9022026431718062, -0.2058322486320998},
-    {0.9006156552330695, -0.2093533763021658},
-    {0.8990342405618964, -0.21286831569545808},
-    {0.8974583698510079, -0.21637708852524504},
-    {0.8958880139982502, -0.21987971639071507},
-    {0.8943231441048035, -0.2233762207777738},
-    {0.8927637314734089, -0.22686662305983513},
-    {0.8912097476066144, -0.23035094449860524},
-    {0.889661164205039, -0.2338292062448592},
-    {0.8881179531656548, -0.23730142933921194},
-    {0.8865800865800866, -0.24076763471288165},
-    {0.88504753673293, -0.2442278431884469},
-    {0.8835202761000863, -0.24768207548059715},
-    {0.8819982773471146, -0.2511303521968768},
-    {0.880481513327601, -0.2545726938384226},
-    {0.878969957081545, -0.2580091208006958},
-    {0.8774635818337618, -0.26143965337420566},
-    {0.8759623609923011, -0.26486431174523073},
-    {0.874466268146883, -0.26828311599652854},
-    {0.8729752770673487, -0.27169608610804474},
-    {0.8714893617021277, -0.2751032419576125},
-    {0.8700084961767205, -0.2785046033216472},
-    {0.8685326547921968, -0.2819001898758357},
-    {0.8670618120237087, -0.2852900211958185},
-    {0.8655959425190194, -0.28867411675786747},
-    {0.8641350210970464, -0.2920524959395569},
-    {0.8626790227464195, -0.29542517802043},
-    {0.8612279226240538, -0.2987921821826576},
-    {0.8597816960537363, -0.30215352751169405},
-    {0.8583403185247276, -0.305509232996926},
-    {0.8569037656903765, -0.308859317532316},
-    {0.8554720133667502, -0.3122037999170402},
-    {0.854045037531276, -0.3155426988561224},
-    {0.8526228143213989, -0.3188760329610608},
-    {0.8512053200332502, -0.3222038207504515},
-    {0.8497925311203319, -0.3255260806506046},
-    {0.848384424192212, -0.3288428309961569},
-    {0.8469809760132341, -0.33215409003067914},
-    {0.8455821635012386, -0.33545987590727844},
-    {0.8441879637262985, -0.33876020668919404},
-    {0.842798353909465, -0.3420551003503915},
-    {0.8414133114215283, -0.34534457477614827},
-    {0.8400328137817884, -0.3486286477636367},
-    {0.8386568386568387, -0.35190733702250304},
-    {0.8372853638593623, -0.3551806601754385},
-    {0.8359183673469388, -0.35844863475874844},
-    {0.8345558272208639, -0.36171127822291677},
-    {0.8331977217249796, -0.3649686079331635},
-    {0.8318440292445166, -0.3682206411700009},
-    {0.8304947283049473, -0.37146739512978233},
-    {0.8291497975708502, -0.37470888692524906},
-    {0.8278092158447857, -0.37794513358606974},
-    {0.8264729620661824, -0.38117615205937877},
-    {0.8251410153102336, -0.3844019592103083},
-    {0.8238133547868061, -0.38762257182251614},
-    {0.8224899598393575, -0.3908380065987097},
-    {0.8211708099438653, -0.3940482801611667},
-    {0.8198558847077662, -0.3972534090522493},
-    {0.8185451638689049, -0.40045340973491617},
-    {0.8172386272944933, -0.4036482985932303},
-    {0.8159362549800797, -0.40683809193286224},
-    {0.8146380270485283, -0.4100228059815886},
-    {0.8133439237490071, -0.41320245688978824},
-    {0.8120539254559873, -0.41637706073093295},
-    {0.8107680126682502, -0.4195466335020761},
-    {0.8094861660079051, -0.4227111911243351},
-    {0.8082083662194159, -0.42587074944337194},
-    {0.8069345941686368, -0.429025324229869},
-    {0.8056648308418568, -0.4321749311800019},
-    {0.8043990573448547, -0.4353195859159067},
-    {0.8031372549019608, -0.4384593039861469},
-    {0.8018794048551292, -0.4415941008661724},
-    {0.800625488663018, -0.4447239919587792},
-    {0.7993754879000781, -0.4478489925945623},
-    {0.7981293842556508, -0.4509691180323666},
-    {0.796887159533074, -0.454084383459734},
-    {0.7956487956487956, -0.45719480399334717},
-    {0.7944142746314973, -0.4603003946794686},
-    {0.7931835786212239, -0.4634011704943787},
-    {0.7919566898685229, -0.46649714634480866},
-    {0.7907335907335907, -0.46958833706837005},
-    {0.7895142636854279, -0.4726747574339817},
-    {0.7882986913010007, -0.475756422142293},
-    {0.787086856264412, -0.4788333458261044},
-    {0.7858787413660783, -0.4819055430507841},
-    {0.7846743295019157, -0.4849730283146813},
-    {0.7834736036725325, -0.4880358160495378},
-    {0.7822765469824293, -0.4910939206208937},
-    {0.7810831426392068, -0.4941473563284934},
-    {0.7798933739527799, -0.4971961374066861},
-    {0.7787072243346007, -0.5002402780248237},
-    {0.7775246772968869, -0.5032797922876558},
-    {0.7763457164518575, -0.5063146942357231},
-    {0.7751703255109765, -0.5093449978457445},
-    {0.7739984882842026, -0.5123707170310051},
-    {0.7728301886792452, -0.5153918656417391},
-    {0.771665410700829, -0.5184084574655088},
-    {0.7705041384499624, -0.5214205062275845},
-    {0.7693463561232157, -0.524428025591317},
-    {0.768192048012003, -0.527431029158511},
-    {0.7670411985018727, -0.5304295304697936},
-    {0.7658937920718025, -0.5334235430049802},
-    {0.7647498132935027, -0.5364130801834387},
-    {0.7636092468307233, -0.539398155364451},
-    {0.7624720774385704, -0.5423787818475689},
-    {0.7613382899628253, -0.5453549728729729},
-    {0.7602078693392724, -0.5483267416218218},
-    {0.7590808005930318, -0.5512941012166056},
-    {0.7579570688378978, -0.5542570647214916},
-    {0.7568366592756837, -0.5572156451426699},
-    {0.7557195571955719, -0.5601698554286965},
-    {0.7546057479734709, -0.563119708470832},
-    {0.753495217071376, -0.5660652171033812},
-    {0.7523879500367376, -0.5690063941040261},
-    {0.7512839325018342, -0.571943252194159},
-    {0.7501831501831502, -0.574875804039214},
-    {0.7490855888807608, -0.5778040622489928},
-    {0.747991234477721, -0.5807280393779916},
-    {0.7469000729394603, -0.5836477479257226},
-    {0.7458120903131829, -0.5865632003370358},
-    {0.7447272727272727, -0.5894744090024373},
-    {0.7436456063907044, -0.5923813862584035},
-    {0.7425670775924583, -0.5952841443876974},
-    {0.7414916727009413, -0.5981826956196782},
-    {0.7404193781634129, -0.6010770521306102},
-    {0.7393501805054151, -0.6039672260439717},
-    {0.738284066330209, -0.6068532294307571},
-    {0.7372210223182145, -0.6097350743097815},
-    {0.7361610352264558, -0.6126127726479795},
-    {0.7351040918880115, -0.6154863363607052},
-    {0.7340501792114695, -0.6183557773120258},
-    {0.7329992841803865, -0.6212211073150176},
-    {0.731951393852752, -0.6240823381320562},
-    {0.7309064953604568, -0.6269394814751078},
-    {0.729864575908767, -0.6297925490060156},
-    {0.7288256227758008, -0.632641552336786},
-    {0.7277896233120114, -0.635486503029872},
-    {0.7267565649396736, -0.6383274125984542},
-    {0.7257264351523742, -0.6411642925067218},
-    {0.7246992215145082, -0.6439971541701486},
-    {0.7236749116607774, -0.6468260089557699},
-    {0.7226534932956952, -0.6496508681824545},
-    {0.7216349541930938, -0.6524717431211791},
-    {0.7206192821956369, -0.6552886449952952},
-    {0.7196064652143359, -0.6581015849807985},
-    {0.7185964912280701, -0.6609105742065957},
-    {0.7175893482831114, -0.6637156237547668},
-    {0.7165850244926522, -0.6665167446608288},
-    {0.7155835080363382, -0.6693139479139957},
-    {0.7145847871598046, -0.6721072444574376},
-    {0.713588850174216, -0.6748966451885368},
-    {0.7125956854558108, -0.6776821609591436},
-    {0.7116052814454482, -0.6804638025758295},
-    {0.710617626648161, -0.6832415808001381},
-    {0.7096327096327096, -0.6860155063488356},
-    {0.7086505190311418, -0.688785589894159},
-    {0.7076710435383552, -0.6915518420640616},
-    {0.7066942719116632, -0.6943142734424586},
-    {0.7057201929703653, -0.6970728945694695},
-    {0.70474879559532, -0.6998277159416597},
-    {0.7037800687285224, -0.7025787480122795},
-    {0.7028140013726836, -0.7053260011915036},
-    {0.7018505825908157, -0.708069485846665},
-    {0.7008898015058179, -0.7108092123024928},
-    {0.6999316473000684, -0.7135451908413423},
-    {0.6989761092150171, -0.7162774317034292},
-    {0.6980231765507839, -0.7190059450870572},
-    {0.697072838665759, -0.7217307411488485},
-    {0.6961250849762066, -0.724451830003969},
-    {0.6951799049558723, -0.7271692217263545},
-    {0.6942372881355933, -0.729882926348934},
-    {0.6932972241029113, -0.7325929538638535},
-    {0.6923597025016903, -0.7352993142226935},
-    {0.6914247130317354, -0.7380020173366912},
-    {0.6904922454484154, -0.740701073076958},
-    {0.6895622895622896, -0.7433964912746936},
-    {0.6886348352387357, -0.746088281721404},
-    {0.6877098723975823, -0.7487764541691116},
-    {0.6867873910127431, -0.7514610183305707},
-    {0.6858673811118553, -0.7541419838794746},
-    {0.6849498327759197, -0.7568193604506676},
-    {0.6840347361389446, -0.7594931576403504},
-    {0.6831220813875917, -0.7621633850062893},
-    {0.6822118587608261, -0.7648300520680177},
-    {0.6813040585495675, -0.7674931683070427},
-    {0.6803986710963456, -0.770152743167046},
-    {0.6794956867949569, -0.7728087860540848},
-    {0.6785950960901259, -0.7754613063367916},
-    {0.6776968894771674, -0.778110313346573},
-    {0.6768010575016523, -0.7807558163778058},
-    {0.6759075907590759, -0.7833978246880329},
-    {0.6750164798945286, -0.7860363474981584},
-    {0.67412771560237, -0.7886713939926396},
-    {0.673241288625904, -0.7913029733196795},
-    {0.6723571897570584, -0.7939310945914176},
-    {0.6714754098360656, -0.7965557668841178},
-    {0.6705959397511461, -0.7991769992383586},
-    {0.6697187704381949, -0.8017948006592183},
-    {0.6688438928804703, -0.8044091801164612},
-    {0.6679712981082844, -0.8070201465447222},
-    {0.6671009771986971, -0.8096277088436887},
-    {0.6662329212752115, 0.5740624852416052},
-    {0.6653671215074723, 0.5714617046410383},
-    {0.6645035691109669, 0.5688643016785652},
-    {0.6636422553467272, 0.5662702675924751},
-    {0.6627831715210356, 0.5636795936551051},
-    {0.6619263089851325, 0.5610922711726645},
-    {0.6610716591349257, 0.5585082914850594},
-    {0.6602192134107028, 0.5559276459657192},
-    {0.6593689632968448, 0.5533503260214226},
-    {0.6585209003215434, 0.5507763230921279},
-    {0.6576750160565189, 0.5482056286508},
-    {0.6568313021167415, 0.5456382342032436},
-    {0.6559897501601537, 0.5430741312879326},
-    {0.655150351887396, 0.5405133114758435},
-    {0.6543130990415336, 0.5379557663702896},
-    {0.6534779834077856, 0.5354014876067553},
-    {0.6526449968132568, 0.5328504668527315},
-    {0.6518141311266709, 0.5303026958075543},
-    {0.6509853782581055, 0.5277581662022411},
-    {0.6501587301587302, 0.5252168697993299},
-    {0.6493341788205453, 0.52267879839272},
-    {0.6485117162761241, 0.5201439438075126},
-    {0.6476913345983555, 0.5176122978998529},
-    {0.6468730259001895, 0.5150838525567724},
-    {0.6460567823343849, 0.512558599696035},
-    {0.6452425960932577, 0.5100365312659787},
-    {0.644430459408433, 0.507517639245365},
-    {0.6436203645505971, 0.5050019156432232},
-    {0.642812303829253, 0.5024893524986999},
-    {0.6420062695924765, 0.49997994188090705},
-    {0.641202254226675, 0.49747367588877184},
-    {0.6404002501563477, 0.49497054665088835},
-    {0.6396002498438476, 0.4924705463253673},
-    {0.6388022457891454, 0.48997366709969087},
-    {0.638006230529595, 0.4874799011905644},
-    {0.6372121966397013, 0.4849892408437716},
-    {0.6364201367308887, 0.48250167833403024},
-    {0.6356300434512725, 0.48001720596484804},
-    {0.6348419094854308, 0.47753581606837897},
-    {0.6340557275541796, 0.4750575010052831},
-    {0.6332714904143476, 0.47258225316458324},
-    {0.6324891908585547, 0.4701100649635267},
-    {0.6317088217149908, 0.4676409288474447},
-    {0.6309303758471966, 0.46517483728961445},
-    {0.6301538461538462, 0.46271178279112113},
-    {0.629379225568531, 0.46025175788072104},
-    {0.6286065070595457, 0.4577947551147064},
-    {0.627835683629675, 0.45534076707676896},
-    {0.6270667483159829, 0.4528897863778666},
-    {0.6262996941896024, 0.45044180565608916},
-    {0.6255345143555284, 0.44799681757652704},
-    {0.62477120195241, 0.44555481483113735},
-    {0.6240097501523462, 0.44311579013861513},
-    {0.6232501521606817, 0.4406797362442607},
-    {0.6224924012158055, 0.4382466459198524},
-    {0.6217364905889496, 0.4358165119635163},
-    {0.6209824135839903, 0.43338932719959905},
-    {0.6202301635372501, 0.43096508447854076},
-    {0.6194797338173019, 0.4285437766767486},
-    {0.6187311178247734, 0.42612539669647026},
-    {0.6179843089921545, 0.42370993746567104},
-    {0.6172393007836046, 0.4212973919379078},
-    {0.6164960866947622, 0.41888775309220705},
-    {0.6157546602525557, 0.41648101393294157},
-    {0.615015015015015, 0.4140771674897083},
-    {0.6142771445710857, 0.4116762068172086},
-    {0.6135410425404434, 0.4092781249951267},
-    {0.6128067025733094, 0.40688291512800934},
-    {0.6120741183502689, 0.4044905703451487},
-    {0.6113432835820896, 0.4021010838004632},
-    {0.6106141920095408, 0.399714448672379},
-    {0.6098868374032163, 0.3973306581637153},
-    {0.6091612135633552, 0.39494970550156566},
-    {0.6084373143196673, 0.39257158393718494},
-    {0.6077151335311572, 0.39019628674587253},
-    {0.6069946650859513, 0.38782380722686005},
-    {0.6062759029011249, 0.3854541387031965},
-    {0.6055588409225311, 0.3830872745216364},
-    {0.6048434731246308, 0.38072320805252613},
-    {0.6041297935103245, 0.37836193268969553},
-    {0.6034177961107837, 0.3760034418503441},
-    {0.6027074749852854, 0.37364772897493265},
-    {0.6019988242210464, 0.3712947875270733},
-    {0.6012918379330593, 0.3689446109934202},
-    {0.6005865102639296, 0.36659719288356246},
-    {0.5998828353837141, 0.3642525267299156},
-    {0.5991808074897601, 0.36191060608761505},
-    {0.5984804208065458, 0.3595714245344097},
-    {0.5977816695855225, 0.357234975670557},
-    {0.5970845481049563, 0.3549012531187162},
-    {0.5963890506697729, 0.35257025052384583},
-    {0.595695171611402, 0.3502419615530982},
-    {0.5950029052876235, 0.3479163798957179},
-    {0.5943122460824144, 0.3455934992629376},
-    {0.5936231884057971, 0.3432733133878765},
-    {0.5929357266936884, 0.34095581602543945},
-    {0.5922498554077501, 0.33864100095221566},
-    {0.5915655690352397, 0.3363288619663782},
-    {0.5908828620888632, 0.33401939288758453},
-    {0.5902017291066283, 0.33171258755687777},
-    {0.5895221646516984, 0.3294084398365871},
-    {0.5888441633122484, 0.3271069436102308},
-    {0.5881677197013211, 0.32480809278241873},
-    {0.5874928284566838, 0.3225118812787548},
-    {0.5868194842406876, 0.3202183030457416},
-    {0.5861476817401259, 0.3179273520506835},
-    {0.5854774156660949, 0.31563902228159263},
-    {0.584808680753855, 0.31335330774709313},
-    {0.5841414717626925, 0.31107020247632766},
-    {0.5834757834757834, 0.3087897005188643},
-    {0.5828116107000569, 0.3065117959446025},
-    {0.5821489482660602, 0.3042364828436804},
-    {0.5814877910278251, 0.30196375532638453},
-    {0.580828133862734, 0.2996936075230565},
-    {0.5801699716713881, 0.2974260335840024},
-    {0.579513299377476, 0.2951610276794041},
-    {0.5788581119276427, 0.2928985839992261},
-    {0.5782044042913608, 0.2906386967531296},
-    {0.577552171460801, 0.28838136017038124},
-    {0.5769014084507043, 0.2861265684997646},
-    {0.5762521102982555, 0.28387431600949425},
-    {0.5756042720629567, 0.28162459698712655},
-    {0.574957888826502, 0.27937740573947367},
-    {0.5743129556926528, 0.277132736592516},
-    {0.5736694677871148, 0.27489058389131776},
-    {0.5730274202574147, 0.2726509419999409},
-    {0.5723868082727781, 0.27041380530135856},
-    {0.5717476270240089, 0.2681791681973733},
-    {0.5711098717233687, 0.2659470251085312},
-    {0.5704735376044568, 0.26371737047403837},
-    {0.5698386199220924, 0.2614901987516788},
-    {0.5692051139521956, 0.2592655044177305},
-    {0.5685730149916713, 0.2570432819668848},
-    {0.5679423183582918, 0.25482352591216245},
-    {0.5673130193905818, 0.25260623078483435},
-    {0.5666851134477033, 0.25039139113433967},
-    {0.5660585959093422, 0.24817900152820646},
-    {0.5654334621755936, 0.24596905655197024},
-    {0.5648097076668506, 0.24376155080909487},
-    {0.5641873278236914, 0.24155647892089432},
-    {0.5635663181067694, 0.23935383552645437},
-    {0.5629466739967015, 0.23715361528255238},
-    {0.5623283909939594, 0.23495581286358092},
-    {0.5617114646187603, 0.23276042296147084},
-    {0.5610958904109589, 0.2305674402856129},
-    {0.5604816639299398, 0.22837685956278345},
-    {0.5598687807545106, 0.22618867553706531},
-    {0.5592572364827962, 0.22400288296977522},
-    {0.5586470267321331, 0.22181947663938661},
-    {0.5580381471389646, 0.2196384513414556},
-    {0.5574305933587371, 0.2174598018885457},
-    {0.5568243610657966, 0.21528352311015445},
-    {0.5562194459532862, 0.2131096098526409},
-    {0.555615843733044, 0.21093805697915027},
-    {0.5550135501355014, 0.20876885936954168},
-    {0.5544125609095831, 0.20660201192031696},
-    {0.5538128718226069, 0.20443750954454726},
-    {0.5532144786601837, 0.20227534717180184},
-    {0.5526173772261198, 0.20011551974807726},
-    {0.5520215633423181, 0.19795802223572598},
-    {0.5514270328486807, 0.1958028496133852},
-    {0.5508337816030123, 0.19364999687590861},
-    {0.5502418054809243, 0.19149945903429544},
-    {0.549651100375738, 0.18935123111561988},
-    {0.5490616621983915, 0.18720530816296518},
-    {0.5484734868773433, 0.18506168523535155},
-    {0.5478865703584804, 0.18292035740767099},
-    {0.547300908605024, 0.1807813197706174},
-    {0.5467164975974372, 0.17864456743061966},
-    {0.5461333333333334, 0.17651009550977453},
-    {0.5455514118273841, 0.17437789914577906},
-    {0.5449707291112293, 0.17224797349186607},
-    {0.5443912812333865, 0.1701203137167362},
-    {0.5438130642591609, 0.16799491500449185},
-    {0.543236074270557, 0.16587177255457436},
-    {0.5426603073661898, 0.1637508815816965},
-    {0.5420857596611964, 0.1616322373157778},
-    {0.5415124272871497, 0.15951583500188182},
-    {0.5409403063919704, 0.1574016699001512},
-    {0.5403693931398417, 0.1552897372857433},
-    {0.5397996837111229, 0.15318003244876852},
-    {0.5392311743022643, 0.15107255069422487},
-    {0.5386638611257233, 0.14896728734193843},
-    {0.5380977404098791, 0.14686423772649776},
-    {0.5375328083989501, 0.1447633971971941},
-    {0.5369690613529103, 0.1426647611179587},
-    {0.536406495547407, 0.14056832486730167},
-    {0.5358451072736787, 0.13847408383825086},
-    {0.5352848928384736, 0.13638203343829097},
-    {0.5347258485639687, 0.13429216908930403},
-    {0.5341679707876891, 0.13220448622750772},
-    {0.5336112558624283, 0.1301189803033968},
-    {0.5330557001561687, 0.12803564678168347},
-    {0.5325013000520021, 0.12595448114123756},
-    {0.531948051948052, 0.1238754788750276},
-    {0.5313959522573949, 0.12179863549006392},
-    {0.5308449974079834, 0.11972394650733864},
-    {0.5302951838425686, 0.11765140746176776},
-    {0.5297465080186239, 0.11558101390213496},
-    {0.5291989664082687, 0.11351276139103228},
-    {0.5286525554981931, 0.11144664550480521},
-    {0.5281072717895823, 0.10938266183349327},
-    {0.5275631117980423, 0.1073208059807764},
-    {0.5270200720535255, 0.10526107356391681},
-    {0.526478149100257, 0.10320346021370333},
-    {0.5259373394966615, 0.10114796157439751},
-    {0.5253976398152899, 0.09909457330367508},
-    {0.5248590466427473, 0.09704329107257434},
-    {0.5243215565796211, 0.09499411056543894},
-    {0.5237851662404092, 0.09294702747986434},
-    {0.5232498722534492, 0.09090203752664455},
-    {0.5227156712608474, 0.08885913642971538},
-    {0.522182559918409, 0.08681831992610436},
-    {0.521650534895568, 0.08477958376587467},
-    {0.5211195928753181, 0.08274292371207356},
-    {0.5205897305541434, 0.08070833554067869},
-    {0.5200609446419502, 0.07867581504054556},
-    {0.519533231861999, 0.07664535801335629},
-    {0.5190065889508363, 0.07461696027356611},
-    {0.5184810126582279, 0.07259061764835244},
-    {0.5179564997470916, 0.07056632597756306},
-    {0.5174330469934311, 0.06854408111366551},
-    {0.5169106511862696, 0.06652387892169492},
-    {0.5163893091275845, 0.06450571527920504},
-    {0.5158690176322418, 0.06248958607621518},
-    {0.5153497735279315, 0.06047548721516306},
-    {0.514831573655103, 0.05846341461085221},
-    {0.5143144148669011, 0.05645336419040441},
-    {0.5137982940291018, 0.05444533189320723},
-    {0.5132832080200501, 0.05243931367086912},
-    {0.5127691537305958, 0.05043530548716616},
-    {0.512256128064032, 0.048433303317996536},
-    {0.511744127936032, 0.04643330315132992},
-    {0.5112331502745882, 0.04443530098716045},
-    {0.5107231920199501, 0.04243929283745755},
-    {0.510214250124564, 0.040445274726120445},
-    {0.5097063215530114, 0.03845324268892791},
-    {0.5091994032819492, 0.036463192773492546},
-    {0.5086934923000497, 0.03447512103921384},
-    {0.5081885856079404, 0.032489023557230094},
-    {0.5076846802181457, 0.030504896410373114},
-    {0.5071817731550272, 0.028522735693121713},
-    {0.5066798614547254, 0.026542537511554984},
-    {0.5061789421651013, 0.024564297983305686},
-    {0.505679012345679, 0.022588013237517825},
-    {0.5051800690675876, 0.020613679414796908},
-    {0.5046821094135042, 0.018641292667167447},
-    {0.5041851304775973, 0.01667084915802757},
-    {0.5036891293654697, 0.014702345062103437},
-    {0.5031941031941032, 0.012735776565406032},
-    {0.5027000490918017, 0.010771139865185133},
-    {0.5022069641981364, 0.008808431169886586},
-    {0.5017148456638902, 0.006847646699107184},
-    {0.5012236906510035, 0.004888782683552877},
-    {0.5007334963325183, 0.0029318353649923803},
-    {0.5, 0.0},
-    {0.7092728264388657, -0.7049340803759049},
-    {0.7135848687807936, -0.7005687939432483},
-    {0.7178700450557317, -0.696177131491463},
-    {0.7221281939292153, -0.6917592583641577},
-    {0.726359155084346, -0.6873153408917592},
-    {0.7305627692278276, -0.6828455463852481},
-    {0.7347388780959635, -0.6783500431298615},
-    {0.7388873244606151, -0.673829000378756},
-    {0.7430079521351217, -0.6692825883466361},
-    {0.7471006059801801, -0.6647109782033449},
-    {0.7511651319096864, -0.6601143420674205},
-    {0.7552013768965365, -0.6554928529996153},
-    {0.7592091889783881, -0.6508466849963809},
-    {0.7631884172633813, -0.6461760129833164},
-    {0.7671389119358204, -0.6414810128085832},
-    {0.7710605242618138, -0.6367618612362842},
-    {0.7749531065948739, -0.6320187359398091},
-    {0.778816512381476, -0.6272518154951441},
-    {0.7826505961665757, -0.62246127937415},
-    {0.7864552135990858, -0.617647307937804},
-    {0.79023022143731, -0.6128100824294097},
-    {0.7939754775543372, -0.6079497849677736},
-    {0.7976908409433912, -0.6030665985403482},
-    {0.8013761717231402, -0.5981607069963423},
-    {0.8050313311429635, -0.5932322950397998},
-    {0.808656181588175, -0.5882815482226453},
-    {0.8122505865852039, -0.5833086529376983},
-    {0.8158144108067338, -0.5783137964116556},
-    {0.819347520076797, -0.5732971666980422},
-    {0.8228497813758263, -0.5682589526701316},
-    {0.8263210628456635, -0.5631993440138341},
-    {0.829761233794523, -0.5581185312205561},
-    {0.8331701647019132, -0.5530167055800276},
-    {0.836547727223512, -0.5478940591731002},
-    {0.8398937941959995, -0.5427507848645159},
-    {0.8432082396418454, -0.5375870762956455},
-    {0.8464909387740521, -0.532403127877198},
-    {0.8497417680008524, -0.5271991347819014},
-    {0.8529606049303636, -0.5219752929371544},
-    {0.8561473283751945, -0.5167317990176499},
-    {0.8593018183570084, -0.5114688504379704},
-    {0.8624239561110405, -0.5061866453451553},
-    {0.8655136240905691, -0.5008853826112408},
-    {0.8685707059713409, -0.49556526182577254},
-    {0.8715950866559511, -0.49022648328829116},
-    {0.8745866522781761, -0.4848692480007911},
-    {0.8775452902072612, -0.479493757660153},
-    {0.8804708890521608, -0.47410021465055},
-    {0.8833633386657316, -0.46868882203582796},
-    {0.8862225301488806, -0.4632597835518602},
-    {0.8890483558546646, -0.45781330359887723},
-    {0.8918407093923427, -0.4523495872337709},
-    {0.8945994856313827, -0.4468688401623742},
-    {0.8973245807054183, -0.44137126873171667},
-    {0.9000158920161603, -0.4358570799222555},
-    {0.9026733182372588, -0.4303264813400826},
-    {0.9052967593181188, -0.4247796812091088},
-    {0.9078861164876663, -0.41921688836322396},
-    {0.9104412922580672, -0.41363831223843456},
-    {0.9129621904283982, -0.4080441628649787},
-    {0.9154487160882678, -0.40243465085941843},
-    {0.9179007756213905, -0.3968099874167103},
-    {0.9203182767091106, -0.39117038430225387},
-    {0.9227011283338785, -0.38551605384391885},
-    {0.9250492407826776, -0.37984720892405116},
-    {0.9273625256504011, -0.374164062971458},
-    {0.9296408958431812, -0.3684668299533723},
-    {0.9318842655816681, -0.3627557243673972},
-    {0.9340925504042589, -0.35703096123343003},
-    {0.9362656671702783, -0.35129275608556715},
-    {0.9384035340631081, -0.34554132496398904},
-    {0.9405060705932683, -0.33977688440682685},
-    {0.9425731976014469, -0.3339996514420094},
-    {0.9446048372614803, -0.32820984357909255},
-    {0.9466009130832835, -0.32240767880106985},
-    {0.9485613499157303, -0.31659337555616585},
-    {0.9504860739494817, -0.3107671527496115},
-    {0.9523750127197659, -0.30492922973540243},
-    {0.9542280951091057, -0.2990798263080405},
-    {0.9560452513499964, -0.29321916269425863},
-    {0.9578264130275329, -0.2873474595447295},
-    {0.9595715130819845, -0.281464937925758},
-    {0.9612804858113206, -0.27557181931095814},
-    {0.9629532668736839, -0.2696683255729151},
-    {0.9645897932898128, -0.2637546789748314},
-    {0.9661900034454125, -0.257831102162159},
-    {0.9677538370934755, -0.25189781815421697},
-    {0.9692812353565485, -0.24595505033579462},
-    {0.9707721407289504, -0.2400030224487415},
-    {0.9722264970789363, -0.23404195858354343},
-    {0.973644249650812, -0.22807208317088573},
-    {0.9750253450669941, -0.22209362097320354},
-    {0.9763697313300211, -0.21610679707621952},
-    {0.9776773578245099, -0.2101118368804696},
-    {0.9789481753190622, -0.20410896609281687},
-    {0.9801821359681174, -0.1980984107179536},
-    {0.9813791933137546, -0.19208039704989244},
-    {0.9825393022874412, -0.18605515166344666},
-    {0.9836624192117303, -0.18002290140569951},
-    {0.9847485018019042, -0.17398387338746382},
-    {0.9857975091675675, -0.16793829497473117},
-    {0.9868094018141855, -0.16188639378011183},
-    {0.9877841416445722, -0.15582839765426523},
-    {0.9887216919603238, -0.1497645346773215},
-    {0.9896220174632009, -0.14369503315029444},
-    {0.9904850842564571, -0.13762012158648604},
-    {0.9913108598461154, -0.13154002870288312},
-    {0.9920993131421918, -0.12545498341154623},
-    {0.9928504144598651, -0.11936521481099137},
-    {0.9935641355205953, -0.11327095217756435},
-    {0.9942404494531879, -0.10717242495680884},
-    {0.9948793307948056, -0.10106986275482782},
-    {0.9954807554919269, -0.094963495329639},
-    {0.996044700901252, -0.0888535525825246},
-    {0.9965711457905548, -0.08274026454937569},
-    {0.997060070339483, -0.07662386139203149},
-    {0.9975114561403035, -0.07050457338961387},
-    {0.997925286198596, -0.06438263092985747},
-    {0.9983015449338929, -0.05825826450043576},
-    {0.9986402181802653, -0.052131704680283324},
-    {0.9989412931868569, -0.04600318213091463},
-    {0.9992047586183639, -0.03987292758773981},
-    {0.9994306045554617, -0.03374117185137759},
-    {0.9996188224951786, -0.027608145778965743},
-    {0.9997694053512153, -0.021474080275469508},
-    {0.9998823474542126, -0.015339206284988102},
-    {0.9999576445519639, -0.00920375478205982},
-    {0.9999952938095762, -0.003067956762965976},
-    {0.9999952938095762, 0.003067956762965976},
-    {0.9999576445519639, 0.00920375478205982},
-    {0.9998823474542126, 0.015339206284988102},
-    {0.9997694053512153, 0.021474080275469508},
-    {0.9996188224951786, 0.027608145778965743},
-    {0.9994306045554617, 0.03374117185137759},
-    {0.9992047586183639, 0.03987292758773981},
-    {0.9989412931868569, 0.04600318213091463},
-    {0.9986402181802653, 0.052131704680283324},
-    {0.9983015449338929, 0.05825826450043576},
-    {0.997925286198596, 0.06438263092985747},
-    {0.9975114561403035, 0.07050457338961387},
-    {0.997060070339483, 0.07662386139203149},
-    {0.9965711457905548, 0.08274026454937569},
-    {0.996044700901252, 0.0888535525825246},
-    {0.9954807554919269, 0.094963495329639},
-    {0.9948793307948056, 0.10106986275482782},
-    {0.9942404494531879, 0.10717242495680884},
-    {0.9935641355205953, 0.11327095217756435},
-    {0.9928504144598651, 0.11936521481099137},
-    {0.9920993131421918, 0.12545498341154623},
-    {0.9913108598461154, 0.13154002870288312},
-    {0.9904850842564571, 0.13762012158648604},
-    {0.9896220174632009, 0.14369503315029444},
-    {0.9887216919603238, 0.1497645346773215},
-    {0.9877841416445722, 0.15582839765426523},
-    {0.9868094018141855, 0.16188639378011183},
-    {0.9857975091675675, 0.16793829497473117},
-    {0.9847485018019042, 0.17398387338746382},
-    {0.9836624192117303, 0.18002290140569951},
-    {0.9825393022874412, 0.18605515166344666},
-    {0.9813791933137546, 0.19208039704989244},
-    {0.9801821359681174, 0.1980984107179536},
-    {0.9789481753190622, 0.20410896609281687},
-    {0.9776773578245099, 0.2101118368804696},
-    {0.9763697313300211, 0.21610679707621952},
-    {0.9750253450669941, 0.22209362097320354},
-    {0.973644249650812, 0.22807208317088573},
-    {0.9722264970789363, 0.23404195858354343},
-    {0.9707721407289504, 0.2400030224487415},
-    {0.9692812353565485, 0.24595505033579462},
-    {0.9677538370934755, 0.25189781815421697},
-    {0.9661900034454125, 0.257831102162159},
-    {0.9645897932898128, 0.2637546789748314},
-    {0.9629532668736839, 0.2696683255729151},
-    {0.9612804858113206, 0.27557181931095814},
-    {0.9595715130819845, 0.281464937925758},
-    {0.9578264130275329, 0.2873474595447295},
-    {0.9560452513499964, 0.29321916269425863},
-    {0.9542280951091057, 0.2990798263080405},
-    {0.9523750127197659, 0.30492922973540243},
-    {0.9504860739494817, 0.3107671527496115},
-    {0.9485613499157303, 0.31659337555616585},
-    {0.9466009130832835, 0.32240767880106985},
-    {0.9446048372614803, 0.32820984357909255},
-    {0.9425731976014469, 0.3339996514420094},
-    {0.9405060705932683, 0.33977688440682685},
-    {0.9384035340631081, 0.34554132496398904},
-    {0.9362656671702783, 0.35129275608556715},
-    {0.9340925504042589, 0.35703096123343003},
-    {0.9318842655816681, 0.3627557243673972},
-    {0.9296408958431812, 0.3684668299533723},
-    {0.9273625256504011, 0.374164062971458},
-    {0.9250492407826776, 0.37984720892405116},
-    {0.9227011283338785, 0.38551605384391885},
-    {0.9203182767091106, 0.39117038430225387},
-    {0.9179007756213905, 0.3968099874167103},
-    {0.9154487160882678, 0.40243465085941843},
-    {0.9129621904283982, 0.4080441628649787},
-    {0.9104412922580672, 0.41363831223843456},
-    {0.9078861164876663, 0.41921688836322396},
-    {0.9052967593181188, 0.4247796812091088},
-    {0.9026733182372588, 0.4303264813400826},
-    {0.9000158920161603, 0.4358570799222555},
-    {0.8973245807054183, 0.44137126873171667},
-    {0.8945994856313827, 0.4468688401623742},
-    {0.8918407093923427, 0.4523495872337709},
-    {0.8890483558546646, 0.45781330359887723},
-    {0.8862225301488806, 0.4632597835518602},
-    {0.8833633386657316, 0.46868882203582796},
-    {0.8804708890521608, 0.47410021465055},
-    {0.8775452902072612, 0.479493757660153},
-    {0.8745866522781761, 0.4848692480007911},
-    {0.8715950866559511, 0.49022648328829116},
-    {0.8685707059713409, 0.49556526182577254},
-    {0.8655136240905691, 0.5008853826112408},
-    {0.8624239561110405, 0.5061866453451553},
-    {0.8593018183570084, 0.5114688504379704},
-    {0.8561473283751945, 0.5167317990176499},
-    {0.8529606049303636, 0.5219752929371544},
-    {0.8497417680008524, 0.5271991347819014},
-    {0.8464909387740521, 0.532403127877198},
-    {0.8432082396418454, 0.5375870762956455},
-    {0.8398937941959995, 0.5427507848645159},
-    {0.836547727223512, 0.5478940591731002},
-    {0.8331701647019132, 0.5530167055800276},
-    {0.829761233794523, 0.5581185312205561},
-    {0.8263210628456635, 0.5631993440138341},
-    {0.8228497813758263, 0.5682589526701316},
-    {0.819347520076797, 0.5732971666980422},
-    {0.8158144108067338, 0.5783137964116556},
-    {0.8122505865852039, 0.5833086529376983},
-    {0.808656181588175, 0.5882815482226453},
-    {0.8050313311429635, 0.5932322950397998},
-    {0.8013761717231402, 0.5981607069963423},
-    {0.7976908409433912, 0.6030665985403482},
-    {0.7939754775543372, 0.6079497849677736},
-    {0.79023022143731, 0.6128100824294097},
-    {0.7864552135990858, 0.617647307937804},
-    {0.7826505961665757, 0.62246127937415},
-    {0.778816512381476, 0.6272518154951441},
-    {0.7749531065948739, 0.6320187359398091},
-    {0.7710605242618138, 0.6367618612362842},
-    {0.7671389119358204, 0.6414810128085832},
-    {0.7631884172633813, 0.6461760129833164},
-    {0.7592091889783881, 0.6508466849963809},
-    {0.7552013768965365, 0.6554928529996153},
-    {0.7511651319096864, 0.6601143420674205},
-    {0.7471006059801801, 0.6647109782033449},
-    {0.7430079521351217, 0.6692825883466361},
-    {0.7388873244606151, 0.673829000378756},
-    {0.7347388780959635, 0.6783500431298615},
-    {0.7305627692278276, 0.6828455463852481},
-    {0.726359155084346, 0.6873153408917592},
-    {0.7221281939292153, 0.6917592583641577},
-    {0.7178700450557317, 0.696177131491463},
-    {0.7135848687807936, 0.7005687939432483},
-    {0.7092728264388657, 0.7049340803759049},
-};
+#ifndef SDDE_RNG_HALF
+#define SDDE_RNG_HALF 1
+#endif
+#define SDDE_RNG_LOG_ENTRIES 512
+#define SDDE_RNG_FINE_ENTRIES 2048
+#define SDDE_RNG_OFF_FINE 512
+#define SDDE_RNG_OFF_COARSE 2560
+#define SDDE_RNG_TAB_ENTRIES_MAX (2560 + 4096)
+#define SDDE_RNG_TAB_ENTRIES (2560 + (SDDE_RNG_HALF ? 4096 : 2048))
 #define SDDE_RNG_TWO_LN2 1.3862943611198906
+#ifdef __CUDACC__
+namespace sdde {
+// log1p(r) = r + r^2 (L[0] + L[1] r + L[2] r^2 + L[3] r^3), |r| <= 2^-9
+static __constant__ double RNG_LOG1P_C[4] = {-0.5, 0.3333333333333333, -0.25, 0.2};
 }  // namespace sdde
+#endif

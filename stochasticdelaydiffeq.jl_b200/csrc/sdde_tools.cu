@@ -1,7 +1,9 @@
 // sdde_tools.cu -- test hooks and micro-benchmarks of the C ABI: the normals the step kernels draw, measured DFMA and
 // copy peaks of this GPU (roofline denominators), page-locked host memory helpers.
 #include <algorithm>
+#include <cstring>
 
+#include "rng_table.hpp"
 #include "sdde_internal.cuh"
 #include "sdde_kernels.cuh"
 #define fail sdde_fail
@@ -10,9 +12,10 @@ namespace sdde {
 
 // test hook: the normals the step kernels would draw, laid out [n][c][traj]
 __global__ void philox_dump_kernel(double *out, long long n_traj, long long traj_off, long long n_steps, int nc, u32 k0,
-                                   u32 k1) {
-    __shared__ double2 ltab[SDDE_RNG_TAB_ENTRIES];
-    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += blockDim.x) ltab[i] = RNG_TAB[i];
+                                   u32 k1, const double2 *__restrict__ rng_tab) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
+    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += blockDim.x) ltab[i] = rng_tab[i];
     __syncthreads();
     u32 rk[20];
     philox_round_keys(k0, k1, rk);
@@ -56,11 +59,24 @@ int sdde_b200_philox_normals(sdde_ctx *c, uint64_t seed, int64_t traj_offset, in
     CU_CHECK(cudaSetDevice(c->device));
     const size_t bytes = (size_t)n_steps * n_noise * n_traj * 8;
     CU_CHECK(c->out[0].reserve(bytes));
-    sdde::philox_dump_kernel<<<(unsigned)((n_traj + 127) / 128), 128, 0, c->compute>>>(
-        (double *)c->out[0].p, n_traj, traj_offset, n_steps, n_noise, (sdde::u32)(seed & 0xffffffffu), (sdde::u32)(seed >> 32));
+    CU_CHECK(cudaFuncSetAttribute(sdde::philox_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDDE_RNG_SMEM_BYTES));
+    sdde::philox_dump_kernel<<<(unsigned)((n_traj + 127) / 128), 128, SDDE_RNG_SMEM_BYTES, c->compute>>>(
+        (double *)c->out[0].p, n_traj, traj_offset, n_steps, n_noise, (sdde::u32)(seed & 0xffffffffu), (sdde::u32)(seed >> 32),
+        (const double2 *)c->rng_tab.p);
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaMemcpyAsync(out_host, c->out[0].p, bytes, cudaMemcpyDeviceToHost, c->compute));
     CU_CHECK(cudaStreamSynchronize(c->compute));
+    return SDDE_OK;
+}
+
+// test hook: the host copy of the generator's table (sdde_rng_tables.cuh), 2 * n_entries doubles; no device needed
+int sdde_b200_rng_table(double *out, int64_t cap_doubles, int64_t *n_entries) {
+    const int n = sdde::rng_table_entries();
+    if (n_entries) *n_entries = n;
+    if (out) {
+        if (cap_doubles < 2 * (int64_t)n) return fail(SDDE_ERR_BAD_DESC, "buffer too small for %d table entries", n);
+        memcpy(out, sdde::rng_table_host(), sizeof(double) * 2 * (size_t)n);
+    }
     return SDDE_OK;
 }
 

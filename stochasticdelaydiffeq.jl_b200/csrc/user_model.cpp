@@ -67,7 +67,7 @@ std::string wrap_source(const char *user) {
     s += "\n}  // namespace sdde\n";
     s += "extern \"C\" __device__ const int sdde_user_dims[10] = {sdde::UserModel::NS, sdde::UserModel::NL, sdde::UserModel::NW,\n"
          "  sdde::UserModel::NP, sdde::UserModel::DIAG ? 1 : 0, sdde::Tune<sdde::UserModel>::TPT, sdde::Tune<sdde::UserModel>::B,\n"
-         "  (int)sizeof(sdde::StepRec<sdde::UserModel::NL>), 0, 0};\n"
+         "  (int)sizeof(sdde::StepRec<sdde::UserModel::NL>), sdde::Tune<sdde::UserModel>::BLOCK, sdde::Tune<sdde::UserModel>::MINB};\n"
          "extern \"C\" __global__ void sdde_user_probe(int *o) { for (int i = 0; i < 10; ++i) o[i] = sdde_user_dims[i]; }\n";
     return s;
 }
@@ -100,7 +100,7 @@ int UserModels::compile(const char *source, std::string &err, const char *name) 
     if (e != cudaSuccess) { err = std::string("user model probe failed: ") + cudaGetErrorString(e); return -1; }
     Entry en;
     en.ns = dims[0]; en.nl = dims[1]; en.nw = dims[2]; en.np = dims[3]; en.diag = dims[4] != 0;
-    en.tpt = dims[5]; en.batch = dims[6]; en.rec_size = dims[7];
+    en.tpt = dims[5]; en.batch = dims[6]; en.rec_size = dims[7]; en.block = dims[8]; en.min_ctas = dims[9];
     if (en.ns < 1 || en.ns > SDDE_MAX_STATE || en.nl < 1 || en.nl > SDDE_MAX_LAG || en.nw < 1 || en.nw > SDDE_MAX_NOISE ||
         en.np < 0 || en.np > SDDE_MAX_PARAM) {
         err = "UserModel dimensions out of range";
@@ -140,6 +140,7 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
     k = KernelInfo();
     k.fn = en.kernels[(size_t)v];
     k.is_user = true;
+    k.block = en.block; k.min_ctas = en.min_ctas;
     k.tpt = en.tpt; k.batch = (alg == 4 && en.batch > 1) ? en.batch / 2 : en.batch;
     k.n_stage = alg == 4 ? 2 : 1;
     k.rec_size = 48 + 32 * en.nl * k.n_stage;

@@ -26,7 +26,7 @@ class UserModels {
    private:
     struct Entry {
         std::vector<void *> kernels;          // cudaKernel_t per (alg, noise, ptraj)
-        int ns = 0, nl = 0, nw = 0, np = 0, tpt = 1, batch = 1, rec_size = 0;
+        int ns = 0, nl = 0, nw = 0, np = 0, tpt = 1, batch = 1, rec_size = 0, block = 128, min_ctas = 1;
         bool diag = true;
         std::string name;
         std::string source;                   // wrapped program text (variants are compiled lazily from it)

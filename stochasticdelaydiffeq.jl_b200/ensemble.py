@@ -40,28 +40,73 @@ class EnsembleB200:
 # ---------------------------------------------------------------------------------------------
 # saveat expansion: /root/reference/src/solve.jl:32-34, 411-415, 659-677
 # ---------------------------------------------------------------------------------------------
+def _rat(x: float):
+    """[EXT] Base.rat (julia/base/twiceprecision.jl): continued-fraction approximation num/den of a Float64 with both
+    terms <= maxintfloat(Float32) = 2^24; returns the previous convergent when the next one would overflow that bound."""
+    m = 16777216.0
+    y, a, b, c, d = x, 1, 0, 0, 1
+    while abs(y) <= m:
+        f = math.trunc(y)
+        y -= f
+        a, c = f * a + c, a
+        b, d = f * b + d, b
+        if max(abs(a), abs(b)) > 16777216:
+            return c, d
+        if b != 0 and a / b == x:
+            break
+        y = math.inf if y == 0 else 1.0 / y
+    return a, b
+
+
 def _julia_range(a: float, s: float, b: float) -> np.ndarray:
-    """Elements of the Julia range a:s:b.  Julia lifts (a, s) to a common rational grid and evaluates each element
-    in twice precision; for decimal inputs that equals (na + k*ns)/d with na = a*d, ns = s*d integers."""
-    for d in (1, 10, 100, 1000, 10_000, 100_000, 1_000_000):
-        na, ns = round(a * d), round(s * d)
-        if na / d == a and ns / d == s and ns > 0:
-            n = int(math.floor((b * d - na) / ns + 1e-9))
-            return np.array([(na + k * ns) / d for k in range(n + 1)], dtype=np.float64)
-    n = int(math.floor((b - a) / s + 1e-9))
-    return np.array([a + k * s for k in range(n + 1)], dtype=np.float64)
+    """Elements of the Julia Float64 range ``a:s:b`` ([EXT] Base.(:)(start::T, step::T, stop::T) where T<:IEEEFloat,
+    julia/base/twiceprecision.jl).  When start, step and stop all have exact small-rational lifts the range is
+    ``(start_n + k*step_n)/den`` evaluated in twice precision -- modelled here by exact integer arithmetic and ONE
+    rounding; otherwise start and step are taken literally, the length is ``round((stop-start)/step) + 1`` minus an
+    overshoot correction, and the elements are ``start + k*step`` in twice precision (exact rational sum, one rounding)."""
+    from fractions import Fraction
+    from math import gcd
+    if s == 0:
+        raise ValueError("range step cannot be zero")
+    between = lambda lo, x, hi: lo <= x <= hi or hi <= x <= lo
+    step_n, step_d = _rat(s)
+    if step_d != 0 and step_n / step_d == s:
+        start_n, start_d = _rat(a)
+        stop_n, stop_d = _rat(b)
+        if start_d != 0 and stop_d != 0 and start_n / start_d == a and stop_n / stop_d == b:
+            den = start_d * (step_d // gcd(start_d, step_d))
+            m = 9007199254740992.0
+            if den != 0 and abs(a * den) <= m and abs(s * den) <= m and den % start_d == 0 and den % step_d == 0:
+                start_n, step_n = round(a * den), round(s * den)
+                num, dd = den * stop_n - stop_d * start_n, step_n * stop_d
+                q = abs(num) // abs(dd) * (1 if (num >= 0) == (dd > 0) else -1)      # Julia div truncates toward zero
+                ln = max(0, q + 1)
+                if between(a, a + (ln - 1) * s, b + s / 2) and not between(a, a + ln * s, b):
+                    return np.array([float(Fraction(start_n + k * step_n, den)) for k in range(ln)], dtype=np.float64)
+    lf = (b - a) / s
+    if lf < 0:
+        ln = 0
+    elif lf == 0:
+        ln = 1
+    else:
+        ln = int(round(lf)) + 1                      # Python and Julia both round half to even
+        last = a + (ln - 1) * s
+        ln -= int(a < b < last) + int(a > b > last)
+    fa, fs = Fraction(a), Fraction(s)
+    return np.array([float(fa + k * fs) for k in range(ln)], dtype=np.float64)
 
 
 def expand_saveat(saveat, t0: float, tf: float):
-    """-> (saveat times pushed to the heap, save_start default, save_end default)."""
+    """-> (saveat times pushed to the heap, save_start default, save_end default); /root/reference/src/solve.jl:661-677:
+    a number s pushes ``(t0+s):s:tf`` when ``(t0:s:tf)[end] == tf``, else ``(t0+s):s:(tf-s)``."""
     if saveat is None:
         return np.zeros(0), True, True
     if np.isscalar(saveat):
         s = float(saveat)
         if s <= 0:
             raise ValueError("saveat must be positive")
-        pts = _julia_range(t0, s, tf)
-        sv = pts[1:] if pts[-1] == tf else np.array([x for x in pts[1:] if x <= tf - s])
+        full = _julia_range(t0, s, tf)
+        sv = _julia_range(t0 + s, s, tf) if full.size and full[-1] == tf else _julia_range(t0 + s, s, tf - s)
         return np.asarray(sv, dtype=np.float64), True, True
     arr = np.asarray(list(saveat), dtype=np.float64)
     if arr.size == 0:
@@ -592,8 +637,10 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
         if hasattr(out_arr, "data_ptr"):
             if out_arr.is_cuda != (ea.output == "device"):
                 raise ValueError("out tensor residency does not match EnsembleB200(output=...)")
-            if not out_arr.is_contiguous():
-                raise ValueError("out must be contiguous")
+            if not out_arr.is_contiguous() or str(out_arr.dtype) != "torch.float64":
+                raise ValueError("out must be a contiguous float64 tensor")   # the kernel writes 8 bytes per element
+            if out_arr.is_cuda and out_arr.device.index != device:
+                raise ValueError(f"out lives on cuda:{out_arr.device.index}, the solve runs on cuda:{device}")
             out_ptr = out_arr.data_ptr()
         else:
             if not out_arr.flags.c_contiguous or out_arr.dtype != np.float64:

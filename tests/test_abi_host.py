@@ -19,11 +19,54 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "sdde_b200.h")).read()
     declared = sorted(set(re.findall(r"SDDE_API[^;(]*?\b(sdde_b200_\w+)\s*\(", hdr)))
-    assert declared == sorted(capi.EXPORTS) and len(declared) == 25
+    assert declared == sorted(capi.EXPORTS) and len(declared) == 26
     L = capi.lib()
     for name in declared:
         assert hasattr(L, name), name
     assert L.sdde_b200_version() == 100
+
+
+def test_rng_table_is_correctly_rounded():
+    """The generator's table is computed on the host in long double (csrc/rng_table.cpp); every entry must be the float64
+    nearest to the 200-bit mpmath value, up to the rare double-rounding case (<= 0.51 ulp).  Layout: sdde_rng_tables.cuh."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    tab = capi.rng_table()
+    assert tab.shape == (512 + 2048 + 4096, 2)
+    half_pi = mp.pi / 2
+
+    def ulps(x, exact):
+        if exact == 0:
+            return 0.0 if x == 0.0 else np.inf
+        return float(abs(mp.mpf(float(x)) - exact) / mp.mpf(float(np.spacing(abs(float(exact))))))
+
+    worst = 0.0
+    for k in range(512):
+        c = mp.mpf(2) if k == 511 else 1 + (mp.mpf(k) + mp.mpf("0.5")) / 512
+        inv = float(1 / c)
+        assert tab[k, 0] == inv                                   # the reciprocal itself is correctly rounded
+        m2ln = 2 * mp.log(mp.mpf(inv)) + (2 * mp.log(2) if k >= 256 else 0)
+        worst = max(worst, ulps(tab[k, 1], m2ln))
+    assert tab[511, 1] == 0.0
+    for b in range(0, 2048, 7):
+        beta = half_pi * ((mp.mpf(b) + mp.mpf("0.5")) / 2 ** 22 - mp.mpf(1) / 2 ** 12)
+        worst = max(worst, ulps(tab[512 + b, 0], mp.cos(beta)), ulps(tab[512 + b, 1], mp.sin(beta)))
+    for i in range(0, 4096, 5):
+        h, a = i >> 11, i & 2047
+        alpha = half_pi * (h + (mp.mpf(a) + mp.mpf("0.5")) / 2 ** 11 - mp.mpf("0.5"))
+        worst = max(worst, ulps(tab[2560 + i, 0], mp.cos(alpha)), ulps(tab[2560 + i, 1], mp.sin(alpha)))
+    assert worst <= 0.51, worst
+    # the angle decomposition covers the oracle's angles: theta = (pi/2)(q + (f + 1/2) 2^-22 - 1/2) = alpha + beta + s pi
+    rng = np.random.default_rng(5)
+    for wb in rng.integers(0, 2 ** 32, size=200, dtype=np.uint64):
+        wb = int(wb)
+        q, f = wb >> 30, (wb >> 8) & 0x3FFFFF
+        theta = half_pi * (q + (mp.mpf(f) + mp.mpf("0.5")) / 2 ** 22 - mp.mpf("0.5"))
+        ca, sa = tab[2560 + ((wb >> 19) & 0xFFF)]
+        cb, sb = tab[512 + ((wb >> 8) & 0x7FF)]
+        sgn = -1.0 if wb >> 31 else 1.0
+        assert abs(sgn * (ca * cb - sa * sb) - float(mp.cos(theta))) < 4e-16
+        assert abs(sgn * (sa * cb + ca * sb) - float(mp.sin(theta))) < 4e-16
 
 
 def test_struct_layout_matches_header():
