@@ -10,11 +10,19 @@ A "step" is one pass of the hot path over one batch: one whole ensemble solve of
 10^6 trajectories PER GPU, in-kernel Philox increments).  Trajectories shard across ranks with no data-path collective
 (weak scaling: per-GPU work fixed); the only collective is the NCCL all-gather of the (count, mean, M2) moment triples.
 
-  value  = whole-job trajectory-steps/s with the result left in HBM (device-resident output, no D2H)
-  e2e    = the same through the public API with HOST buffers: descriptor H2D + D2H of the saved paths into pinned
-           host memory inside the timed region
-  roofline.achieved = 16.4 algorithmic bytes per trajectory-step x trajectory-steps per launch
-           / CUDA-event duration of the step kernel (events recorded by the library on its compute stream)
+  value    = whole-job trajectory-steps/s with the result left in HBM (device-resident output, no D2H)
+  e2e      = the same through the public API with HOST buffers, every step: the library's caches are dropped, so the
+             schedule is replayed and its tables (~0.8 MB) are uploaded again (H2D), and the 4 GB of saved paths are
+             written into pinned host memory (D2H) inside the timed region; `pcie_ceiling_gbs` is the rate plain
+             cudaMemcpyAsync reaches for the same bytes with all ranks copying at once
+  roofline = 16.4 algorithmic bytes per trajectory-step x trajectory-steps per launch
+             / CUDA-event duration of the step kernel (events recorded by the library on its compute stream)
+  configs  = the other BASELINE.json configs, short device-resident runs: C1, C3 (order_discontinuity_t0 = 0 and 2), C4
+             (thread per trajectory and cooperative lanes), C5 at 10^8 paths IN TOTAL (NCCL moment merge inside the timed
+             region), C2 strong (10^6 paths in total) -- each with its kernel, CUDA-event time and algorithmic GB/s
+  checks   = agreement computed in the run: a slice of this rank's shard re-solved alone with its global trajectory
+             offset (bit for bit), the library's merged moments against a Chan merge of per-rank two-pass moments and
+             identical on every rank, the order statistics selected across ranks against a single-rank selection
 
 The reference (Julia) cannot run here (no Julia in the image); the reference arm and cpu_baseline
 time oracle/libsdde_oracle.so, the C++ restatement of the reference's per-trajectory algorithm, on the host cores.
@@ -33,12 +41,19 @@ sys.path[:0] = [ROOT]
 METRIC = "trajectory-steps/sec (10^6-path Mackey-Glass SDDE, EM)"
 UNIT = "trajectory-steps/s"
 ALG_BYTES_PER_TRAJ_STEP = 16.4        # 8 B delayed-node read + 8 B new-node write + 8*501/10000 B saved output
-WORKLOAD = dict(workload="C2 stochastic Mackey-Glass beta=0.2 gamma=0.1 n=10 sigma=0.1 tau=17 u0=h=1.2, EM(split) dt=0.05, "
-                         "t in [0,500] (10000 steps), saveat=1.0 (501 points)", trajectories_per_gpu=1_000_000,
-                noise="in-kernel Philox4x32-10 (4 normals per call: 40-bit radius, 24-bit angle per Box-Muller pair) + float64 Box-Muller",
-                l2="working set 2.7 GB ring + 4.0 GB output per launch >> 126 MB L2 (no explicit flush needed)")
 T_END, DT, TAU = 500.0, 0.05, 17.0
+N_STEPS, N_SAVE = 10000, 501          # schedule replay of this workload (asserted against the library's schedule below)
 P_MG = (0.2, 0.1, 10.0, 0.1)
+TRAJ_PER_GPU = 1_000_000
+
+
+def workload_config(world, n_traj=TRAJ_PER_GPU):
+    """The `config` block: a function of the world size only, identical in both arms (ours / reference)."""
+    return dict(workload="C2 stochastic Mackey-Glass beta=0.2 gamma=0.1 n=10 sigma=0.1 tau=17 u0=h=1.2, EM(split) dt=0.05, "
+                         "t in [0,500] (10000 steps), saveat=1.0 (501 points), independent N(0, dt) increments per step",
+                trajectories_per_gpu=n_traj, trajectories_total=n_traj * world, n_steps=N_STEPS, n_save=N_SAVE,
+                parallelism=f"trajectory-shard x{world}",
+                l2="working set 2.7 GB ring + 4.0 GB output per launch >> 126 MB L2 (no explicit flush needed)")
 
 
 def mg_problem(S):
@@ -59,7 +74,7 @@ class ClockSampler:
         if os.environ.get("SDDE_BENCH_NO_SAMPLER"):
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -106,9 +121,8 @@ class ClockSampler:
 
 
 def cpu_reference_run(steps, warmup, sample_paths=None):
-    """The reference's per-trajectory algorithm (C++ restatement) on all host cores; returns (value, info)."""
+    """The reference's per-trajectory algorithm (C++ restatement) on all host cores; returns (value, info, ms per pass)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
     import c_oracle
     import sdde_oracle as O
     cores = os.cpu_count() or 1
@@ -123,10 +137,166 @@ def cpu_reference_run(steps, warmup, sample_paths=None):
     total = sum(times)
     value = n * n_steps * len(times) / total
     info = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "rng": "Philox4x32-10 + libm Box-Muller (log, sqrt, sin, cos per pair) -- NOT the reference's Xoroshiro128+ / ziggurat "
+                   "randn, which is several times cheaper per normal; the restatement also omits Julia's per-trajectory __init, "
+                   "deepcopy and dynamic dispatch",
             "sample": f"{n} of the 10^6 trajectories x {n_steps} steps per pass, {len(times)} passes, C++ restatement of the "
-                      f"reference's per-trajectory loop (oracle/sdde_oracle.cpp), std::thread static chunks over {cores} cores; "
-                      "not the Julia reference (Julia is not in the image)"}
+                      f"reference's per-trajectory loop (oracle/sdde_oracle.cpp: growing history + binary search), std::thread "
+                      f"static chunks over {cores} cores; not the Julia reference (Julia is not in the image)"}
     return value, info, total / len(times) * 1e3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs (short, device-resident) and the agreement checks
+# ------------------------------------------------------------------------------------------------------------------
+def _c4_params(S):
+    import numpy as np
+    A = -1.0 * np.eye(4) + 0.1 * (np.ones((4, 4)) - np.eye(4))
+    B1 = 0.3 * np.eye(4)
+    B2 = -0.2 * np.roll(np.eye(4), 1, axis=1)
+    M = np.zeros((4, 2))
+    for (i, j) in [(0, 0), (1, 0), (1, 1), (2, 1), (3, 1)]:
+        M[i, j] = 0.1
+    return S.linsys_params(A, [B1, B2], np.zeros(4), M, np.zeros((4, 2)))
+
+
+def config_block(S, torch, dist, local, world, barrier_sync, peak_gbs):
+    """Every BASELINE.json config besides the headline one; per config: kernel name, CUDA-event kernel time (max over
+    ranks), wall time of the solve call (max over ranks), whole-job trajectory-steps/s, algorithmic bytes per
+    trajectory-step (16 n_state per lag read+write ... + saved output) and the fraction of the HBM figure."""
+    dev = torch.device(f"cuda:{local}")
+    u4 = [1.0, 0.5, 0.25, 0.125]
+    mg = lambda tau, T, o0=0: S.SDDEProblem(S.mackey_glass.f, S.mackey_glass.g, 1.2, 1.2, (0.0, T), P_MG, constant_lags=(tau,),
+                                            order_discontinuity_t0=o0)
+    lin = S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, (0.0, 10.0), (-1.0, 0.5, 0.2), constant_lags=(1.0,))
+    m4 = S.linsys(4, 2, 2)
+    c4 = S.SDDEProblem(m4.f, m4.g, u4, S.AffineHistory(tuple(u4), (0.0,) * 4), (0.0, 20.0), _c4_params(S),
+                       constant_lags=(1.0, 2.5))
+    M = TRAJ_PER_GPU
+    # name, problem, alg, solve kwargs, trajectories (total), sharded over ranks?, ensemble alg kwargs, bytes(n_state, n_lag reads)
+    runs = [
+        ("C1 linear scalar EM dt=0.01 T=10 saveat=0.1, 10^6 paths/GPU", lin, S.EM(), dict(dt=0.01, saveat=0.1), M * world, {}, 16.0, 1),
+        ("C3 Mackey-Glass tau=17.02 RKMil(Ito) order_discontinuity_t0=0 T=100, 10^6 paths/GPU", mg(17.02, 100.0, 0), S.RKMil(),
+         dict(dt=0.05, saveat=1.0, adaptive=False), M * world, {}, 16.0, 1),
+        ("C3 Mackey-Glass tau=17.02 RKMil(Ito) order_discontinuity_t0=2 T=100, 10^6 paths/GPU", mg(17.02, 100.0, 2), S.RKMil(),
+         dict(dt=0.05, saveat=1.0, adaptive=False), M * world, {}, 16.0, 1),
+        ("C4 4-state 2-lag 4x2 noise EM dt=0.01 T=20 saveat=0.5, thread per trajectory, 10^6 paths/GPU", c4, S.EM(),
+         dict(dt=0.01, saveat=0.5), M * world, {}, 96.0, 4),
+        ("C4 same, cooperative lanes (4 lanes per trajectory), 2.5x10^5 paths/GPU", c4, S.EM(), dict(dt=0.01, saveat=0.5),
+         (M // 4) * world, dict(lanes_per_traj=4), 96.0, 4),
+        ("C5 linear scalar EM, 10^8 paths IN TOTAL, moments only at saveat=1.0, merge of the moment triples inside the timed region",
+         lin, S.EM(), dict(dt=0.01, saveat=1.0, moments=True, paths=False), 100_000_000, {}, 16.0, 1),
+        ("C2 strong: the headline workload with 10^6 paths IN TOTAL", mg(TAU, T_END), S.EM(), dict(dt=DT, saveat=1.0), M, {}, 16.0, 1),
+    ]
+    out = []
+    for name, prob, alg, kw, n_total, eakw, ring_bytes, n_state in runs:
+        ea = S.EnsembleB200(device=local, distributed=world > 1, output="device", **eakw)
+        ep = S.EnsembleProblem(prob)
+        reps, best_wall, best_k, sim = 3, None, None, None
+        for r in range(reps):
+            barrier_sync()
+            t0 = time.perf_counter()
+            sim = S.solve(ep, alg, ea, trajectories=n_total, seed=0xC0F16 + r, **kw)
+            barrier_sync()
+            t = torch.tensor([time.perf_counter() - t0, sim.timing["kernel_ms"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if r > 0 and (best_wall is None or float(t[0]) < best_wall):        # first pass is the warm-up
+                best_wall, best_k = float(t[0]), float(t[1])
+        tm = sim.timing
+        n_steps, n_save = tm["n_steps"], tm["n_save"]
+        bps = ring_bytes + 8.0 * n_state * n_save / n_steps
+        per_gpu = -(-n_total // world)
+        gbs = bps * per_gpu * n_steps / (best_k * 1e-3) / 1e9
+        out.append({"name": name, "kernel": tm["kernel_name"], "trajectories_total": n_total, "n_steps": n_steps, "n_save": n_save,
+                    "waves_per_gpu": tm["waves"], "kernel_ms": best_k, "ms": best_wall * 1e3,
+                    "value": n_total * n_steps / best_wall, "value_kernel_only": n_total * n_steps / (best_k * 1e-3),
+                    "alg_bytes_per_step": bps, "achieved_gbs_per_gpu": gbs, "frac": gbs / peak_gbs,
+                    "regs_per_thread": tm["regs_per_thread"], "block_threads": tm["block_threads"]})
+        del sim
+    return out
+
+
+def checks_block(S, torch, dist, local, world, rank, eprob, out_dev, n_traj, seed):
+    """Agreement checks computed in the run (all ranks take part; every entry is True on success)."""
+    import numpy as np
+    dev = torch.device(f"cuda:{local}")
+    checks = {}
+
+    def all_true(flag):
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t[0]))
+
+    ea = S.EnsembleB200(device=local, distributed=world > 1, output="device")
+    sim = S.solve(eprob, S.EM(), ea, dt=DT, saveat=1.0, trajectories=n_traj * world, seed=seed, out=out_dev, moments=True)
+    lo = sim.traj_offset
+    # (1) partition invariance: 4096 paths from the middle of this rank's shard, solved alone with their global offset
+    k0 = (n_traj // 2) & ~1
+    alone = S.solve(eprob, S.EM(), S.EnsembleB200(device=local, output="device"), dt=DT, saveat=1.0, trajectories=4096, seed=seed,
+                    traj_offset=lo + k0)
+    checks["slice_resolved_alone_bit_identical"] = all_true(torch.equal(alone.out, sim.out[:, :, k0:k0 + 4096]))
+    # (2) merged moments: identical on every rank, and equal to the Chan merge of per-rank TWO-PASS moments
+    x = sim.out[:, 0, :]
+    mean = x.mean(dim=1)
+    m2 = ((x - mean[:, None]) ** 2).sum(dim=1)
+    mine = torch.stack([torch.full_like(mean, float(x.shape[1])), mean, m2], dim=1)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(parts, mine)
+    else:
+        parts = [mine]
+    acc = parts[0].cpu().numpy().copy()
+    for r in range(1, world):
+        acc = S.merge_moments(acc, parts[r].cpu().numpy())
+    lib_m = np.asarray(sim.moments)[:, 0, :]
+    checks["merged_moments_equal_two_pass_chan_merge"] = all_true(
+        bool(np.array_equal(lib_m[:, 0], acc[:, 0])) and bool(np.allclose(lib_m[:, 1], acc[:, 1], rtol=1e-12, atol=1e-15)) and
+        bool(np.allclose(lib_m[:, 2], acc[:, 2], rtol=1e-9, atol=1e-12)))
+    mt = torch.from_numpy(np.ascontiguousarray(lib_m)).to(dev)
+    mparts = [torch.empty_like(mt) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(mparts, mt)
+        checks["merged_moments_identical_on_all_ranks"] = all(torch.equal(mparts[0], p) for p in mparts)
+    else:
+        checks["merged_moments_identical_on_all_ranks"] = True
+    del sim, alone, x
+    # (3) order statistics selected over all ranks (histograms all-reduced over NCCL) == selection on one rank
+    n_q = 200_001
+    small = S.SDDEProblem(S.mackey_glass.f, S.mackey_glass.g, 1.2, 1.2, (0.0, 50.0), P_MG, constant_lags=(TAU,))
+    kw = dict(dt=DT, saveat=1.0, trajectories=n_q, seed=seed + 1)
+    d = S.solve(S.EnsembleProblem(small), S.EM(), ea, **kw)
+    med_all = S.timeseries_steps_quantile(d, [0.05, 0.95], median=True)
+    one = S.solve(S.EnsembleProblem(small), S.EM(), S.EnsembleB200(device=local, output="device"), **kw)
+    med_one = S.timeseries_steps_quantile(one, [0.05, 0.95], median=True)
+    checks["distributed_quantiles_equal_single_rank"] = all_true(bool(np.array_equal(med_all, med_one)))
+    srt = torch.sort(one.out[:, 0, :], dim=1).values
+    checks["median_equals_sorted_middle"] = all_true(bool(np.array_equal(med_one[:, 0, 2], srt[:, n_q // 2].cpu().numpy())))
+    checks["all"] = all(bool(v) for v in checks.values())
+    return checks
+
+
+def pcie_ceiling(torch, dist, local, world, out_dev, out_host, barrier_sync):
+    """What plain copy engines reach for the e2e arm's D2H bytes: every rank copies its device-resident paths into its pinned
+    host buffer with ONE cudaMemcpyAsync at the same time; aggregate GB/s = all bytes / slowest rank."""
+    dev = torch.device(f"cuda:{local}")
+    best = None
+    for r in range(3):
+        barrier_sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out_host.copy_(out_dev, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if r > 0:
+            best = float(t[0]) if best is None else min(best, float(t[0]))
+    nbytes = out_dev.numel() * 8
+    return {"pcie_ceiling_gbs": nbytes * world / (best * 1e-3) / 1e9, "pcie_ceiling_ms": best,
+            "pcie_ceiling_per_gpu_gbs": nbytes / (best * 1e-3) / 1e9}
 
 
 def main():
@@ -135,10 +305,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--trajectories", type=int, default=WORKLOAD["trajectories_per_gpu"])
+    ap.add_argument("--trajectories", type=int, default=TRAJ_PER_GPU)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the with-moments and summary arms (A/B timing runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the with-moments, summary, configs and checks arms (A/B timing runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -151,7 +321,7 @@ def main():
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": dict(WORKLOAD, trajectories_per_gpu=None, sample=info["sample"]),
+                          "config": workload_config(max(1, args.gpus), args.trajectories),
                           "cpu_baseline": info, "gpu_launches": 0,
                           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
@@ -181,6 +351,8 @@ def main():
     eprob = S.EnsembleProblem(prob)
     sch = S.schedule(prob, S.EM(), dt=DT, saveat=1.0)
     n_steps, n_save = sch.n_steps, len(sch.save_t)
+    assert (n_steps, n_save) == (N_STEPS, N_SAVE)
+    ctx = S.get_context(local)
     ea_dev = S.EnsembleB200(device=local, distributed=world > 1, output="device")
     out_dev = torch.empty((n_save, 1, n_traj), dtype=torch.float64, device=dev)
 
@@ -230,10 +402,18 @@ def main():
     with_moments = {"value": n_total * n_steps * Km / float(elm[0]), "unit": UNIT, "ms_per_step": float(elm[0]) / Km * 1e3, "steps": Km,
                     "merge": "NCCL all_gather of (count, mean, M2) + Chan merge" if world > 1 else "single GPU: no collective"}
 
+    peaks, peak_src = {}, "fallback (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0}
+
     # ---- summary arm (extra, not the headline): the ensemble never leaves HBM, the host receives mean, variance, median and
-    #      5 % / 95 % bands per saved time point (EnsembleSummary: moment kernels + exact order statistics on the device) ----
+    #      5 % / 95 % bands per saved time point (EnsembleSummary: moment kernels + exact order statistics, selected over all
+    #      ranks when the ensemble is sharded) -- the design answer to EnsembleProblem's `reduction` ----
     e2e_summary = None
-    if world == 1 and not args.no_extras:
+    if not args.no_extras:
         for i in range(2):
             S.EnsembleSummary(one_pass(i, ea_dev, out_dev, True))
         barrier_sync()
@@ -242,12 +422,21 @@ def main():
         for i in range(Ks):
             summ = S.EnsembleSummary(one_pass(W + i, ea_dev, out_dev, True))
         barrier_sync()
-        els = time.perf_counter() - t0s
-        e2e_summary = {"value": n_total * n_steps * Ks / els, "unit": UNIT, "ms_per_step": els / Ks * 1e3, "steps": Ks,
+        els = torch.tensor([time.perf_counter() - t0s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(els, op=dist.ReduceOp.MAX)
+        e2e_summary = {"value": n_total * n_steps * Ks / float(els[0]), "unit": UNIT, "ms_per_step": float(els[0]) / Ks * 1e3, "steps": Ks,
                        "d2h_bytes_per_step": int(summ.u.nbytes + summ.v.nbytes + summ.med.nbytes + summ.qlow.nbytes + summ.qhigh.nbytes),
-                       "what": "solve + mean/variance + median + 5%/95% quantile bands computed on the device, only the summary crosses PCIe"}
+                       "what": "solve + mean/variance + median + 5%/95% quantile bands of the WHOLE ensemble computed on the device(s), "
+                               "only the summary crosses PCIe"}
 
-    # ---- end-to-end arm: host buffers, pinned, D2H inside the timed region ----
+    configs = checks = None
+    if not args.no_extras:
+        configs = config_block(S, torch, dist, local, world, barrier_sync, peaks["hbm_gbs"])
+        checks = checks_block(S, torch, dist, local, world, rank, eprob, out_dev, n_traj, 0xB2000001)
+
+    # ---- end-to-end arm: host buffers, pinned; per step the library's caches are dropped (schedule replay + table upload =
+    #      the step's H2D) and the saved paths land in host memory (D2H) inside the timed region ----
     e2e = None
     if not args.no_e2e:
         out_host = torch.empty((n_save, 1, n_traj), dtype=torch.float64, pin_memory=True)
@@ -257,16 +446,22 @@ def main():
         barrier_sync()
         t0 = time.perf_counter()
         Ke = max(1, min(K, 3))
+        h2d = d2h = 0
         for i in range(Ke):
+            ctx.set_option("drop_caches", 1)
             simh = one_pass(W + i, ea_host, out_host, False)
             checksum = float(out_host[-1, 0, :8].sum())          # the host reads the step's result
+            h2d += int(simh.timing["h2d_bytes"]); d2h += int(simh.timing["d2h_bytes"])
         barrier_sync()
         el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total * n_steps * Ke / float(el[0]), "unit": UNIT,
-               "h2d_bytes_per_step": int(simh.timing["h2d_bytes"]), "d2h_bytes_per_step": int(simh.timing["d2h_bytes"]),
-               "ms_per_step": float(el[0]) / Ke * 1e3, "waves": simh.timing["waves"], "steps": Ke}
+               "h2d_bytes_per_step": h2d // Ke, "d2h_bytes_per_step": d2h // Ke,
+               "ms_per_step": float(el[0]) / Ke * 1e3, "waves": simh.timing["waves"], "steps": Ke, "how": simh.timing["kernel_name"],
+               "d2h_gbs_all_ranks": d2h / Ke * world / (float(el[0]) / Ke) / 1e9}
+        one_pass(0, ea_dev, out_dev, False)
+        e2e.update(pcie_ceiling(torch, dist, local, world, out_dev, out_host, barrier_sync))
         del out_host
 
     if rank != 0:
@@ -276,45 +471,44 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel (per launch, this rank) ----
-    peaks, peak_src = {}, "fallback"
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_src = "measured (MEASURED_PEAKS.json)"
-    except Exception:
-        peaks = {"hbm_gbs": 6650.0}
     alg_bytes = ALG_BYTES_PER_TRAJ_STEP * n_traj * n_steps
     k_ms = sum(kernel_ms) / K
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, prof = None, {}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
         traffic = prof.get("bench_launch_dram_bytes")
     except Exception:
-        prof = {}
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_source": peak_src, "kernel": timing["kernel_name"], "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": alg_bytes, "regs_per_thread": timing["regs_per_thread"]}
-    # the co-limiting resource: FP64 pipe (measured DFMA peak of this GPU, reported alongside)
+                "traffic": traffic, "traffic_source": (f"ncu --set full capture of this kernel committed under profiles/ ({prof.get('capture')}, "
+                                                       f"commit {prof.get('commit')}); not re-measured in this run") if traffic else None,
+                "peak_source": peak_src, "kernel": timing["kernel_name"], "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "regs_per_thread": timing["regs_per_thread"],
+                "block_threads": timing["block_threads"]}
+    # the co-limiting resource: FP64 pipe (measured DFMA peak of this GPU, reported alongside; the micro-benchmark runs
+    # AFTER every timed region, only the CPU leg below follows it)
     import ctypes as C
     v = C.c_double(0)
-    ctx = S.get_context(local)
     S._capi.check(S.lib().sdde_b200_dfma_peak(ctx.handle, C.byref(v)))
     roofline["fp64"] = {"measured_dfma_peak_tflops": v.value, "fp64_pipe_pct_ncu": prof.get("fp64_pipe_pct"),
                         "note": "FP64-pipe utilisation comes from the committed ncu capture (profiles/), not from this run"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        # about 10-15 s of CPU work: 15 000 trajectories per core x 10 000 steps in one pass (plus a short warm-up pass)
+        # about 10-15 s of CPU work: 15 000 trajectories per core x 10 000 steps in one pass
         _, cpu_baseline, _ = cpu_reference_run(1, 0, sample_paths=(os.cpu_count() or 1) * 15000)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(WORKLOAD, trajectories_per_gpu=n_traj, trajectories_total=n_total, n_steps=n_steps, n_save=n_save,
-                           parallelism=f"trajectory-shard x{world}", ring_slots=timing["ring_slots"],
-                           ensemble_mean_at_tf=mean_end),
-            "clocks": clocks, "e2e": e2e, "with_moments": with_moments, "e2e_summary": e2e_summary, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernel_ms_per_step_max_over_ranks": kms_max}
+            "config": workload_config(world, n_traj),
+            "rng": "in-kernel Philox4x32-10 keyed by (seed, global trajectory id), 4 normals per call (40-bit radius, 24-bit angle per "
+                   "Box-Muller pair), float64 Box-Muller from shared-memory tables",
+            "ring_slots": timing["ring_slots"], "ensemble_mean_at_tf": mean_end,
+            "clocks": clocks, "e2e": e2e, "with_moments": with_moments, "e2e_summary": e2e_summary, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernel_ms_per_step_max_over_ranks": kms_max,
+            "configs": configs, "checks": checks}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

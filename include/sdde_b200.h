@@ -134,6 +134,12 @@ typedef struct sdde_desc {
                                          NoiseGrid(t, W) on ANY grid covering [t0, tf] -- W(t) is then interpolated
                                          linearly at the step ends like [EXT] DiffEqNoiseProcess NoiseGrid does */
     int64_t n_noise_t;
+    const double *d_disc_t;           /* d_discontinuities keyword (src/solve.jl:20-23): times of user-declared discontinuities; */
+    const int32_t *d_disc_order2;     /*   2 x order of each (Discontinuity{tType, Rational{Int}}: orders are multiples of 1/2 here). */
+    int64_t n_d_disc;                 /*   They become tstops (src/solve.jl:644-647) and seed the propagation heap (:688-699). */
+    int64_t out_rows;                 /* capacity guard: rows (save points x saved states) the caller's out / moments buffers hold;
+                                         0 = unchecked.  A solve that needs more rows fails with SDDE_ERR_BAD_DESC instead of
+                                         writing past the buffers (e.g. save_everystep with a buffer sized for saveat). */
 } sdde_desc;
 
 /* Host-side schedule (trajectory independent): the replay of src/solve.jl:574-610 time stepping with

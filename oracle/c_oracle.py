@@ -26,6 +26,8 @@ class Desc(C.Structure):
         ("saveat", C.c_void_p), ("tstops", C.c_void_p), ("noise", C.c_void_p),
         ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64), ("out_pitch", C.c_int64),
         ("n_save_idxs", C.c_int32), ("save_idxs", C.c_int32 * 8), ("reserved1", C.c_int32),
+        ("noise_t", C.c_void_p), ("n_noise_t", C.c_int64),
+        ("d_disc_t", C.c_void_p), ("d_disc_order2", C.c_void_p), ("n_d_disc", C.c_int64), ("out_rows", C.c_int64),
     ]
 
 
@@ -46,7 +48,7 @@ def lib():
 
 def solve(model_id, alg, n_state, n_lag, n_noise, params, u0, h0, h1, lags, t0, tf, dt, saveat_times, n_save, *,
           save_start=True, save_end=True, save_everystep=False, order0=0, declared=True, n_traj=1, traj_offset=0,
-          seed=0, dW=None, noise_grid=None, n_threads=1):
+          seed=0, dW=None, noise_grid=None, n_threads=1, d_discontinuities=()):
     """-> (out[n_save, n_state, n_traj], status[n_traj], elapsed seconds, steps)."""
     d = Desc()
     d.struct_size = C.sizeof(Desc)
@@ -69,6 +71,11 @@ def solve(model_id, alg, n_state, n_lag, n_noise, params, u0, h0, h1, lags, t0, 
     sv = np.ascontiguousarray(saveat_times, dtype=np.float64)
     d.saveat, d.n_saveat = (sv.ctypes.data if sv.size else None), sv.size
     d.n_traj, d.traj_offset, d.seed = n_traj, traj_offset, seed
+    dd = [(float(x[0]), int(round(2 * x[1]))) if isinstance(x, (tuple, list)) else (float(x), 0) for x in d_discontinuities]
+    dd_t = np.array([x[0] for x in dd], dtype=np.float64)
+    dd_o = np.array([x[1] for x in dd], dtype=np.int32)
+    if dd:
+        d.d_disc_t, d.d_disc_order2, d.n_d_disc = dd_t.ctypes.data, dd_o.ctypes.data, len(dd)
     nz, nrows = None, 0
     if dW is not None:
         nz = np.ascontiguousarray(dW, dtype=np.float64); d.noise_mode = 1; nrows = nz.shape[0]

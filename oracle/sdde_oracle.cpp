@@ -183,12 +183,15 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
     const bool add_prop = order0_2 <= alg_order2 && d->constant_lags_declared && nl > 0;
     TimeHeap tst, sv;
     DiscHeap disc;
-    if (!add_prop && d->n_tstops == 0) tst.push(tf);
+    if (!add_prop && d->n_tstops == 0 && d->n_d_disc == 0) tst.push(tf);
     else {
         for (int i = 0; i < d->n_tstops; ++i) if (t0 < d->tstops[i] && d->tstops[i] <= tf) tst.push(d->tstops[i]);
+        for (int64_t i = 0; i < d->n_d_disc; ++i) if (t0 < d->d_disc_t[i] && d->d_disc_t[i] <= tf) tst.push(d->d_disc_t[i]);   // src/solve.jl:643-646
         if (add_prop) for (int l = 0; l < nl; ++l) if (d->lags[l] < tf - t0) tst.push(t0 + d->lags[l]);
         tst.push(tf);
     }
+    for (int64_t i = 0; i < d->n_d_disc; ++i)       // src/solve.jl:690-699
+        if (t0 < d->d_disc_t[i] && d->d_disc_t[i] < tf && d->d_disc_order2[i] <= alg_order2 + 2) disc.push(Disc{d->d_disc_t[i], d->d_disc_order2[i]});
     if (add_prop) for (int l = 0; l < nl; ++l) if (d->lags[l] < tf - t0) disc.push(Disc{t0 + d->lags[l], order0_2 + 1});
     for (int i = 0; i < d->n_saveat; ++i) sv.push(d->saveat[i]);
 

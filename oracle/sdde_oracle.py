@@ -160,11 +160,12 @@ def _float_range(a: float, s: float, b: float) -> np.ndarray:
             big = float(1 << 53)
             if den != 0 and abs(a * den) <= big and abs(s * den) <= big and den % ad == 0 and den % sd == 0:
                 n0, ns = int(round(a * den)), int(round(s * den))
-                top, bot = den * bn - bd * n0, ns * bd
+                bot = ns * bd
+                top = den * bn - bd * n0 + bot       # len = div(den*stop_n - stop_d*start_n + step_n*stop_d, step_n*stop_d)
                 quo = abs(top) // abs(bot)
                 if (top < 0) != (bot < 0):
                     quo = -quo                       # Julia's div truncates
-                n = max(0, quo + 1)
+                n = max(0, quo)
                 if inside(a, a + (n - 1) * s, b + s / 2) and not inside(a, a + n * s, b):
                     return np.array([float(Fraction(n0 + k * ns, den)) for k in range(n)], dtype=np.float64)
     lf = (b - a) / s
@@ -183,7 +184,7 @@ def _float_range(a: float, s: float, b: float) -> np.ndarray:
 
 def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_lags_declared=True,
                    saveat_times=(), save_start=True, save_end=True, save_everystep=False,
-                   tstops=(), neutral=False, maxsteps=50_000_000) -> Schedule:
+                   tstops=(), neutral=False, maxsteps=50_000_000, d_discontinuities=()) -> Schedule:
     """Replay the reference's (trajectory-independent) time stepping in float64.
 
     Follows the queue construction of src/solve.jl:613-713 and the loop of src/solve.jl:574-610 with
@@ -207,11 +208,16 @@ def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_
     if add_prop:
         maxlag = tf - t0
         next_order = order0 if neutral else order0 + Fraction(1, 2)
-    if not add_prop and len(tstops) == 0:
+    # d_discontinuities keyword (src/solve.jl:20-23): (t, order) pairs, or bare times = order 0
+    ddisc = [(float(d[0]), Fraction(d[1])) if isinstance(d, (tuple, list)) else (float(d), Fraction(0)) for d in d_discontinuities]
+    if not ddisc and not add_prop and len(tstops) == 0:
         heapq.heappush(tst, tf)
     else:
         for x in tstops:
             x = float(x)
+            if t0 < x <= tf:
+                heapq.heappush(tst, x)
+        for (x, _) in ddisc:                       # src/solve.jl:643-646
             if t0 < x <= tf:
                 heapq.heappush(tst, x)
         if add_prop:
@@ -220,6 +226,9 @@ def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_
                     heapq.heappush(tst, t0 + lag)
         heapq.heappush(tst, tf)
     # ---- src/solve.jl:701-710 : discontinuity heap ------------------------------------------
+    for (x, od) in ddisc:                          # src/solve.jl:690-699
+        if t0 < x < tf and od <= alg_order + 1:
+            heapq.heappush(disc, (x, od))
     if add_prop:
         for lag in lags:
             if lag < maxlag:

@@ -39,6 +39,7 @@ class SddeDesc(C.Structure):
         ("n_traj", C.c_int64), ("traj_offset", C.c_int64), ("seed", C.c_uint64), ("out_pitch", C.c_int64),
         ("n_save_idxs", C.c_int32), ("save_idxs", C.c_int32 * 8), ("reserved1", C.c_int32),
         ("noise_t", C.c_void_p), ("n_noise_t", C.c_int64),
+        ("d_disc_t", C.c_void_p), ("d_disc_order2", C.c_void_p), ("n_d_disc", C.c_int64), ("out_rows", C.c_int64),
     ]
 
 
@@ -177,6 +178,9 @@ class Context:
         if not self._h:
             raise SddeError(-100, L.sdde_b200_last_error().decode(errors="replace"))
         self.device = int(device)
+        for kv in filter(None, os.environ.get("SDDE_B200_OPTS", "").split(",")):     # A/B runs: "ring_blocked=0,lean=0"
+            k, v = kv.split("=")
+            self.set_option(k.strip(), int(v))
 
     def set_option(self, key: str, value: int):
         check(lib().sdde_b200_set_option(self._h, key.encode(), int(value)))

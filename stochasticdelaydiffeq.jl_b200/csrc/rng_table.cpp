@@ -17,7 +17,7 @@ std::once_flag g_once;
 
 void build() {
     const long double half_pi = acosl(-1.0L) / 2.0L;
-    g_table.assign((size_t)SDDE_RNG_TAB_ENTRIES_MAX * 2, 0.0);
+    g_table.assign((size_t)SDDE_RNG_TAB_ENTRIES * 2, 0.0);
     for (int k = 0; k < SDDE_RNG_LOG_ENTRIES; ++k) {
         long double c = 1.0L + ((long double)k + 0.5L) / 512.0L;
         if (k == 511) c = 2.0L;                              // top bin anchored at u = 1: table value exactly 0
@@ -28,17 +28,16 @@ void build() {
         g_table[2 * (size_t)k] = inv;
         g_table[2 * (size_t)k + 1] = (double)m2ln;
     }
-    for (int b = 0; b < SDDE_RNG_FINE_ENTRIES; ++b) {
-        const long double beta = half_pi * (((long double)b + 0.5L) * 0x1p-22L - 0x1p-12L);
-        g_table[2 * (size_t)(SDDE_RNG_OFF_FINE + b)] = (double)cosl(beta);
-        g_table[2 * (size_t)(SDDE_RNG_OFF_FINE + b) + 1] = (double)sinl(beta);
+    auto put = [&](int idx, long double ang) {
+        g_table[2 * (size_t)idx] = (double)cosl(ang);
+        g_table[2 * (size_t)idx + 1] = (double)sinl(ang);
+    };
+    for (int i = 0; i < 512; ++i) {
+        const int h = i >> 8, a = i & 255;
+        put(SDDE_RNG_OFF_COARSE + i, half_pi * ((long double)h + ((long double)a + 0.5L) * 0x1p-8L - 0.5L));
     }
-    for (int i = 0; i < 4096; ++i) {
-        const int h = i >> 11, a = i & 2047;
-        const long double alpha = half_pi * ((long double)h + ((long double)a + 0.5L) * 0x1p-11L - 0.5L);
-        g_table[2 * (size_t)(SDDE_RNG_OFF_COARSE + i)] = (double)cosl(alpha);
-        g_table[2 * (size_t)(SDDE_RNG_OFF_COARSE + i) + 1] = (double)sinl(alpha);
-    }
+    for (int b = 0; b < 128; ++b) put(SDDE_RNG_OFF_MID + b, half_pi * (((long double)b + 0.5L) * 0x1p-15L - 0x1p-9L));
+    for (int c = 0; c < 128; ++c) put(SDDE_RNG_OFF_FINE + c, half_pi * (((long double)c + 0.5L) * 0x1p-22L - 0x1p-16L));
 }
 }  // namespace
 
@@ -46,6 +45,6 @@ const double *rng_table_host() {
     std::call_once(g_once, build);
     return g_table.data();
 }
-int rng_table_entries() { return SDDE_RNG_TAB_ENTRIES_MAX; }
+int rng_table_entries() { return SDDE_RNG_TAB_ENTRIES; }
 
 }  // namespace sdde

@@ -46,11 +46,14 @@ std::string build_schedule(const ScheduleInput &in, Schedule &S) {
 
     TimeHeap tst;
     DiscHeap disc;
-    if (!add_prop && in.tstops.empty()) {
+    if (in.disc_t.size() != in.disc_order2.size()) return "d_discontinuities: times and orders differ in length";
+    if (in.disc_t.empty() && !add_prop && in.tstops.empty()) {
         tst.push(tf);                                     // src/solve.jl:635-636
     } else {
         for (double x : in.tstops)
             if (t0 < x && x <= tf) tst.push(x);           // :638-641
+        for (double x : in.disc_t)
+            if (t0 < x && x <= tf) tst.push(x);           // :643-646
         if (add_prop) {
             const double maxlag = tf - t0;
             for (double lag : in.lags)
@@ -58,6 +61,9 @@ std::string build_schedule(const ScheduleInput &in, Schedule &S) {
         }
         tst.push(tf);                                     // :657
     }
+    for (size_t i = 0; i < in.disc_t.size(); ++i)         // :690-699: interior, order <= alg_maximum_order + 1
+        if (t0 < in.disc_t[i] && in.disc_t[i] < tf && in.disc_order2[i] <= in.alg_order2 + 2)
+            disc.push(Disc{in.disc_t[i], in.disc_order2[i]});
     if (add_prop) {
         const double maxlag = tf - t0;
         for (double lag : in.lags)

@@ -31,6 +31,8 @@ struct ScheduleInput {
     bool neutral = false;
     std::vector<double> saveat;         // explicit interior(+end) save times
     std::vector<double> tstops;         // user tstops
+    std::vector<double> disc_t;         // user d_discontinuities: times ...
+    std::vector<int> disc_order2;       // ... and 2 x order
     bool save_start = true, save_end = true, save_everystep = false;
     int64_t max_steps = 200000000;
 };

@@ -148,6 +148,8 @@ int check_desc(const sdde_desc *d) {
     if (!d->u0) return fail(SDDE_ERR_BAD_DESC, "u0 is NULL");
     if (d->n_saveat < 0 || (d->n_saveat > 0 && !d->saveat)) return fail(SDDE_ERR_BAD_DESC, "saveat array missing");
     if (d->n_tstops < 0 || (d->n_tstops > 0 && !d->tstops)) return fail(SDDE_ERR_BAD_DESC, "tstops array missing");
+    if (d->n_d_disc < 0 || (d->n_d_disc > 0 && (!d->d_disc_t || !d->d_disc_order2)))
+        return fail(SDDE_ERR_BAD_DESC, "d_discontinuities arrays missing");
     if (d->n_traj < 0) return fail(SDDE_ERR_BAD_DESC, "n_traj < 0");
     if (d->history_mode != SDDE_HISTORY_DENSE)
         return fail(SDDE_ERR_UNSUPPORTED, "only the dense history mode exists on the GPU path (SURVEY.md H1)");
@@ -178,6 +180,8 @@ std::string schedule_key(const sdde_desc *d) {
     add(d->lags, sizeof(double) * (size_t)d->n_lag);
     if (d->n_saveat > 0) add(d->saveat, sizeof(double) * (size_t)d->n_saveat);
     if (d->n_tstops > 0) add(d->tstops, sizeof(double) * (size_t)d->n_tstops);
+    add(&d->n_d_disc, sizeof(d->n_d_disc));
+    if (d->n_d_disc > 0) { add(d->d_disc_t, sizeof(double) * (size_t)d->n_d_disc); add(d->d_disc_order2, sizeof(int32_t) * (size_t)d->n_d_disc); }
     return k;
 }
 
@@ -191,6 +195,7 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     in.constant_lags_declared = d->constant_lags_declared != 0;
     if (d->n_saveat > 0) in.saveat.assign(d->saveat, d->saveat + d->n_saveat);
     if (d->n_tstops > 0) in.tstops.assign(d->tstops, d->tstops + d->n_tstops);
+    if (d->n_d_disc > 0) { in.disc_t.assign(d->d_disc_t, d->d_disc_t + d->n_d_disc); in.disc_order2.assign(d->d_disc_order2, d->d_disc_order2 + d->n_d_disc); }
     in.save_start = d->save_start != 0;
     in.save_end = d->save_end != 0;
     in.save_everystep = d->save_everystep != 0;
@@ -367,10 +372,10 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
         memcpy(rec + 40, &inv_sq, 8);
     }
     // Mark the batches (of the size the kernel will run: `batch` steps, starting at multiples of `batch` inside every
-    // chunk) that qualify for the lean body of run_batch: every lookup of every step is a ring hit of ONE kind
-    // (all exact / all interpolating), nodes and stored slots are consecutive ring slots without a wrap, dt and theta are
-    // bitwise the same for all steps, at most 255 saves per step.  The mark and the packed save counts live in the
-    // batch's first record.
+    // chunk) that qualify for a lean body of run_batch: every lookup of every step reads the ring, the stored slots are
+    // consecutive ring slots without a wrap, dt is bitwise the same for all steps, at most 255 saves per step; "exact"
+    // when in addition every lookup hits a node exactly and the nodes are consecutive slots.  The mark and the packed
+    // save counts live in the batch's first record.
     if (batch < 1) return;                                  // option "lean" = 0: every batch takes the general body
     const int NLK = L * S.n_stage;
     auto rd64 = [](const unsigned char *p) { long long v; memcpy(&v, p, 8); return v; };
@@ -380,7 +385,7 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
             unsigned char *r0 = steps.data() + (size_t)n * k.rec_size;
             int m0;
             memcpy(&m0, r0 + 28, 4);
-            bool ok = true, all_exact = true, all_interp = true;
+            bool ok = true, all_exact = true;
             unsigned long long packed = 0;
             for (int kk = 0; kk < batch && ok; ++kk) {
                 const unsigned char *r = steps.data() + (size_t)(n + kk) * k.rec_size;
@@ -390,17 +395,14 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
                 packed |= (unsigned long long)(nsave[(size_t)(n + kk)] & 255) << (8 * kk);
                 for (int l = 0; l < NLK && ok; ++l) {
                     const int mode = S.lk_mode[(size_t)(n + kk) * NLK + l];
-                    all_exact = all_exact && mode == sdde::LK_EXACT;
-                    all_interp = all_interp && mode == sdde::LK_INTERP;
+                    ok = ok && (mode == sdde::LK_EXACT || mode == sdde::LK_INTERP);          // every lookup reads the ring
                     const unsigned char *lk = r + 48 + 32 * l, *lk0 = r0 + 48 + 32 * l;
-                    ok = ok && rd64(lk + 16) == rd64(lk0 + 16) + kk * slot_bytes;            // nodes consecutive
-                    if (mode == sdde::LK_INTERP)
-                        ok = ok && memcmp(lk, lk0, 8) == 0 && rd64(lk + 8) == rd64(lk + 16) - slot_bytes;   // one theta; lo just below hi
+                    all_exact = all_exact && mode == sdde::LK_EXACT && rd64(lk + 16) == rd64(lk0 + 16) + kk * slot_bytes;
                 }
             }
-            ok = ok && (all_exact || all_interp) && batch <= 8;
+            ok = ok && batch <= 8;
             if (ok) {
-                m0 |= all_exact ? SDDE_MASK_FAST_EXACT : SDDE_MASK_FAST_INTERP;
+                m0 |= all_exact ? SDDE_MASK_FAST_EXACT : SDDE_MASK_FAST_RING;
                 memcpy(r0 + 28, &m0, 4);
                 memcpy(r0 + 48 + 24, &packed, 8);            // lk[0].pad
             }
@@ -513,7 +515,9 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "jit_linsys")) c->opt_jit_linsys = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
     else if (!strcmp(key, "zero_copy")) c->opt_zero_copy = value != 0;
+    else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); c->mem_key.clear(); }   // next solve replays the schedule and re-uploads its tables
     else if (!strcmp(key, "lean")) { c->opt_lean = value != 0; c->table_key.clear(); }
+    else if (!strcmp(key, "balance")) c->opt_balance = value != 0;
     else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
@@ -651,6 +655,9 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     const int64_t OP = d->out_pitch > 0 ? d->out_pitch : NT;      // row pitch of the caller's out array
     if (d->out_pitch != 0 && d->out_pitch < NT) return fail(SDDE_ERR_BAD_DESC, "out_pitch < n_traj");
     if (N >= (int64_t)1 << 30) return fail(SDDE_ERR_UNSUPPORTED, "more than 2^30 steps");
+    if (d->out_rows > 0 && rows > d->out_rows && (d->want_paths || d->want_moments))
+        return fail(SDDE_ERR_BAD_DESC, "this solve saves %lld rows (%lld save points x %d states) but the caller's buffers hold %lld "
+                    "(sdde_desc.out_rows): size them from sdde_b200_schedule", (long long)rows, (long long)n_save, NSAVED, (long long)d->out_rows);
     if (tm) {
         tm->n_steps = N; tm->n_save = n_save; tm->ring_slots = S.ring_slots; tm->block_threads = K.block;
         tm->traj_per_thread = K.tpt;
@@ -722,7 +729,8 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     wave = std::min(wave, std::max<int64_t>(wq, mem_cap));
     wave = std::max<int64_t>(wq, (wave / wq) * wq);
     wave = std::min(wave, ((NT + wq - 1) / wq) * wq);
-    const int64_t pitch = ((wave + per_block - 1) / per_block) * per_block;
+    // (+ one CTA: the tail round of the balanced grid may overshoot the wave by less than one tail CTA, see the launch)
+    const int64_t pitch = ((wave + per_block - 1) / per_block) * per_block + per_block;
     // Wave list.  When the saved paths leave over PCIe (host output) the first waves are small and grow geometrically,
     // so that the D2H stream starts after a few milliseconds instead of after a whole 2^19-trajectory wave
     // and then never idles (measured on C2: D2H engine busy from 4 ms to the end).
@@ -744,10 +752,10 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     // schedule records staged per refill (+ look-ahead records for the next step / next batch prefetch) must fit in shared
     // memory beside the generator's table (in-kernel normals only): the SM's 227 KB, less 1 KB per CTA the system reserves,
     // shared by the CTAs the kernel was compiled to keep resident
-    const size_t tab_bytes = d->noise_mode == SDDE_NOISE_PHILOX ? (size_t)SDDE_RNG_SMEM_BYTES : 0;
+    const size_t tab_bytes = d->noise_mode == SDDE_NOISE_PHILOX ? (size_t)SDDE_RNG_SMEM_BYTES(K.lanes > 1 ? 1 : SDDE_RNG_COPIES) : 0;
     const size_t smem_cap = (size_t)(227 * 1024) / (size_t)std::max(1, K.min_ctas) - 2048;
-    while (chunk > 8 && tab_bytes + (size_t)(chunk + 8) * K.rec_size > smem_cap) chunk = ((chunk / 2) / 8) * 8;
-    const size_t smem = tab_bytes + (size_t)(chunk + 8) * K.rec_size;
+    while (chunk > 8 && tab_bytes + (size_t)(chunk + 16) * K.rec_size > smem_cap) chunk = ((chunk / 2) / 8) * 8;
+    const size_t smem = tab_bytes + (size_t)(chunk + 16) * K.rec_size;
     if (smem > 48 * 1024)      // above the default limit the kernel has to opt in (built-in kernels and NVRTC kernel handles alike)
         CU_CHECK(cudaFuncSetAttribute(K.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int batch = K.batch;
@@ -755,16 +763,17 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     if (batch > S.min_gap + 1 || chunk < 8) batch = 1;     // prefetched nodes must be older than the batch, else step-by-step
     if (batch < K.batch && K.batch > 1) batch = 1;          // the kernel runs its compiled depth or step by step
 
-    // ---- schedule tables -> device (byte offsets depend on the wave pitch) ----
+    const int64_t tpitch = pitch;
+    // ---- schedule tables -> device (byte offsets depend on the ring's row pitch) ----
     std::vector<unsigned char> h_steps;
     std::vector<sdde::SaveRec> h_saves;
     {
         std::string tkey = skey;
-        const int64_t tk[] = {pitch, (int64_t)K.rec_size, (int64_t)K.n_state, (int64_t)batch, (int64_t)chunk, (int64_t)c->opt_lean};
+        const int64_t tk[] = {tpitch, (int64_t)K.rec_size, (int64_t)K.n_state, (int64_t)batch, (int64_t)chunk, (int64_t)c->opt_lean};
         tkey.append((const char *)tk, sizeof(tk));
         if (tkey != c->table_key) {
             c->table_key.clear();
-            pack_tables(S, K, pitch, c->opt_lean ? batch : 0, chunk, h_steps, h_saves);
+            pack_tables(S, K, tpitch, c->opt_lean ? batch : 0, chunk, h_steps, h_saves);
             CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
             CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
             if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
@@ -804,8 +813,8 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     A.steps = (const unsigned char *)c->steps.p;
     A.saves = (const sdde::SaveRec *)c->saves.p;
     A.ring = (double *)c->ring.p;
-    A.ring_pitch = pitch;
-    A.slot_bytes = (long long)NS * pitch * 8;
+    A.ring_pitch = tpitch;
+    A.slot_bytes = (long long)NS * tpitch * 8;
     A.rng_tab = (const double2 *)c->rng_tab.p;
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
@@ -878,7 +887,20 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
         } else {
             A.out = nullptr;
         }
-        const unsigned grid = (unsigned)((nt + per_block - 1) / per_block);
+        // grid: whole rounds of full CTAs (one round = every SM's resident CTAs), then the remainder spread evenly over one
+        // last round of smaller CTAs (whole warps each) -- see the kernel
+        int64_t n_full = (nt + per_block - 1) / per_block, tail = 0, n_tail = 0;
+        if (c->opt_balance && K.lanes == 1) {
+            const int64_t round_ctas = (int64_t)c->sm_count * std::max(1, K.min_ctas), wq_t = (int64_t)32 * K.tpt;
+            n_full = (nt / (round_ctas * per_block)) * round_ctas;
+            const int64_t rem = nt - n_full * per_block;
+            if (rem > 0) {
+                tail = std::min<int64_t>(per_block, (((rem + round_ctas - 1) / round_ctas + wq_t - 1) / wq_t) * wq_t);
+                n_tail = (rem + tail - 1) / tail;
+            }
+        }
+        A.n_full_ctas = (int)n_full; A.tail_traj = (int)tail;
+        const unsigned grid = (unsigned)(n_full + n_tail);
         if (first_kernel) { CU_CHECK(cudaEventRecord(c->ev_k0, c->compute)); first_kernel = false; }
         dbg_mark(c->compute);
         if (K.is_user) {

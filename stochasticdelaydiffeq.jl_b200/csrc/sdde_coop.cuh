@@ -21,13 +21,11 @@ __global__ void __launch_bounds__(SDDE_BLOCK_COOP) sdde_coop_kernel(const __grid
     static_assert(LPT == 4 || LPT == 8, "lanes per trajectory must be 4 or 8");
     typedef StepRec<NL> Rec;
     constexpr int SDDE_BLOCK = SDDE_BLOCK_COOP;
-    constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES : 0;
+    constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES(1) : 0;   // one copy: small CTAs, many per SM
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
     Rec *srec = reinterpret_cast<Rec *>(smem_raw + TAB_BYTES);
-    if (NOISE == K_NOISE_PHILOX) {
-        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += SDDE_BLOCK) ltab[i] = a.rng_tab[i];
-    }
+    const double2 *ltab = nullptr;
+    if (NOISE == K_NOISE_PHILOX) ltab = stage_rng_table<1>(reinterpret_cast<double2 *>(smem_raw), a.rng_tab, SDDE_BLOCK);
     const int j = threadIdx.x % LPT;                                                        // my state component
     const long long tr = ((long long)blockIdx.x * SDDE_BLOCK + threadIdx.x) / LPT;          // wave-local trajectory
     const long long last = a.n_traj - 1;
@@ -85,7 +83,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK_COOP) sdde_coop_kernel(const __grid
             for (int c = 0; c < NW; ++c) {
                 if (NOISE == K_NOISE_PHILOX) {
                     const u64 q = (u64)n * NW + c, call = q >> 2;
-                    if (call != zcall) { philox_normal_quad((u64)(a.traj_gid0 + tr), call, a.rk, ltab, zc); zcall = call; }
+                    if (call != zcall) { philox_normal_quad<1>((u64)(a.traj_gid0 + tr), call, a.rk, ltab, zc); zcall = call; }
                     const double zlo = (q & 1) ? zc[1] : zc[0], zhi = (q & 1) ? zc[3] : zc[2];
                     dw[c] = sq * ((q & 2) ? zhi : zlo);
                 } else {

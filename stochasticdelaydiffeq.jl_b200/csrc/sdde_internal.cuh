@@ -77,6 +77,7 @@ struct sdde_ctx {
     int64_t opt_wave_traj = 0;     // 0 = auto
     int64_t opt_batch = 0;         // 0 = compiled-in depth
     int64_t opt_chunk_steps = 128;
+    int64_t opt_balance = 1;       // spread a wave's last, partial round of CTAs over all SMs (0: full CTAs only)
     int64_t opt_lean = 1;          // mark uniform batches for the lean body of run_batch (0: general body everywhere; A/B and tests)
     int64_t opt_zero_copy = 1;     // page-locked host `out`: the step kernel stores the saved paths straight into it over PCIe
     int64_t opt_ramp_start = (int64_t)1 << 16;   // trajectories of the first wave when paths leave over PCIe (host output)

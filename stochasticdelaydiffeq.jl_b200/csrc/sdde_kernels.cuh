@@ -35,20 +35,24 @@ __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULE
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
-// CTA sizes.  Every CTA that draws in-kernel normals stages the generator's table (72 or 104 KB, sdde_rng_tables.cuh) in
-// shared memory, so the step kernels run FEW, LARGE CTAs per SM: scalar models 2 x 256 threads (SDDE_RNG_HALF = 0) or
-// 1 x 512 threads, multi-state models 1 x 384 threads (168 registers per thread); the cooperative-lanes kernel 128.
+// CTA sizes.  Every CTA that draws in-kernel normals stages eight interleaved copies of the generator's table (160 KB,
+// sdde_rng_tables.cuh) in shared memory, so the step kernels run ONE large CTA per SM: scalar models 512 threads,
+// multi-state models 384 threads (168 registers per thread); the cooperative-lanes kernel 128 threads with one copy.
 #ifndef SDDE_BLOCK_SCALAR
-#define SDDE_BLOCK_SCALAR (SDDE_RNG_HALF ? 512 : 256)
+#define SDDE_BLOCK_SCALAR 512
 #endif
 #ifndef SDDE_BLOCK_MULTI
 #define SDDE_BLOCK_MULTI 384
 #endif
 #define SDDE_BLOCK_COOP 128
-#define SDDE_RNG_SMEM_BYTES (SDDE_RNG_TAB_ENTRIES * 16)   // log + cos/sin tables of the normal generator
+#define SDDE_RNG_SMEM_BYTES(COPIES) (SDDE_RNG_TAB_ENTRIES * 16 * (COPIES))   // log + cos/sin tables of the normal generator
 // first record of a batch whose steps the kernel may run through the lean body (pack_tables decides):
-#define SDDE_MASK_FAST_EXACT (1 << 24)    // every lookup of every step hits a ring node exactly; slots, dt uniform / contiguous
-#define SDDE_MASK_FAST_INTERP (1 << 25)   // every lookup interpolates between consecutive nodes with ONE theta per lag
+#define SDDE_MASK_FAST_EXACT (1 << 24)    // every lookup of every step hits a ring node exactly, on consecutive slots
+#define SDDE_MASK_FAST_RING (1 << 25)     // every lookup of every step reads the ring (exact hits and interpolations mixed)
+// how many batches ahead the delayed-state nodes are pulled towards L1 (bytes in flight per SM = depth x 32 KB)
+#ifndef SDDE_PF_DIST
+#define SDDE_PF_DIST 1
+#endif
 #ifndef SDDE_PHILOX_ROUNDS
 #define SDDE_PHILOX_ROUNDS 10
 #endif
@@ -90,6 +94,8 @@ struct KArgs {
     long long traj_gid0;     // global id of the wave's first trajectory
     const double2 *rng_tab;  // generator table in global memory (sdde_rng_tables.cuh), staged per CTA
     long long slot_bytes;    // one ring slot = NS * ring_pitch * 8 bytes
+    int n_full_ctas;         // CTAs [0, n_full_ctas) integrate BLOCK x TPT trajectories each, the remaining ("tail") CTAs
+    int tail_traj;           // tail_traj each (a multiple of 32 x TPT): the last, partial round is spread over all SMs
     int n_steps, n_saves, ring_slots, chunk_steps, batch, noise_kind;
     int out_vec_ok;          // out rows are 16-byte aligned for double2 stores
     int n_saved;             // states saved per save point (save_idxs)
@@ -180,15 +186,16 @@ __device__ __forceinline__ double rsqrt_approx(double x) {
 // (error beyond any power of 2^-24), so each z stays N(0,1) to far below float64 rounding; the radius keeps 40 bits
 // (tail truncated at 7.5 sigma, probability 5e-14 per draw; spacing of r at 6 sigma: 8e-5).
 // Evaluation: every argument range is known, so no special cases and no libm calls; one shared-memory table
-// (sdde_rng_tables.cuh, staged per CTA):
+// (sdde_rng_tables.cuh, staged per CTA, COPIES interleaved copies, `tab` already points at this lane's copy):
 //   -2 ln u  : u = 2^e' * M'; k = top 9 mantissa bits -> {1/c_k, -2 ln c'_k}; rho = fma(M, 1/c_k, -1) exact, |rho| <= 2^-9,
 //              log1p(rho) = rho + rho^2 (L2 + L3 rho + L4 rho^2 + L5 rho^3)            (truncation < 2^-58)
 //   sqrt     : MUFU.RSQ64H seed y, r0 = t y, e = 1 - r0 y, r = r0 (1 + e/2 + 3 e^2/8) (cubic step)   (<= 1 ulp)
-//   sin, cos : the 2^23 angles of half a turn are alpha_i + beta_b with a 4096-entry and a 2048-entry table of exact
-//              {cos, sin}: ONE angle addition (mul, fma, mul, fma; <= 2 ulp absolute), the other half turn is a sign flip
-//              of the radius.  (Round 1 evaluated sin / cos of the residual angle by polynomials: 11 FP64 instructions
-//              and ~18 integer / select instructions instead of 4 and 5.)
-// 21 FP64 instructions per pair (round 1: 29; the Taylor-only version 39).
+//   sin, cos : the 2^23 angles of half a turn are alpha_i + beta_b + gamma_c with three tables of exact {cos, sin} (512 +
+//              128 + 128 entries): TWO angle additions (8 FP64 instructions; <= 3 ulp absolute), the other half turn is a
+//              sign flip of the radius.  (Round 1 evaluated sin / cos of a residual angle by polynomials: 11 FP64 and ~18
+//              integer / select instructions, and its single-copy tables cost ~10 shared-memory wavefronts per lookup.)
+// 25 FP64 instructions and four conflict-free 128-bit table loads per pair.
+template <int COPIES>
 __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const double2 *__restrict__ tab, double &z0, double &z1) {
     // ---- radius ----
     const double X = __hiloint2double((int)(0x3FF00000u | ((wb & 0xFFu) << 12) | (wa >> 20)), (int)(wa << 12));   // 1 + m 2^-40
@@ -197,14 +204,11 @@ __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const dou
     const int k = (hi >> 11) & 511;
     const int n = 1023 - (hi >> 20) - ((hi >> 19) & 1);                                      // -e' in [0, 41]
     const double M = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(U));    // mantissa in [1,2)
-    const double2 te = tab[k];
+    const double2 te = tab[k * COPIES];
     // ---- angle: table lookups issued early ----
-#if SDDE_RNG_HALF
-    const double2 ca = tab[SDDE_RNG_OFF_COARSE + ((wb >> 19) & 0xFFFu)];
-#else
-    const double2 ca = tab[SDDE_RNG_OFF_COARSE + ((wb >> 19) & 0x7FFu)];
-#endif
-    const double2 cb = tab[SDDE_RNG_OFF_FINE + ((wb >> 8) & 0x7FFu)];
+    const double2 ca = tab[(SDDE_RNG_OFF_COARSE + ((wb >> 22) & 0x1FFu)) * COPIES];
+    const double2 cb = tab[(SDDE_RNG_OFF_MID + ((wb >> 15) & 0x7Fu)) * COPIES];
+    const double2 cc = tab[(SDDE_RNG_OFF_FINE + ((wb >> 8) & 0x7Fu)) * COPIES];
     // ---- -2 ln u ----
     const double rho = fma(M, te.x, -1.0);
     const double dn = __hiloint2double(0x43300000, n) - 4503599627370496.0;                  // (double)n
@@ -219,39 +223,41 @@ __device__ __forceinline__ void normal_pair_from_words(u32 wa, u32 wb, const dou
     const double r0 = t * y;
     const double e = fma(-r0, y, 1.0);
     const double g = fma(r0 * e, fma(e, 0.375, 0.5), r0);
-    // ---- cos / sin (alpha + beta) ----
-    const double cp = fma(ca.x, cb.x, -(ca.y * cb.y));
-    const double sn = fma(ca.y, cb.x, ca.x * cb.y);
-    const int ghi = __double2hiint(g), glo = __double2loint(g);
-#if SDDE_RNG_HALF
-    const double gs = __hiloint2double(ghi ^ (int)(wb & 0x80000000u), glo);                 // second half turn: (-c, -s)
+    // ---- cos / sin (alpha + (beta + gamma)) ----
+    const double cbc = fma(cb.x, cc.x, -(cb.y * cc.y));
+    const double sbc = fma(cb.y, cc.x, cb.x * cc.y);
+    const double cp = fma(ca.x, cbc, -(ca.y * sbc));
+    const double sn = fma(ca.y, cbc, ca.x * sbc);
+    const double gs = __hiloint2double(__double2hiint(g) ^ (int)(wb & 0x80000000u), __double2loint(g));   // second half turn: (-c, -s)
     z0 = gs * cp;
     z1 = gs * sn;
-#else
-    // quadrant rotation: q=0 (c,s), 1 (-s,c), 2 (-c,-s), 3 (s,-c); signs folded into the radius
-    const u32 q = wb >> 30;
-    const bool odd = (q & 1u) != 0;
-    const double cc = odd ? sn : cp, ss = odd ? cp : sn;
-    const double gc = __hiloint2double(ghi ^ (int)(((q + 1u) & 2u) << 30), glo);
-    const double gs = __hiloint2double(ghi ^ (int)((q & 2u) << 30), glo);
-    z0 = gc * cc;
-    z1 = gs * ss;
-#endif
 }
 
 // normals 4*call .. 4*call+3 of trajectory gid
 __device__ __forceinline__ void philox_words(u64 gid, u64 call, const u32 *__restrict__ rk, u32 (&w)[4]) {
     philox4x32_10((u32)gid, (u32)(gid >> 32), (u32)call, (u32)(call >> 32), rk, w);
 }
+template <int COPIES>
 __device__ __forceinline__ void normal_quad_from_words(const u32 (&w)[4], const double2 *__restrict__ ltab, double (&z)[4]) {
-    normal_pair_from_words(w[0], w[1], ltab, z[0], z[1]);
-    normal_pair_from_words(w[2], w[3], ltab, z[2], z[3]);
+    normal_pair_from_words<COPIES>(w[0], w[1], ltab, z[0], z[1]);
+    normal_pair_from_words<COPIES>(w[2], w[3], ltab, z[2], z[3]);
 }
+template <int COPIES>
 __device__ __forceinline__ void philox_normal_quad(u64 gid, u64 call, const u32 *__restrict__ rk,
                                                    const double2 *__restrict__ ltab, double (&z)[4]) {
     u32 w[4];
     philox_words(gid, call, rk, w);
-    normal_quad_from_words(w, ltab, z);
+    normal_quad_from_words<COPIES>(w, ltab, z);
+}
+// stage the table: COPIES interleaved copies (entry i of copy c at index COPIES * i + c); returns this thread's copy
+template <int COPIES>
+__device__ __forceinline__ const double2 *stage_rng_table(double2 *ltab, const double2 *__restrict__ gtab, int nthreads) {
+    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += nthreads) {
+        const double2 v = gtab[i];
+#pragma unroll
+        for (int c = 0; c < COPIES; ++c) ltab[i * COPIES + c] = v;
+    }
+    return ltab + (threadIdx.x & (COPIES - 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,12 +402,15 @@ struct TrajState {
 // BW consecutive steps starting at global step index n (recs[0..BW)).  BW > 1: the delayed-state nodes of all BW
 // steps are loaded up front (the host guarantees they are older than the batch) and n*NC is even, so which half of
 // a Philox pair a step consumes is a compile-time fact.
-// FAST selects the lean body for batches pack_tables marked on their first record (SDDE_MASK_FAST_*): every lookup of
-// the batch is a ring hit of one kind, the nodes and the stored slots are consecutive ring slots without a wrap, dt and
-// theta are the same for all BW steps and no step saves more than 255 points.  The lean body reads only recs[0]
-// (five 128-bit shared-memory loads per batch instead of nine 64-bit loads per step), derives every address from two
-// bases and the slot stride, and has no prehistory / constant-u0 selects; K_FAST_EXACT also drops the blend arithmetic.
-enum { K_FAST_NONE = 0, K_FAST_EXACT = 1, K_FAST_INTERP = 2 };
+// FAST selects a lean body for batches pack_tables marked on their first record (SDDE_MASK_FAST_*): every lookup of the
+// batch reads the ring, the stored slots are consecutive ring slots without a wrap, dt is the same for all BW steps and
+// no step saves more than 255 points.  The lean bodies take dt, sqrt|dt|, the store base and the packed save counts from
+// recs[0] and have no prehistory / constant-u0 selects.  K_FAST_EXACT (every lookup hits a node exactly and the nodes are
+// consecutive slots): one load per step from ONE base, no blend arithmetic -- five 128-bit shared-memory loads per batch
+// instead of nine 64-bit loads per step.  K_FAST_RING (exact hits and interpolations mixed -- t_n - tau lands on either
+// side of a node by rounding, so even "exact" lags interpolate with theta ~ 1e-16 on some steps): per-step theta and
+// node offsets as in the general body.
+enum { K_FAST_NONE = 0, K_FAST_EXACT = 1, K_FAST_RING = 2 };
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW, int FAST>
 __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL * alg_stages(ALG)> *recs, int n,
                                           char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec,
@@ -414,32 +423,14 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
     const long long slot = a.slot_bytes;
     // ---- all delayed-state loads of the batch, unconditionally (prehistory records point at slot 0) ----
     double xlo[BW][NLK][NS][TPT], xhi[BW][NLK][NS][TPT];
-    if constexpr (LEAN) {
+    if constexpr (FAST == K_FAST_EXACT) {
 #pragma unroll
         for (int l = 0; l < NLK; ++l) {
             const char *phi = ringb + recs[0].lk[l].off_hi;
-            if (FAST == K_FAST_INTERP) {
-                const bool reuse = (recs[0].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1): already in registers
-                const char *plo = ringb + recs[0].lk[l].off_lo;
-#pragma unroll
-                for (int j = 0; j < NS; ++j) {
-                    if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[0][l][j]);
-                    else {
-#pragma unroll
-                        for (int tt = 0; tt < TPT; ++tt) xlo[0][l][j][tt] = st.carry[l][j][tt];
-                    }
-                }
-            }
 #pragma unroll
             for (int k = 0; k < BW; ++k)
 #pragma unroll
-                for (int j = 0; j < NS; ++j) {
-                    ld_traj<TPT>(reinterpret_cast<const double *>(phi + k * slot + j * jstride), xhi[k][l][j]);
-                    if (FAST == K_FAST_INTERP && k > 0) {
-#pragma unroll
-                        for (int tt = 0; tt < TPT; ++tt) xlo[k][l][j][tt] = xhi[k - 1][l][j][tt];
-                    }
-                }
+                for (int j = 0; j < NS; ++j) ld_traj<TPT>(reinterpret_cast<const double *>(phi + k * slot + j * jstride), xhi[k][l][j]);
         }
     } else {
 #pragma unroll
@@ -477,7 +468,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         for (int k = 0; k < BW; ++k)
 #pragma unroll
             for (int l = 0; l < NLK; ++l) {
-                const char *phi = ringb + recs[BW + k].lk[l].off_hi;
+                const char *phi = ringb + recs[SDDE_PF_DIST * BW + k].lk[l].off_hi;
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(phi + j * jstride));
@@ -516,14 +507,14 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                         }
 #pragma unroll
                         for (int tt = 0; tt < TPT; ++tt) {
-                            normal_quad_from_words(st.wn[tt], ltab, st.zc[tt]);
+                            normal_quad_from_words<SDDE_RNG_COPIES>(st.wn[tt], ltab, st.zc[tt]);
                             philox_words((u64)(a.traj_gid0 + tr0 + tt), call + (u64)(BW * NC / 4), a.rk, st.wn[tt]);
                         }
                         st.wcall = call + (u64)(BW * NC / 4);
                     } else {
 #pragma unroll
                         for (int tt = 0; tt < TPT; ++tt)
-                            philox_normal_quad((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt]);
+                            philox_normal_quad<SDDE_RNG_COPIES>((u64)(a.traj_gid0 + tr0 + tt), call, a.rk, ltab, st.zc[tt]);
                     }
                     st.zcall = call;
                 }
@@ -568,8 +559,8 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 for (int j = 0; j < NS; ++j)
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt) ul[tt][l / NL][l % NL][j] = xhi[k][l][j][tt];
-            } else if constexpr (FAST == K_FAST_INTERP) {
-                const double th = r.lk[l].theta, omt = 1.0 - th;
+            } else if constexpr (FAST == K_FAST_RING) {
+                const double th = recs[k].lk[l].theta, omt = 1.0 - th;
 #pragma unroll
                 for (int j = 0; j < NS; ++j)
 #pragma unroll
@@ -670,16 +661,23 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
 __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
     constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP, BLOCK = Tune<M>::BLOCK;
-    constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES : 0;   // supplied noise: no generator table
+    constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES(SDDE_RNG_COPIES) : 0;   // supplied noise: no generator table
     typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);                  // tables of the normal generator
     Rec *srec = reinterpret_cast<Rec *>(smem_raw + TAB_BYTES);
-    if (NOISE == K_NOISE_PHILOX) {
-        for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += BLOCK) ltab[i] = a.rng_tab[i];
-    }
+    // Trajectories of this CTA.  One CTA is resident per SM, so a wave of W trajectories would take ceil(W / (SMs x BLOCK x
+    // TPT)) full rounds with the last one mostly idle (10^6 paths = 6.6 rounds on 148 SMs: 7 rounds of time).  The host
+    // therefore launches whole rounds of full CTAs followed by ONE round of equally sized smaller "tail" CTAs; warps of a
+    // tail CTA that have no trajectories leave before the first barrier.
+    const bool full = (int)blockIdx.x < a.n_full_ctas;
+    const long long cta0 = full ? (long long)blockIdx.x * (BLOCK * TPT)
+                                : (long long)a.n_full_ctas * (BLOCK * TPT) + (long long)((int)blockIdx.x - a.n_full_ctas) * a.tail_traj;
+    const int nact = full ? BLOCK : a.tail_traj / TPT;                      // active threads (a multiple of 32)
+    if ((int)threadIdx.x >= nact) return;
+    const double2 *ltab = nullptr;                                          // this lane's copy of the generator's table
+    if (NOISE == K_NOISE_PHILOX) ltab = stage_rng_table<SDDE_RNG_COPIES>(reinterpret_cast<double2 *>(smem_raw), a.rng_tab, nact);
 
-    const long long tr0 = ((long long)blockIdx.x * BLOCK + threadIdx.x) * TPT;  // wave-local trajectory index
+    const long long tr0 = cta0 + (long long)threadIdx.x * TPT;              // wave-local trajectory index
     const long long last = a.n_traj - 1;
 
     // ---- per-trajectory "__init": state, parameters, noise state (src/solve.jl:137, 302-339) ----
@@ -745,24 +743,25 @@ __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solv
     const bool batched = (B > 1) && (a.batch >= B);   // host: batch = min(B, min_gap + 1); chunk_steps % B == 0
     for (int n0 = 0; n0 < a.n_steps; n0 += a.chunk_steps) {
         const int cnt = (a.n_steps - n0 < a.chunk_steps) ? (a.n_steps - n0) : a.chunk_steps;
-        const int nrec = (a.n_steps - n0 - cnt >= B) ? cnt + B : ((a.n_steps - n0 > cnt) ? cnt + 1 : cnt);   // look-ahead records
+        constexpr int LOOK = (B > 1) ? SDDE_PF_DIST * B : 1;                                   // look-ahead records (prefetch)
+        const int nrec = (a.n_steps - n0 - cnt >= LOOK) ? cnt + LOOK : a.n_steps - n0;
         __syncthreads();
         {   // stage this chunk of the schedule in shared memory
             const uint4 *src = reinterpret_cast<const uint4 *>(a.steps + (size_t)n0 * sizeof(Rec));
             uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + TAB_BYTES);
             const int nvec = nrec * (int)(sizeof(Rec) / 16);
-            for (int i = threadIdx.x; i < nvec; i += BLOCK) dst[i] = src[i];
+            for (int i = threadIdx.x; i < nvec; i += nact) dst[i] = src[i];
         }
         __syncthreads();
         int nb = 0;
         if (batched) {
             for (; nb + B <= cnt; nb += B) {
                 const int fm = srec[nb].ring_mask;
-                const bool pfn = nb + 2 * B <= nrec;   // next batch's records staged: prefetch its nodes
+                const bool pfn = nb + (SDDE_PF_DIST + 1) * B <= nrec;   // the records of the batch to prefetch are staged
                 if (fm & SDDE_MASK_FAST_EXACT)
                     run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_EXACT>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
-                else if (fm & SDDE_MASK_FAST_INTERP)
-                    run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_INTERP>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+                else if (fm & SDDE_MASK_FAST_RING)
+                    run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_RING>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
                 else
                     run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_NONE>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
             }
@@ -773,8 +772,8 @@ __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solv
             const bool pfn = pf && (nb + 1 < nrec);
             if (fm & SDDE_MASK_FAST_EXACT)
                 run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_EXACT>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
-            else if (fm & SDDE_MASK_FAST_INTERP)
-                run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_INTERP>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+            else if (fm & SDDE_MASK_FAST_RING)
+                run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_RING>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
             else
                 run_batch<M, ALG, NOISE, PTRAJ, TPT, 1, K_FAST_NONE>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
         }

@@ -1,6 +1,7 @@
 // sdde_tools.cu -- test hooks and micro-benchmarks of the C ABI: the normals the step kernels draw, measured DFMA and
 // copy peaks of this GPU (roofline denominators), page-locked host memory helpers.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "rng_table.hpp"
@@ -14,8 +15,7 @@ namespace sdde {
 __global__ void philox_dump_kernel(double *out, long long n_traj, long long traj_off, long long n_steps, int nc, u32 k0,
                                    u32 k1, const double2 *__restrict__ rng_tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *ltab = reinterpret_cast<double2 *>(smem_raw);
-    for (int i = threadIdx.x; i < SDDE_RNG_TAB_ENTRIES; i += blockDim.x) ltab[i] = rng_tab[i];
+    const double2 *ltab = stage_rng_table<SDDE_RNG_COPIES>(reinterpret_cast<double2 *>(smem_raw), rng_tab, (int)blockDim.x);
     __syncthreads();
     u32 rk[20];
     philox_round_keys(k0, k1, rk);
@@ -24,7 +24,7 @@ __global__ void philox_dump_kernel(double *out, long long n_traj, long long traj
     const long long nq = n_steps * nc;
     for (long long call = 0; call * 4 < nq; ++call) {
         double z[4];
-        philox_normal_quad((u64)(traj_off + tr), (u64)call, rk, ltab, z);
+        philox_normal_quad<SDDE_RNG_COPIES>((u64)(traj_off + tr), (u64)call, rk, ltab, z);
         for (int i = 0; i < 4; ++i)
             if (4 * call + i < nq) out[(4 * call + i) * n_traj + tr] = z[i];
     }
@@ -59,8 +59,8 @@ int sdde_b200_philox_normals(sdde_ctx *c, uint64_t seed, int64_t traj_offset, in
     CU_CHECK(cudaSetDevice(c->device));
     const size_t bytes = (size_t)n_steps * n_noise * n_traj * 8;
     CU_CHECK(c->out[0].reserve(bytes));
-    CU_CHECK(cudaFuncSetAttribute(sdde::philox_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDDE_RNG_SMEM_BYTES));
-    sdde::philox_dump_kernel<<<(unsigned)((n_traj + 127) / 128), 128, SDDE_RNG_SMEM_BYTES, c->compute>>>(
+    CU_CHECK(cudaFuncSetAttribute(sdde::philox_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SDDE_RNG_SMEM_BYTES(SDDE_RNG_COPIES)));
+    sdde::philox_dump_kernel<<<(unsigned)((n_traj + 255) / 256), 256, SDDE_RNG_SMEM_BYTES(SDDE_RNG_COPIES), c->compute>>>(
         (double *)c->out[0].p, n_traj, traj_offset, n_steps, n_noise, (sdde::u32)(seed & 0xffffffffu), (sdde::u32)(seed >> 32),
         (const double2 *)c->rng_tab.p);
     CU_CHECK(cudaGetLastError());
@@ -127,7 +127,10 @@ int sdde_b200_hbm_peak(sdde_ctx *c, double *gbs) {
 void *sdde_b200_alloc_pinned(int64_t bytes) {
     void *p = nullptr;
     if (bytes <= 0) return nullptr;
-    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault);
+    // SDDE_B200_PINNED_FLAGS (measurement hook, tools/e2e_ab.py): cudaHostAlloc flags, e.g. 4 = write-combined, 1 = portable
+    const char *fl = getenv("SDDE_B200_PINNED_FLAGS");
+    const unsigned flags = fl ? (unsigned)atoi(fl) : cudaHostAllocDefault;
+    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, flags);
     if (e != cudaSuccess) { cudaGetLastError(); fail(SDDE_ERR_CUDA - (int)e, "cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); return nullptr; }
     return p;
 }

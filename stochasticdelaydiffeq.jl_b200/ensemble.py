@@ -78,9 +78,9 @@ def _julia_range(a: float, s: float, b: float) -> np.ndarray:
             m = 9007199254740992.0
             if den != 0 and abs(a * den) <= m and abs(s * den) <= m and den % start_d == 0 and den % step_d == 0:
                 start_n, step_n = round(a * den), round(s * den)
-                num, dd = den * stop_n - stop_d * start_n, step_n * stop_d
-                q = abs(num) // abs(dd) * (1 if (num >= 0) == (dd > 0) else -1)      # Julia div truncates toward zero
-                ln = max(0, q + 1)
+                dd = step_n * stop_d
+                num = den * stop_n - stop_d * start_n + dd                          # "+ 1" folded into the dividend, as Julia does
+                ln = max(0, abs(num) // abs(dd) * (1 if (num >= 0) == (dd > 0) else -1))   # Julia's div truncates toward zero
                 if between(a, a + (ln - 1) * s, b + s / 2) and not between(a, a + ln * s, b):
                     return np.array([float(Fraction(start_n + k * step_n, den)) for k in range(ln)], dtype=np.float64)
     lf = (b - a) / s
@@ -127,7 +127,7 @@ class _Marshalled:
 
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
-             want_moments, lanes_per_traj=0, save_idxs=None, noise_t=None) -> _Marshalled:
+             want_moments, lanes_per_traj=0, save_idxs=None, noise_t=None, d_discontinuities=()) -> _Marshalled:
     if not isinstance(alg, (EM, RKMil, EulerHeun)):
         raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil and EulerHeun, fixed step)")
     if adaptive is None:
@@ -169,6 +169,15 @@ def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_
     m.keep += [sv, ts]
     d.saveat, d.n_saveat = capi.np_ptr(sv).value if sv.size else None, sv.size
     d.tstops, d.n_tstops = capi.np_ptr(ts).value if ts.size else None, ts.size
+    # d_discontinuities keyword (src/solve.jl:20-23): Discontinuity(t, order) pairs, or bare times (order 0)
+    dd = [(float(x[0]), x[1]) if isinstance(x, (tuple, list)) else (float(x), 0) for x in d_discontinuities]
+    if any(round(2 * o) != 2 * o for _, o in dd):
+        raise ValueError("discontinuity orders must be multiples of 1/2")
+    dd_t = np.array([t for t, _ in dd], dtype=np.float64)
+    dd_o = np.array([int(round(2 * o)) for _, o in dd], dtype=np.int32)
+    m.keep += [dd_t, dd_o]
+    if dd:
+        d.d_disc_t, d.d_disc_order2, d.n_d_disc = capi.np_ptr(dd_t).value, capi.np_ptr(dd_o).value, len(dd)
     if p_batch is not None:
         if p_batch.shape != (model.n_param, n_traj):
             raise ValueError(f"p_batch must have shape ({model.n_param}, {n_traj})")
@@ -239,7 +248,7 @@ def _resolve_model(prob, ctx):
 
 
 def schedule(prob: SDDEProblem, alg, *, dt, saveat=None, save_everystep=None, save_start=None, save_end=None,
-             tstops=(), adaptive=None) -> Schedule:
+             tstops=(), adaptive=None, d_discontinuities=()) -> Schedule:
     """The trajectory-independent step/lookup/save schedule the library will use (host only, no GPU needed)."""
     model = prob.model
     if isinstance(model, UserModel):
@@ -249,7 +258,7 @@ def schedule(prob: SDDEProblem, alg, *, dt, saveat=None, save_everystep=None, sa
     m = _marshal(prob, model, alg, dt=dt, saveat=saveat, save_everystep=save_everystep, save_start=save_start,
                  save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=0, traj_offset=0, seed=0, p_batch=None,
                  u0_batch=None, noise=None, noise_mode=capi.NOISE_PHILOX, noise_mem=0, out_mem=0, want_paths=0,
-                 want_moments=0)
+                 want_moments=0, d_discontinuities=d_discontinuities)
     s = capi.SddeSchedule()
     capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(s)))
     try:
@@ -428,15 +437,25 @@ def _quantiles_across_ranks(ctx, dev, ptr, on_dev, n_rows, n_local, n_total, pro
     hist = torch.empty(n_rows * n_rank.value * 2048, dtype=torch.int32, device=tdev)
     capi.check(L.sdde_b200_qsel_begin(ctx.handle, ptr if n_local else None, capi.MEM_DEVICE if on_dev else capi.MEM_HOST, n_rows,
                                       n_local, max(n_local, 1), n_total, pp, probs.size, 1 if median else 0, hist.data_ptr()))
+    on_nccl = dist.get_backend() == "nccl"          # gloo (tests: two ranks sharing one GPU) reduces through the host
+
+    def all_reduce_sum(t):
+        if on_nccl:
+            dist.all_reduce(t)
+        else:
+            h = t.cpu()
+            dist.all_reduce(h)
+            t.copy_(h)
+
     for p in range(6):
         capi.check(L.sdde_b200_qsel_local(ctx.handle, p))
-        dist.all_reduce(hist)                       # counts per (row, rank, digit) over the whole ensemble
+        all_reduce_sum(hist)                        # counts per (row, rank, digit) over the whole ensemble
         torch.cuda.synchronize(tdev)
         capi.check(L.sdde_b200_qsel_apply(ctx.handle, p))
     nan = np.zeros(n_rows, dtype=np.int64)
     capi.check(L.sdde_b200_qsel_nan(ctx.handle, capi.np_ptr(nan).value, 0))
     t = torch.from_numpy(nan).to(tdev)
-    dist.all_reduce(t)
+    all_reduce_sum(t)
     nan = t.cpu().numpy()
     capi.check(L.sdde_b200_qsel_nan(ctx.handle, capi.np_ptr(nan).value, 1))
     capi.check(L.sdde_b200_qsel_end(ctx.handle, capi.np_ptr(res).value))
@@ -544,7 +563,8 @@ def shard_range(n_total: int, rank: int, world: int):
 
 def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, trajectories=1, saveat=None,
           save_everystep=None, save_start=None, save_end=None, tstops=(), adaptive=None, seed=0, moments=False,
-          paths=True, noise_increments=None, noise_grid=None, out=None, callback=None, save_idxs=None, **kwargs):
+          paths=True, noise_increments=None, noise_grid=None, out=None, callback=None, save_idxs=None, traj_offset=0,
+          d_discontinuities=(), **kwargs):
     """Ensemble solve on the B200 path.  ``prob`` is an ``EnsembleProblem`` (or an ``SDDEProblem`` -> one trajectory).
 
     noise_increments[n_steps, n_chan, trajectories]  supplied dW (validation; reference: prob.noise branch src/solve.jl:340-353)
@@ -552,6 +572,11 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
                    (t[n_grid], W[n_grid, n_chan, trajectories]) = NoiseGrid(t, W) on any grid covering tspan (W is
                    interpolated linearly at the step ends, like the reference's NoiseGrid)
     out                                               preallocated result buffer: numpy (ideally pinned) or torch CUDA tensor
+    d_discontinuities                                 times, or (time, order) pairs, of discontinuities the user declares
+                   (src/solve.jl:20-23): they become tstops and propagate by the constant lags like the one at t0
+    traj_offset                                       global id of this call's first trajectory (default 0): the in-kernel Philox
+                   streams are keyed by (seed, global trajectory id), so a slice [k, k+n) of a larger ensemble solved with
+                   traj_offset=k reproduces those trajectories bit for bit (what the ranks of a sharded solve do internally)
     """
     if callback is not None:
         raise NotImplementedError("callbacks are outside this path (SURVEY.md section 8(f))")
@@ -568,15 +593,18 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
         rank, world = dist.get_rank(), dist.get_world_size()
     lo, hi = shard_range(n_total, rank, world)
     n_traj = hi - lo
+    gid0 = int(traj_offset) + lo          # global id of this rank's first trajectory
 
     device = ea.device if ea.device is not None else (ea.devices[0] if ea.devices else _default_device())
+    if isinstance(device, capi.Context):
+        device = device.device
     ctx = capi.get_context(device)
     ctx.set_option("wave_traj", int(ea.wave_traj or 0))     # per solve: a forced wave size must not leak into later solves
     model = _resolve_model(base, ctx)
     if not paths and not moments:
         raise ValueError("nothing to return: ask for paths, moments or both")
     seed = _choose_seed(seed, base.seed, ea.distributed and world > 1)
-    p_batch, u0_batch = eprob.batches(n_traj, lo)
+    p_batch, u0_batch = eprob.batches(n_traj, gid0)      # per-trajectory data is indexed by global id
 
     t0w = time.perf_counter()
     noise_mode, noise_mem, noise_ptr, keep = capi.NOISE_PHILOX, capi.MEM_HOST, None, []
@@ -602,13 +630,15 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
             raise ValueError(f"supplied noise must have shape [n, {model.n_chan}, {n_traj}]")
 
     m = _marshal(base, model, alg, dt=dt, saveat=saveat, save_everystep=save_everystep, save_start=save_start,
-                 save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=lo, seed=seed,
+                 save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=gid0, seed=seed,
                  p_batch=p_batch, u0_batch=u0_batch, noise=noise_ptr, noise_mode=noise_mode, noise_mem=noise_mem,
                  out_mem=capi.MEM_DEVICE if ea.output == "device" else capi.MEM_HOST, want_paths=paths,
-                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj, save_idxs=save_idxs, noise_t=grid_t)
+                 want_moments=moments, lanes_per_traj=ea.lanes_per_traj, save_idxs=save_idxs, noise_t=grid_t,
+                 d_discontinuities=d_discontinuities)
     d = m.desc
     skey = (d.alg, d.t0, d.tf, d.dt, tuple(d.lags[i] for i in range(d.n_lag)), d.order_discontinuity_t0,
-            d.constant_lags_declared, d.save_start, d.save_end, d.save_everystep, m.keep[0].tobytes(), m.keep[1].tobytes())
+            d.constant_lags_declared, d.save_start, d.save_end, d.save_everystep, m.keep[0].tobytes(), m.keep[1].tobytes(),
+            m.keep[2].tobytes(), m.keep[3].tobytes())
     if _sched_cache.get("key") != skey:
         sch = capi.SddeSchedule()
         capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(sch)))
@@ -646,6 +676,7 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
             if not out_arr.flags.c_contiguous or out_arr.dtype != np.float64:
                 raise ValueError("out must be a C-contiguous float64 array")
             out_ptr = capi.np_ptr(out_arr).value
+    m.desc.out_rows = n_save * n_saved          # capacity of out / moments: the library refuses to write more rows than this
     mom = np.zeros((n_save, n_saved, 3), dtype=np.float64) if moments else None
     # per-trajectory return codes only make sense with per-trajectory solutions; a moments-only run gets the count
     status = np.empty(n_traj, dtype=np.uint8) if paths else None
@@ -654,7 +685,9 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     if ea.devices and len(ea.devices) > 1:
         if ea.output != "host":
             raise ValueError("EnsembleB200(devices=...) returns host arrays")
-        hs = (C.c_void_p * len(ea.devices))(*[capi.get_context(dv).handle for dv in ea.devices])
+        # an entry is a device index (this process's cached context of that GPU) or a capi.Context (two contexts may share a GPU)
+        hs = (C.c_void_p * len(ea.devices))(*[dv.handle if isinstance(dv, capi.Context) else capi.get_context(dv).handle
+                                               for dv in ea.devices])
         tms = (capi.SddeTiming * len(ea.devices))()
         capi.check(capi.lib().sdde_b200_solve_multi(hs, len(ea.devices), C.byref(m.desc), out_ptr,
                                                     capi.np_ptr(mom).value if moments else None,

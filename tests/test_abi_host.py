@@ -32,7 +32,7 @@ def test_rng_table_is_correctly_rounded():
     mp = pytest.importorskip("mpmath")
     mp.mp.prec = 200
     tab = capi.rng_table()
-    assert tab.shape == (512 + 2048 + 4096, 2)
+    assert tab.shape == (512 + 512 + 128 + 128, 2)
     half_pi = mp.pi / 2
 
     def ulps(x, exact):
@@ -48,25 +48,30 @@ def test_rng_table_is_correctly_rounded():
         m2ln = 2 * mp.log(mp.mpf(inv)) + (2 * mp.log(2) if k >= 256 else 0)
         worst = max(worst, ulps(tab[k, 1], m2ln))
     assert tab[511, 1] == 0.0
-    for b in range(0, 2048, 7):
-        beta = half_pi * ((mp.mpf(b) + mp.mpf("0.5")) / 2 ** 22 - mp.mpf(1) / 2 ** 12)
-        worst = max(worst, ulps(tab[512 + b, 0], mp.cos(beta)), ulps(tab[512 + b, 1], mp.sin(beta)))
-    for i in range(0, 4096, 5):
-        h, a = i >> 11, i & 2047
-        alpha = half_pi * (h + (mp.mpf(a) + mp.mpf("0.5")) / 2 ** 11 - mp.mpf("0.5"))
-        worst = max(worst, ulps(tab[2560 + i, 0], mp.cos(alpha)), ulps(tab[2560 + i, 1], mp.sin(alpha)))
+    for i in range(512):
+        h, a = i >> 8, i & 255
+        alpha = half_pi * (h + (mp.mpf(a) + mp.mpf("0.5")) / 2 ** 8 - mp.mpf("0.5"))
+        worst = max(worst, ulps(tab[512 + i, 0], mp.cos(alpha)), ulps(tab[512 + i, 1], mp.sin(alpha)))
+    for b in range(128):
+        beta = half_pi * ((mp.mpf(b) + mp.mpf("0.5")) / 2 ** 15 - mp.mpf(1) / 2 ** 9)
+        gamma = half_pi * ((mp.mpf(b) + mp.mpf("0.5")) / 2 ** 22 - mp.mpf(1) / 2 ** 16)
+        worst = max(worst, ulps(tab[1024 + b, 0], mp.cos(beta)), ulps(tab[1024 + b, 1], mp.sin(beta)),
+                    ulps(tab[1152 + b, 0], mp.cos(gamma)), ulps(tab[1152 + b, 1], mp.sin(gamma)))
     assert worst <= 0.51, worst
-    # the angle decomposition covers the oracle's angles: theta = (pi/2)(q + (f + 1/2) 2^-22 - 1/2) = alpha + beta + s pi
+    # the angle decomposition covers the oracle's angles: theta = (pi/2)(q + (f + 1/2) 2^-22 - 1/2) = alpha + beta + gamma + s pi,
+    # evaluated with the kernel's operation order (two angle additions)
     rng = np.random.default_rng(5)
-    for wb in rng.integers(0, 2 ** 32, size=200, dtype=np.uint64):
+    for wb in rng.integers(0, 2 ** 32, size=300, dtype=np.uint64):
         wb = int(wb)
         q, f = wb >> 30, (wb >> 8) & 0x3FFFFF
         theta = half_pi * (q + (mp.mpf(f) + mp.mpf("0.5")) / 2 ** 22 - mp.mpf("0.5"))
-        ca, sa = tab[2560 + ((wb >> 19) & 0xFFF)]
-        cb, sb = tab[512 + ((wb >> 8) & 0x7FF)]
+        ca, sa = tab[512 + ((wb >> 22) & 0x1FF)]
+        cb, sb = tab[1024 + ((wb >> 15) & 0x7F)]
+        cc, sc = tab[1152 + ((wb >> 8) & 0x7F)]
+        cbc, sbc = cb * cc - sb * sc, sb * cc + cb * sc
         sgn = -1.0 if wb >> 31 else 1.0
-        assert abs(sgn * (ca * cb - sa * sb) - float(mp.cos(theta))) < 4e-16
-        assert abs(sgn * (sa * cb + ca * sb) - float(mp.sin(theta))) < 4e-16
+        assert abs(sgn * (ca * cbc - sa * sbc) - float(mp.cos(theta))) < 5e-16
+        assert abs(sgn * (sa * cbc + ca * sbc) - float(mp.sin(theta))) < 5e-16
 
 
 def test_struct_layout_matches_header():
@@ -159,6 +164,148 @@ def test_error_behaviour_mirrors_reference_guards():
         S.SDDEProblem(lambda u, h, p, t: u, S.linear1.g, 1.0, 1.0, (0, 1), (1, 1, 1), constant_lags=(1.0,))
     with pytest.raises(ValueError):
         S.SDDEProblem(S.linear1.f, S.hayes.g, 1.0, 1.0, (0, 1), (1, 1, 1), constant_lags=(1.0,))
+
+
+def test_d_discontinuities_keyword_schedule_equals_oracle():
+    """d_discontinuities (src/solve.jl:20-23): user-declared discontinuities become tstops (:643-646), enter the
+    discontinuity heap when their order is <= alg_order + 1 (:690-699) and propagate by the constant lags like the one
+    at t0 (src/integrators/utils.jl:42-118).  Product schedule == oracle replay, bit for bit; hand-checked facts below."""
+    c = cases.c1(T=6.0, saveat=0.5)
+    dd = [(0.37, 0), (2.2137, 1), 4.05, (4.4137, 3)]         # orders 0, 1, (bare time = 0), 3 (> alg_order + 1: a tstop only)
+    for alg, algid in ((S.EM(), 0), (S.RKMil(), 2)):
+        kw = c.with_(alg=algid).solve_kwargs()
+        s = S.schedule(c.problem(), alg, d_discontinuities=dd, **kw)
+        sv, ss, se = O.expand_saveat(c.saveat, *c.tspan)
+        o = O.build_schedule(0.0, 6.0, c.dt, c.lags, algid, saveat_times=sv, save_start=ss, save_end=se, d_discontinuities=dd)
+        for k in ["t", "dt", "sqdt", "lk_mode", "lk_idx", "lk_theta", "save_t", "save_step", "save_theta", "save_exact"]:
+            assert np.array_equal(np.asarray(getattr(s, k)), np.asarray(getattr(o, k))), (algid, k)
+        t = np.asarray(s.t)
+        for x in (0.37, 2.2137, 4.05, 4.4137):                # every declared time is hit exactly
+            assert np.any(t == x), x
+        assert np.any(t == 0.37 + 1.0)                        # order 0 at 0.37 propagates by the lag (order 1/2 <= alg_order + 1/2)
+        # order 1 at 2.2137: next order 3/2 -- tracked by RKMil (alg_order 1: 3/2 <= 3/2), not by EM (alg_order 1/2: 3/2 > 1)
+        assert bool(np.any(t == 2.2137 + 1.0)) == (algid == 2)
+        # (4.4137, order 3) is a tstop only: the steps after it restart from 4.4137, so 5.4137 is reached by plain stepping
+        # either way -- what shows the difference is the tstop list
+        assert bool(np.any(np.asarray(s.tstops_hit) == 2.2137 + 1.0)) == (algid == 2)
+    base = S.schedule(c.problem(), S.EM(), **c.solve_kwargs())
+    assert len(base.t) < len(s.t)
+    with pytest.raises(ValueError):
+        S.schedule(c.problem(), S.EM(), d_discontinuities=[(1.0, 0.25)], **c.solve_kwargs())
+
+
+def test_julia_float_ranges_known_answers():
+    """[EXT] Base.(:)(start, step, stop) for Float64 (twiceprecision.jl), as restated for saveat expansion
+    (src/solve.jl:661-671).  Known answers of Julia itself: 0.1:0.1:0.5 and 0:0.1:1 hit the decimal values exactly (the
+    rational lift), 1/3-steps land on correctly rounded thirds, a non-rational step falls back to start + k*step."""
+    from sdde_b200.ensemble import _julia_range, _rat
+    assert _rat(0.1) == (1, 10) and _rat(0.05) == (1, 20) and _rat(1 / 3) == (1, 3) and _rat(17.02) == (851, 50)
+    assert _julia_range(0.1, 0.1, 0.5).tolist() == [0.1, 0.2, 0.3, 0.4, 0.5]
+    assert _julia_range(0.0, 0.1, 1.0).tolist() == [0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0]
+    assert _julia_range(1 / 3, 1 / 3, 2.0).tolist() == [1 / 3, 2 / 3, 1.0, 4 / 3, 5 / 3, 2.0]
+    assert _julia_range(0.0, 0.3, 1.0).tolist() == [0.0, 0.3, 0.6, 0.9]
+    assert len(_julia_range(0.0, 1.0, 500.0)) == 501 and _julia_range(1.0, 1.0, 0.5).size == 0
+    r = _julia_range(0.0, np.pi / 7, 3.0)                    # literal branch: len = round(3/(pi/7)) + 1 = 8 -> overshoots 3.0 -> 7
+    assert r.size == 7 and abs(r[-1] - 6 * (np.pi / 7)) <= 5e-16 and r[-1] <= 3.0
+    for (a, s_, b) in [(0.0, 0.1, 1.0), (0.1, 0.1, 0.5), (1 / 3, 1 / 3, 2.0), (0.0, np.pi / 7, 3.0), (0.25, 0.07, 9.3), (2.0, 1e-3, 2.5)]:
+        assert np.array_equal(_julia_range(a, s_, b), O._float_range(a, s_, b))      # product == oracle restatement
+    # saveat expansion built from them (number form): (t0+s):s:tf when (t0:s:tf)[end] == tf, else up to tf - s
+    assert S.expand_saveat(0.3, 0.0, 1.0)[0].tolist() == [0.3, 0.6]
+    assert S.expand_saveat(0.25, 0.0, 1.0)[0].tolist() == [0.25, 0.5, 0.75, 1.0]
+    assert S.expand_saveat(1 / 3, 0.0, 1.0)[0].tolist() == [1 / 3, 2 / 3, 1.0]
+
+
+def test_descriptor_mirrors_have_the_header_size():
+    """The product's ctypes mirror, the oracle's own copy of it and the C header agree on sizeof(sdde_desc) and on the
+    offsets of the fields added last (a stale mirror reads garbage past its end)."""
+    import subprocess, tempfile
+    import c_oracle
+    src = ('#include "sdde_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",sizeof(sdde_desc),'
+           'offsetof(sdde_desc,noise_t),offsetof(sdde_desc,d_disc_t),offsetof(sdde_desc,n_d_disc),offsetof(sdde_desc,out_rows));}')
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "a.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "a.c"), "-o", os.path.join(td, "a")], check=True)
+        want = [int(x) for x in subprocess.run([os.path.join(td, "a")], capture_output=True, text=True, check=True).stdout.split()]
+    for D in (capi.SddeDesc, c_oracle.Desc):
+        assert [C.sizeof(D), D.noise_t.offset, D.d_disc_t.offset, D.n_d_disc.offset, D.out_rows.offset] == want, D
+
+
+def _c_struct_fields(hdr, name):
+    """[(field, ctype, count)] of `typedef struct name {...} name;` in the header (pointers -> 'ptr')."""
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    consts = {k: int(v) for k, v in re.findall(r"#define (SDDE_MAX_\w+) (\d+)", hdr)}
+    out = []
+    for decl in filter(None, (d.strip() for d in body.split(";"))):
+        m = re.match(r"(?:const\s+)?(\w+)\s+(.*)", decl)
+        ctype, rest = m.group(1), m.group(2)
+        for item in (x.strip() for x in rest.split(",")):
+            ptr = item.startswith("*")
+            item = item.lstrip("* ")
+            am = re.match(r"(\w+)\[(\w+)\]", item)
+            if am:
+                n = am.group(2)
+                out.append((am.group(1), ctype, consts[n] if n in consts else int(n)))
+            else:
+                out.append((item, "ptr" if ptr else ctype, 1))
+    return out
+
+
+def _julia_struct_fields(src, name):
+    body = re.search(r"mutable struct %s\n(.*?)\nend" % name, src, re.S).group(1)
+    out = []
+    for ln in body.splitlines():
+        m = re.match(r"\s*(\w+)::([^=]+?)\s*=", ln)
+        if m:
+            out.append((m.group(1), m.group(2).strip()))
+    return out
+
+
+def test_julia_struct_mirrors_match_header():
+    """julia/EnsembleB200.jl cannot run here (no Julia in the image); its hand-written mirrors of sdde_desc, sdde_schedule
+    and sdde_timing are therefore checked textually: same field names in the same order, Julia types of the same size and
+    kind as the C types, same total size as gcc's sizeof -- and every ccall names an exported symbol with as many argument
+    types as the header's prototype has parameters."""
+    import subprocess, tempfile
+    hdr = open(os.path.join(ROOT, "include", "sdde_b200.h")).read()
+    jl = open(os.path.join(ROOT, "julia", "EnsembleB200.jl")).read()
+    csize = {"int32_t": 4, "int64_t": 8, "uint64_t": 8, "double": 8, "ptr": 8, "char": 1}
+    jkind = {"Int32": ("int32_t", 4), "Int64": ("int64_t", 8), "UInt64": ("uint64_t", 8), "Float64": ("double", 8), "UInt8": ("char", 1)}
+    sizes = {}
+    for cname, jname in (("sdde_desc", "SddeDesc"), ("sdde_schedule", "SddeSchedule"), ("sdde_timing", "SddeTiming")):
+        cf, jf = _c_struct_fields(hdr, cname), _julia_struct_fields(jl, jname)
+        assert [f[0] for f in cf] == [f[0] for f in jf], (cname, [f[0] for f in cf], [f[0] for f in jf])
+        off = 0
+        for (fname, ctype, count), (_, jt) in zip(cf, jf):
+            if ctype == "ptr":
+                assert jt.startswith("Ptr{"), (cname, fname, jt)
+                sz, n = 8, 1
+            elif count > 1:
+                m = re.match(r"NTuple\{(\d+),\s*(\w+)\}", jt)
+                assert m and int(m.group(1)) == count and jkind[m.group(2)] == (ctype, csize[ctype]), (cname, fname, jt)
+                sz, n = csize[ctype], count
+            else:
+                assert jkind[jt] == (ctype, csize[ctype]), (cname, fname, jt)
+                sz, n = csize[ctype], 1
+            off = (off + sz - 1) // sz * sz + sz * n              # natural alignment, as both compilers lay it out
+        sizes[cname] = (off + 7) // 8 * 8
+    src = '#include "sdde_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu\\n",sizeof(sdde_desc),sizeof(sdde_schedule),sizeof(sdde_timing));}'
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "a.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "a.c"), "-o", os.path.join(td, "a")], check=True)
+        want = [int(x) for x in subprocess.run([os.path.join(td, "a")], capture_output=True, text=True, check=True).stdout.split()]
+    assert [sizes["sdde_desc"], sizes["sdde_schedule"], sizes["sdde_timing"]] == want
+    # every ccall: exported symbol, argument-type count == parameter count of the header's prototype
+    protos = {}
+    for name, params in re.findall(r"SDDE_API[^;(]*?\b(sdde_b200_\w+)\s*\(([^;]*?)\)\s*;", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S), re.S):
+        params = params.strip()
+        protos[name] = 0 if params in ("", "void") else params.count(",") + 1
+    calls = re.findall(r"ccall\(\(:(sdde_b200_\w+), libsdde\),\s*[\w{}.]+,\s*\(([^()]*(?:\{[^{}]*\}[^()]*)*)\)", jl)
+    assert len(calls) >= 10
+    for name, argt in calls:
+        assert name in protos and name in capi.EXPORTS, name
+        n = len([a for a in argt.split(",") if a.strip()])
+        assert n == protos[name], (name, n, protos[name])
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():

@@ -1,5 +1,7 @@
-"""-m gpu, needs >= 2 GPUs (skipped otherwise): one process driving several GPUs through sdde_b200_solve_multi gives
-exactly the single-GPU result (paths bit for bit; moments up to the merge order)."""
+"""-m gpu: one process driving several contexts through sdde_b200_solve_multi gives exactly the single-context result
+(paths bit for bit; moments up to the merge order), and the distributed order statistics equal the single-rank ones.
+On a 1-GPU box the split / traj_offset / merge legs run with two contexts (or two ranks over gloo) sharing GPU 0; the
+NCCL legs need >= 2 GPUs and are skipped otherwise."""
 import numpy as np
 import pytest
 
@@ -11,6 +13,44 @@ pytestmark = pytest.mark.gpu
 
 def _ngpu():
     return max(0, S.lib().sdde_b200_device_count())
+
+
+def test_two_contexts_on_one_gpu_equal_one_context():
+    """sdde_b200_solve_multi with two contexts that share GPU 0: contiguous global-id ranges, per-context traj_offset,
+    repacked supplied noise, sliced per-trajectory parameters, host Chan merge of the moment triples (two ranks on one
+    device cannot form an NCCL group, so the library takes its host merge)."""
+    from sdde_b200 import _capi as capi
+    ca, cb = capi.Context(0), capi.Context(0)
+    try:
+        case = cases.c2(T=40.0)
+        n = 5001
+        kw = dict(trajectories=n, seed=77, moments=True, **case.solve_kwargs())
+        a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), **kw)
+        b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(devices=(ca, cb)), **kw)
+        assert np.array_equal(a.out, b.out) and np.array_equal(a.status, b.status)
+        assert np.allclose(a.moments, b.moments, rtol=1e-12)
+        assert b.timing["moment_merge"] == 1          # host merge
+        # three contexts, uneven split (1667 + 1667 + 1667 = 5001), paths only
+        cc = capi.Context(0)
+        try:
+            c3 = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(devices=(ca, cb, cc)), trajectories=n, seed=77,
+                         **case.solve_kwargs())
+        finally:
+            cc.close()
+        assert np.array_equal(a.out, c3.out)
+        # supplied noise + per-trajectory parameters are sliced per context
+        c1 = cases.c1(T=3.0)
+        sch = c1.oracle_schedule()
+        dW = cases.increments(sch, 1, 1001)
+        pb = np.stack([-1.0 + 0.1 * np.arange(1001) / 1001, 0.5 * np.ones(1001), 0.2 * np.ones(1001)])
+        kw = dict(trajectories=1001, noise_increments=dW, **c1.solve_kwargs())
+        a = S.solve(S.EnsembleProblem(c1.problem(), p_batch=pb), S.EM(), S.EnsembleB200(device=0), **kw)
+        b = S.solve(S.EnsembleProblem(c1.problem(), p_batch=pb), S.EM(), S.EnsembleB200(devices=(ca, cb)), **kw)
+        assert np.array_equal(a.out, b.out)
+        ref, _ = c1.oracle(dW, params=pb)
+        assert cases.scaled_err(b.out, ref) < 1e-12
+    finally:
+        ca.close(); cb.close()
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
@@ -43,7 +83,7 @@ def test_two_gpus_one_process_equals_one_gpu():
     assert cases.scaled_err(b.out, ref) < 1e-12
 
 
-def _summary_worker(rank, world, port, q):
+def _summary_worker(rank, world, port, q, backend="nccl"):
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -54,8 +94,12 @@ def _summary_worker(rank, world, port, q):
     import cases
     import sdde_b200 as S
     import sdde_oracle as O
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    gpu = rank if backend == "nccl" else 0            # gloo: both ranks share GPU 0 (1-GPU boxes)
+    torch.cuda.set_device(gpu)
+    if backend == "nccl":
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device(f"cuda:{gpu}"))
+    else:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     # (1) synthetic rows, identical on both ranks; each rank holds its columns only (uneven shards, ties, a NaN on rank 1)
     n = 50_001
     rng = np.random.default_rng(123)
@@ -73,9 +117,9 @@ def _summary_worker(rank, world, port, q):
     # (2) a distributed solve: EnsembleSummary over both GPUs == statistics of the same ensemble solved on one GPU
     case = cases.c2(T=20.0)
     kw = dict(trajectories=20_001, seed=5, moments=True, **case.solve_kwargs())
-    d = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=rank, distributed=True, output="device"), **kw)
+    d = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=gpu, distributed=True, output="device"), **kw)
     summ = S.EnsembleSummary(d)
-    one = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=rank, output="device"), **kw)
+    one = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=gpu, output="device"), **kw)
     ref1 = S.EnsembleSummary(one)
     ok_solve = (bool(np.array_equal(summ.med, ref1.med)) and bool(np.array_equal(summ.qlow, ref1.qlow)) and
                 bool(np.array_equal(summ.qhigh, ref1.qhigh)) and bool(np.allclose(summ.u, ref1.u, rtol=1e-12)) and summ.num_monte == 20_001)
@@ -84,16 +128,13 @@ def _summary_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_order_statistics_across_two_ranks_nccl():
-    """One process per GPU (the torchrun layout): per digit pass each rank histograms its own trajectories, the histograms
-    are all-reduced over NCCL, and both ranks end with the exact order statistics of the whole ensemble."""
+def _run_two_ranks(backend):
     import os
     import torch.multiprocessing as mp
-    port = 29700 + os.getpid() % 200
+    port = 29700 + os.getpid() % 200 + (0 if backend == "nccl" else 250)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_summary_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_summary_worker, args=(r, 2, port, q, backend)) for r in range(2)]
     for p in ps:
         p.start()
     res = [q.get(timeout=300) for _ in ps]
@@ -101,3 +142,17 @@ def test_order_statistics_across_two_ranks_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True, True, True), (1, True, True, True)]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_order_statistics_across_two_ranks_nccl():
+    """One process per GPU (the torchrun layout): per digit pass each rank histograms its own trajectories, the histograms
+    are all-reduced over NCCL, and both ranks end with the exact order statistics of the whole ensemble."""
+    _run_two_ranks("nccl")
+
+
+def test_order_statistics_across_two_ranks_sharing_one_gpu():
+    """The same two-rank selection with both ranks on GPU 0 and gloo as the group's backend (histograms reduced through the
+    host): shard ranges, per-rank histograms, the agreed bin decisions, the distributed solve + merged moments -- every leg
+    but the NCCL transport itself runs on a 1-GPU box."""
+    _run_two_ranks("gloo")

@@ -515,3 +515,117 @@ def test_schedule_chunk_sizes_give_identical_paths(chunk):
             ctx.set_option("chunk_steps", 128)
         runs.append((case.name, np.array_equal(ref.out, got.out)))
     assert all(ok for _, ok in runs), runs
+
+
+def test_d_discontinuities_keyword_paths_match_oracle():
+    """User-declared discontinuities (src/solve.jl:20-23): extra clipped steps at the declared times and at their
+    lag-propagated images; per-path parity under shared increments, EM and RKMil."""
+    import sdde_oracle as O
+    dd = [(0.37, 0), (2.2137, 1), 4.05]
+    for algid in (0, 2):
+        case = cases.c1(T=6.0, saveat=0.5).with_(alg=algid)
+        sv, ss, se = O.expand_saveat(case.saveat, *case.tspan)
+        sch = O.build_schedule(0.0, 6.0, case.dt, case.lags, algid, saveat_times=sv, save_start=ss, save_end=se, d_discontinuities=dd)
+        dW = cases.increments(sch, 1, 700)
+        sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[algid], S.EnsembleB200(device=0), trajectories=700,
+                      noise_increments=dW, d_discontinuities=dd, **case.solve_kwargs())
+        ref, _ = O.solve_ensemble(case.omodel, case.p, case.u0, case.h0, case.h1, case.lags, sch, algid, dW)
+        assert sim.timing["n_steps"] == sch.n_steps > cases.c1(T=6.0, saveat=0.5).oracle_schedule().n_steps
+        assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_out_rows_guard_rejects_undersized_buffers():
+    """sdde_desc.out_rows: a caller that sized `out` for 2 save points but asks for save_everystep gets SDDE_ERR_BAD_DESC,
+    not a heap overflow (the failure mode of a binding that computes n_save itself)."""
+    import ctypes as C
+    from sdde_b200 import _capi as capi
+    from sdde_b200.ensemble import _marshal
+    case = cases.c1(T=1.0, saveat=None)
+    m = _marshal(case.problem(), S.linear1, S.EM(), dt=0.01, saveat=None, save_everystep=True, save_start=None, save_end=None, tstops=(),
+                 adaptive=None, n_traj=64, traj_offset=0, seed=1, p_batch=None, u0_batch=None, noise=None,
+                 noise_mode=capi.NOISE_PHILOX, noise_mem=0, out_mem=capi.MEM_HOST, want_paths=1, want_moments=0)
+    out = np.zeros((2, 1, 64))
+    m.desc.out_rows = 2
+    rc = capi.lib().sdde_b200_solve(S.get_context(0).handle, C.byref(m.desc), capi.np_ptr(out), None, None, None)
+    assert rc == -1 and b"out_rows" in capi.lib().sdde_b200_last_error()
+    assert np.all(out == 0.0)
+    m.desc.out_rows = 100                      # one row short of the 101 points save_everystep produces on [0, 1] with dt = 0.01
+    big = np.zeros((101, 1, 64))
+    assert capi.lib().sdde_b200_solve(S.get_context(0).handle, C.byref(m.desc), capi.np_ptr(big), None, None, None) == -1
+    m.desc.out_rows = 101
+    assert capi.lib().sdde_b200_solve(S.get_context(0).handle, C.byref(m.desc), capi.np_ptr(big), None, None, None) == 0
+    assert np.all(big[0] == 1.0) and np.all(np.isfinite(big)) and np.all(big[-1] != 0.0)
+
+
+def test_torch_out_must_be_float64_on_the_solve_device():
+    import torch
+    case = cases.c1(T=1.0, saveat=0.5)
+    kw = dict(trajectories=128, seed=1, **case.solve_kwargs())
+    with pytest.raises(ValueError, match="float64"):
+        S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"),
+                out=torch.empty((3, 1, 128), dtype=torch.float32, device="cuda:0"), **kw)
+    with pytest.raises(ValueError, match="float64"):
+        S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0),
+                out=torch.empty((3, 1, 128), dtype=torch.float16).pin_memory(), **kw)
+
+
+@pytest.mark.parametrize("hist", [1.0e3, 30.0, 1.0e-3])
+@pytest.mark.parametrize("alg", [2, 3])
+def test_near_cancellation_division_and_inverse_sqrt(hist, alg):
+    """The two non-IEEE shortcuts of the parity path at their worst cases: div_pos (MUFU.RCP64H + cubic step instead of
+    '/') with denominators 1 + x^10 from 1 + 1e-30 to 1e30, and RKMil's difference quotient (g(u~) - g(u)) * (1/sqrt dt)
+    instead of / sqrt dt on steps of length 1e-14 and 3e-9 (user tstops), where g(u~) - g(u) cancels all but ~9 digits.
+    Same 1e-12 bound against the oracle, which divides."""
+    case = cases.c2(T=3.0, alg=alg).with_(h0=[hist], u0=[1.2])
+    t1, t2 = 0.6200000000000001, 1.37
+    ts = [t1, t1 + 1e-14, t2, t2 + 3e-9]
+    import sdde_oracle as O
+    sv, ss, se = O.expand_saveat(case.saveat, *case.tspan)
+    sch = O.build_schedule(0.0, 3.0, case.dt, case.lags, alg, saveat_times=sv, save_start=ss, save_end=se, tstops=ts)
+    assert np.min(sch.dt) < 2e-14 and np.sum(sch.dt < 1e-8) >= 2
+    dW = cases.increments(sch, 1, 512)
+    sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[alg], S.EnsembleB200(device=0), trajectories=512,
+                  noise_increments=dW, tstops=ts, save_everystep=True, **{k: v for k, v in case.solve_kwargs().items() if k != "saveat"})
+    sch_all = O.build_schedule(0.0, 3.0, case.dt, case.lags, alg, saveat_times=[], save_everystep=True, tstops=ts)
+    ref, _ = O.solve_ensemble(case.omodel, case.p, case.u0, case.h0, case.h1, case.lags, sch_all, alg, dW)
+    assert sim.out.shape == ref.shape and cases.relerr(sim.out, ref) < TOL
+
+
+def test_noise_grid_regrid_more_than_65535_rows():
+    """NoiseGrid on its own grid with more schedule nodes than gridDim.y allows (the regrid kernel indexes rows on grid.x)."""
+    import sdde_oracle as O
+    case = cases.c1(T=7.0, saveat=1.0).with_(dt=1e-4)
+    sch = case.oracle_schedule()
+    assert sch.n_steps > 65535
+    n = 64
+    rng = np.random.default_rng(9)
+    ts = np.linspace(0.0, 7.0, 3001)
+    Wg = np.cumsum(np.sqrt(np.diff(ts, prepend=0.0))[:, None, None] * rng.standard_normal((ts.size, 1, n)), axis=0)
+    dW = O.noise_grid_increments(O.noise_grid_on_nodes(ts, Wg, sch.t))
+    ref, _ = case.oracle(dW)
+    sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, noise_grid=(ts, Wg),
+                  **case.solve_kwargs())
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_balanced_tail_round_gives_identical_paths():
+    """The launch geometry (whole rounds of full CTAs + one round of smaller tail CTAs, option "balance") must not change a
+    single bit: Philox mode (streams keyed by global id) on an ensemble with full AND tail CTAs, against full CTAs only."""
+    case = cases.c2(T=10.0)
+    n = 148 * 1024 + 3 * 1024 + 130          # one full round on 148 SMs + a tail round
+    kw = dict(trajectories=n, seed=99, **case.solve_kwargs())
+    ctx = S.get_context(0)
+    a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), **kw)
+    ctx.set_option("balance", 0)
+    try:
+        b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), **kw)
+    finally:
+        ctx.set_option("balance", 1)
+    import torch
+    assert torch.equal(a.out, b.out) and bool(torch.isfinite(a.out).all())
+    ctx.set_option("lean", 0)
+    try:
+        c = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), **kw)
+    finally:
+        ctx.set_option("lean", 1)
+    assert torch.equal(a.out, c.out)          # the lean batch bodies compute exactly what the general body computes

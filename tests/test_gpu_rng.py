@@ -80,6 +80,57 @@ def test_k3_ensemble_mean_against_exact_recurrence():
     assert sim.moments[0, 0, 2] == 0.0 and sim.moments[0, 0, 1] == 1.0
 
 
+def test_c5_full_size_moments_against_exact_recurrence():
+    """BASELINE.json configs[4] at its full size: the C1 model, 10^8 trajectories, moments only at saveat = 1.0 (the
+    ensemble runs in ~96 waves of 2^20; wave moments are Chan-merged).  The exact mean recurrence K3 is a zero-Monte-Carlo-
+    error target: 10^8 paths resolve it to ~1e-5 relative, tolerance 5 standard errors.  Costs ~0.4 s of GPU time."""
+    case = cases.c1(T=10.0, saveat=1.0)
+    n = 100_000_000
+    sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=n, seed=0xC5, moments=True,
+                  paths=False, **case.solve_kwargs())
+    sch = case.oracle_schedule()
+    m = O.exact_mean_linear1(sch, -1.0, 0.5, 1.0, 1.0, 0.0, 1.0)
+    mean, var = S.timeseries_steps_meanvar(sim)
+    idx = [int(np.argmin(np.abs(sch.t - t))) for t in sim.t]
+    se = np.sqrt(var[:, 0] / n)
+    assert np.all(sim.moments[:, 0, 0] == n) and sim.n_unstable == 0 and sim.timing["waves"] >= 90
+    assert np.all(np.abs(mean[:, 0] - m[idx])[1:] < 5 * se[1:] + 1e-13)
+    assert np.all(se[1:] / np.abs(m[idx][1:]) < 1e-4)            # the test has the resolution it claims
+    # a second seed gives a different, equally consistent estimate (the streams are keyed by the seed)
+    sim2 = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=4_000_000, seed=0xC6,
+                   moments=True, paths=False, **case.solve_kwargs())
+    mean2, var2 = S.timeseries_steps_meanvar(sim2)
+    assert np.all(np.abs(mean2[:, 0] - m[idx])[1:] < 5 * np.sqrt(var2[:, 0] / 4_000_000)[1:] + 1e-13)
+    assert not np.array_equal(mean2[1:], mean[1:])
+
+
+def test_device_normals_large_sample_quality():
+    """1.3e8 draws (2^17 trajectories x 1024 steps): moments to 5 standard errors, tail masses beyond 3, 4 and 5 sigma,
+    lag-1..4 autocorrelation along a trajectory (the four normals of one Philox call and the call boundary), correlation
+    between neighbouring trajectories (counters differing in one bit) and a 64-bin chi-square of the probability integral
+    transform.  This is the gate for any change of the generator (table layout, Philox round count)."""
+    from scipy import special, stats
+    nt, ns = 1 << 17, 1024
+    z = device_normals(0xFEEDFACE, 1 << 40, nt, ns, 1).reshape(ns, nt)
+    n = z.size
+    flat = z.ravel()
+    assert abs(flat.mean()) < 5 / np.sqrt(n)
+    assert abs(flat.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs(np.mean(flat ** 3)) < 5 * np.sqrt(15 / n)
+    assert abs(np.mean(flat ** 4) - 3) < 5 * np.sqrt(96 / n)
+    for k in (3.0, 4.0, 5.0):
+        p = special.erfc(k / np.sqrt(2))
+        assert abs(np.mean(np.abs(flat) > k) - p) < 5 * np.sqrt(p / n), k
+    for lag in (1, 2, 3, 4):
+        assert abs(np.mean(z[:-lag] * z[lag:])) < 5 / np.sqrt(z[:-lag].size), lag
+    assert abs(np.mean(z[:, :-1] * z[:, 1:])) < 5 / np.sqrt(z[:, :-1].size)
+    assert abs(np.mean(z[:, ::2] * z[:, 1::2])) < 5 / np.sqrt(z[:, ::2].size)
+    u = special.ndtr(flat[: 1 << 26])
+    cnt = np.bincount(np.minimum((u * 64).astype(np.int64), 63), minlength=64)
+    chi2 = np.sum((cnt - u.size / 64) ** 2 / (u.size / 64))
+    assert chi2 < stats.chi2.ppf(1 - 1e-6, 63), chi2
+
+
 def _strong_order(alg, algid):
     """test/analyticless_convergence_tests.jl:30-36,52-61: Hayes, dts = 2^-8..2^-4, fine 2^-9, 300 paths, shared noise:
     coarse increments are sums of the fine Brownian path's increments."""

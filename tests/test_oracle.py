@@ -225,3 +225,35 @@ def test_oracle_sort_is_julias_total_order():
     assert np.array_equal(np.signbit(s), [True, True, True, False, False, False]) and s[0] == -1.0 and s[-1] == 1.0
     # the median of an odd count is an order statistic itself: [-1, -0, -0, +0, 1] -> -0.0
     assert np.signbit(O.julia_median(np.array([0.0, -0.0, 1.0, -0.0, -1.0]))) and not np.signbit(O.julia_median(np.array([0.0, -0.0, 1.0, 0.0, -1.0])))
+
+
+def test_export_for_julia_kit_is_consistent(tmp_path):
+    """The hand-off kit for pinning the oracle against the real reference (tests/golden/export_for_julia.py ->
+    julia/replay_fixtures.jl): the exported dense solutions restricted to the saveat grid are the committed golden vectors,
+    the Brownian paths start at 0 and the manifest lists every array the Julia script reads."""
+    import subprocess, sys, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "export_for_julia.py"), str(tmp_path)], check=True,
+                   capture_output=True)
+    man = open(tmp_path / "manifest.toml").read()
+    names = re.findall(r"^\[(\w+)\]", man, re.M)
+    assert {"c2_em", "c3_rkmil_o0", "c3_rkmil_o2", "c4_em", "c2_euler_heun"} <= set(names)
+    g = np.load(os.path.join(root, "tests", "golden", "golden_v1.npz"))
+    for name in names:
+        nn = int(re.search(r"\[%s\].*?n_nodes = (\d+)" % name, man, re.S).group(1))
+        ns = int(re.search(r"\[%s\].*?n_state = (\d+)" % name, man, re.S).group(1))
+        nc = int(re.search(r"\[%s\].*?n_chan = (\d+)" % name, man, re.S).group(1))
+        t = np.fromfile(tmp_path / f"{name}_t.bin")
+        W = np.fromfile(tmp_path / f"{name}_W.bin").reshape(16, nc, nn)
+        U = np.fromfile(tmp_path / f"{name}_dense.bin").reshape(16, ns, nn)
+        assert t.size == nn and np.all(np.diff(t) > 0) and np.all(W[:, :, 0] == 0.0) and np.all(np.isfinite(U))
+        if name + "_out" in g.files and name != "c4_em":
+            # golden: saveat = 1.0 on [0, 40]; the save times are schedule nodes here, so the dense solution contains them
+            idx = [int(np.argmin(np.abs(t - k))) for k in range(41)]
+            if np.max(np.abs(t[idx] - np.arange(41))) > 1e-9:
+                continue                     # re-phased grid (tau = 17.02, order 0): the integer times are interpolated saves
+            # (not bit-equal: the kit feeds W = cumsum(dW) and the increments are re-derived from it, as the reference does)
+            assert np.allclose(U[:, :, idx].transpose(2, 1, 0), g[name + "_out"], rtol=1e-10, atol=0)
+    jl = open(os.path.join(root, "julia", "replay_fixtures.jl")).read()
+    for key in ("n_nodes", "n_state", "n_chan", "alg_option", "order_discontinuity_t0", "_dense.bin", "_W.bin", "_t.bin"):
+        assert key in jl and (key.startswith("_") or key in man)
