@@ -304,7 +304,8 @@ end
 # ------------------------------------------------------------------------------------------------------------------
 alg_id(::EM{true}) = Int32(0)
 alg_id(::EM{false}) = Int32(1)
-alg_id(a::Union{RKMil, RKMilCommute}) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(2) : Int32(3)   # diagonal noise: same update
+alg_id(a::RKMil) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(2) : Int32(3)
+alg_id(a::RKMilCommute) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(5) : Int32(6)   # diagonal models run the RKMil kernel
 alg_id(::EulerHeun) = Int32(4)
 
 last_error() = unsafe_string(ccall((:sdde_b200_last_error, libsdde), Cstring, ()))

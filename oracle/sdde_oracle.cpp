@@ -281,13 +281,35 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
                     for (int j = 1; j < M.nw; ++j) noise = noise + gv[i * M.nw + j] * dw[j];
                     u[i] = K[i] + noise;
                 }
-            } else {
+            } else if ((alg == SDDE_ALG_RKMILC_ITO || alg == SDDE_ALG_RKMILC_STRAT) && !M.diag) {
+                // [EXT] RKMilCommuteConstantCache on a noise matrix: J = dW dW'/2 (Ito: - |dt|/2 I); per column j
+                // K_j = (Ito ? K : uprev) + sqrt(dt) G[:, j], Dg_j = (G(K_j) - G(u)) / sqrt(dt), correction += Dg_j J[:, j]
+                const int nw = M.nw;
+                double gt[SDDE_MAX_STATE * SDDE_MAX_NOISE], Kj[SDDE_MAX_STATE], mil[SDDE_MAX_STATE];
                 M.g(gv, uprev, hcb, p, t);
-                for (int j = 0; j < ns; ++j) ut[j] = (alg == SDDE_ALG_RKMIL_ITO ? K[j] : uprev[j]) + gv[j] * sq;
+                for (int i = 0; i < ns; ++i) mil[i] = 0.0;
+                for (int j = 0; j < nw; ++j) {
+                    for (int i = 0; i < ns; ++i) Kj[i] = (alg == SDDE_ALG_RKMILC_ITO ? K[i] : uprev[i]) + sq * gv[i * nw + j];
+                    M.g(gt, Kj, hcb, p, t);
+                    for (int k = 0; k < nw; ++k) {
+                        double Jkj = 0.5 * (dw[k] * dw[j]);
+                        if (alg == SDDE_ALG_RKMILC_ITO && k == j) Jkj = Jkj - 0.5 * std::fabs(dtn);
+                        for (int i = 0; i < ns; ++i) mil[i] = mil[i] + ((gt[i * nw + k] - gv[i * nw + k]) / sq) * Jkj;
+                    }
+                }
+                for (int i = 0; i < ns; ++i) {
+                    double noise = gv[i * nw] * dw[0];
+                    for (int j = 1; j < nw; ++j) noise = noise + gv[i * nw + j] * dw[j];
+                    u[i] = (K[i] + noise) + mil[i];
+                }
+            } else {
+                const bool ito = alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMILC_ITO;   // RKMilCommute on diagonal noise == RKMil
+                M.g(gv, uprev, hcb, p, t);
+                for (int j = 0; j < ns; ++j) ut[j] = (ito ? K[j] : uprev[j]) + gv[j] * sq;
                 M.g(g2, ut, hcb, p, t);
                 for (int j = 0; j < ns; ++j) {
                     const double ggp = (g2[j] - gv[j]) / sq;
-                    const double w2 = alg == SDDE_ALG_RKMIL_ITO ? (dw[j] * dw[j] - std::fabs(dtn)) : (dw[j] * dw[j]);
+                    const double w2 = ito ? (dw[j] * dw[j] - std::fabs(dtn)) : (dw[j] * dw[j]);
                     const double mil = ggp * w2 / 2.0;
                     u[j] = (K[j] + gv[j] * dw[j]) + mil;
                 }

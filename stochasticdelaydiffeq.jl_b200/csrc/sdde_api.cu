@@ -138,8 +138,8 @@ int check_desc(const sdde_desc *d) {
     if (d->struct_size != (int32_t)sizeof(sdde_desc))
         return fail(SDDE_ERR_BAD_DESC, "sdde_desc.struct_size = %d, library expects %d (ABI mismatch)", d->struct_size,
                     (int)sizeof(sdde_desc));
-    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_EULER_HEUN)
-        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / EulerHeun, fixed step)", d->alg);
+    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_RKMILC_STRAT)
+        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / RKMilCommute / EulerHeun, fixed step)", d->alg);
     if (d->n_lag < 1 || d->n_lag > SDDE_MAX_LAG) return fail(SDDE_ERR_BAD_DESC, "n_lag = %d out of range", d->n_lag);
     if (d->n_state < 1 || d->n_state > SDDE_MAX_STATE) return fail(SDDE_ERR_BAD_DESC, "n_state = %d out of range", d->n_state);
     if (d->n_noise < 1 || d->n_noise > SDDE_MAX_NOISE) return fail(SDDE_ERR_BAD_DESC, "n_noise = %d out of range", d->n_noise);
@@ -189,7 +189,8 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     sdde::ScheduleInput in;
     in.t0 = d->t0; in.tf = d->tf; in.dt = d->dt;
     in.lags.assign(d->lags, d->lags + d->n_lag);
-    in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT) ? 2 : 1;   // [EXT] alg_order: EM, EulerHeun 1//2
+    in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT || d->alg == SDDE_ALG_RKMILC_ITO ||
+                     d->alg == SDDE_ALG_RKMILC_STRAT) ? 2 : 1;   // [EXT] alg_order: RKMil, RKMilCommute 1//1; EM, EulerHeun 1//2
     in.n_stage = d->alg == SDDE_ALG_EULER_HEUN ? 2 : 1;
     in.order_discontinuity_t0 = d->order_discontinuity_t0;
     in.constant_lags_declared = d->constant_lags_declared != 0;
@@ -253,9 +254,22 @@ std::string linsys_jit_source(int ns, int nl, int nw, const double *p) {
     return src;
 }
 
+int select_kernel_alg(sdde_ctx *ctx, const sdde_desc *d, int alg, sdde::KernelInfo &k);
+
+// RKMilCommute: a noise-matrix model has its own kernels (alg 5 / 6); on a diagonal model the update is the RKMil one
+// written with the iterated integral, so the RKMil kernels (alg 2 / 3) serve
 int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
+    if (d->alg == SDDE_ALG_RKMILC_ITO || d->alg == SDDE_ALG_RKMILC_STRAT) {
+        sdde::KernelInfo probe;
+        const int as_rkmil = d->alg - SDDE_ALG_RKMILC_ITO + SDDE_ALG_RKMIL_ITO;
+        if (select_kernel_alg(ctx, d, as_rkmil, probe) == SDDE_OK && probe.fn && probe.diag) { k = probe; return SDDE_OK; }
+    }
+    return select_kernel_alg(ctx, d, d->alg, k);
+}
+
+int select_kernel_alg(sdde_ctx *ctx, const sdde_desc *d, int alg, sdde::KernelInfo &k) {
     const bool ptraj = d->param_stride != 0;
-    const int alg = d->alg, nz = d->noise_mode;
+    const int nz = d->noise_mode;
     switch (d->model_id) {
         case SDDE_MODEL_LINEAR1: k = sdde::select_linear1(alg, nz, ptraj); break;
         case SDDE_MODEL_HAYES: k = sdde::select_hayes(alg, nz, ptraj); break;

@@ -66,12 +66,14 @@ inline KernelInfo make_coop_info(const char *name) {
         SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
         return KernelInfo();                                    \
     }
-// EM only (non-diagonal noise: [EXT] RKMil requires diagonal noise)
+// noise-matrix models: EM, EulerHeun, RKMilCommute ([EXT] RKMil itself requires diagonal noise)
 #define SDDE_DEFINE_SELECT_EM(FUNC, M, NAME)                    \
     KernelInfo FUNC(int alg, int noise, bool ptraj) {           \
         SDDE_SEL_ALG(M, NAME, K_ALG_EM_SPLIT)                   \
         SDDE_SEL_ALG(M, NAME, K_ALG_EM_NOSPLIT)                 \
         SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_RKMILC_ITO)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_RKMILC_STRAT)               \
         return KernelInfo();                                    \
     }
 

@@ -29,7 +29,8 @@ typedef unsigned long long u64;
 
 enum { K_LK_PRE = 0, K_LK_EXACT = 1, K_LK_INTERP = 2 };
 enum { K_NOISE_PHILOX = 0, K_NOISE_DW = 1, K_NOISE_GRID = 2 };
-enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3, K_ALG_EULER_HEUN = 4 };
+enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3, K_ALG_EULER_HEUN = 4,
+       K_ALG_RKMILC_ITO = 5, K_ALG_RKMILC_STRAT = 6 };   // RKMilCommute on a noise MATRIX (diagonal models run it as RKMil)
 // history lookup times per step: EulerHeun evaluates f and g a second time at t + dt
 __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULER_HEUN ? 2 : 1; }
 
@@ -320,6 +321,38 @@ __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)
     M::f(du, u, ul, p, t);
 #pragma unroll
     for (int j = 0; j < NS; ++j) K[j] = u[j] + dt * du[j];
+    if constexpr ((ALG == K_ALG_RKMILC_ITO || ALG == K_ALG_RKMILC_STRAT) && !M::DIAG) {
+        // [EXT] RKMilCommuteConstantCache, noise matrix G (NS x NW) with commutative columns:
+        //   J = dW dW'/2 (Ito: - |dt|/2 on the diagonal);  per column j: K_j = (Ito ? K : u) + sqrt(dt) G[:, j]  (the stage
+        //   point of RKMil's diagonal branch; with K under Stratonovich the scheme drops to strong order ~0.7, tests/test_oracle.py),
+        //   Dg_j = (G(K_j) - G(u)) / sqrt(dt),  correction += Dg_j J[:, j];   u+ = (K + G dW) + correction
+        constexpr int NW = M::NW;
+        double L[NS * NW], mil[NS];
+        M::g(L, u, ul, p, t);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) mil[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            double Kj[NS], gt[NS * NW];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) Kj[i] = (ALG == K_ALG_RKMILC_ITO ? K[i] : u[i]) + sq * L[i * NW + j];
+            M::g(gt, Kj, ul, p, t);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                const double Jkj = (ALG == K_ALG_RKMILC_ITO && k == j) ? (0.5 * (dw[k] * dw[j]) - 0.5 * fabs(dt)) : 0.5 * (dw[k] * dw[j]);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) mil[i] = mil[i] + ((gt[i * NW + k] - L[i * NW + k]) * isq) * Jkj;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double noise = L[i * NW] * dw[0];
+#pragma unroll
+            for (int j = 1; j < NW; ++j) noise = noise + L[i * NW + j] * dw[j];
+            u[i] = (K[i] + noise) + mil[i];
+        }
+        return;
+    }
     if (ALG == K_ALG_EM_SPLIT || ALG == K_ALG_EM_NOSPLIT) {
         if (M::DIAG) {
             double gv[NS];

@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi as capi
-from .problem import EM, EulerHeun, RKMil, EnsembleProblem, SDDEProblem, UserModel, _as_history
+from .problem import (EM, EulerHeun, RKMil, EnsembleProblem, FinalState, MomentsReduction, SaveIdxs, SDDEProblem, UserModel,
+                      _as_history)
 
 
 @dataclass
@@ -586,6 +587,15 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     eprob = EnsembleProblem(prob) if single else prob
     ea = ensemblealg or EnsembleB200()
     base = eprob.prob
+    # EnsembleProblem.output_func / reduction -> what the device computes (julia/EnsembleB200.jl does the same mapping)
+    if isinstance(eprob.output_func, FinalState):
+        saveat, save_everystep, save_start, save_end = [base.tspan[1]], False, False, True
+    elif isinstance(eprob.output_func, SaveIdxs):
+        if save_idxs is not None and tuple(np.atleast_1d(save_idxs)) != eprob.output_func.idxs:
+            raise ValueError("save_idxs keyword and SaveIdxs output_func disagree")
+        save_idxs = eprob.output_func.idxs
+    if isinstance(eprob.reduction, MomentsReduction):
+        moments, paths = True, False
     n_total = int(trajectories)
     rank, world = 0, 1
     if ea.distributed:

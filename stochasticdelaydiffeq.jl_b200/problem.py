@@ -46,8 +46,13 @@ class RKMil:
 @dataclass(frozen=True)
 class RKMilCommute(RKMil):
     """Milstein for commutative noise ([EXT] StochasticDiffEq RKMilCommute; reference smoke test test/test_prob_sol.jl:44-49).
-    On this path only diagonal noise is supported, where its update ``K + L dW + Dg (dW^2/2 [- dt/2])`` is the RKMil
-    update written with the iterated integral J: the same kernel serves both (they differ by rounding only)."""
+    On diagonal noise its update ``K + L dW + Dg (dW^2/2 [- dt/2])`` is the RKMil update written with the iterated
+    integral J and the library runs the RKMil kernel; on a noise MATRIX with commutative columns (e.g. ``linsys`` with
+    G_ij = M_ij u_i) it evaluates G once more per noise column: ``u+ = K + G dW + sum_j Dg_j J[:, j]``."""
+
+    @property
+    def alg_id(self):
+        return capi.ALG_RKMILC_ITO if self.interpretation == "Ito" else capi.ALG_RKMILC_STRAT
 
 
 @dataclass(frozen=True)
@@ -246,6 +251,30 @@ class SDDEProblem:
         return q
 
 
+# ---------------------------------------------------------------------------------------------
+# EnsembleProblem.output_func / reduction ([EXT] SciMLBase): arbitrary host closures in SciML.  The forms below are the
+# ones this path can express on the device (same names and meaning as in julia/EnsembleB200.jl); anything else raises.
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class FinalState:
+    """output_func ``(sol, i) -> (sol.u[end], false)``: only the state at tf is saved (saveat = [tf], save_start = False)."""
+
+
+@dataclass(frozen=True)
+class SaveIdxs:
+    """output_func keeping some state components (0-based) == the ``save_idxs`` keyword (src/solve.jl:355-356)."""
+    idxs: tuple
+
+    def __post_init__(self):
+        object.__setattr__(self, "idxs", tuple(int(i) for i in np.atleast_1d(self.idxs)))
+
+
+@dataclass(frozen=True)
+class MomentsReduction:
+    """reduction accumulating (count, mean, M2) per saved time point and state -- what EnsembleAnalysis.timeseries_steps_meanvar
+    computes from a finished ensemble.  On this path: moments on the device, no paths leave the GPU (24 bytes per saved value)."""
+
+
 class EnsembleProblem:
     """``EnsembleProblem(prob; prob_func=None, output_func=None, reduction=None)`` ([EXT] SciMLBase).
 
@@ -256,9 +285,13 @@ class EnsembleProblem:
 
     def __init__(self, prob: SDDEProblem, *, prob_func=None, output_func=None, reduction=None, p_batch=None,
                  u0_batch=None, safetycopy=True):
-        if output_func is not None or reduction is not None:
-            raise NotImplementedError("output_func/reduction run on the host in SciML; on this path use "
-                                      "saveat + moments (EnsembleAnalysis) instead")
+        if output_func is not None and not isinstance(output_func, (FinalState, SaveIdxs)):
+            raise NotImplementedError("output_func is a host closure in SciML and cannot run on the device; expressible on this "
+                                      "path: FinalState(), SaveIdxs(idxs), or the saveat / save_idxs keywords")
+        if reduction is not None and not isinstance(reduction, MomentsReduction):
+            raise NotImplementedError("reduction is a host closure in SciML and cannot run on the device; expressible on this "
+                                      "path: MomentsReduction() (mean / variance per time point); order statistics: EnsembleSummary")
+        self.output_func, self.reduction = output_func, reduction
         self.prob = prob
         self.prob_func = prob_func
         self.p_batch = None if p_batch is None else np.ascontiguousarray(p_batch, dtype=np.float64)

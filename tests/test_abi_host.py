@@ -499,7 +499,13 @@ def test_problem_surface_argument_checks_without_gpu():
                                  constant_lags=(1.0,)), S.EM(), dt=0.1)
     with pytest.raises(NotImplementedError):              # RKMil is adaptive by default in the reference
         S.schedule(prob, S.RKMil(), dt=0.1)
-    assert S.RKMilCommute().alg_id == S.RKMil().alg_id and S.RKMilCommute("Stratonovich").alg_id == S.RKMil("Stratonovich").alg_id
+    # RKMilCommute has its own ids (5 / 6); a diagonal model is served by the RKMil kernels inside the library
+    assert (S.RKMilCommute().alg_id, S.RKMilCommute("Stratonovich").alg_id) == (5, 6) and isinstance(S.RKMilCommute(), S.RKMil)
+    # output_func / reduction: the expressible forms are accepted, arbitrary closures are refused
+    S.EnsembleProblem(prob, output_func=S.FinalState(), reduction=S.MomentsReduction())
+    S.EnsembleProblem(prob, output_func=S.SaveIdxs([0]))
+    with pytest.raises(NotImplementedError):
+        S.EnsembleProblem(prob, reduction=lambda u, data, I: (u, False))
     with pytest.raises(ValueError):
         S.RKMil("Foo")
 

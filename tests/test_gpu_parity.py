@@ -629,3 +629,70 @@ def test_balanced_tail_round_gives_identical_paths():
     finally:
         ctx.set_option("lean", 1)
     assert torch.equal(a.out, c.out)          # the lean batch bodies compute exactly what the general body computes
+
+
+@pytest.mark.parametrize("alg", [5, 6])
+def test_rkmil_commute_on_a_noise_matrix_matches_oracle(alg):
+    """RKMilCommute (test/test_prob_sol.jl:44-49) on C4's 4 x 2 noise matrix (G_ij = M_ij u_i: commutative columns): one
+    more G evaluation per noise column and step; per-path parity under shared increments."""
+    case = cases.c4(T=8.0).with_(alg=alg)
+    sim, ref, _ = run_case(case, 1536)
+    assert "alg%d" % alg in sim.timing["kernel_name"]
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_rkmil_commute_on_diagonal_noise_is_the_rkmil_kernel():
+    case = cases.c3(order0=0, T=30.0)
+    sch = case.oracle_schedule()
+    dW = cases.increments(sch, 1, 600)
+    kw = dict(trajectories=600, noise_increments=dW, **case.solve_kwargs())
+    for interp in ("Ito", "Stratonovich"):
+        a = S.solve(S.EnsembleProblem(case.problem()), S.RKMil(interp), S.EnsembleB200(device=0), **kw)
+        b = S.solve(S.EnsembleProblem(case.problem()), S.RKMilCommute(interp), S.EnsembleB200(device=0), **kw)
+        assert np.array_equal(a.out, b.out)
+    with pytest.raises(S.SddeError, match="diagonal"):          # plain RKMil still refuses a noise matrix, like the reference
+        S.solve(S.EnsembleProblem(cases.c4(T=1.0).problem()), S.RKMil(), S.EnsembleB200(device=0), trajectories=64, dt=0.01,
+                adaptive=False)
+
+
+def test_rkmil_commute_strong_order_against_exact_solution_on_device():
+    """du_i = a_i u_i dt + sum_j M_ij u_i dW_j has the exact solution u_i(0) exp((a_i - sum_j M_ij^2 / 2) t + sum_j M_ij W_j):
+    the device RKMilCommute converges to it with strong order 1.0 +- 0.3 (the reference's band for Milstein-type solvers,
+    test/analyticless_convergence_tests.jl:62-91)."""
+    M = np.array([[0.5, 0.3], [-0.4, 0.6]])
+    a = (-0.3, 0.2)
+    model = S.linsys(2, 1, 2)
+    p = S.linsys_params(np.diag(a), [np.zeros((2, 2))], np.zeros(2), M, np.zeros((2, 2)))
+    n, T, fine = 600, 1.0, 2.0 ** -9
+    rng = np.random.default_rng(12)
+    dWf = rng.standard_normal((int(T / fine), 2, n)) * np.sqrt(fine)
+    u0 = [1.0, 0.7]
+    exact = np.array(u0)[:, None] * np.exp((np.array(a) - 0.5 * (M ** 2).sum(axis=1))[:, None] * T + M @ dWf.sum(axis=0))
+    prob = S.SDDEProblem(model.f, model.g, u0, S.AffineHistory(tuple(u0), (0.0, 0.0)), (0.0, T), p, constant_lags=(1.0,))
+    dts = 2.0 ** -np.arange(7, 2, -1)
+    errs = []
+    for dt in dts:
+        k = int(round(dt / fine))
+        dW = dWf.reshape(-1, k, 2, n).sum(axis=1)
+        sim = S.solve(S.EnsembleProblem(prob), S.RKMilCommute(), S.EnsembleB200(device=0), trajectories=n, dt=dt, saveat=[T],
+                      save_start=False, adaptive=False, noise_increments=dW)
+        errs.append(np.mean(np.abs(sim.out[-1] - exact)))
+    slope = np.polyfit(np.log(dts), np.log(errs), 1)[0]
+    assert abs(slope - 1.0) < 0.3, slope
+
+
+def test_output_func_and_reduction_forms():
+    """EnsembleProblem(output_func = FinalState() / SaveIdxs(...), reduction = MomentsReduction()): the forms of SciML's host
+    closures this path can express map onto saveat = [tf], save_idxs and device moments."""
+    case = cases.c4(T=2.0)
+    base = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0), trajectories=512, seed=5, moments=True,
+                   **case.solve_kwargs())
+    fin = S.solve(S.EnsembleProblem(case.problem(), output_func=S.FinalState()), S.EM(), S.EnsembleB200(device=0), trajectories=512,
+                  seed=5, dt=case.dt)
+    assert fin.out.shape == (1, 4, 512) and np.array_equal(fin.out[0], base.out[-1]) and fin.t.tolist() == [2.0]
+    sub = S.solve(S.EnsembleProblem(case.problem(), output_func=S.SaveIdxs([3, 1])), S.EM(), S.EnsembleB200(device=0), trajectories=512,
+                  seed=5, **case.solve_kwargs())
+    assert np.array_equal(sub.out, base.out[:, [3, 1], :])
+    red = S.solve(S.EnsembleProblem(case.problem(), reduction=S.MomentsReduction()), S.EM(), S.EnsembleB200(device=0),
+                  trajectories=512, seed=5, **case.solve_kwargs())
+    assert red.out is None and np.allclose(red.moments, base.moments, rtol=1e-12, atol=1e-15)

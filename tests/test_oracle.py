@@ -257,3 +257,61 @@ def test_export_for_julia_kit_is_consistent(tmp_path):
     jl = open(os.path.join(root, "julia", "replay_fixtures.jl")).read()
     for key in ("n_nodes", "n_state", "n_chan", "alg_option", "order_discontinuity_t0", "_dense.bin", "_W.bin", "_t.bin"):
         assert key in jl and (key.startswith("_") or key in man)
+
+
+def _linsys_2x2(M, a=(0.0, 0.0)):
+    """2 states, 1 lag (unused: B = 0), 2 noise channels: du_i = a_i u_i dt + sum_j M_ij u_i dW_j  (commutative columns)."""
+    A = np.diag(a)
+    p = np.concatenate([A.ravel(), np.zeros(4), np.zeros(2), np.asarray(M, float).ravel(), np.zeros(4)])
+    return O.get_model(O.MODEL_LINSYS, 2, 1, 2), p
+
+
+def test_k1_rkmil_commute_one_step_known_answer():
+    """RKMilCommute on a 2 x 2 noise matrix, one step, hand-derived (see the arithmetic below): f = 0, u = (1, 2),
+    G = [[0.1 u1, 0.2 u1], [0.3 u2, 0]], dt = 0.25, dW = (0.4, -0.2).
+      G = [[.1,.2],[.6,0]];  K_1 = u + .5 G[:,1] = (1.05, 2.3) -> Dg_1 = [[.01,.02],[.18,0]];  K_2 = (1.1, 2) -> Dg_2 = [[.02,.04],[0,0]]
+      Ito: J = dW dW'/2 - dt/2 I = [[-.045,-.04],[-.04,-.105]];  mil = Dg_1 J[:,1] + Dg_2 J[:,2] = (-.00625, -.0081)
+      u+ = u + G dW + mil = (1 + 0 - .00625, 2 + .24 - .0081) = (0.99375, 2.2319)
+      Stratonovich: J = dW dW'/2 -> mil = (0, .0144) -> u+ = (1.0, 2.2544)
+    The same numbers follow from the analytic Milstein term sum_{j1,j2} M_ij1 M_ij2 u_i J[j2,j1] of this G."""
+    model, p = _linsys_2x2([[0.1, 0.2], [0.3, 0.0]])
+    dW = np.array([0.4, -0.2]).reshape(1, 2, 1)
+    for alg, want in ((O.ALG_RKMILC_ITO, (0.99375, 2.2319)), (O.ALG_RKMILC_STRAT, (1.0, 2.2544))):
+        sch = O.build_schedule(0.0, 0.25, 0.25, [1.0], alg, saveat_times=[], save_everystep=True)
+        assert sch.n_steps == 1
+        out, st = O.solve_ensemble(model, p, [1.0, 2.0], [1.0, 2.0], [0.0, 0.0], [1.0], sch, alg, dW)
+        assert np.allclose(out[-1, :, 0], want, rtol=0, atol=2e-15), (alg, out[-1, :, 0])
+        co, _, _, _ = __import__("c_oracle").solve(O.MODEL_LINSYS, alg, 2, 1, 2, p, [1.0, 2.0], [1.0, 2.0], [0.0, 0.0], [1.0], 0.0, 0.25, 0.25,
+                                                   [], 2, save_everystep=True, dW=dW)
+        assert np.array_equal(co, out)
+
+
+def test_rkmil_commute_strong_order_one_against_exact_solution():
+    """The commutative Milstein algebra itself, independent of any recollection of the reference's code: for
+    du_i = a_i u_i dt + sum_j M_ij u_i dW_j the exact solution is u_i(0) exp((a_i - sum_j M_ij^2/2) t + sum_j M_ij W_j(t))
+    (Ito) resp. exp(a_i t + sum_j M_ij W_j(t)) (Stratonovich); the scheme must converge to it with strong order 1.0
+    (the reference's own acceptance band for its Milstein-type solvers: 1.0 +- 0.3, test/analyticless_convergence_tests.jl:62-91),
+    where EM on the same paths shows 0.5."""
+    M = np.array([[0.5, 0.3], [-0.4, 0.6]])
+    a = (-0.3, 0.2)
+    model, p = _linsys_2x2(M, a)
+    n, T, fine = 400, 1.0, 2.0 ** -9
+    rng = np.random.default_rng(11)
+    dWf = rng.standard_normal((int(T / fine), 2, n)) * np.sqrt(fine)
+    WT = dWf.sum(axis=0)
+    u0 = np.array([1.0, 0.7])
+
+    def err(alg, dt, exact):
+        sch = O.build_schedule(0.0, T, dt, [1.0], alg, saveat_times=[T], save_start=False)
+        k = int(round(dt / fine))
+        dW = dWf.reshape(sch.n_steps, k, 2, n).sum(axis=1)
+        out, _ = O.solve_ensemble(model, p, u0, u0, [0.0, 0.0], [1.0], sch, alg, dW)
+        return np.mean(np.abs(out[-1] - exact))
+
+    drift_ito = (np.array(a) - 0.5 * (M ** 2).sum(axis=1))[:, None] * T
+    ex_ito = u0[:, None] * np.exp(drift_ito + M @ WT)
+    ex_str = u0[:, None] * np.exp(np.array(a)[:, None] * T + M @ WT)
+    dts = 2.0 ** -np.arange(7, 2, -1)
+    for alg, exact, want in ((O.ALG_RKMILC_ITO, ex_ito, 1.0), (O.ALG_RKMILC_STRAT, ex_str, 1.0), (O.ALG_EM_SPLIT, ex_ito, 0.5)):
+        slope = np.polyfit(np.log(dts), np.log([err(alg, dt, exact) for dt in dts]), 1)[0]
+        assert abs(slope - want) < 0.3, (alg, slope)
