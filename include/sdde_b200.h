@@ -60,7 +60,13 @@ enum { SDDE_ALG_EM_SPLIT = 0,      /* EM() == EM(true) */
        SDDE_ALG_RKMIL_STRAT = 3,   /* RKMil(interpretation=:Stratonovich), adaptive=false */
        SDDE_ALG_EULER_HEUN = 4,    /* EulerHeun() (Stratonovich): second f/g evaluation at t+dt (test/test_prob_sol.jl:34) */
        SDDE_ALG_RKMILC_ITO = 5,    /* RKMilCommute() (test/test_prob_sol.jl:44-49): commutative noise; a diagonal model runs the */
-       SDDE_ALG_RKMILC_STRAT = 6 };/*   RKMil kernel, a noise-matrix model evaluates G once more per noise column */
+       SDDE_ALG_RKMILC_STRAT = 6,  /*   RKMil kernel, a noise-matrix model evaluates G once more per noise column */
+       SDDE_ALG_WANGLI3SMIL_A = 7, /* WangLi3SMil_A .. _F (test/test_prob_sol.jl:50-61), diagonal noise: three-stage Milstein methods, */
+       SDDE_ALG_WANGLI3SMIL_B = 8, /*   restated as the six orders of (drift, Ito correction, Stratonovich-Milstein diffusion) -- */
+       SDDE_ALG_WANGLI3SMIL_C = 9, /*   LOW confidence in the letter <-> order map, see DESIGN.md section 6 */
+       SDDE_ALG_WANGLI3SMIL_D = 10,
+       SDDE_ALG_WANGLI3SMIL_E = 11,
+       SDDE_ALG_WANGLI3SMIL_F = 12 };
 
 /* ---- built-in model zoo: the device-side replacement of the closures that
  *      src/functionwrapper.jl:8-9,35-36 builds around the user's f(u,h,p,t), g(u,h,p,t).

@@ -307,6 +307,9 @@ alg_id(::EM{false}) = Int32(1)
 alg_id(a::RKMil) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(2) : Int32(3)
 alg_id(a::RKMilCommute) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32(5) : Int32(6)   # diagonal models run the RKMil kernel
 alg_id(::EulerHeun) = Int32(4)
+alg_id(::WangLi3SMil_A) = Int32(7); alg_id(::WangLi3SMil_B) = Int32(8); alg_id(::WangLi3SMil_C) = Int32(9)
+alg_id(::WangLi3SMil_D) = Int32(10); alg_id(::WangLi3SMil_E) = Int32(11); alg_id(::WangLi3SMil_F) = Int32(12)
+const B200Alg = Union{EM, RKMil, RKMilCommute, EulerHeun, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D, WangLi3SMil_E, WangLi3SMil_F}
 
 last_error() = unsafe_string(ccall((:sdde_b200_last_error, libsdde), Cstring, ()))
 check(rc) = rc == 0 || error("libsdde_b200 ($rc): " * last_error())
@@ -359,7 +362,7 @@ function saved_times(d::SddeDesc)
     return ts, nsteps
 end
 
-function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::Union{EM, RKMil, RKMilCommute, EulerHeun}, ea::EnsembleB200;
+function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::B200Alg, ea::EnsembleB200;
         trajectories, dt, saveat = Float64[], tstops = Float64[], d_discontinuities = (), adaptive = false, seed = UInt64(0),
         moments = false, save_idxs = nothing, save_everystep = isempty(saveat), save_start = nothing, save_end = nothing,
         noise_increments = nothing, pinned = true, kwargs...)

@@ -31,6 +31,7 @@ function algorithm(name, opt)
     name == "EM" && return EM(opt == "true")
     name == "RKMil" && return RKMil(interpretation = Symbol(opt))
     name == "EulerHeun" && return EulerHeun()
+    startswith(name, "WangLi3SMil_") && return getfield(StochasticDiffEq, Symbol(name))()
     error("unknown algorithm $name")
 end
 

@@ -281,6 +281,28 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
                     for (int j = 1; j < M.nw; ++j) noise = noise + gv[i * M.nw + j] * dw[j];
                     u[i] = K[i] + noise;
                 }
+            } else if (alg >= SDDE_ALG_WANGLI3SMIL_A && alg <= SDDE_ALG_WANGLI3SMIL_F) {
+                // [EXT, LOW confidence] WangLi3SMil_A..F = the six orders of D (drift), C (Ito correction), M (Stratonovich
+                // Milstein diffusion), every f / g at the step's t; see oracle/sdde_oracle.py for the operators
+                static const char *orders[6] = {"DCM", "DMC", "CDM", "CMD", "MDC", "MCD"};
+                const char *ord = orders[alg - SDDE_ALG_WANGLI3SMIL_A];
+                double k[SDDE_MAX_STATE], k1[SDDE_MAX_STATE], tmp[SDDE_MAX_STATE];
+                for (int j = 0; j < ns; ++j) u[j] = uprev[j];
+                for (int s3 = 0; s3 < 3; ++s3) {
+                    if (ord[s3] == 'D') {
+                        M.f(du, u, hcb, p, t);
+                        for (int j = 0; j < ns; ++j) u[j] = u[j] + dtn * du[j];
+                    } else {
+                        M.g(k, u, hcb, p, t);
+                        for (int j = 0; j < ns; ++j) tmp[j] = u[j] + k[j] * sq;
+                        M.g(k1, tmp, hcb, p, t);
+                        for (int j = 0; j < ns; ++j) {
+                            const double dgg = (k1[j] - k[j]) / sq;
+                            if (ord[s3] == 'C') u[j] = u[j] - (dtn * 0.5) * dgg;
+                            else u[j] = (u[j] + k[j] * dw[j]) + ((dw[j] * dw[j]) * 0.5) * dgg;
+                        }
+                    }
+                }
             } else if ((alg == SDDE_ALG_RKMILC_ITO || alg == SDDE_ALG_RKMILC_STRAT) && !M.diag) {
                 // [EXT] RKMilCommuteConstantCache on a noise matrix: J = dW dW'/2 (Ito: - |dt|/2 I); per column j
                 // K_j = (Ito ? K : uprev) + sqrt(dt) G[:, j], Dg_j = (G(K_j) - G(u)) / sqrt(dt), correction += Dg_j J[:, j]

@@ -46,6 +46,9 @@ ALG_RKMIL_STRAT = 3   # RKMil(interpretation = :Stratonovich)
 ALG_EULER_HEUN = 4    # EulerHeun()  (Stratonovich; second f/g evaluation at t + dt)
 ALG_RKMILC_ITO = 5    # RKMilCommute()  -- commutative noise; on diagonal noise the RKMil update
 ALG_RKMILC_STRAT = 6  # RKMilCommute(interpretation = :Stratonovich)
+ALG_WANGLI_A, ALG_WANGLI_B, ALG_WANGLI_C, ALG_WANGLI_D, ALG_WANGLI_E, ALG_WANGLI_F = 7, 8, 9, 10, 11, 12   # WangLi3SMil_A .. _F
+# stage operators of WangLi3SMil_x in execution order: 'D' drift, 'C' Ito correction, 'M' Stratonovich-Milstein diffusion
+WANGLI_ORDER = {7: "DCM", 8: "DMC", 9: "CDM", 10: "CMD", 11: "MDC", 12: "MCD"}
 
 # [EXT] StochasticDiffEq.alg_order: EM 1//2, RKMil 1//1  (call site src/solve.jl:248)
 ALG_ORDER = {
@@ -56,9 +59,10 @@ ALG_ORDER = {
     ALG_EULER_HEUN: Fraction(1, 2),
     ALG_RKMILC_ITO: Fraction(1, 1),
     ALG_RKMILC_STRAT: Fraction(1, 1),
+    **{a: Fraction(1, 1) for a in range(7, 13)},
 }
 N_STAGE = {ALG_EM_SPLIT: 1, ALG_EM_NOSPLIT: 1, ALG_RKMIL_ITO: 1, ALG_RKMIL_STRAT: 1, ALG_EULER_HEUN: 2, ALG_RKMILC_ITO: 1,
-           ALG_RKMILC_STRAT: 1}
+           ALG_RKMILC_STRAT: 1, **{a: 1 for a in range(7, 13)}}
 
 # lookup modes in the schedule tables
 LK_PRE = 0      # t < t0            -> user history h(p, t)
@@ -695,6 +699,30 @@ def solve_ensemble(model: Model, params, u0, h0, h1, lags, sched: Schedule, alg,
                 for j in range(1, m):
                     noise = noise + gv[:, j, :] * dw[j]
                 unew = K + noise
+        elif alg in WANGLI_ORDER:
+            # [EXT] StochasticDiffEq WangLi3SMil_A..F (Wang & Li's three-stage Milstein methods), diagonal noise.
+            # LOW CONFIDENCE: restated from memory of src/perform_step/low_order.jl -- three "#stage" blocks per method, each
+            # applying one operator to the running u, all f / g at the step's t (hence one history lookup per lag and step):
+            #   D: u <- u + dt f(u)
+            #   C: k = g(u); k1 = (g(u + k sqdt) - k)/sqdt; u <- u - (dt/2) k1
+            #   M: k = g(u); k1 = (g(u + k sqdt) - k)/sqdt; u <- u + k dW + (dW^2/2) k1
+            # D.C.M composes to u + f dt + g dW + g'g (dW^2 - dt)/2 + O(dt^1.5): Milstein.  The six letters are taken to be the
+            # six orders of (D, C, M) (WANGLI_ORDER); the letter <-> order assignment is an ASSUMPTION.  What is pinned here
+            # without Julia: hand-derived one-step answers per order and strong order 1.0 on the reference's own convergence
+            # problem (tests/test_oracle.py); what needs Julia: julia/replay_fixtures.jl.
+            if not model.diagonal:
+                raise ValueError("WangLi3SMil is implemented for diagonal noise only")
+            unew = u
+            for op in WANGLI_ORDER[alg]:
+                if op == "D":
+                    unew = unew + dt * model.f(unew, ul, p, t)
+                else:
+                    k = model.g(unew, ul, p, t)
+                    k1 = (model.g(unew + k * sq, ul, p, t) - k) / sq
+                    if op == "C":
+                        unew = unew - (dt * 0.5) * k1
+                    else:
+                        unew = (unew + k * dw) + ((dw * dw) * 0.5) * k1
         elif alg in (ALG_RKMILC_ITO, ALG_RKMILC_STRAT) and not model.diagonal:
             # [EXT] StochasticDiffEq RKMilCommuteConstantCache, noise matrix G [ns, m] with commutative columns (MED
             # confidence, restated from memory; the Milstein algebra itself is checked against the exact solution of a

@@ -13,6 +13,7 @@ import numpy as np
 SDDE_MAX_STATE, SDDE_MAX_LAG, SDDE_MAX_NOISE, SDDE_MAX_PARAM = 8, 4, 8, 128
 
 ALG_EM_SPLIT, ALG_EM_NOSPLIT, ALG_RKMIL_ITO, ALG_RKMIL_STRAT, ALG_EULER_HEUN, ALG_RKMILC_ITO, ALG_RKMILC_STRAT = 0, 1, 2, 3, 4, 5, 6
+ALG_WANGLI3SMIL_A = 7     # .. ALG_WANGLI3SMIL_F = 12
 MODEL_LINEAR1, MODEL_HAYES, MODEL_MACKEY_GLASS, MODEL_LINSYS, MODEL_SIR, MODEL_SCALAR_ADD = 0, 1, 2, 3, 4, 5
 MODEL_USER_BASE = 1000
 NOISE_PHILOX, NOISE_SUPPLIED_DW, NOISE_SUPPLIED_GRID = 0, 1, 2

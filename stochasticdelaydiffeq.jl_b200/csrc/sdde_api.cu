@@ -138,8 +138,8 @@ int check_desc(const sdde_desc *d) {
     if (d->struct_size != (int32_t)sizeof(sdde_desc))
         return fail(SDDE_ERR_BAD_DESC, "sdde_desc.struct_size = %d, library expects %d (ABI mismatch)", d->struct_size,
                     (int)sizeof(sdde_desc));
-    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_RKMILC_STRAT)
-        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / RKMilCommute / EulerHeun, fixed step)", d->alg);
+    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_WANGLI3SMIL_F)
+        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / RKMilCommute / EulerHeun / WangLi3SMil, fixed step)", d->alg);
     if (d->n_lag < 1 || d->n_lag > SDDE_MAX_LAG) return fail(SDDE_ERR_BAD_DESC, "n_lag = %d out of range", d->n_lag);
     if (d->n_state < 1 || d->n_state > SDDE_MAX_STATE) return fail(SDDE_ERR_BAD_DESC, "n_state = %d out of range", d->n_state);
     if (d->n_noise < 1 || d->n_noise > SDDE_MAX_NOISE) return fail(SDDE_ERR_BAD_DESC, "n_noise = %d out of range", d->n_noise);
@@ -190,7 +190,7 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     in.t0 = d->t0; in.tf = d->tf; in.dt = d->dt;
     in.lags.assign(d->lags, d->lags + d->n_lag);
     in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT || d->alg == SDDE_ALG_RKMILC_ITO ||
-                     d->alg == SDDE_ALG_RKMILC_STRAT) ? 2 : 1;   // [EXT] alg_order: RKMil, RKMilCommute 1//1; EM, EulerHeun 1//2
+                     d->alg == SDDE_ALG_RKMILC_STRAT || d->alg >= SDDE_ALG_WANGLI3SMIL_A) ? 2 : 1;   // [EXT] alg_order: RKMil, RKMilCommute, WangLi3SMil 1//1; EM, EulerHeun 1//2
     in.n_stage = d->alg == SDDE_ALG_EULER_HEUN ? 2 : 1;
     in.order_discontinuity_t0 = d->order_discontinuity_t0;
     in.constant_lags_declared = d->constant_lags_declared != 0;
@@ -258,7 +258,19 @@ int select_kernel_alg(sdde_ctx *ctx, const sdde_desc *d, int alg, sdde::KernelIn
 
 // RKMilCommute: a noise-matrix model has its own kernels (alg 5 / 6); on a diagonal model the update is the RKMil one
 // written with the iterated integral, so the RKMil kernels (alg 2 / 3) serve
+// WangLi3SMil_A..F -> stage operators in execution order, 2 bits each (0 = D drift, 1 = C Ito correction, 2 = M diffusion)
+static int wangli_stage_order(int alg) {
+    static const int order[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};   // A: D C M, B: D M C, C: C D M, D: C M D, E: M D C, F: M C D
+    const int *o = order[alg - SDDE_ALG_WANGLI3SMIL_A];
+    return o[0] | (o[1] << 2) | (o[2] << 4);
+}
+
 int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
+    if (d->alg >= SDDE_ALG_WANGLI3SMIL_A) {
+        const int rc = select_kernel_alg(ctx, d, sdde::K_ALG_WANGLI, k);
+        if (rc == SDDE_OK && !k.diag) return fail(SDDE_ERR_UNSUPPORTED, "WangLi3SMil is implemented for diagonal noise only");
+        return rc;
+    }
     if (d->alg == SDDE_ALG_RKMILC_ITO || d->alg == SDDE_ALG_RKMILC_STRAT) {
         sdde::KernelInfo probe;
         const int as_rkmil = d->alg - SDDE_ALG_RKMILC_ITO + SDDE_ALG_RKMIL_ITO;
@@ -324,6 +336,8 @@ int select_kernel_alg(sdde_ctx *ctx, const sdde_desc *d, int alg, sdde::KernelIn
         if ((alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMIL_STRAT))
             return fail(SDDE_ERR_UNSUPPORTED, "RKMil requires diagonal noise (model %d has a non-diagonal noise matrix)",
                         d->model_id);
+        if (alg == sdde::K_ALG_WANGLI)
+            return fail(SDDE_ERR_UNSUPPORTED, "WangLi3SMil is implemented for diagonal noise only (model %d has a noise matrix)", d->model_id);
         return fail(SDDE_ERR_UNSUPPORTED, "no kernel for model %d shape (%d states, %d lags, %d noise) alg %d", d->model_id,
                     d->n_state, d->n_lag, d->n_noise, alg);
     }
@@ -335,7 +349,7 @@ int select_kernel_alg(sdde_ctx *ctx, const sdde_desc *d, int alg, sdde::KernelIn
     return SDDE_OK;
 }
 
-void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pitch, int batch, int chunk,
+void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pitch, int batch, int chunk, bool interp_body,
                  std::vector<unsigned char> &steps, std::vector<sdde::SaveRec> &saves) {
     const int64_t N = S.n_steps();
     const int L = S.n_lag;
@@ -399,7 +413,7 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
             unsigned char *r0 = steps.data() + (size_t)n * k.rec_size;
             int m0;
             memcpy(&m0, r0 + 28, 4);
-            bool ok = true, all_exact = true;
+            bool ok = true, all_exact = true, all_interp = true;
             unsigned long long packed = 0;
             for (int kk = 0; kk < batch && ok; ++kk) {
                 const unsigned char *r = steps.data() + (size_t)(n + kk) * k.rec_size;
@@ -411,12 +425,14 @@ void pack_tables(const sdde::Schedule &S, const sdde::KernelInfo &k, int64_t pit
                     const int mode = S.lk_mode[(size_t)(n + kk) * NLK + l];
                     ok = ok && (mode == sdde::LK_EXACT || mode == sdde::LK_INTERP);          // every lookup reads the ring
                     const unsigned char *lk = r + 48 + 32 * l, *lk0 = r0 + 48 + 32 * l;
-                    all_exact = all_exact && mode == sdde::LK_EXACT && rd64(lk + 16) == rd64(lk0 + 16) + kk * slot_bytes;
+                    const bool consec = rd64(lk + 16) == rd64(lk0 + 16) + kk * slot_bytes;    // upper nodes on consecutive slots
+                    all_exact = all_exact && mode == sdde::LK_EXACT && consec;
+                    all_interp = all_interp && mode == sdde::LK_INTERP && consec && rd64(lk + 8) == rd64(lk + 16) - slot_bytes;
                 }
             }
             ok = ok && batch <= 8;
             if (ok) {
-                m0 |= all_exact ? SDDE_MASK_FAST_EXACT : SDDE_MASK_FAST_RING;
+                m0 |= all_exact ? SDDE_MASK_FAST_EXACT : (all_interp && batch > 1 && interp_body) ? SDDE_MASK_FAST_INTERP : SDDE_MASK_FAST_RING;
                 memcpy(r0 + 28, &m0, 4);
                 memcpy(r0 + 48 + 24, &packed, 8);            // lk[0].pad
             }
@@ -530,7 +546,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
     else if (!strcmp(key, "zero_copy")) c->opt_zero_copy = value != 0;
     else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); c->mem_key.clear(); }   // next solve replays the schedule and re-uploads its tables
-    else if (!strcmp(key, "lean")) { c->opt_lean = value != 0; c->table_key.clear(); }
+    else if (!strcmp(key, "lean")) { c->opt_lean = value; c->table_key.clear(); }   // 0: general body only, 1: all lean bodies, 2: without the consecutive-interpolation body (A/B)
     else if (!strcmp(key, "balance")) c->opt_balance = value != 0;
     else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
@@ -787,7 +803,7 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
         tkey.append((const char *)tk, sizeof(tk));
         if (tkey != c->table_key) {
             c->table_key.clear();
-            pack_tables(S, K, tpitch, c->opt_lean ? batch : 0, chunk, h_steps, h_saves);
+            pack_tables(S, K, tpitch, c->opt_lean ? batch : 0, chunk, c->opt_lean != 2, h_steps, h_saves);
             CU_CHECK(c->steps.reserve(std::max<size_t>(16, h_steps.size())));
             CU_CHECK(c->saves.reserve(std::max<size_t>(16, h_saves.size() * sizeof(sdde::SaveRec))));
             if (!h_steps.empty()) CU_CHECK(cudaMemcpyAsync(c->steps.p, h_steps.data(), h_steps.size(), cudaMemcpyHostToDevice, c->compute));
@@ -833,6 +849,7 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
     A.n_saved = NSAVED;
+    A.stage_order = d->alg >= SDDE_ALG_WANGLI3SMIL_A ? wangli_stage_order(d->alg) : 0;
     A.prefetch = (S.min_gap >= 1) ? 1 : 0;
     for (int j = 0; j < SDDE_K_MAX_STATE; ++j) A.save_row[j] = d->n_save_idxs > 0 ? -1 : (j < NS ? j : -1);
     for (int i = 0; i < d->n_save_idxs; ++i) A.save_row[d->save_idxs[i]] = i;

@@ -64,6 +64,7 @@ inline KernelInfo make_coop_info(const char *name) {
         SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_ITO)                  \
         SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_STRAT)                \
         SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_WANGLI)                     \
         return KernelInfo();                                    \
     }
 // noise-matrix models: EM, EulerHeun, RKMilCommute ([EXT] RKMil itself requires diagonal noise)

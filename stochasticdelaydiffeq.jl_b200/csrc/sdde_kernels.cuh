@@ -30,7 +30,8 @@ typedef unsigned long long u64;
 enum { K_LK_PRE = 0, K_LK_EXACT = 1, K_LK_INTERP = 2 };
 enum { K_NOISE_PHILOX = 0, K_NOISE_DW = 1, K_NOISE_GRID = 2 };
 enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3, K_ALG_EULER_HEUN = 4,
-       K_ALG_RKMILC_ITO = 5, K_ALG_RKMILC_STRAT = 6 };   // RKMilCommute on a noise MATRIX (diagonal models run it as RKMil)
+       K_ALG_RKMILC_ITO = 5, K_ALG_RKMILC_STRAT = 6,     // RKMilCommute on a noise MATRIX (diagonal models run it as RKMil)
+       K_ALG_WANGLI = 7 };                               // WangLi3SMil_A..F: one kernel, the stage order is a run-time argument
 // history lookup times per step: EulerHeun evaluates f and g a second time at t + dt
 __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULER_HEUN ? 2 : 1; }
 
@@ -50,6 +51,7 @@ __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULE
 // first record of a batch whose steps the kernel may run through the lean body (pack_tables decides):
 #define SDDE_MASK_FAST_EXACT (1 << 24)    // every lookup of every step hits a ring node exactly, on consecutive slots
 #define SDDE_MASK_FAST_RING (1 << 25)     // every lookup of every step reads the ring (exact hits and interpolations mixed)
+#define SDDE_MASK_FAST_INTERP (1 << 26)   // every lookup interpolates between CONSECUTIVE slots (the steady state of a lag on the grid)
 // how many batches ahead the delayed-state nodes are pulled towards L1 (bytes in flight per SM = depth x 32 KB)
 #ifndef SDDE_PF_DIST
 #define SDDE_PF_DIST 1
@@ -95,6 +97,8 @@ struct KArgs {
     long long traj_gid0;     // global id of the wave's first trajectory
     const double2 *rng_tab;  // generator table in global memory (sdde_rng_tables.cuh), staged per CTA
     long long slot_bytes;    // one ring slot = NS * ring_pitch * 8 bytes
+    int stage_order;         // K_ALG_WANGLI: the three stage operators in execution order, 2 bits each (0 drift, 1 Ito
+                             // correction, 2 Stratonovich-Milstein diffusion), first stage in the low bits
     int n_full_ctas;         // CTAs [0, n_full_ctas) integrate BLOCK x TPT trajectories each, the remaining ("tail") CTAs
     int tail_traj;           // tail_traj each (a multiple of 32 x TPT): the last, partial round is spread over all SMs
     int n_steps, n_saves, ring_slots, chunk_steps, batch, noise_kind;
@@ -289,9 +293,42 @@ struct RegParams {
 // ------------------------------------------------------------------------------------------------
 template <class M, int ALG, class P>
 __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)[alg_stages(ALG)][M::NL][M::NS], const P &p,
-                                         double t, double dt, double sq, double isq, const double *dw) {
+                                         double t, double dt, double sq, double isq, const double *dw, int stage_order = 0) {
     constexpr int NS = M::NS;
     const double (&ul)[M::NL][M::NS] = uls[0];
+    if constexpr (ALG == K_ALG_WANGLI && M::DIAG) {
+        // [EXT] StochasticDiffEq WangLi3SMil_A..F (three-stage Milstein methods of Wang & Li, diagonal noise; reference smoke
+        // and convergence tests test/test_prob_sol.jl:50-61, test/analyticless_convergence_tests.jl:62-91).  LOW confidence
+        // restatement (see oracle/sdde_oracle.py): each step composes three stage operators, every f / g evaluated at the
+        // step's t with the step's delayed states, the derivative g'g by a forward difference of width sqrt(dt):
+        //   D  u <- u + dt f(u)
+        //   C  k = g(u), k1 = (g(u + k sqrt(dt)) - k)/sqrt(dt);  u <- u - (dt/2) k1                  (Ito correction)
+        //   M  k = g(u), k1 = (g(u + k sqrt(dt)) - k)/sqrt(dt);  u <- u + k dW + (dW^2/2) k1         (Stratonovich Milstein)
+        // and the six letters are the six orders of (D, C, M); `stage_order` carries the order (warp-uniform branches).
+#pragma unroll
+        for (int sgi = 0; sgi < 3; ++sgi) {
+            const int op = (stage_order >> (2 * sgi)) & 3;
+            if (op == 0) {
+                double du[NS];
+                M::f(du, u, ul, p, t);
+#pragma unroll
+                for (int j = 0; j < NS; ++j) u[j] = u[j] + dt * du[j];
+            } else {
+                double k[NS], tmp[NS], k1[NS];
+                M::g(k, u, ul, p, t);
+#pragma unroll
+                for (int j = 0; j < NS; ++j) tmp[j] = u[j] + k[j] * sq;
+                M::g(k1, tmp, ul, p, t);
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    const double d = (k1[j] - k[j]) * isq;
+                    if (op == 1) u[j] = u[j] - (dt * 0.5) * d;
+                    else u[j] = (u[j] + k[j] * dw[j]) + ((dw[j] * dw[j]) * 0.5) * d;
+                }
+            }
+        }
+        return;
+    }
     if (ALG == K_ALG_EULER_HEUN) {
         // [EXT] EulerHeunConstantCache: tmp = u + f dt + g dW;  u+ = u + dt/2 (f + f(tmp, t+dt)) + 1/2 (g + g(tmp, t+dt)) dW
         constexpr int NW = M::DIAG ? 1 : M::NW, NG = M::DIAG ? NS : NS * M::NW;
@@ -443,7 +480,9 @@ struct TrajState {
 // instead of nine 64-bit loads per step.  K_FAST_RING (exact hits and interpolations mixed -- t_n - tau lands on either
 // side of a node by rounding, so even "exact" lags interpolate with theta ~ 1e-16 on some steps): per-step theta and
 // node offsets as in the general body.
-enum { K_FAST_NONE = 0, K_FAST_EXACT = 1, K_FAST_RING = 2 };
+// K_FAST_INTERP: every lookup interpolates and both bracketing nodes advance by one slot per step (lo(k) = hi(k-1)): loads
+// from one base like the exact body, only theta is read per step.
+enum { K_FAST_NONE = 0, K_FAST_EXACT = 1, K_FAST_RING = 2, K_FAST_INTERP = 3 };
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW, int FAST>
 __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL * alg_stages(ALG)> *recs, int n,
                                           char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec,
@@ -456,14 +495,31 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
     const long long slot = a.slot_bytes;
     // ---- all delayed-state loads of the batch, unconditionally (prehistory records point at slot 0) ----
     double xlo[BW][NLK][NS][TPT], xhi[BW][NLK][NS][TPT];
-    if constexpr (FAST == K_FAST_EXACT) {
+    if constexpr (FAST == K_FAST_EXACT || FAST == K_FAST_INTERP) {
 #pragma unroll
         for (int l = 0; l < NLK; ++l) {
             const char *phi = ringb + recs[0].lk[l].off_hi;
+            if (FAST == K_FAST_INTERP) {
+                const bool reuse = (recs[0].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1) of the previous batch: in registers
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(phi - slot + j * jstride), xlo[0][l][j]);
+                    else {
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) xlo[0][l][j][tt] = st.carry[l][j][tt];
+                    }
+                }
+            }
 #pragma unroll
             for (int k = 0; k < BW; ++k)
 #pragma unroll
-                for (int j = 0; j < NS; ++j) ld_traj<TPT>(reinterpret_cast<const double *>(phi + k * slot + j * jstride), xhi[k][l][j]);
+                for (int j = 0; j < NS; ++j) {
+                    ld_traj<TPT>(reinterpret_cast<const double *>(phi + k * slot + j * jstride), xhi[k][l][j]);
+                    if (FAST == K_FAST_INTERP && k > 0) {
+#pragma unroll
+                        for (int tt = 0; tt < TPT; ++tt) xlo[k][l][j][tt] = xhi[k - 1][l][j][tt];
+                    }
+                }
         }
     } else {
 #pragma unroll
@@ -592,7 +648,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 for (int j = 0; j < NS; ++j)
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt) ul[tt][l / NL][l % NL][j] = xhi[k][l][j][tt];
-            } else if constexpr (FAST == K_FAST_RING) {
+            } else if constexpr (FAST == K_FAST_RING || FAST == K_FAST_INTERP) {
                 const double th = recs[k].lk[l].theta, omt = 1.0 - th;
 #pragma unroll
                 for (int j = 0; j < NS; ++j)
@@ -638,8 +694,8 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         // perform_step!
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
-            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, isq, dw[tt]);
-            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, isq, dw[tt]);
+            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, isq, dw[tt], a.stage_order);
+            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, isq, dw[tt], a.stage_order);
 #pragma unroll
             for (int j = 0; j < NS; ++j) useq[k + 1][tt][j] = st.u[tt][j];
         }
@@ -793,6 +849,8 @@ __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solv
                 const bool pfn = nb + (SDDE_PF_DIST + 1) * B <= nrec;   // the records of the batch to prefetch are staged
                 if (fm & SDDE_MASK_FAST_EXACT)
                     run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_EXACT>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
+                else if (fm & SDDE_MASK_FAST_INTERP)
+                    run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_INTERP>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
                 else if (fm & SDDE_MASK_FAST_RING)
                     run_batch<M, ALG, NOISE, PTRAJ, TPT, B, K_FAST_RING>(a, st, srec + nb, n0 + nb, ringb, ltab, tr0, last, out_vec, pfn);
                 else

@@ -13,7 +13,7 @@ namespace sdde {
 
 namespace {
 
-const int kAlgs = 7, kNoises = 3;
+const int kAlgs = 8, kNoises = 3;
 inline int variant_index(int alg, int noise, bool ptraj) { return (alg * kNoises + noise) * 2 + (ptraj ? 1 : 0); }
 
 std::string nvrtc_log(nvrtcProgram prog) {
@@ -119,6 +119,7 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
     Entry &en = entries_[(size_t)idx];
     if (!en.diag && (alg == 2 || alg == 3)) { k = KernelInfo(); return true; }   // caller reports "RKMil requires diagonal noise"
     if (en.diag && (alg == 5 || alg == 6)) { k = KernelInfo(); return true; }    // caller falls back to the RKMil kernels
+    if (!en.diag && alg == 7) { k = KernelInfo(); return true; }                 // WangLi3SMil: diagonal noise only
     const int v = variant_index(alg, noise, ptraj);
     if (!en.kernels[(size_t)v]) {
         char expr[256];

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi as capi
-from .problem import (EM, EulerHeun, RKMil, EnsembleProblem, FinalState, MomentsReduction, SaveIdxs, SDDEProblem, UserModel,
+from .problem import (EM, EulerHeun, RKMil, WangLi3SMil, EnsembleProblem, FinalState, MomentsReduction, SaveIdxs, SDDEProblem, UserModel,
                       _as_history)
 
 
@@ -129,8 +129,9 @@ class _Marshalled:
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
              want_moments, lanes_per_traj=0, save_idxs=None, noise_t=None, d_discontinuities=()) -> _Marshalled:
-    if not isinstance(alg, (EM, RKMil, EulerHeun)):
-        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil and EulerHeun, fixed step)")
+    if not isinstance(alg, (EM, RKMil, EulerHeun, WangLi3SMil)):
+        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil, RKMilCommute, EulerHeun and WangLi3SMil_A-F, "
+                                  "fixed step)")
     if adaptive is None:
         adaptive = isinstance(alg, RKMil)      # [EXT] isadaptive(RKMil) = true, src/solve.jl:40
     if adaptive:

@@ -56,6 +56,47 @@ class RKMilCommute(RKMil):
 
 
 @dataclass(frozen=True)
+class WangLi3SMil:
+    """``WangLi3SMil_A()`` .. ``WangLi3SMil_F()`` ([EXT] StochasticDiffEq; reference tests test/test_prob_sol.jl:50-61 and
+    test/analyticless_convergence_tests.jl:62-91): Wang & Li's three-stage Milstein methods, diagonal noise, strong order 1.
+    Restated as the six orders of (drift, Ito correction, Stratonovich-Milstein diffusion) -- LOW confidence in the
+    letter <-> order assignment, see DESIGN.md section 6."""
+    variant: str = "A"
+
+    def __post_init__(self):
+        if self.variant not in "ABCDEF" or len(self.variant) != 1:
+            raise ValueError("variant must be one of 'A' .. 'F'")
+
+    @property
+    def alg_id(self):
+        return capi.ALG_WANGLI3SMIL_A + "ABCDEF".index(self.variant)
+
+
+def WangLi3SMil_A():
+    return WangLi3SMil("A")
+
+
+def WangLi3SMil_B():
+    return WangLi3SMil("B")
+
+
+def WangLi3SMil_C():
+    return WangLi3SMil("C")
+
+
+def WangLi3SMil_D():
+    return WangLi3SMil("D")
+
+
+def WangLi3SMil_E():
+    return WangLi3SMil("E")
+
+
+def WangLi3SMil_F():
+    return WangLi3SMil("F")
+
+
+@dataclass(frozen=True)
 class EulerHeun:
     """Euler-Heun (Stratonovich), fixed step: second drift/diffusion evaluation at t + dt, i.e. a second set of
     delayed-state lookups per step ([EXT] StochasticDiffEq EulerHeun; reference smoke test test/test_prob_sol.jl:34)."""

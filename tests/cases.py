@@ -4,7 +4,7 @@ import sdde_b200 as S
 import sdde_oracle as O
 
 ALG_MAP = {0: S.EM(True), 1: S.EM(False), 2: S.RKMil("Ito"), 3: S.RKMil("Stratonovich"), 4: S.EulerHeun(),
-           5: S.RKMilCommute("Ito"), 6: S.RKMilCommute("Stratonovich")}
+           5: S.RKMilCommute("Ito"), 6: S.RKMilCommute("Stratonovich"), **{7 + i: S.WangLi3SMil("ABCDEF"[i]) for i in range(6)}}
 
 
 class Case:

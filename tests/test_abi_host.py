@@ -328,7 +328,7 @@ def test_abi_rejects_bad_descriptors():
     d = capi.SddeDesc()
     assert L.sdde_b200_schedule(C.byref(d), C.byref(sch)) == -1 and b"struct_size" in L.sdde_b200_last_error()
     d.struct_size = C.sizeof(capi.SddeDesc)
-    d.alg = 9
+    d.alg = 99
     assert L.sdde_b200_schedule(C.byref(d), C.byref(sch)) == -2
     assert L.sdde_b200_schedule(None, C.byref(sch)) == -1
 

@@ -1,6 +1,6 @@
 """-m gpu: randomised parity sweep.  Random combinations of model, algorithm, lag(s), step size, time span, discontinuity
-order, saveat form, user tstops, affine history, per-trajectory parameters / initial states, noise source (increments or
-NoiseGrid), forced wave sizes and schedule-chunk sizes -- every one compared path by path with the oracle under shared
+order, saveat form, user tstops, user d_discontinuities, affine history, per-trajectory parameters / initial states, noise source (increments or
+NoiseGrid), forced wave sizes, schedule-chunk sizes, lean batch bodies and balanced launch geometry on / off -- every one compared path by path with the oracle under shared
 noise (1e-12).  Exercises the table packing (carried nodes, ring size, clipped steps, records at chunk boundaries, the
 next-batch prefetch), the step-by-step fallback for short lags, and the wave loop, in combinations the named tests miss."""
 import numpy as np
@@ -21,22 +21,22 @@ def _random_case(rng):
     order0 = int(rng.choice([0, 0, 1, 2]))
     if kind == "linear1":
         lag = float(rng.choice([0.05, 0.3, 1.0, 0.777, 2.5 * dt, 1.0 * dt]))
-        c = cases.c1(T=T).with_(lags=[lag], dt=dt, alg=int(rng.choice([0, 1, 2, 3, 4])), order0=order0,
+        c = cases.c1(T=T).with_(lags=[lag], dt=dt, alg=int(rng.choice([0, 1, 2, 3, 4, 5, 6])), order0=order0,
                                 h0=[float(rng.uniform(0.5, 1.5))], h1=[float(rng.choice([0.0, 0.3]))])
     elif kind == "mg":
         lag = float(rng.choice([0.5, 1.7, 17.0 / 8, 3.01]))
-        c = cases.c2(T=T, tau=lag).with_(dt=dt, alg=int(rng.choice([0, 1, 2, 3, 4])), order0=order0)
+        c = cases.c2(T=T, tau=lag).with_(dt=dt, alg=int(rng.choice([0, 1, 2, 3, 4, 5])), order0=order0)
     elif kind == "hayes":
         c = cases.hayes(T=min(T, 3.0), dt=dt, alg=int(rng.choice([0, 2, 3, 4])), beta=float(rng.choice([0.0, -1.2])))
         c = c.with_(order0=order0)
     elif kind == "scalar_add":
         c = cases.scalar_add(T=T).with_(dt=dt, alg=int(rng.choice([0, 1, 4])), order0=order0)
     elif kind == "c4":
-        c = cases.c4(T=min(T, 4.0)).with_(dt=dt, alg=int(rng.choice([0, 1, 4])), order0=order0,
+        c = cases.c4(T=min(T, 4.0)).with_(dt=dt, alg=int(rng.choice([0, 1, 4, 5, 6])), order0=order0,
                                          lags=[float(rng.choice([0.5, 1.0])), float(rng.choice([1.3, 2.5]))])
     else:
         c = cases.sir(T=min(T, 4.0), dt=0.02).with_(alg=int(rng.choice([0, 1, 4])))
-    if c.alg in (2, 3, 4) and c.dt > min(c.lags):
+    if c.alg in (2, 3, 4, 5, 6) and c.dt > min(c.lags):
         c = c.with_(dt=min(c.lags) / 2)                       # src/solve.jl:581-585 guard
     t0, tf = c.tspan
     form = rng.choice(["number", "list", "everystep"])
@@ -57,12 +57,15 @@ def test_random_configuration_matches_oracle(seed):
     n = int(rng.choice([97, 256, 1000, 1537]))
     tst = sorted(set(float(np.round(x, 2)) for x in rng.uniform(c.tspan[0], c.tspan[1], size=int(rng.integers(0, 3)))))
     tst = [x for x in tst if c.tspan[0] < x < c.tspan[1]]
-    if c.alg in (2, 3, 4):
+    if c.alg in (2, 3, 4, 5, 6):
         tst = []                                              # extra stops could make a step longer than the smallest lag
+    # user-declared discontinuities (src/solve.jl:20-23): times with orders 0 / 1, propagated by the lags like the one at t0
+    dd = [(float(np.round(x, 3)), int(rng.integers(0, 2))) for x in rng.uniform(c.tspan[0], c.tspan[1], size=int(rng.integers(0, 3)))]
+    dd = [d for d in dd if c.tspan[0] < d[0] < c.tspan[1]] if c.alg in (0, 1) else []
     sv, ss, se = O.expand_saveat(c.saveat, *c.tspan)
     sch = O.build_schedule(c.tspan[0], c.tspan[1], c.dt, c.lags, c.alg, order_discontinuity_t0=c.order0,
                            constant_lags_declared=c.declared, saveat_times=sv, save_start=ss, save_end=se,
-                           save_everystep=c.saveat is None, tstops=tst)
+                           save_everystep=c.saveat is None, tstops=tst, d_discontinuities=dd)
     nchan = c.model.n_chan
     dW = cases.increments(sch, nchan, n, key=555 + seed)
     ptraj = bool(rng.integers(0, 2))
@@ -71,8 +74,8 @@ def test_random_configuration_matches_oracle(seed):
         pb = np.repeat(np.asarray(c.p, float)[:, None], n, axis=1) * (1.0 + 0.05 * rng.random((len(c.p), n)))
         ub = np.repeat(np.asarray(c.u0, float)[:, None], n, axis=1) * (1.0 + 0.05 * rng.random((len(c.u0), n)))
     ref, st = O.solve_ensemble(c.omodel, pb if ptraj else c.p, ub if ptraj else c.u0, c.h0, c.h1, c.lags, sch, c.alg, dW)
-    kw = dict(dt=c.dt, saveat=c.saveat, tstops=tst)
-    if c.alg in (2, 3):
+    kw = dict(dt=c.dt, saveat=c.saveat, tstops=tst, d_discontinuities=dd)
+    if c.alg in (2, 3, 5, 6):
         kw["adaptive"] = False
     noise = {}
     if rng.integers(0, 2):
@@ -87,12 +90,14 @@ def test_random_configuration_matches_oracle(seed):
     wave = int(rng.choice([0, 0, 128, 512]))
     ctx = S.get_context(0)
     ctx.set_option("chunk_steps", int(rng.choice([128, 8, 24, 1024])))
+    lean, balance = int(rng.integers(0, 4) > 0), int(rng.integers(0, 4) > 0)          # mostly on (the defaults), sometimes off
+    ctx.set_option("lean", lean); ctx.set_option("balance", balance)
     try:
         sim = S.solve(S.EnsembleProblem(c.problem(), p_batch=pb, u0_batch=ub), cases.ALG_MAP[c.alg],
                       S.EnsembleB200(device=0, wave_traj=wave or None), trajectories=n, **kw, **noise)
     finally:
-        ctx.set_option("chunk_steps", 128)
-    what = (c.name, c.alg, c.lags, c.dt, c.tspan, c.order0, c.saveat if not isinstance(c.saveat, list) else "list", tst, n, ptraj, wave,
+        ctx.set_option("chunk_steps", 128); ctx.set_option("lean", 1); ctx.set_option("balance", 1)
+    what = (c.name, c.alg, c.lags, c.dt, c.tspan, c.order0, c.saveat if not isinstance(c.saveat, list) else "list", tst, dd, n, ptraj, wave, lean, balance,
             list(noise)[0], sim.timing["kernel_name"])
     assert sim.out.shape == ref.shape, what
     assert np.array_equal(sim.t, sch.save_t), what
@@ -122,7 +127,7 @@ def test_random_configuration_philox_paths_do_not_depend_on_the_launch_geometry(
     c = _random_case(rng)
     n = int(rng.choice([300, 1000, 2049]))
     kw = dict(dt=c.dt, saveat=c.saveat, trajectories=n, seed=1234 + seed)
-    if c.alg in (2, 3):
+    if c.alg in (2, 3, 5, 6):
         kw["adaptive"] = False
     prob = S.EnsembleProblem(c.problem())
     base = S.solve(prob, cases.ALG_MAP[c.alg], S.EnsembleB200(device=0), **kw)

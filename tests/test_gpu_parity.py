@@ -696,3 +696,20 @@ def test_output_func_and_reduction_forms():
     red = S.solve(S.EnsembleProblem(case.problem(), reduction=S.MomentsReduction()), S.EM(), S.EnsembleB200(device=0),
                   trajectories=512, seed=5, **case.solve_kwargs())
     assert red.out is None and np.allclose(red.moments, base.moments, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("alg", [7, 8, 9, 10, 11, 12])
+def test_wangli3smil_paths_match_oracle(alg):
+    """WangLi3SMil_A .. _F (test/test_prob_sol.jl:50-61), one device kernel with the stage order as an argument: per-path
+    parity with the oracle's six orders under shared increments on the reference's Hayes problem (multiplicative noise with
+    the delayed term) and on Mackey-Glass off the grid."""
+    for case in (cases.hayes(T=3.0, dt=2.0 ** -6, beta=-1.2, saveat=0.25).with_(alg=alg), cases.c3(0, T=30.0).with_(alg=alg)):
+        sch = case.oracle_schedule()
+        dW = cases.increments(sch, 1, 700)
+        sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[alg], S.EnsembleB200(device=0), trajectories=700,
+                      noise_increments=dW, **case.solve_kwargs())
+        ref, _ = case.oracle(dW)
+        assert "alg%d" % alg in sim.timing["kernel_name"]
+        assert cases.scaled_err(sim.out, ref) < TOL, case.name
+    with pytest.raises(S.SddeError, match="diagonal"):
+        S.solve(S.EnsembleProblem(cases.c4(T=1.0).problem()), cases.ALG_MAP[alg], S.EnsembleB200(device=0), trajectories=64, dt=0.01)

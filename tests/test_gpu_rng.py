@@ -175,3 +175,9 @@ def test_k6_strong_order_rkmil_stratonovich():
 def test_k6_strong_order_euler_heun():
     # test/analyticless_convergence_tests.jl:42-46 asserts 1.0 +- 0.3 for EulerHeun on the same problem
     assert abs(_strong_order(S.EulerHeun(), 4) - 1.0) < 0.3
+
+
+@pytest.mark.parametrize("variant", list("ABCDEF"))
+def test_k6_strong_order_wangli3smil(variant):
+    # test/analyticless_convergence_tests.jl:62-91 asserts 1.0 +- 0.3 for WangLi3SMil_A .. _F on the same problem
+    assert abs(_strong_order(S.WangLi3SMil(variant), 7 + "ABCDEF".index(variant)) - 1.0) < 0.3

@@ -315,3 +315,59 @@ def test_rkmil_commute_strong_order_one_against_exact_solution():
     for alg, exact, want in ((O.ALG_RKMILC_ITO, ex_ito, 1.0), (O.ALG_RKMILC_STRAT, ex_str, 1.0), (O.ALG_EM_SPLIT, ex_ito, 0.5)):
         slope = np.polyfit(np.log(dts), np.log([err(alg, dt, exact) for dt in dts]), 1)[0]
         assert abs(slope - want) < 0.3, (alg, slope)
+
+
+def test_k1_wangli3smil_one_step_known_answers():
+    """WangLi3SMil_A..F, one step of the Hayes test problem, against the composition of the three stage operators written
+    out with plain floats (f = a u + b x_tau + c and g = alpha u + beta x_tau + gamma are affine in u, so the six orders give
+    six different numbers; x_tau = h(p, -1) = 0 on the first step):
+       D(x) = x + dt (a x + c);   C(x) = x - dt/2 * alpha (alpha x + gamma);   M(x) = x + (alpha x + gamma) dW + dW^2/2 * alpha (alpha x + gamma)
+    where alpha (alpha x + gamma) is what the forward difference (g(x + g(x) sqrt(dt)) - g(x)) / sqrt(dt) gives for an affine g."""
+    a, b, c, al, be, ga = -4.0, -2.0, 10.0, -1.3, -1.2, 1.1
+    dt, dW = 0.1, 0.2
+    D = lambda x: x + dt * (a * x + c)
+    C = lambda x: x - (dt / 2) * (al * (al * x + ga))
+    Mm = lambda x: x + (al * x + ga) * dW + (dW * dW / 2) * (al * (al * x + ga))
+    ops = {"D": D, "C": C, "M": Mm}
+    model = O.get_model(O.MODEL_HAYES)
+    p = [1.0, a, b, c, al, be, ga]
+    got = {}
+    for alg, order in O.WANGLI_ORDER.items():
+        x = 1.0
+        for o in order:
+            x = ops[o](x)
+        sch = O.build_schedule(0.0, dt, dt, [1.0], alg, saveat_times=[], save_everystep=True)
+        out, _ = O.solve_ensemble(model, p, [1.0], [1.0], [1.0], [1.0], sch, alg, np.full((1, 1, 1), dW))
+        assert abs(out[-1, 0, 0] - x) < 5e-15, (order, out[-1, 0, 0], x)
+        co, _, _, _ = __import__("c_oracle").solve(O.MODEL_HAYES, alg, 1, 1, 1, p, [1.0], [1.0], [1.0], [1.0], 0.0, dt, dt, [], 2,
+                                                   save_everystep=True, dW=np.full((1, 1, 1), dW))
+        assert np.array_equal(co, out)
+        got[order] = out[-1, 0, 0]
+    # C and M are affine maps with the same fixed point -gamma/alpha for an affine g, so they commute: 4 distinct values here
+    assert len({round(v, 12) for v in got.values()}) == 4 and abs(got["DCM"] - got["DMC"]) < 1e-15 and abs(got["CMD"] - got["MCD"]) < 1e-15
+    # all of them are Milstein to leading order: u + f dt + g dW + g g' (dW^2 - dt)/2 at u = 1
+    mil = 1.0 + dt * (a + c) + (al + ga) * dW + al * (al + ga) * (dW * dW - dt) / 2
+    assert all(abs(v - mil) < 0.25 for v in got.values())       # dt = 0.1 with a = -4 is coarse: O(dt^1.5..2) apart
+
+
+def test_wangli3smil_strong_order_one_on_the_reference_convergence_problem():
+    """test/analyticless_convergence_tests.jl:62-91 asserts strong order 1.0 +- 0.3 for WangLi3SMil_A..F on the Hayes problem
+    (dts = 2^-8..2^-4 against a 2^-9 run, shared Brownian path); the same estimate with the oracle for two of the six orders
+    (all six run on the device, tests/test_gpu_rng.py)."""
+    n, T, fine = 100, 4.0, 2.0 ** -9
+    rng = np.random.default_rng(2027)
+    dWf = rng.standard_normal((int(round(T / fine)), 1, n)) * np.sqrt(fine)
+    model = O.get_model(O.MODEL_HAYES)
+    p = [1.0, -4.0, -2.0, 10.0, -1.3, 0.0, 1.1]
+
+    def run(alg, dt):
+        sch = O.build_schedule(0.0, T, dt, [1.0], alg, saveat_times=[T], save_start=False)
+        k = int(round(dt / fine))
+        out, _ = O.solve_ensemble(model, p, [1.0], [1.0], [1.0], [1.0], sch, alg, dWf.reshape(sch.n_steps, k, 1, n).sum(axis=1))
+        return out[-1, 0]
+
+    dts = 2.0 ** -np.arange(8, 3, -1)
+    for alg in (O.ALG_WANGLI_A, O.ALG_WANGLI_F):
+        ref = run(alg, fine)
+        slope = np.polyfit(np.log(dts), np.log([np.mean(np.abs(run(alg, dt) - ref)) for dt in dts]), 1)[0]
+        assert abs(slope - 1.0) < 0.3, (alg, slope)

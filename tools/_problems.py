@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sdde_b200 as S  # noqa: E402
 
 ALG_MAP = {0: S.EM(True), 1: S.EM(False), 2: S.RKMil("Ito"), 3: S.RKMil("Stratonovich"), 4: S.EulerHeun(),
-           5: S.RKMilCommute("Ito"), 6: S.RKMilCommute("Stratonovich")}
+           5: S.RKMilCommute("Ito"), 6: S.RKMilCommute("Stratonovich"), **{7 + i: S.WangLi3SMil("ABCDEF"[i]) for i in range(6)}}
 
 
 class Case:

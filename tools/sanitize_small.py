@@ -11,7 +11,8 @@ def run(case, n=777, **kw):
                    moments=True, **case.solve_kwargs(), **kw)
 
 for case in (cases.c1(T=3.0), cases.c2(T=40.0), cases.c3(T=40.0), cases.c3(order0=2, T=40.0, alg=3), cases.c2(T=30.0, alg=4),
-             cases.c4(T=4.0), cases.sir(T=4.0, dt=0.02), cases.scalar_add(T=3.0), cases.hayes(T=2.0)):
+             cases.c4(T=4.0), cases.c4(T=2.0).with_(alg=5), cases.sir(T=4.0, dt=0.02), cases.scalar_add(T=3.0), cases.hayes(T=2.0),
+             cases.hayes(T=2.0, alg=9), cases.c2(T=25.0, alg=12)):
     sim = run(case)
     print(case.name, "ok", float(np.asarray(sim.out)[-1].mean()), flush=True)
 # supplied increments, per-trajectory parameters, several waves, device output, quantiles
@@ -27,3 +28,9 @@ ea = S.EnsembleB200(device=0, lanes_per_traj=4)
 c4 = cases.c4(T=2.0)
 simc = S.solve(S.EnsembleProblem(c4.problem()), S.EM(), ea, trajectories=333, seed=3, **c4.solve_kwargs())
 print("coop ok", flush=True)
+# launch geometry: full CTAs + a tail round, and a wave that ends inside a warp (in-kernel Philox: the production path)
+case = cases.c2(T=20.0)
+for n in (148 * 1024 + 1500, 2 * 148 * 1024, 1025, 63):
+    sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), trajectories=n, seed=5,
+                  moments=True, **case.solve_kwargs())
+    print("geometry ok", n, sim.timing["waves"], flush=True)
