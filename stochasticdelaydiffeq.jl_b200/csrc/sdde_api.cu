@@ -846,6 +846,7 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     A.ring_pitch = tpitch;
     A.slot_bytes = (long long)NS * tpitch * 8;
     A.rng_tab = (const double2 *)c->rng_tab.p;
+    A.ring_bytes = (long long)S.ring_slots * NS * pitch * 8;
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
     A.n_saved = NSAVED;
@@ -908,13 +909,13 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
         A.n_traj = nt;
         A.traj_gid0 = d->traj_offset + off;
         if (out_dev) {
-            A.out = zero_copy ? out_mapped : out; A.out_pitch = OP; A.out_off = off;
+            A.out = zero_copy ? out_mapped : out; A.out_pitch = OP; A.out_off = off; A.out_bytes = (long long)rows * OP * 8;
             A.out_vec_ok = ((OP % 4) == 0 && (off % 4) == 0 && ((uintptr_t)A.out % 16) == 0) ? 1 : 0;
             if (zero_copy) d2h += nt * 8 * rows;
         } else if (need_stage) {
             const int b = (d->want_paths && n_waves > 1) ? buf : 0;
             if (d->want_paths && w >= 2) CU_CHECK(cudaStreamWaitEvent(c->compute, c->ev_copied[b], 0));  // staging buffer free again
-            A.out = (double *)c->out[b].p; A.out_pitch = pitch; A.out_off = 0; A.out_vec_ok = 1;
+            A.out = (double *)c->out[b].p; A.out_pitch = pitch; A.out_off = 0; A.out_vec_ok = 1; A.out_bytes = (long long)rows * pitch * 8;
         } else {
             A.out = nullptr;
         }

@@ -97,6 +97,7 @@ struct KArgs {
     long long traj_gid0;     // global id of the wave's first trajectory
     const double2 *rng_tab;  // generator table in global memory (sdde_rng_tables.cuh), staged per CTA
     long long slot_bytes;    // one ring slot = NS * ring_pitch * 8 bytes
+    long long ring_bytes, out_bytes;   // extents of the ring and of `out` (bounds-checked builds, -DSDDE_CHECKED: every ring / out access traps when outside)
     int stage_order;         // K_ALG_WANGLI: the three stage operators in execution order, 2 bits each (0 drift, 1 Ito
                              // correction, 2 Stratonovich-Milstein diffusion), first stage in the low bits
     int n_full_ctas;         // CTAs [0, n_full_ctas) integrate BLOCK x TPT trajectories each, the remaining ("tail") CTAs
@@ -428,6 +429,17 @@ __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)
 // ------------------------------------------------------------------------------------------------
 // vector helpers: TPT adjacent trajectories per thread
 // ------------------------------------------------------------------------------------------------
+// -DSDDE_CHECKED: a verification build (compute-sanitizer is not available on the measurement pool): every ring and `out`
+// access of the step kernel is checked against the buffer extents and traps when outside (tools/sanitize_small.py)
+#ifdef SDDE_CHECKED
+#define SDDE_CHECK_RING(a, ptr, nbytes) do { const long long _o = (const char *)(ptr) - (const char *)(a).ring; \
+        if (_o < 0 || _o + (long long)(nbytes) > (a).ring_bytes) __trap(); } while (0)
+#define SDDE_CHECK_OUT(a, ptr, nbytes) do { const long long _o = (const char *)(ptr) - (const char *)(a).out; \
+        if (_o < 0 || _o + (long long)(nbytes) > (a).out_bytes) __trap(); } while (0)
+#else
+#define SDDE_CHECK_RING(a, ptr, nbytes) do { } while (0)
+#define SDDE_CHECK_OUT(a, ptr, nbytes) do { } while (0)
+#endif
 template <int TPT> __device__ __forceinline__ void ld_traj(const double *p, double (&v)[TPT]);
 template <> __device__ __forceinline__ void ld_traj<1>(const double *p, double (&v)[1]) { v[0] = *p; }
 template <> __device__ __forceinline__ void ld_traj<2>(const double *p, double (&v)[2]) {
@@ -503,7 +515,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                 const bool reuse = (recs[0].ring_mask & (0x100 << l)) != 0;    // lo(n) is hi(n-1) of the previous batch: in registers
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
-                    if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(phi - slot + j * jstride), xlo[0][l][j]);
+                    if (!reuse) { SDDE_CHECK_RING(a, phi - slot + j * jstride, 8 * TPT); ld_traj<TPT>(reinterpret_cast<const double *>(phi - slot + j * jstride), xlo[0][l][j]); }
                     else {
 #pragma unroll
                         for (int tt = 0; tt < TPT; ++tt) xlo[0][l][j][tt] = st.carry[l][j][tt];
@@ -514,6 +526,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
             for (int k = 0; k < BW; ++k)
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
+                    SDDE_CHECK_RING(a, phi + k * slot + j * jstride, 8 * TPT);
                     ld_traj<TPT>(reinterpret_cast<const double *>(phi + k * slot + j * jstride), xhi[k][l][j]);
                     if (FAST == K_FAST_INTERP && k > 0) {
 #pragma unroll
@@ -534,7 +547,8 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #endif
 #pragma unroll
                 for (int j = 0; j < NS; ++j) {
-                    if (!reuse) ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]);
+                    if (!reuse) { SDDE_CHECK_RING(a, plo + j * jstride, 8 * TPT); ld_traj<TPT>(reinterpret_cast<const double *>(plo + j * jstride), xlo[k][l][j]); }
+                    SDDE_CHECK_RING(a, phi + j * jstride, 8 * TPT);
                     ld_traj<TPT>(reinterpret_cast<const double *>(phi + j * jstride), xhi[k][l][j]);
                     if (reuse) {
 #pragma unroll
@@ -706,6 +720,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
             double v[TPT];
 #pragma unroll
             for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
+            SDDE_CHECK_RING(a, pst + j * jstride, 8 * TPT);
             st_traj<TPT>(reinterpret_cast<double *>(pst + j * jstride), v);
         }
     }
@@ -733,11 +748,11 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                     }
                     if (a.out && a.save_row[j] >= 0) {
                         double *op = a.out + ((long long)st.ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr0;
-                        if (out_vec) { if (tr0 <= last) st_traj<TPT>(op, v); }
+                        if (out_vec) { if (tr0 <= last) { SDDE_CHECK_OUT(a, op, 8 * TPT); st_traj<TPT>(op, v); } }
                         else {
 #pragma unroll
                             for (int tt = 0; tt < TPT; ++tt)
-                                if (tr0 + tt <= last) op[tt] = v[tt];
+                                if (tr0 + tt <= last) { SDDE_CHECK_OUT(a, op + tt, 8); op[tt] = v[tt]; }
                         }
                     }
                 }
@@ -803,6 +818,7 @@ __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solv
         double v[TPT];
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
+        SDDE_CHECK_RING(a, ringb + (long long)j * a.ring_pitch * 8, 8 * TPT);
         st_traj<TPT>(reinterpret_cast<double *>(ringb + (long long)j * a.ring_pitch * 8), v);
     }
 
@@ -818,11 +834,11 @@ __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solv
                     double v[TPT];
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt) v[tt] = st.u[tt][j];
-                    if (tr0 <= last) st_traj<TPT>(op, v);
+                    if (tr0 <= last) { SDDE_CHECK_OUT(a, op, 8 * TPT); st_traj<TPT>(op, v); }
                 } else {
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt)
-                        if (tr0 + tt <= last) op[tt] = st.u[tt][j];
+                        if (tr0 + tt <= last) { SDDE_CHECK_OUT(a, op + tt, 8); op[tt] = st.u[tt][j]; }
                 }
             }
         }
