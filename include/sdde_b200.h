@@ -66,7 +66,11 @@ enum { SDDE_ALG_EM_SPLIT = 0,      /* EM() == EM(true) */
        SDDE_ALG_WANGLI3SMIL_C = 9, /*   LOW confidence in the letter <-> order map, see DESIGN.md section 6 */
        SDDE_ALG_WANGLI3SMIL_D = 10,
        SDDE_ALG_WANGLI3SMIL_E = 11,
-       SDDE_ALG_WANGLI3SMIL_F = 12 };
+       SDDE_ALG_WANGLI3SMIL_F = 12,
+       SDDE_ALG_SRA1 = 13,         /* SRA1(), SRA3(), SOSRA() with adaptive=false (test/test_prob_sol.jl:74-87 runs them adaptively): */
+       SDDE_ALG_SRA3 = 14,         /*   Roessler's stochastic Runge-Kutta methods for ADDITIVE noise; a second increment dZ per step  */
+       SDDE_ALG_SOSRA = 15,        /*   (src/solve.jl:308-312), f at t + c0_i dt and g at t + c1_i dt with their own history lookups  */
+       SDDE_ALG_SRA_TABLEAU = 16 };/* SRA(tableau=...): sdde_desc.sra_tableau (SRA2, SOSRA2, ... as the caller's StochasticDiffEq builds them) */
 
 /* ---- built-in model zoo: the device-side replacement of the closures that
  *      src/functionwrapper.jl:8-9,35-36 builds around the user's f(u,h,p,t), g(u,h,p,t).
@@ -79,7 +83,9 @@ enum { SDDE_MODEL_LINEAR1 = 0,       /* du=(a u + b u(t-tau))dt + s u dW        
        SDDE_MODEL_SCALAR_ADD = 5,    /* test/events.jl:4-5  du=a u(t-tau)dt + b dW   p=(a,b)                   */
        SDDE_MODEL_USER_BASE = 1000 };
 
-/* ---- noise source: src/solve.jl:304-353 (WienerProcess vs prob.noise) ---- */
+/* ---- noise source: src/solve.jl:304-353 (WienerProcess vs prob.noise).  Channels per step: n_chan = n_state (diagonal
+ *      noise) or n_noise (noise matrix); the SRA algorithms use 2 n_chan rows per step, dW in [0, n_chan), dZ in
+ *      [n_chan, 2 n_chan) (NoiseGrid(t, W, Z)) ---- */
 enum { SDDE_NOISE_PHILOX = 0,        /* in-kernel Philox4x32-10 + float64 Box-Muller, dW = sqrt|dt_n| * xi          */
        SDDE_NOISE_SUPPLIED_DW = 1,   /* noise[n][c][traj] = increment of step n (already scaled)                    */
        SDDE_NOISE_SUPPLIED_GRID = 2  /* noise[n][c][traj] = W(t_n) on the schedule's own nodes n=0..N (NoiseGrid):  */
@@ -148,6 +154,11 @@ typedef struct sdde_desc {
     int64_t out_rows;                 /* capacity guard: rows (save points x saved states) the caller's out / moments buffers hold;
                                          0 = unchecked.  A solve that needs more rows fails with SDDE_ERR_BAD_DESC instead of
                                          writing past the buffers (e.g. save_everystep with a buffer sized for saveat). */
+    const double *sra_tableau;        /* SDDE_ALG_SRA_TABLEAU: [c0(s) | c1(s) | A0(s x s, row i = stage i) | B0(s x s) | alpha(s) | beta1(s) |
+                                         beta2(s)] of an explicit Roessler SRA tableau, s = sra_stages <= 3, at most 4 distinct stage
+                                         times ([EXT] StochasticDiffEq RosslerSRA fields c0, c1, A0', B0', alpha, beta1, beta2) */
+    int32_t sra_stages;
+    int32_t sra_order2;               /* 2 x alg_order of the tableau (discontinuity propagation depth); 0 = 4 ([EXT] alg_order 2//1) */
 } sdde_desc;
 
 /* Host-side schedule (trajectory independent): the replay of src/solve.jl:574-610 time stepping with

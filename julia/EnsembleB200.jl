@@ -84,6 +84,9 @@ Base.@kwdef mutable struct SddeDesc
     d_disc_order2::Ptr{Int32} = C_NULL
     n_d_disc::Int64 = 0
     out_rows::Int64 = 0
+    sra_tableau::Ptr{Float64} = C_NULL
+    sra_stages::Int32 = 0
+    sra_order2::Int32 = 0
 end
 
 Base.@kwdef mutable struct SddeSchedule
@@ -309,7 +312,20 @@ alg_id(a::RKMilCommute) = StochasticDiffEq.alg_interpretation(a) == :Ito ? Int32
 alg_id(::EulerHeun) = Int32(4)
 alg_id(::WangLi3SMil_A) = Int32(7); alg_id(::WangLi3SMil_B) = Int32(8); alg_id(::WangLi3SMil_C) = Int32(9)
 alg_id(::WangLi3SMil_D) = Int32(10); alg_id(::WangLi3SMil_E) = Int32(11); alg_id(::WangLi3SMil_F) = Int32(12)
-const B200Alg = Union{EM, RKMil, RKMilCommute, EulerHeun, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D, WangLi3SMil_E, WangLi3SMil_F}
+# Roessler SRA methods for additive noise, adaptive = false; the library holds SRA1 / SRA3 / SOSRA, any other explicit tableau
+# (SRA(), SRA2(), SOSRA2(), SRA(tableau = ...)) crosses the ABI as numbers: [c0 | c1 | A0 (row = stage) | B0 | alpha | beta1 | beta2]
+alg_id(::SRA1) = Int32(13); alg_id(::SRA3) = Int32(14); alg_id(::SOSRA) = Int32(15)
+alg_id(::Union{SRA, SRA2, SOSRA2}) = Int32(16)
+sra_tableau_of(a::SRA) = a.tableau
+sra_tableau_of(::SRA2) = StochasticDiffEq.constructSRA2()
+sra_tableau_of(::SOSRA2) = StochasticDiffEq.constructSOSRA2()
+function sra_flat(tab)                       # RosslerSRA stores A0', B0' (column = stage): Julia's column-major vec() of them IS the row-per-stage layout
+    s = length(tab.α)
+    s <= 3 || error("at most 3 SRA stages on this path")
+    return Float64[tab.c₀; tab.c₁; vec(tab.A₀); vec(tab.B₀); tab.α; tab.β₁; tab.β₂], Int32(s)
+end
+const B200Alg = Union{EM, RKMil, RKMilCommute, EulerHeun, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D, WangLi3SMil_E, WangLi3SMil_F,
+                      SRA, SRA1, SRA2, SRA3, SOSRA, SOSRA2}
 
 last_error() = unsafe_string(ccall((:sdde_b200_last_error, libsdde), Cstring, ()))
 check(rc) = rc == 0 || error("libsdde_b200 ($rc): " * last_error())
@@ -431,7 +447,13 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::B200Alg, 
         n_save_idxs = length(idxs), save_idxs = ntuple(i -> i <= length(idxs) ? idxs[i] : Int32(0), 8),
         d_disc_t = pointer(dd_t), d_disc_order2 = pointer(dd_o), n_d_disc = length(dd_t),
         seed = seed == 0 ? (prob.seed == 0 ? rand(UInt64) : prob.seed) : seed)                # src/solve.jl:302
-    GC.@preserve p u0 sv ts_user nz dd_t dd_o begin
+    sra_tab = Float64[]
+    if alg isa Union{SRA, SRA2, SOSRA2}
+        sra_tab, d.sra_stages = sra_flat(sra_tableau_of(alg))
+        d.sra_tableau = pointer(sra_tab)
+        d.sra_order2 = Int32(2 * StochasticDiffEq.alg_order(alg))
+    end
+    GC.@preserve p u0 sv ts_user nz dd_t dd_o sra_tab begin
         ts, _ = saved_times(d)                                  # the library's count: never recomputed on this side
         n_save = length(ts)
         d.out_rows = n_save * n_saved                           # the library refuses to write more rows than the buffers hold

@@ -28,6 +28,7 @@ class Desc(C.Structure):
         ("n_save_idxs", C.c_int32), ("save_idxs", C.c_int32 * 8), ("reserved1", C.c_int32),
         ("noise_t", C.c_void_p), ("n_noise_t", C.c_int64),
         ("d_disc_t", C.c_void_p), ("d_disc_order2", C.c_void_p), ("n_d_disc", C.c_int64), ("out_rows", C.c_int64),
+        ("sra_tableau", C.c_void_p), ("sra_stages", C.c_int32), ("sra_order2", C.c_int32),
     ]
 
 
@@ -48,7 +49,7 @@ def lib():
 
 def solve(model_id, alg, n_state, n_lag, n_noise, params, u0, h0, h1, lags, t0, tf, dt, saveat_times, n_save, *,
           save_start=True, save_end=True, save_everystep=False, order0=0, declared=True, n_traj=1, traj_offset=0,
-          seed=0, dW=None, noise_grid=None, n_threads=1, d_discontinuities=()):
+          seed=0, dW=None, noise_grid=None, n_threads=1, d_discontinuities=(), tableau=None):
     """-> (out[n_save, n_state, n_traj], status[n_traj], elapsed seconds, steps)."""
     d = Desc()
     d.struct_size = C.sizeof(Desc)
@@ -76,6 +77,11 @@ def solve(model_id, alg, n_state, n_lag, n_noise, params, u0, h0, h1, lags, t0, 
     dd_o = np.array([x[1] for x in dd], dtype=np.int32)
     if dd:
         d.d_disc_t, d.d_disc_order2, d.n_d_disc = dd_t.ctypes.data, dd_o.ctypes.data, len(dd)
+    if 13 <= alg <= 16:      # SRA family: the C++ restatement takes the coefficients from the Python oracle's table
+        import sdde_oracle as _O
+        tab = _O.sra_tableau(alg, tableau)
+        flat = tab.flat()
+        d.sra_tableau, d.sra_stages = flat.ctypes.data, tab.stages
     nz, nrows = None, 0
     if dW is not None:
         nz = np.ascontiguousarray(dW, dtype=np.float64); d.noise_mode = 1; nrows = nz.shape[0]

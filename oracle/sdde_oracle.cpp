@@ -168,11 +168,16 @@ typedef std::priority_queue<Disc, std::vector<Disc>, DiscLater> DiscHeap;
 // Returns number of steps taken.
 int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double *dW, int64_t n_steps_noise,
                   double *out, int64_t n_save_expected, uint8_t *status) {
-    const int ns = M.ns, nl = M.nl, nc = M.diag ? M.ns : M.nw;
+    const int alg = d->alg;
+    const bool sra = alg >= SDDE_ALG_SRA1 && alg <= SDDE_ALG_SRA_TABLEAU;      // two increments per channel and step: dW, dZ
+    const int nc1 = M.diag ? M.ns : M.nw, nc = sra ? 2 * nc1 : nc1;
+    const int ns = M.ns, nl = M.nl;
     const int64_t NT = d->n_traj;
     const double t0 = d->t0, tf = d->tf, dt = d->dt;
-    const int alg = d->alg;
-    const int alg_order2 = (alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMIL_STRAT) ? 2 : 1;
+    // [EXT] StochasticDiffEq.alg_order: EM, EulerHeun 1//2; RKMil, RKMilCommute, WangLi3SMil 1//1; SRA family 2//1
+    const int alg_order2 = sra ? (alg == SDDE_ALG_SRA_TABLEAU && d->sra_order2 > 0 ? d->sra_order2 : 4)
+                               : ((alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMIL_STRAT || alg == SDDE_ALG_RKMILC_ITO ||
+                                   alg == SDDE_ALG_RKMILC_STRAT || (alg >= SDDE_ALG_WANGLI3SMIL_A && alg <= SDDE_ALG_WANGLI3SMIL_F)) ? 2 : 1);
     double p[SDDE_MAX_PARAM];
     for (int i = 0; i < d->n_param; ++i) p[i] = d->param_stride ? d->params[i * d->param_stride + traj] : d->params[i];
     double u[SDDE_MAX_STATE], uprev[SDDE_MAX_STATE], u0[SDDE_MAX_STATE];
@@ -228,9 +233,9 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
 
     int64_t n = 0;
     double zc[4] = {0, 0, 0, 0}; uint64_t zcall = ~0ull;
-    double curW[SDDE_MAX_NOISE] = {0};
+    double curW[2 * SDDE_MAX_NOISE] = {0};
     if (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID) for (int c = 0; c < nc; ++c) curW[c] = dW[(int64_t)c * NT + traj];
-    double du[SDDE_MAX_STATE], K[SDDE_MAX_STATE], gv[SDDE_MAX_STATE * SDDE_MAX_NOISE], g2[SDDE_MAX_STATE], ut[SDDE_MAX_STATE], dw[SDDE_MAX_NOISE];
+    double du[SDDE_MAX_STATE], K[SDDE_MAX_STATE], gv[SDDE_MAX_STATE * SDDE_MAX_NOISE], g2[SDDE_MAX_STATE], ut[SDDE_MAX_STATE], dw[2 * SDDE_MAX_NOISE];
     while (!tst.empty()) {
         while (t < tst.top()) {
             // loopheader! / apply_step!: uprev <- u, dt_n <- min(dt, tstop - t), draw dW ~ N(0,|dt_n|)
@@ -254,7 +259,49 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
             tq = t;
             M.f(du, uprev, hcb, p, t);
             for (int j = 0; j < ns; ++j) K[j] = uprev[j] + dtn * du[j];
-            if (alg == SDDE_ALG_EULER_HEUN) {
+            if (sra) {
+                // [EXT] StochasticDiffEq SRAConstantCache (Roessler SRA, additive noise), tableau supplied by the caller
+                // (oracle/sdde_oracle.py holds the restated SRA1 / SRA3 / SOSRA coefficients): see solve_ensemble there.
+                const int S = d->sra_stages, nwv = M.diag ? 1 : M.nw, ng = M.diag ? ns : ns * M.nw;
+                const double *c0 = d->sra_tableau, *c1 = c0 + S, *A0 = c1 + S, *B0 = A0 + S * S, *al = B0 + S * S, *b1 = al + S, *b2 = b1 + S;
+                double chi2[SDDE_MAX_NOISE], fs[3][SDDE_MAX_STATE], gs[3][SDDE_MAX_STATE * SDDE_MAX_NOISE], H[SDDE_MAX_STATE];
+                for (int c = 0; c < nc1; ++c) chi2[c] = 0.5 * (dw[c] + dw[nc1 + c] / std::sqrt(3.0));
+                for (int i = 0; i < S; ++i) {
+                    for (int j = 0; j < ns; ++j) H[j] = uprev[j];
+                    if (i > 0) {
+                        double A[SDDE_MAX_STATE], B[SDDE_MAX_STATE * SDDE_MAX_NOISE];
+                        for (int j = 0; j < ns; ++j) A[j] = A0[i * S] * fs[0][j];
+                        for (int q = 0; q < ng; ++q) B[q] = B0[i * S] * gs[0][q];
+                        for (int jj = 1; jj < i; ++jj) {
+                            for (int j = 0; j < ns; ++j) A[j] = A[j] + A0[i * S + jj] * fs[jj][j];
+                            for (int q = 0; q < ng; ++q) B[q] = B[q] + B0[i * S + jj] * gs[jj][q];
+                        }
+                        for (int j = 0; j < ns; ++j) {
+                            double noise = B[j * nwv] * chi2[M.diag ? j : 0];
+                            for (int k = 1; k < nwv; ++k) noise = noise + B[j * nwv + k] * chi2[k];
+                            H[j] = (uprev[j] + dtn * A[j]) + noise;
+                        }
+                    }
+                    tq = t + c0[i] * dtn;
+                    M.f(fs[i], H, hcb, p, tq);
+                    tq = t + c1[i] * dtn;
+                    M.g(gs[i], H, hcb, p, tq);
+                }
+                tq = t;
+                for (int j = 0; j < ns; ++j) {
+                    double at = al[0] * fs[0][j];
+                    for (int i = 1; i < S; ++i) at = at + al[i] * fs[i][j];
+                    double bn = 0.0, en = 0.0;
+                    for (int k = 0; k < nwv; ++k) {
+                        double bt = b1[0] * gs[0][j * nwv + k], e2 = b2[0] * gs[0][j * nwv + k];
+                        for (int i = 1; i < S; ++i) { bt = bt + b1[i] * gs[i][j * nwv + k]; e2 = e2 + b2[i] * gs[i][j * nwv + k]; }
+                        const int c = M.diag ? j : k;
+                        bn = k == 0 ? bt * dw[c] : bn + bt * dw[c];
+                        en = k == 0 ? e2 * chi2[c] : en + e2 * chi2[c];
+                    }
+                    u[j] = ((uprev[j] + dtn * at) + bn) + en;
+                }
+            } else if (alg == SDDE_ALG_EULER_HEUN) {
                 // [EXT] EulerHeunConstantCache; second evaluation at t + dt
                 const int nwv = M.diag ? 1 : M.nw;
                 double g1[SDDE_MAX_STATE * SDDE_MAX_NOISE], gg2[SDDE_MAX_STATE * SDDE_MAX_NOISE], tmp[SDDE_MAX_STATE], f2[SDDE_MAX_STATE];

@@ -50,7 +50,80 @@ ALG_WANGLI_A, ALG_WANGLI_B, ALG_WANGLI_C, ALG_WANGLI_D, ALG_WANGLI_E, ALG_WANGLI
 # stage operators of WangLi3SMil_x in execution order: 'D' drift, 'C' Ito correction, 'M' Stratonovich-Milstein diffusion
 WANGLI_ORDER = {7: "DCM", 8: "DMC", 9: "CDM", 10: "CMD", 11: "MDC", 12: "MCD"}
 
-# [EXT] StochasticDiffEq.alg_order: EM 1//2, RKMil 1//1  (call site src/solve.jl:248)
+# SRA1(), SRA3(), SOSRA(), SRA(tableau=...) with adaptive=false: Roessler's stochastic Runge-Kutta methods for ADDITIVE noise
+# (the reference's smoke tests test/test_prob_sol.jl:74-87 run them adaptively; this path is fixed-step).  They draw a second
+# increment dZ per step (src/solve.jl:308-312): the noise array carries 2 n_chan rows per step, dW first, then dZ.
+ALG_SRA1, ALG_SRA3, ALG_SOSRA, ALG_SRA_TABLEAU = 13, 14, 15, 16
+SRA_ALGS = (ALG_SRA1, ALG_SRA3, ALG_SOSRA, ALG_SRA_TABLEAU)
+SRA_MAX_SETS = 4      # lookup sets per step in the schedule tables (distinct evaluation times, padded with t_n)
+
+
+@dataclass
+class SraTableau:
+    """[EXT] StochasticDiffEq RosslerSRA: c0, c1, A0[i][j] / B0[i][j] (stage i from earlier stage j), alpha, beta1, beta2."""
+    c0: tuple
+    c1: tuple
+    A0: tuple
+    B0: tuple
+    alpha: tuple
+    beta1: tuple
+    beta2: tuple
+
+    @property
+    def stages(self):
+        return len(self.alpha)
+
+    def flat(self):
+        """Layout of sdde_desc.sra_tableau: [c0 | c1 | A0 row-major | B0 row-major | alpha | beta1 | beta2]."""
+        out = list(self.c0) + list(self.c1)
+        for M in (self.A0, self.B0):
+            for row in M:
+                out += list(row)
+        return np.array(out + list(self.alpha) + list(self.beta1) + list(self.beta2), dtype=np.float64)
+
+    def stage_sets(self):
+        """Deduplicated evaluation times (set 0 = t_n itself) and the set each f / g evaluation uses."""
+        cset = [0.0]
+
+        def idx(c):
+            if c not in cset:
+                cset.append(c)
+            return cset.index(c)
+        fset, gset = [], []
+        for i in range(self.stages):              # first-seen order over f_0, g_0, f_1, g_1, ...
+            fset.append(idx(self.c0[i]))
+            gset.append(idx(self.c1[i]))
+        return cset, fset, gset
+
+
+# [EXT] constructSRA1 / constructSRA3 (Roessler 2010, strong order 1.5 for additive noise) and constructSOSRA (Rackauckas &
+# Nie 2018, stability-optimised; coefficients restated from memory -- the order conditions they must satisfy are checked
+# in tests/test_oracle.py)
+SRA_TABLEAUS = {
+    ALG_SRA1: SraTableau(c0=(0.0, 0.75), c1=(1.0, 0.0), A0=((0.0, 0.0), (0.75, 0.0)), B0=((0.0, 0.0), (1.5, 0.0)),
+                         alpha=(1.0 / 3.0, 2.0 / 3.0), beta1=(1.0, 0.0), beta2=(-1.0, 1.0)),
+    ALG_SRA3: SraTableau(c0=(0.0, 1.0, 0.5), c1=(1.0, 0.0, 0.0),
+                         A0=((0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.25, 0.25, 0.0)),
+                         B0=((0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (1.0, 0.5, 0.0)),
+                         alpha=(1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0), beta1=(1.0, 0.0, 0.0), beta2=(-1.0, 1.0, 0.0)),
+    ALG_SOSRA: SraTableau(c0=(0.0, 0.6923962376159507, 1.0), c1=(0.0, 0.041248171110700504, 1.0),
+                          A0=((0.0, 0.0, 0.0), (0.6923962376159507, 0.0, 0.0), (-3.1609142252828395, 4.1609142252828395, 0.0)),
+                          B0=((0.0, 0.0, 0.0), (1.3371632704399763, 0.0, 0.0), (1.442371048468624, 1.8632741501139225, 0.0)),
+                          alpha=(0.2889874966892885, 0.6859880440839937, 0.025024459226717772),
+                          beta1=(-16.792534242221663, 17.514995785380226, 0.27753845684143835),
+                          beta2=(0.4237535769069274, 0.6010381474428539, -1.0247917243497813)),
+}
+
+
+def sra_tableau(alg, tableau=None) -> SraTableau:
+    if alg == ALG_SRA_TABLEAU:
+        if tableau is None:
+            raise ValueError("ALG_SRA_TABLEAU needs a tableau")
+        return tableau
+    return SRA_TABLEAUS[alg]
+
+
+# [EXT] StochasticDiffEq.alg_order: EM 1//2, RKMil 1//1, SRA family 2//1  (call site src/solve.jl:248)
 ALG_ORDER = {
     ALG_EM_SPLIT: Fraction(1, 2),
     ALG_EM_NOSPLIT: Fraction(1, 2),
@@ -60,9 +133,10 @@ ALG_ORDER = {
     ALG_RKMILC_ITO: Fraction(1, 1),
     ALG_RKMILC_STRAT: Fraction(1, 1),
     **{a: Fraction(1, 1) for a in range(7, 13)},
+    **{a: Fraction(2, 1) for a in SRA_ALGS},
 }
 N_STAGE = {ALG_EM_SPLIT: 1, ALG_EM_NOSPLIT: 1, ALG_RKMIL_ITO: 1, ALG_RKMIL_STRAT: 1, ALG_EULER_HEUN: 2, ALG_RKMILC_ITO: 1,
-           ALG_RKMILC_STRAT: 1, **{a: 1 for a in range(7, 13)}}
+           ALG_RKMILC_STRAT: 1, **{a: 1 for a in range(7, 13)}, **{a: SRA_MAX_SETS for a in SRA_ALGS}}
 
 # lookup modes in the schedule tables
 LK_PRE = 0      # t < t0            -> user history h(p, t)
@@ -193,7 +267,8 @@ def _float_range(a: float, s: float, b: float) -> np.ndarray:
 
 def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_lags_declared=True,
                    saveat_times=(), save_start=True, save_end=True, save_everystep=False,
-                   tstops=(), neutral=False, maxsteps=50_000_000, d_discontinuities=()) -> Schedule:
+                   tstops=(), neutral=False, maxsteps=50_000_000, d_discontinuities=(), tableau=None,
+                   alg_order=None) -> Schedule:
     """Replay the reference's (trajectory-independent) time stepping in float64.
 
     Follows the queue construction of src/solve.jl:613-713 and the loop of src/solve.jl:574-610 with
@@ -204,7 +279,7 @@ def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_
     if not tf > t0:
         raise ValueError("only forward integration (tdir=+1) is supported on this path")
     lags = [float(x) for x in lags]
-    alg_order = ALG_ORDER[alg]
+    alg_order = ALG_ORDER[alg] if alg_order is None else Fraction(alg_order)
     order0 = Fraction(order_discontinuity_t0)
     if dt == 0.0 and len(tstops) == 0:
         # src/solve.jl:121-123
@@ -321,6 +396,12 @@ def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_
     N = len(dts)
     L = len(lags)
     NSTG = N_STAGE[alg]
+    stage_c = [float(sg) for sg in range(NSTG)]          # EulerHeun: sets at t_n and t_n + dt_n
+    if alg in SRA_ALGS:                                  # lookup set k at t_n + c_k dt_n, padded with t_n
+        cset, _, _ = sra_tableau(alg, tableau).stage_sets()
+        if len(cset) > SRA_MAX_SETS:
+            raise ValueError("the SRA tableau has more than 4 distinct stage times")
+        stage_c = cset + [0.0] * (SRA_MAX_SETS - len(cset))
     tarr = np.array(ts, dtype=np.float64)
     lk_mode = np.zeros((N, NSTG * L), dtype=np.int32)
     lk_idx = np.full((N, NSTG * L), -1, dtype=np.int64)
@@ -329,7 +410,7 @@ def build_schedule(t0, tf, dt, lags, alg, *, order_discontinuity_t0=0, constant_
     for k in range(N):
         tn = ts[k]
         for sg in range(NSTG):
-            tq = tn if sg == 0 else tn + dts[k]          # EulerHeun's second evaluation: f(tmp, p, t + dt)
+            tq = tn + stage_c[sg] * dts[k]               # EulerHeun's second evaluation: f(tmp, p, t + dt)
             for l, lag in enumerate(lags):
                 e = sg * L + l
                 tl = tq - lag
@@ -611,7 +692,7 @@ def _history_affine(h0, h1, t, nt):
 
 
 def solve_ensemble(model: Model, params, u0, h0, h1, lags, sched: Schedule, alg, dW, *,
-                   history_mode="dense", history_fn=None, return_dense=False):
+                   history_mode="dense", history_fn=None, return_dense=False, tableau=None):
     """Integrate ``n_traj`` trajectories with the supplied increments ``dW[n, c, traj]``.
 
     u0: [ns] or [ns, nt].  Returns (out[n_save, ns, nt], status[nt]) (+ dense [N+1, ns, nt]).
@@ -625,7 +706,8 @@ def solve_ensemble(model: Model, params, u0, h0, h1, lags, sched: Schedule, alg,
     N = sched.n_steps
     nt = dW.shape[2]
     ns, nl, m = model.n_state, model.n_lag, model.n_noise
-    assert dW.shape[0] >= N and dW.shape[1] == (ns if model.diagonal else m)
+    nc = ns if model.diagonal else m
+    assert dW.shape[0] >= N and dW.shape[1] == (2 * nc if alg in SRA_ALGS else nc)
     p = _as_params(params, nt)
     u0a = np.asarray(u0, dtype=np.float64)
     u = np.repeat(u0a[:, None], nt, axis=1).copy() if u0a.ndim == 1 else u0a.copy()
@@ -668,7 +750,48 @@ def solve_ensemble(model: Model, params, u0, h0, h1, lags, sched: Schedule, alg,
         dw = dW[n]
         fu = model.f(u, ul, p, t)
         K = u + dt * fu
-        if alg == ALG_EULER_HEUN:
+        if alg in SRA_ALGS:
+            # [EXT] StochasticDiffEq SRAConstantCache (perform_step! of sri/sra methods, additive noise).  With
+            # chi2 = (dW + dZ/sqrt(3))/2 = I_(1,0)/dt:
+            #   H_i = uprev + dt sum_{j<i} A0[i][j] f(H_j, t + c0_j dt) + (sum_{j<i} B0[i][j] g(H_j, t + c1_j dt)) chi2
+            #   u+  = uprev + dt sum_i alpha_i f_i + (sum_i beta1_i g_i) dW + (sum_i beta2_i g_i) chi2
+            # Through the SDDE wrappers (src/functionwrapper.jl:8-9,35-36) every f / g call looks its delayed states up at
+            # its own time argument, in the history that still ends at t_n.  (SRA1 has a hand-unrolled perform_step! in the
+            # reference: same quantities, sums associated differently -- rounding-level differences only.)
+            tab = sra_tableau(alg, tableau)
+            dwv, dz = dw[:nc], dw[nc:2 * nc]
+            chi2 = 0.5 * (dwv + dz / math.sqrt(3.0))
+
+            def times(G, w):                                          # G w: diagonal or matrix noise
+                if model.diagonal:
+                    return G * w
+                acc = G[:, 0, :] * w[0]
+                for j in range(1, m):
+                    acc = acc + G[:, j, :] * w[j]
+                return acc
+            fs, gs = [], []
+            for i in range(tab.stages):
+                H = u
+                if i > 0:
+                    A = tab.A0[i][0] * fs[0]
+                    B = tab.B0[i][0] * gs[0]
+                    for j in range(1, i):
+                        A = A + tab.A0[i][j] * fs[j]
+                        B = B + tab.B0[i][j] * gs[j]
+                    H = (u + dt * A) + times(B, chi2)
+                tf_ = t + tab.c0[i] * dt
+                tg_ = t + tab.c1[i] * dt
+                fs.append(model.f(H, [lookup(tf_ - float(lag)) for lag in lags], p, tf_))
+                gs.append(model.g(H, [lookup(tg_ - float(lag)) for lag in lags], p, tg_))
+            at = tab.alpha[0] * fs[0]
+            bt = tab.beta1[0] * gs[0]
+            e2 = tab.beta2[0] * gs[0]
+            for i in range(1, tab.stages):
+                at = at + tab.alpha[i] * fs[i]
+                bt = bt + tab.beta1[i] * gs[i]
+                e2 = e2 + tab.beta2[i] * gs[i]
+            unew = ((u + dt * at) + times(bt, dwv)) + times(e2, chi2)
+        elif alg == ALG_EULER_HEUN:
             # [EXT] EulerHeunConstantCache: the second f/g evaluation happens at t + dt, so its delayed states are
             # looked up at (t + dt) - tau in the history that still ends at t_n
             ul2 = [lookup((t + dt) - float(lag)) for lag in lags]

@@ -11,12 +11,12 @@ from .ensemble import (EnsembleB200, EnsembleSolution, EnsembleSummary, Schedule
                        solve, timepoint_meanvar, timeseries_steps_mean, timeseries_steps_meanvar, timeseries_steps_median,
                        timeseries_steps_quantile)
 from .problem import (EM, EulerHeun, AffineHistory, ConstantHistory, EnsembleProblem, FinalState, Model, MomentsReduction, RKMil, RKMilCommute,
-                      SaveIdxs, SDDEProblem, UserModel, WangLi3SMil, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D,
+                      SaveIdxs, SDDEProblem, SOSRA, SRA, SRA1, SRA3, UserModel, WangLi3SMil, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D,
                       WangLi3SMil_E, WangLi3SMil_F, hayes,
                       linear1, linsys, linsys_params, mackey_glass, scalar_add, sir)
 
 __all__ = [
-    "EM", "RKMil", "RKMilCommute", "EulerHeun", "WangLi3SMil", "WangLi3SMil_A", "WangLi3SMil_B", "WangLi3SMil_C", "WangLi3SMil_D",
+    "EM", "RKMil", "RKMilCommute", "EulerHeun", "SRA", "SRA1", "SRA3", "SOSRA", "WangLi3SMil", "WangLi3SMil_A", "WangLi3SMil_B", "WangLi3SMil_C", "WangLi3SMil_D",
     "WangLi3SMil_E", "WangLi3SMil_F", "FinalState", "SaveIdxs", "MomentsReduction", "SDDEProblem", "EnsembleProblem", "EnsembleB200", "EnsembleSolution", "solve", "schedule", "Schedule",
     "expand_saveat", "merge_moments", "pinned_empty", "shard_range", "timeseries_steps_meanvar", "timeseries_steps_mean",
     "timepoint_meanvar", "timeseries_steps_quantile", "timeseries_steps_median", "EnsembleSummary", "AffineHistory", "ConstantHistory", "Model", "UserModel", "linear1", "hayes", "mackey_glass",

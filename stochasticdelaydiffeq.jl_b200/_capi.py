@@ -14,6 +14,7 @@ SDDE_MAX_STATE, SDDE_MAX_LAG, SDDE_MAX_NOISE, SDDE_MAX_PARAM = 8, 4, 8, 128
 
 ALG_EM_SPLIT, ALG_EM_NOSPLIT, ALG_RKMIL_ITO, ALG_RKMIL_STRAT, ALG_EULER_HEUN, ALG_RKMILC_ITO, ALG_RKMILC_STRAT = 0, 1, 2, 3, 4, 5, 6
 ALG_WANGLI3SMIL_A = 7     # .. ALG_WANGLI3SMIL_F = 12
+ALG_SRA1, ALG_SRA3, ALG_SOSRA, ALG_SRA_TABLEAU = 13, 14, 15, 16
 MODEL_LINEAR1, MODEL_HAYES, MODEL_MACKEY_GLASS, MODEL_LINSYS, MODEL_SIR, MODEL_SCALAR_ADD = 0, 1, 2, 3, 4, 5
 MODEL_USER_BASE = 1000
 NOISE_PHILOX, NOISE_SUPPLIED_DW, NOISE_SUPPLIED_GRID = 0, 1, 2
@@ -41,6 +42,7 @@ class SddeDesc(C.Structure):
         ("n_save_idxs", C.c_int32), ("save_idxs", C.c_int32 * 8), ("reserved1", C.c_int32),
         ("noise_t", C.c_void_p), ("n_noise_t", C.c_int64),
         ("d_disc_t", C.c_void_p), ("d_disc_order2", C.c_void_p), ("n_d_disc", C.c_int64), ("out_rows", C.c_int64),
+        ("sra_tableau", C.c_void_p), ("sra_stages", C.c_int32), ("sra_order2", C.c_int32),
     ]
 
 

@@ -139,6 +139,7 @@ std::string build_schedule(const ScheduleInput &in, Schedule &S) {
     // History lookups: [EXT] HistoryFunction three regimes + LinearInterpolationData.
     // Stage 0 looks up t_n - tau (every f/g call of EM and RKMil); stage 1 (EulerHeun's second evaluation, at t + dt)
     // looks up (t_n + dt_n) - tau against the SAME dense history, which ends at t_n while the step is being taken.
+    // SRA tableaus: lookup set k at (t_n + c_k dt_n) - tau (the evaluation times of f / g, deduplicated by the caller).
     const int64_t N = n;
     const int NSTG = in.n_stage;
     S.n_stage = NSTG;
@@ -150,7 +151,8 @@ std::string build_schedule(const ScheduleInput &in, Schedule &S) {
     for (int64_t k = 0; k < N; ++k) {
         const double tn = S.t[(size_t)k];
         for (int sg = 0; sg < NSTG; ++sg) {
-            const double tq = sg == 0 ? tn : tn + S.dt[(size_t)k];
+            const double cs = in.stage_c.empty() ? (double)sg : in.stage_c[(size_t)sg];
+            const double tq = cs == 0.0 ? tn : (cs == 1.0 ? tn + S.dt[(size_t)k] : tn + cs * S.dt[(size_t)k]);
             for (int l = 0; l < L; ++l) {
                 const double tl = tq - in.lags[(size_t)l];
                 const size_t e = ((size_t)k * NSTG + sg) * L + l;

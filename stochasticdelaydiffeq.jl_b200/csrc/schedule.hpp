@@ -26,6 +26,7 @@ struct ScheduleInput {
     std::vector<double> lags;
     int alg_order2 = 1;                 // 2*alg_order: EM 1, RKMil 2, EulerHeun 1  ([EXT] StochasticDiffEq.alg_order)
     int n_stage = 1;                    // history lookup times per step: stage 0 at t_n, stage 1 at t_n + dt_n (EulerHeun)
+    std::vector<double> stage_c;        // lookup set k is taken at t_n + stage_c[k] dt_n; empty = {0, 1, ...} (EulerHeun: {0, 1})
     int order_discontinuity_t0 = 0;
     bool constant_lags_declared = true;
     bool neutral = false;

@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "rng_table.hpp"
+#include "sra_tableau.hpp"
 #include "sdde_internal.cuh"
 #include "sdde_dispatch.cuh"
 
@@ -133,13 +134,21 @@ cudaError_t sdde_launch_merge_moments(cudaStream_t stream, const double *src, lo
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+inline bool is_sra(int alg) { return alg >= SDDE_ALG_SRA1 && alg <= SDDE_ALG_SRA_TABLEAU; }
+
 int check_desc(const sdde_desc *d) {
     if (!d) return fail(SDDE_ERR_BAD_DESC, "descriptor is NULL");
     if (d->struct_size != (int32_t)sizeof(sdde_desc))
         return fail(SDDE_ERR_BAD_DESC, "sdde_desc.struct_size = %d, library expects %d (ABI mismatch)", d->struct_size,
                     (int)sizeof(sdde_desc));
-    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_WANGLI3SMIL_F)
-        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / RKMilCommute / EulerHeun / WangLi3SMil, fixed step)", d->alg);
+    if (d->alg < SDDE_ALG_EM_SPLIT || d->alg > SDDE_ALG_SRA_TABLEAU)
+        return fail(SDDE_ERR_UNSUPPORTED, "algorithm %d is not on this path (EM / RKMil / RKMilCommute / EulerHeun / WangLi3SMil / SRA, fixed step)", d->alg);
+    if (is_sra(d->alg)) {
+        sdde::SraHost tab;
+        const std::string err = sdde::sra_resolve(d->alg, d->sra_tableau, d->sra_stages, tab);
+        if (!err.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", err.c_str());
+        if (d->n_lag * SDDE_SRA_MAX_SETS > 8) return fail(SDDE_ERR_UNSUPPORTED, "the SRA kernels take at most 2 lags");
+    }
     if (d->n_lag < 1 || d->n_lag > SDDE_MAX_LAG) return fail(SDDE_ERR_BAD_DESC, "n_lag = %d out of range", d->n_lag);
     if (d->n_state < 1 || d->n_state > SDDE_MAX_STATE) return fail(SDDE_ERR_BAD_DESC, "n_state = %d out of range", d->n_state);
     if (d->n_noise < 1 || d->n_noise > SDDE_MAX_NOISE) return fail(SDDE_ERR_BAD_DESC, "n_noise = %d out of range", d->n_noise);
@@ -182,6 +191,10 @@ std::string schedule_key(const sdde_desc *d) {
     if (d->n_tstops > 0) add(d->tstops, sizeof(double) * (size_t)d->n_tstops);
     add(&d->n_d_disc, sizeof(d->n_d_disc));
     if (d->n_d_disc > 0) { add(d->d_disc_t, sizeof(double) * (size_t)d->n_d_disc); add(d->d_disc_order2, sizeof(int32_t) * (size_t)d->n_d_disc); }
+    if (d->alg == SDDE_ALG_SRA_TABLEAU && d->sra_tableau && d->sra_stages >= 1 && d->sra_stages <= 3) {   // stage times and order shape the schedule
+        add(&d->sra_stages, sizeof(d->sra_stages)); add(&d->sra_order2, sizeof(d->sra_order2));
+        add(d->sra_tableau, sizeof(double) * (size_t)(2 * d->sra_stages));
+    }
     return k;
 }
 
@@ -192,6 +205,15 @@ int make_schedule(const sdde_desc *d, sdde::Schedule &S) {
     in.alg_order2 = (d->alg == SDDE_ALG_RKMIL_ITO || d->alg == SDDE_ALG_RKMIL_STRAT || d->alg == SDDE_ALG_RKMILC_ITO ||
                      d->alg == SDDE_ALG_RKMILC_STRAT || d->alg >= SDDE_ALG_WANGLI3SMIL_A) ? 2 : 1;   // [EXT] alg_order: RKMil, RKMilCommute, WangLi3SMil 1//1; EM, EulerHeun 1//2
     in.n_stage = d->alg == SDDE_ALG_EULER_HEUN ? 2 : 1;
+    if (is_sra(d->alg)) {
+        // lookup set k at t_n + cset[k] dt_n: the deduplicated evaluation times of the tableau's f and g calls (unused sets repeat t_n)
+        sdde::SraHost tab;
+        const std::string terr = sdde::sra_resolve(d->alg, d->sra_tableau, d->sra_stages, tab);
+        if (!terr.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", terr.c_str());
+        in.alg_order2 = (d->alg == SDDE_ALG_SRA_TABLEAU && d->sra_order2 > 0) ? d->sra_order2 : tab.order2;
+        in.n_stage = SDDE_SRA_MAX_SETS;
+        in.stage_c.assign(tab.cset, tab.cset + SDDE_SRA_MAX_SETS);
+    }
     in.order_discontinuity_t0 = d->order_discontinuity_t0;
     in.constant_lags_declared = d->constant_lags_declared != 0;
     if (d->n_saveat > 0) in.saveat.assign(d->saveat, d->saveat + d->n_saveat);
@@ -266,6 +288,7 @@ static int wangli_stage_order(int alg) {
 }
 
 int select_kernel(sdde_ctx *ctx, const sdde_desc *d, sdde::KernelInfo &k) {
+    if (is_sra(d->alg)) return select_kernel_alg(ctx, d, sdde::K_ALG_SRA, k);
     if (d->alg >= SDDE_ALG_WANGLI3SMIL_A) {
         const int rc = select_kernel_alg(ctx, d, sdde::K_ALG_WANGLI, k);
         if (rc == SDDE_OK && !k.diag) return fail(SDDE_ERR_UNSUPPORTED, "WangLi3SMil is implemented for diagonal noise only");
@@ -336,6 +359,9 @@ int select_kernel_alg(sdde_ctx *ctx, const sdde_desc *d, int alg, sdde::KernelIn
         if ((alg == SDDE_ALG_RKMIL_ITO || alg == SDDE_ALG_RKMIL_STRAT))
             return fail(SDDE_ERR_UNSUPPORTED, "RKMil requires diagonal noise (model %d has a non-diagonal noise matrix)",
                         d->model_id);
+        if (alg == sdde::K_ALG_SRA)
+            return fail(SDDE_ERR_UNSUPPORTED, "SRA1 / SRA3 / SOSRA / SRA(tableau) need additive noise: built-in models hayes and scalar_add, "
+                        "or a compiled user model (model %d has no SRA kernel)", d->model_id);
         if (alg == sdde::K_ALG_WANGLI)
             return fail(SDDE_ERR_UNSUPPORTED, "WangLi3SMil is implemented for diagonal noise only (model %d has a noise matrix)", d->model_id);
         return fail(SDDE_ERR_UNSUPPORTED, "no kernel for model %d shape (%d states, %d lags, %d noise) alg %d", d->model_id,
@@ -850,7 +876,17 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     A.n_steps = (int)N; A.n_saves = (int)n_save; A.ring_slots = S.ring_slots; A.chunk_steps = chunk; A.batch = batch;
     A.noise_kind = d->noise_mode;
     A.n_saved = NSAVED;
-    A.stage_order = d->alg >= SDDE_ALG_WANGLI3SMIL_A ? wangli_stage_order(d->alg) : 0;
+    A.stage_order = (d->alg >= SDDE_ALG_WANGLI3SMIL_A && d->alg <= SDDE_ALG_WANGLI3SMIL_F) ? wangli_stage_order(d->alg) : 0;
+    if (is_sra(d->alg)) {
+        sdde::SraHost tab;
+        sdde::sra_resolve(d->alg, d->sra_tableau, d->sra_stages, tab);     // validated by check_desc
+        A.sra.s = tab.s;
+        for (int i = 0; i < 3; ++i) {
+            A.sra.fset[i] = tab.fset[i]; A.sra.gset[i] = tab.gset[i]; A.sra.c0[i] = tab.c0[i]; A.sra.c1[i] = tab.c1[i];
+            A.sra.alpha[i] = tab.alpha[i]; A.sra.beta1[i] = tab.beta1[i]; A.sra.beta2[i] = tab.beta2[i];
+            for (int j = 0; j < 3; ++j) { A.sra.A0[i][j] = tab.A0[i][j]; A.sra.B0[i][j] = tab.B0[i][j]; }
+        }
+    }
     A.prefetch = (S.min_gap >= 1) ? 1 : 0;
     for (int j = 0; j < SDDE_K_MAX_STATE; ++j) A.save_row[j] = d->n_save_idxs > 0 ? -1 : (j < NS ? j : -1);
     for (int i = 0; i < d->n_save_idxs; ++i) A.save_row[d->save_idxs[i]] = i;

@@ -24,7 +24,7 @@ struct KernelInfo {
 template <class M, int ALG, int NOISE, bool PT>
 inline KernelInfo make_info(const char *name) {
     KernelInfo k;
-    constexpr int BB = (alg_stages(ALG) > 1 && Tune<M>::B > 1) ? Tune<M>::B / 2 : Tune<M>::B;   // two lookup sets per step
+    constexpr int BB = alg_batch(ALG, Tune<M>::B);   // several lookup sets per step: shallower batches
     k.fn = (const void *)&sdde_solve_kernel<M, ALG, NOISE, PT, Tune<M>::TPT, BB>;
     k.block = Tune<M>::BLOCK;
     k.min_ctas = TuneK<M, ALG>::MINB;
@@ -32,7 +32,7 @@ inline KernelInfo make_info(const char *name) {
     k.batch = BB;
     k.n_stage = alg_stages(ALG);
     k.rec_size = (int)sizeof(StepRec<M::NL * alg_stages(ALG)>);
-    k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = M::DIAG ? M::NS : M::NW; k.n_param = M::NP;
+    k.n_state = M::NS; k.n_lag = M::NL; k.n_noise = M::NW; k.n_chan = (M::DIAG ? M::NS : M::NW) * alg_noise_mult(ALG); k.n_param = M::NP;
     k.diag = M::DIAG;
     k.name = name;
     return k;
@@ -65,6 +65,18 @@ inline KernelInfo make_coop_info(const char *name) {
         SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_STRAT)                \
         SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
         SDDE_SEL_ALG(M, NAME, K_ALG_WANGLI)                     \
+        return KernelInfo();                                    \
+    }
+// diagonal-noise models whose g can be additive (u-independent): the above + the SRA tableau kernel
+#define SDDE_DEFINE_SELECT_DIAG_SRA(FUNC, M, NAME)              \
+    KernelInfo FUNC(int alg, int noise, bool ptraj) {           \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EM_SPLIT)                   \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EM_NOSPLIT)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_ITO)                  \
+        SDDE_SEL_ALG(M, NAME, K_ALG_RKMIL_STRAT)                \
+        SDDE_SEL_ALG(M, NAME, K_ALG_EULER_HEUN)                 \
+        SDDE_SEL_ALG(M, NAME, K_ALG_WANGLI)                     \
+        SDDE_SEL_ALG(M, NAME, K_ALG_SRA)                        \
         return KernelInfo();                                    \
     }
 // noise-matrix models: EM, EulerHeun, RKMilCommute ([EXT] RKMil itself requires diagonal noise)

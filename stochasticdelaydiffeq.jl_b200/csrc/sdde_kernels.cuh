@@ -31,9 +31,19 @@ enum { K_LK_PRE = 0, K_LK_EXACT = 1, K_LK_INTERP = 2 };
 enum { K_NOISE_PHILOX = 0, K_NOISE_DW = 1, K_NOISE_GRID = 2 };
 enum { K_ALG_EM_SPLIT = 0, K_ALG_EM_NOSPLIT = 1, K_ALG_RKMIL_ITO = 2, K_ALG_RKMIL_STRAT = 3, K_ALG_EULER_HEUN = 4,
        K_ALG_RKMILC_ITO = 5, K_ALG_RKMILC_STRAT = 6,     // RKMilCommute on a noise MATRIX (diagonal models run it as RKMil)
-       K_ALG_WANGLI = 7 };                               // WangLi3SMil_A..F: one kernel, the stage order is a run-time argument
-// history lookup times per step: EulerHeun evaluates f and g a second time at t + dt
-__host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULER_HEUN ? 2 : 1; }
+       K_ALG_WANGLI = 7,                                 // WangLi3SMil_A..F: one kernel, the stage order is a run-time argument
+       K_ALG_SRA = 8 };                                  // SRA1 / SRA3 / SOSRA / any Roessler SRA tableau (additive noise): one
+                                                         // kernel, the tableau is a run-time argument (KArgs::sra)
+// history lookup times per step: EulerHeun evaluates f and g a second time at t + dt; an SRA tableau evaluates f at
+// t + c0_i dt and g at t + c1_i dt -- up to SDDE_SRA_MAX_SETS distinct times per step (the host deduplicates them)
+#define SDDE_SRA_MAX_STAGES 3
+#define SDDE_SRA_MAX_SETS 4
+__host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULER_HEUN ? 2 : (alg == K_ALG_SRA ? SDDE_SRA_MAX_SETS : 1); }
+// normals per noise channel and step: the SRA methods draw a second, independent increment dZ (W.dZ of
+// /root/reference/src/solve.jl:308-312 `alg_needs_extra_process`); channels [0, NC) are dW, [NC, 2 NC) are dZ
+__host__ __device__ constexpr int alg_noise_mult(int alg) { return alg == K_ALG_SRA ? 2 : 1; }
+// batch depth a kernel is compiled with: multi-stage algorithms hold one node set per lookup time and step
+__host__ __device__ constexpr int alg_batch(int alg, int b) { return alg_stages(alg) >= 3 ? 1 : ((alg_stages(alg) > 1 && b > 1) ? b / 2 : b); }
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
@@ -83,6 +93,16 @@ struct StepRec {
     } lk[NL];
 };
 
+// Roessler SRA tableau (additive noise) as the kernel sees it: stage i evaluates f with the delayed states of lookup set
+// fset[i] at t + c0[i] dt and g with those of set gset[i] at t + c1[i] dt
+struct SraTab {
+    int s;                                       // stages (1 .. SDDE_SRA_MAX_STAGES)
+    int fset[SDDE_SRA_MAX_STAGES], gset[SDDE_SRA_MAX_STAGES];
+    double c0[SDDE_SRA_MAX_STAGES], c1[SDDE_SRA_MAX_STAGES];
+    double A0[SDDE_SRA_MAX_STAGES][SDDE_SRA_MAX_STAGES], B0[SDDE_SRA_MAX_STAGES][SDDE_SRA_MAX_STAGES];   // [stage i][earlier stage j]
+    double alpha[SDDE_SRA_MAX_STAGES], beta1[SDDE_SRA_MAX_STAGES], beta2[SDDE_SRA_MAX_STAGES];
+};
+
 struct KArgs {
     const unsigned char *steps;
     const SaveRec *saves;
@@ -112,6 +132,7 @@ struct KArgs {
     double hist_c0[SDDE_K_MAX_STATE], hist_c1[SDDE_K_MAX_STATE];
     double u0c[SDDE_K_MAX_STATE];
     double p[SDDE_K_MAX_PARAM];
+    SraTab sra;              // K_ALG_SRA only
 };
 
 // tuning knobs per model shape
@@ -294,9 +315,96 @@ struct RegParams {
 // ------------------------------------------------------------------------------------------------
 template <class M, int ALG, class P>
 __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)[alg_stages(ALG)][M::NL][M::NS], const P &p,
-                                         double t, double dt, double sq, double isq, const double *dw, int stage_order = 0) {
+                                         double t, double dt, double sq, double isq, const double *dw, int stage_order = 0,
+                                         const SraTab *sra = nullptr) {
     constexpr int NS = M::NS;
     const double (&ul)[M::NL][M::NS] = uls[0];
+    if constexpr (ALG == K_ALG_SRA) {
+        // [EXT] StochasticDiffEq SRAConstantCache (Roessler's SRA methods for additive noise; reference smoke tests
+        // test/test_prob_sol.jl:74-87 run them adaptively -- here adaptive=false).  With chi2 = (dW + dZ/sqrt(3))/2 = I_(1,0)/dt:
+        //   H_i = u + dt sum_{j<i} A0[i][j] f_j + (sum_{j<i} B0[i][j] g_j) chi2,   f_j = f(H_j, t + c0_j dt),  g_j = g(H_j, t + c1_j dt)
+        //   u+  = u + dt sum_i alpha_i f_i + (sum_i beta1_i g_i) dW + (sum_i beta2_i g_i) chi2
+        // Through the SDDE wrappers (src/functionwrapper.jl:8-9,35-36) every f / g evaluation looks the delayed states up at
+        // ITS OWN time: the host deduplicates the stage times into lookup sets, `fset` / `gset` say which set an evaluation uses.
+        constexpr int NL = M::NL, NW = M::DIAG ? 1 : M::NW, NC = M::DIAG ? NS : M::NW, NG = M::DIAG ? NS : NS * M::NW;
+        const double *dz = dw + NC;
+        double chi2[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) chi2[c] = 0.5 * (dw[c] + dz[c] * 0.57735026918962573);   // reference: dZ / sqrt(3) (1 ulp apart)
+        double fs[SDDE_SRA_MAX_STAGES][NS], gs[SDDE_SRA_MAX_STAGES][NG];
+#pragma unroll
+        for (int i = 0; i < SDDE_SRA_MAX_STAGES; ++i) {
+            if (i < sra->s) {                                  // warp-uniform
+                double H[NS];
+#pragma unroll
+                for (int j = 0; j < NS; ++j) H[j] = u[j];
+                if (i > 0) {
+                    double A[NS], B[NG];
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) A[j] = sra->A0[i][0] * fs[0][j];
+#pragma unroll
+                    for (int q = 0; q < NG; ++q) B[q] = sra->B0[i][0] * gs[0][q];
+#pragma unroll
+                    for (int jj = 1; jj < i; ++jj) {
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) A[j] = A[j] + sra->A0[i][jj] * fs[jj][j];
+#pragma unroll
+                        for (int q = 0; q < NG; ++q) B[q] = B[q] + sra->B0[i][jj] * gs[jj][q];
+                    }
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        double noise = B[j * NW] * chi2[M::DIAG ? j : 0];
+#pragma unroll
+                        for (int k = 1; k < NW; ++k) noise = noise + B[j * NW + k] * chi2[k];
+                        H[j] = (u[j] + dt * A[j]) + noise;
+                    }
+                }
+                double ulf[NL][NS], ulg[NL][NS];
+                const int sf = sra->fset[i], sg = sra->gset[i];
+#pragma unroll
+                for (int l = 0; l < NL; ++l)
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        double vf = uls[0][l][j], vg = uls[0][l][j];
+#pragma unroll
+                        for (int k = 1; k < SDDE_SRA_MAX_SETS; ++k) {
+                            vf = (sf == k) ? uls[k][l][j] : vf;
+                            vg = (sg == k) ? uls[k][l][j] : vg;
+                        }
+                        ulf[l][j] = vf; ulg[l][j] = vg;
+                    }
+                M::f(fs[i], H, ulf, p, t + sra->c0[i] * dt);
+                M::g(gs[i], H, ulg, p, t + sra->c1[i] * dt);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) fs[i][j] = 0.0;
+#pragma unroll
+                for (int q = 0; q < NG; ++q) gs[i][q] = 0.0;
+            }
+        }
+        double at[NS], bt[NG], e2[NG];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) at[j] = sra->alpha[0] * fs[0][j];
+#pragma unroll
+        for (int q = 0; q < NG; ++q) { bt[q] = sra->beta1[0] * gs[0][q]; e2[q] = sra->beta2[0] * gs[0][q]; }
+#pragma unroll
+        for (int i = 1; i < SDDE_SRA_MAX_STAGES; ++i) {
+            if (i < sra->s) {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) at[j] = at[j] + sra->alpha[i] * fs[i][j];
+#pragma unroll
+                for (int q = 0; q < NG; ++q) { bt[q] = bt[q] + sra->beta1[i] * gs[i][q]; e2[q] = e2[q] + sra->beta2[i] * gs[i][q]; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            double bn = bt[j * NW] * dw[M::DIAG ? j : 0], en = e2[j * NW] * chi2[M::DIAG ? j : 0];
+#pragma unroll
+            for (int k = 1; k < NW; ++k) { bn = bn + bt[j * NW + k] * dw[k]; en = en + e2[j * NW + k] * chi2[k]; }
+            u[j] = ((u[j] + dt * at[j]) + bn) + en;
+        }
+        return;
+    }
     if constexpr (ALG == K_ALG_WANGLI && M::DIAG) {
         // [EXT] StochasticDiffEq WangLi3SMil_A..F (three-stage Milstein methods of Wang & Li, diagonal noise; reference smoke
         // and convergence tests test/test_prob_sol.jl:50-61, test/analyticless_convergence_tests.jl:62-91).  LOW confidence
@@ -475,10 +583,10 @@ struct TrajState {
     u64 zcall;                // its call index
     u32 wn[TPT][4];           // Philox words of call wcall, computed one batch ahead (batched path): the 10-round
     u64 wcall;                // dependent chain then has no consumer inside the batch and hides under its FP64 work
-    double curW[TPT][NC];     // NoiseGrid mode: current W
+    double curW[TPT][2 * NC]; // NoiseGrid mode: current W (and Z for the algorithms that draw dZ)
     bool bad[TPT];
     int ks;                   // next SaveRec
-    double carry[M::NL * 2][NS][TPT];   // upper nodes of the previous step's lookups (consecutive steps share a node)
+    double carry[M::NL * SDDE_SRA_MAX_SETS][NS][TPT];   // upper nodes of the previous step's lookups (consecutive steps share a node)
 };
 
 // BW consecutive steps starting at global step index n (recs[0..BW)).  BW > 1: the delayed-state nodes of all BW
@@ -499,7 +607,7 @@ template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int BW, int FAST>
 __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRAJ> &st, const StepRec<M::NL * alg_stages(ALG)> *recs, int n,
                                           char *ringb, const double2 *ltab, long long tr0, long long last, bool out_vec,
                                           bool prefetch_next) {
-    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NSTG = alg_stages(ALG), NLK = NL * NSTG;
+    constexpr int NS = M::NS, NL = M::NL, NC = (M::DIAG ? M::NS : M::NW) * alg_noise_mult(ALG), NSTG = alg_stages(ALG), NLK = NL * NSTG;
     constexpr bool STATIC_RNG = (BW > 1) && ((BW * NC) % 4 == 0);   // batch start n*NC is then a multiple of 4 as well
     constexpr bool LEAN = FAST != K_FAST_NONE;
     typedef StepRec<NLK> Rec;
@@ -708,8 +816,8 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
         // perform_step!
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
-            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, isq, dw[tt], a.stage_order);
-            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, isq, dw[tt], a.stage_order);
+            if (PTRAJ) sde_step<M, ALG>(st.u[tt], ul[tt], st.preg[tt], tn, dtn, sq, isq, dw[tt], a.stage_order, &a.sra);
+            else sde_step<M, ALG>(st.u[tt], ul[tt], ConstParams{a.p}, tn, dtn, sq, isq, dw[tt], a.stage_order, &a.sra);
 #pragma unroll
             for (int j = 0; j < NS; ++j) useq[k + 1][tt][j] = st.u[tt][j];
         }
@@ -764,7 +872,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 
 template <class M, int ALG, int NOISE, bool PTRAJ, int TPT, int B>
 __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solve_kernel(const __grid_constant__ KArgs a) {
-    constexpr int NS = M::NS, NL = M::NL, NC = M::DIAG ? M::NS : M::NW, NP = M::NP, BLOCK = Tune<M>::BLOCK;
+    constexpr int NS = M::NS, NL = M::NL, NC = (M::DIAG ? M::NS : M::NW) * alg_noise_mult(ALG), NP = M::NP, BLOCK = Tune<M>::BLOCK;
     constexpr int TAB_BYTES = (NOISE == K_NOISE_PHILOX) ? SDDE_RNG_SMEM_BYTES(SDDE_RNG_COPIES) : 0;   // supplied noise: no generator table
     typedef StepRec<NL * alg_stages(ALG)> Rec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -805,7 +913,7 @@ __global__ void __launch_bounds__(Tune<M>::BLOCK, TuneK<M, ALG>::MINB) sdde_solv
     st.wcall = ~0ull;
     st.ks = 0;
 #pragma unroll
-    for (int l = 0; l < NL * 2; ++l)
+    for (int l = 0; l < NL * SDDE_SRA_MAX_SETS; ++l)
 #pragma unroll
         for (int j = 0; j < NS; ++j)
 #pragma unroll

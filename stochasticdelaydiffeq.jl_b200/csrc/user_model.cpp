@@ -13,7 +13,7 @@ namespace sdde {
 
 namespace {
 
-const int kAlgs = 8, kNoises = 3;
+const int kAlgs = 9, kNoises = 3;
 inline int variant_index(int alg, int noise, bool ptraj) { return (alg * kNoises + noise) * 2 + (ptraj ? 1 : 0); }
 
 std::string nvrtc_log(nvrtcProgram prog) {
@@ -122,11 +122,11 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
     if (!en.diag && alg == 7) { k = KernelInfo(); return true; }                 // WangLi3SMil: diagonal noise only
     const int v = variant_index(alg, noise, ptraj);
     if (!en.kernels[(size_t)v]) {
-        char expr[256];
+        char expr[320];
         snprintf(expr, sizeof(expr),
-                 "sdde::sdde_solve_kernel<sdde::UserModel, %d, %d, %s, sdde::Tune<sdde::UserModel>::TPT, %s>",
-                 alg, noise, ptraj ? "true" : "false",
-                 alg == 4 ? "(sdde::Tune<sdde::UserModel>::B > 1 ? sdde::Tune<sdde::UserModel>::B / 2 : 1)" : "sdde::Tune<sdde::UserModel>::B");
+                 "sdde::sdde_solve_kernel<sdde::UserModel, %d, %d, %s, sdde::Tune<sdde::UserModel>::TPT, "
+                 "sdde::alg_batch(%d, sdde::Tune<sdde::UserModel>::B)>",      // the batch depth depends on the algorithm
+                 alg, noise, ptraj ? "true" : "false", alg);
         std::vector<char> cubin;
         std::string lowered;
         if (!compile_one(en.source, expr, cubin, lowered, err)) return false;
@@ -143,10 +143,10 @@ bool UserModels::select(int model_id, int alg, int noise, bool ptraj, KernelInfo
     k.fn = en.kernels[(size_t)v];
     k.is_user = true;
     k.block = en.block; k.min_ctas = en.min_ctas;
-    k.tpt = en.tpt; k.batch = (alg == 4 && en.batch > 1) ? en.batch / 2 : en.batch;
-    k.n_stage = alg == 4 ? 2 : 1;
+    k.tpt = en.tpt; k.batch = alg_batch(alg, en.batch);
+    k.n_stage = alg_stages(alg);
     k.rec_size = 48 + 32 * en.nl * k.n_stage;
-    k.n_state = en.ns; k.n_lag = en.nl; k.n_noise = en.nw; k.n_chan = en.diag ? en.ns : en.nw; k.n_param = en.np;
+    k.n_state = en.ns; k.n_lag = en.nl; k.n_noise = en.nw; k.n_chan = (en.diag ? en.ns : en.nw) * alg_noise_mult(alg); k.n_param = en.np;
     k.diag = en.diag;
     k.name = en.name.c_str();
     return true;

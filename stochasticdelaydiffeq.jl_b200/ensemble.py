@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _capi as capi
-from .problem import (EM, EulerHeun, RKMil, WangLi3SMil, EnsembleProblem, FinalState, MomentsReduction, SaveIdxs, SDDEProblem, UserModel,
+from .problem import (EM, EulerHeun, RKMil, SRA, WangLi3SMil, EnsembleProblem, FinalState, MomentsReduction, SaveIdxs, SDDEProblem, UserModel,
                       _as_history)
 
 
@@ -129,11 +129,11 @@ class _Marshalled:
 def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_start, save_end, tstops, adaptive,
              n_traj, traj_offset, seed, p_batch, u0_batch, noise, noise_mode, noise_mem, out_mem, want_paths,
              want_moments, lanes_per_traj=0, save_idxs=None, noise_t=None, d_discontinuities=()) -> _Marshalled:
-    if not isinstance(alg, (EM, RKMil, EulerHeun, WangLi3SMil)):
-        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil, RKMilCommute, EulerHeun and WangLi3SMil_A-F, "
-                                  "fixed step)")
+    if not isinstance(alg, (EM, RKMil, EulerHeun, WangLi3SMil, SRA)):
+        raise NotImplementedError(f"{type(alg).__name__} is not on this path (EM, RKMil, RKMilCommute, EulerHeun, WangLi3SMil_A-F, "
+                                  "SRA1 / SRA3 / SOSRA / SRA(tableau), fixed step)")
     if adaptive is None:
-        adaptive = isinstance(alg, RKMil)      # [EXT] isadaptive(RKMil) = true, src/solve.jl:40
+        adaptive = isinstance(alg, (RKMil, SRA))      # [EXT] isadaptive(RKMil) = isadaptive(SRA1) = true, src/solve.jl:40
     if adaptive:
         raise NotImplementedError("adaptive stepping is outside this path: pass adaptive=False (RKMil is adaptive by "
                                   "default in the reference, src/solve.jl:40)")
@@ -142,6 +142,12 @@ def _marshal(prob: SDDEProblem, model, alg, *, dt, saveat, save_everystep, save_
     d = m.desc
     d.struct_size = C.sizeof(capi.SddeDesc)
     d.model_id, d.alg = model.model_id, alg.alg_id
+    if isinstance(alg, SRA):
+        flat, stages = alg.flat_tableau()
+        if flat is not None:
+            m.keep_extra = flat
+            d.sra_tableau, d.sra_stages = capi.np_ptr(flat).value, stages
+        d.sra_order2 = int(round(2 * alg.order))
     d.n_state, d.n_noise, d.n_lag, d.n_param = model.n_state, model.n_noise, model.n_lag, model.n_param
     if len(prob.lags) != model.n_lag:
         raise ValueError(f"model {model.name} looks up {model.n_lag} lag(s), problem declares {len(prob.lags)}")
@@ -637,8 +643,9 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
             nz = np.ascontiguousarray(nz, dtype=np.float64)
             noise_ptr = capi.np_ptr(nz).value
         keep.append(nz)
-        if nz.shape[1] != model.n_chan or nz.shape[2] != n_traj:
-            raise ValueError(f"supplied noise must have shape [n, {model.n_chan}, {n_traj}]")
+        n_rows = model.n_chan * getattr(alg, "noise_mult", 1)       # SRA: dW rows, then dZ rows
+        if nz.shape[1] != n_rows or nz.shape[2] != n_traj:
+            raise ValueError(f"supplied noise must have shape [n, {n_rows}, {n_traj}]")
 
     m = _marshal(base, model, alg, dt=dt, saveat=saveat, save_everystep=save_everystep, save_start=save_start,
                  save_end=save_end, tstops=tstops, adaptive=adaptive, n_traj=n_traj, traj_offset=gid0, seed=seed,
@@ -649,7 +656,8 @@ def solve(prob, alg, ensemblealg: EnsembleB200 | None = None, *, dt=0.0, traject
     d = m.desc
     skey = (d.alg, d.t0, d.tf, d.dt, tuple(d.lags[i] for i in range(d.n_lag)), d.order_discontinuity_t0,
             d.constant_lags_declared, d.save_start, d.save_end, d.save_everystep, m.keep[0].tobytes(), m.keep[1].tobytes(),
-            m.keep[2].tobytes(), m.keep[3].tobytes())
+            m.keep[2].tobytes(), m.keep[3].tobytes(), d.sra_order2,
+            m.keep_extra.tobytes() if getattr(m, "keep_extra", None) is not None else b"")
     if _sched_cache.get("key") != skey:
         sch = capi.SddeSchedule()
         capi.check(capi.lib().sdde_b200_schedule(C.byref(m.desc), C.byref(sch)))

@@ -106,6 +106,59 @@ class EulerHeun:
         return capi.ALG_EULER_HEUN
 
 
+@dataclass(frozen=True)
+class SRA:
+    """Roessler's stochastic Runge-Kutta methods for ADDITIVE noise, fixed step ([EXT] StochasticDiffEq ``SRA(tableau=...)``,
+    ``SRA1()``, ``SRA3()``, ``SOSRA()``; the reference's smoke tests test/test_prob_sol.jl:74-87 run them adaptively -- pass
+    ``adaptive=False`` here).  Strong order 1.5 when g does not depend on u.  Every step draws a second increment dZ
+    (src/solve.jl:308-312), so supplied noise has ``2 * n_chan`` rows per step: dW first, then dZ (``NoiseGrid(t, W, Z)``).
+    Every f / g evaluation of a stage looks its delayed states up at the stage's own time ``t + c dt``.
+
+    ``tableau`` = dict with ``c0, c1, A0, B0, alpha, beta1, beta2`` (``A0[i][j]``: weight of stage j in stage i; at most
+    3 stages and 4 distinct stage times); ``name`` selects a built-in one instead."""
+    name: str = "SRA1"
+    tableau: object = None
+    order: float = 2.0          # [EXT] alg_order of the SRA family (depth of the discontinuity propagation)
+
+    def __post_init__(self):
+        if self.tableau is None and self.name not in ("SRA1", "SRA3", "SOSRA"):
+            raise ValueError("built-in SRA tableaus: 'SRA1', 'SRA3', 'SOSRA' (pass tableau=... for another one)")
+
+    @property
+    def alg_id(self):
+        if self.tableau is not None:
+            return capi.ALG_SRA_TABLEAU
+        return {"SRA1": capi.ALG_SRA1, "SRA3": capi.ALG_SRA3, "SOSRA": capi.ALG_SOSRA}[self.name]
+
+    noise_mult = 2
+
+    def flat_tableau(self):
+        """-> (float64 array in the layout of sdde_desc.sra_tableau, stages) or (None, 0) for a built-in tableau."""
+        if self.tableau is None:
+            return None, 0
+        tb = self.tableau
+        s = len(tb["alpha"])
+        A0, B0 = np.asarray(tb["A0"], dtype=np.float64), np.asarray(tb["B0"], dtype=np.float64)
+        if A0.shape != (s, s) or B0.shape != (s, s) or any(len(tb[k]) != s for k in ("c0", "c1", "beta1", "beta2")):
+            raise ValueError("SRA tableau: c0, c1, alpha, beta1, beta2 need s entries, A0 and B0 s x s")
+        flat = np.concatenate([np.asarray(tb["c0"], dtype=np.float64), np.asarray(tb["c1"], dtype=np.float64), A0.ravel(), B0.ravel(),
+                               np.asarray(tb["alpha"], dtype=np.float64), np.asarray(tb["beta1"], dtype=np.float64),
+                               np.asarray(tb["beta2"], dtype=np.float64)])
+        return np.ascontiguousarray(flat), s
+
+
+def SRA1():
+    return SRA("SRA1")
+
+
+def SRA3():
+    return SRA("SRA3")
+
+
+def SOSRA():
+    return SRA("SOSRA")
+
+
 # ---------------------------------------------------------------------------------------------
 # model zoo handles: model.f / model.g are what the user passes as f and g
 # ---------------------------------------------------------------------------------------------

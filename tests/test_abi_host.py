@@ -381,6 +381,46 @@ def test_version_and_struct_guard_fields():
     assert hasattr(d, "out_pitch") and hasattr(d, "n_save_idxs") and len(d.save_idxs) == 8
 
 
+def test_randomised_sra_schedules_equal_oracle_bitwise():
+    """SRA1 / SRA3 / SOSRA / a caller's tableau: four lookup sets per step at t_n + c_k dt_n (the deduplicated stage times of
+    the tableau, padded with t_n), discontinuities tracked to order 2 ([EXT] alg_order of the SRA family): the product's
+    schedule equals the oracle's replay bit for bit on 60 random problems."""
+    rng = np.random.default_rng(1315)
+    custom = dict(c0=(0.0, 0.5), c1=(0.25, 1.0), A0=((0.0, 0.0), (0.5, 0.0)), B0=((0.0, 0.0), (1.0, 0.0)),
+                  alpha=(0.25, 0.75), beta1=(0.5, 0.5), beta2=(1.0, -1.0))
+    otab = O.SraTableau(**custom)
+    for trial in range(60):
+        nl = int(rng.integers(1, 3))
+        t0 = float(rng.choice([0.0, -1.5]))
+        T = float(rng.choice([1.0, 3.7, 10.0]))
+        dt = float(rng.choice([0.01, 0.05, 0.1, 2.0 ** -5, 0.03, 0.25]))
+        lags = sorted(float(x) for x in rng.choice([0.3, 0.5, 1.0, 1.7, 17.02 / 4, 0.05 * 7, 0.25], size=nl, replace=False))
+        dt = min(dt, min(lags) / float(rng.choice([1.0, 2.0])))          # src/solve.jl:581-585 guard; dt == tau allowed
+        alg = int(rng.choice([13, 14, 15, 16]))
+        order0 = int(rng.choice([0, 0, 1, 3]))
+        saveat = rng.choice([None, 0.5, 0.37])
+        saveat = None if saveat is None else float(saveat)
+        model = S.hayes if nl == 1 else S.linsys(2, 2, 1)
+        u0 = [1.0] * model.n_state
+        prob = S.SDDEProblem(model.f, model.g, u0 if model.n_state > 1 else 1.0, S.ConstantHistory(u0), (t0, t0 + T),
+                             np.zeros(model.n_param), constant_lags=tuple(lags), order_discontinuity_t0=order0)
+        palg = S.SRA(tableau=custom) if alg == 16 else cases.ALG_MAP[alg]
+        s = S.schedule(prob, palg, dt=dt, saveat=saveat, adaptive=False)
+        sv, ss, se = O.expand_saveat(saveat, t0, t0 + T)
+        o = O.build_schedule(t0, t0 + T, dt, lags, alg, order_discontinuity_t0=order0, saveat_times=sv, save_start=ss,
+                             save_end=se, save_everystep=saveat is None, tableau=otab if alg == 16 else None)
+        assert o.lk_mode.shape[1] == 4 * nl
+        for k in ["t", "dt", "sqdt", "lk_mode", "lk_idx", "lk_theta", "save_t", "save_step", "save_theta", "save_exact"]:
+            a, b = getattr(s, k), getattr(o, k)
+            assert a.shape == b.shape and np.array_equal(a, b), (trial, k, t0, T, dt, lags, alg, order0, saveat)
+        assert list(s.tstops_hit) == o.tstops_hit
+    with pytest.raises(S.SddeError, match="explicit"):
+        bad = dict(custom, A0=((0.0, 0.1), (0.5, 0.0)))
+        S.schedule(prob, S.SRA(tableau=bad), dt=0.01, adaptive=False)
+    with pytest.raises(NotImplementedError, match="adaptive"):
+        S.schedule(prob, S.SRA1(), dt=0.01)                   # [EXT] isadaptive(SRA1): the reference would step adaptively
+
+
 def test_randomised_schedules_equal_oracle_bitwise():
     """120 random (tspan, dt, lags, algorithm, order_discontinuity_t0, saveat) combinations: the product's C++ schedule
     builder and the oracle's Python replay agree on every bit of every table."""

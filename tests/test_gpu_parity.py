@@ -713,3 +713,74 @@ def test_wangli3smil_paths_match_oracle(alg):
         assert cases.scaled_err(sim.out, ref) < TOL, case.name
     with pytest.raises(S.SddeError, match="diagonal"):
         S.solve(S.EnsembleProblem(cases.c4(T=1.0).problem()), cases.ALG_MAP[alg], S.EnsembleB200(device=0), trajectories=64, dt=0.01)
+
+
+# ----------------------------------------------------------------------------------------------
+# SRA1 / SRA3 / SOSRA / SRA(tableau): Roessler's methods for additive noise, fixed step (test/test_prob_sol.jl:74-87)
+# ----------------------------------------------------------------------------------------------
+def _sra_noise(sch, nc, n, key=13):
+    """[n_steps, 2 nc, n]: dW rows, then dZ rows, both N(0, dt_n)."""
+    return cases.increments(sch, 2 * nc, n, key=key)
+
+
+SRA_CUSTOM = dict(c0=(0.0, 0.5), c1=(0.25, 1.0), A0=((0.0, 0.0), (0.5, 0.0)), B0=((0.0, 0.0), (1.0, 0.0)),
+                  alpha=(0.25, 0.75), beta1=(0.5, 0.5), beta2=(1.0, -1.0))
+
+
+@pytest.mark.parametrize("alg", [13, 14, 15, 16])
+def test_sra_paths_match_oracle(alg):
+    """Per-path parity under shared (dW, dZ): the reference's additive Hayes problem with a delayed term in g (beta != 0: g
+    is evaluated at t + c1 dt with its own history lookup), lag on the grid, off the grid (every stage interpolates) and
+    equal to dt (the t + dt stages read the node being left); and the additive scalar model of test/events.jl."""
+    import sdde_oracle as O
+    palg = S.SRA(tableau=SRA_CUSTOM) if alg == 16 else cases.ALG_MAP[alg]
+    otab = O.SraTableau(**SRA_CUSTOM) if alg == 16 else None
+    n = 700
+    for lag, dt, T in ((1.0, 2.0 ** -6, 3.0), (0.33, 0.05, 2.0), (0.05, 0.05, 1.0)):
+        case = cases.hayes(T=T, dt=dt, beta=0.6, saveat=0.25).with_(alg=alg, lags=[lag])
+        case.p = np.array([lag, -4.0, -2.0, 10.0, 0.0, 0.6, 0.1])
+        sv, ss, se = O.expand_saveat(0.25, 0.0, T)
+        sch = O.build_schedule(0.0, T, dt, [lag], alg, saveat_times=sv, save_start=ss, save_end=se, tableau=otab)
+        nz = _sra_noise(sch, 1, n)
+        sim = S.solve(S.EnsembleProblem(case.problem()), palg, S.EnsembleB200(device=0), trajectories=n,
+                      noise_increments=nz, dt=dt, saveat=0.25, adaptive=False)
+        ref, _ = O.solve_ensemble(case.omodel, case.p, case.u0, case.h0, case.h1, [lag], sch, alg, nz, tableau=otab)
+        assert np.array_equal(sim.t, sch.save_t)
+        assert "alg%d" % alg in sim.timing["kernel_name"]
+        assert cases.scaled_err(sim.out, ref) < TOL, (alg, lag)
+    case = cases.scalar_add(T=4.0).with_(alg=alg)
+    sv, ss, se = O.expand_saveat(0.5, 0.0, 4.0)
+    sch = O.build_schedule(0.0, 4.0, 0.01, case.lags, alg, saveat_times=sv, save_start=ss, save_end=se, tableau=otab)
+    nz = _sra_noise(sch, 1, 257)
+    sim = S.solve(S.EnsembleProblem(case.problem()), palg, S.EnsembleB200(device=0), trajectories=257, noise_increments=nz,
+                  dt=0.01, saveat=0.5, adaptive=False)
+    ref, _ = O.solve_ensemble(case.omodel, case.p, case.u0, case.h0, case.h1, case.lags, sch, alg, nz, tableau=otab)
+    assert cases.scaled_err(sim.out, ref) < TOL
+
+
+def test_sra_noise_grid_with_z_and_in_kernel_philox():
+    """NoiseGrid(t, W, Z) on the schedule's nodes reproduces the increment run; with in-kernel Philox the two increments of
+    step n are normals 2n and 2n + 1 of the trajectory's stream (the oracle draws the same stream)."""
+    import sdde_oracle as O
+    alg, n, T, dt = 13, 512, 2.0, 0.05
+    case = cases.hayes(T=T, dt=dt, beta=0.6, saveat=0.5).with_(alg=alg)
+    case.p = np.array([1.0, -4.0, -2.0, 10.0, 0.0, 0.6, 0.1])
+    sch = case.oracle_schedule()
+    nz = _sra_noise(sch, 1, n)
+    inc = S.solve(S.EnsembleProblem(case.problem()), S.SRA1(), S.EnsembleB200(device=0), trajectories=n, noise_increments=nz,
+                  **case.solve_kwargs())
+    WZ = np.concatenate([np.zeros((1, 2, n)), np.cumsum(nz, axis=0)], axis=0)
+    grid = S.solve(S.EnsembleProblem(case.problem()), S.SRA1(), S.EnsembleB200(device=0), trajectories=n, noise_grid=WZ,
+                   **case.solve_kwargs())
+    assert cases.scaled_err(grid.out, inc.out) < 1e-11           # W[n+1] - W[n] re-derives dW to rounding
+    seed = 0xB2000002
+    phx = S.solve(S.EnsembleProblem(case.problem()), S.SRA1(), S.EnsembleB200(device=0), trajectories=n, seed=seed,
+                  **case.solve_kwargs())
+    z = O.philox_normals(np.arange(n, dtype=np.uint64), sch.n_steps, 2, seed)
+    ref, _ = case.oracle(z * sch.sqdt[:, None, None])
+    assert cases.scaled_err(phx.out, ref) < 1e-11
+    with pytest.raises(ValueError, match=r"\[n, 2, "):
+        S.solve(S.EnsembleProblem(case.problem()), S.SRA1(), S.EnsembleB200(device=0), trajectories=n, noise_increments=nz[:, :1],
+                **case.solve_kwargs())
+    with pytest.raises(S.SddeError, match="additive"):
+        S.solve(S.EnsembleProblem(cases.c2(T=5.0).problem()), S.SRA1(), S.EnsembleB200(device=0), trajectories=64, dt=0.05, adaptive=False)

@@ -161,3 +161,35 @@ def test_user_model_history_argument_checks():
         S.SDDEProblem(um.f, um.g, [1.0, 0.5], 1.0, (0.0, 1.0), [1.0, 0.1], constant_lags=(0.5, 1.0))
     with pytest.raises(AttributeError):
         plain.h
+
+
+def test_user_model_additive_noise_with_sosra():
+    """A user model with additive (u-independent, time- and delay-dependent) noise under SOSRA: the NVRTC build of the SRA
+    kernel (four lookup sets per step, two increments per channel) against the oracle."""
+    src = r"""
+struct UserModel {
+    static constexpr int NS = 2, NL = 1, NW = 2, NP = 3;
+    static constexpr bool DIAG = true;
+    template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double t) {
+        du[0] = u[1];
+        du[1] = -p[0] * u[0] - p[1] * ul[0][0] + sin(t);
+    }
+    template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*ul)[NS], const P &p, double t) {
+        gv[0] = p[2];
+        gv[1] = p[2] * (1.0 + t) + 0.1 * ul[0][1];
+    }
+};
+"""
+    def g(u, ul, p, t):
+        return np.stack([p[2] + 0.0 * u[0], p[2] * (1.0 + t) + 0.1 * ul[0][1]])
+    um = S.UserModel(src, 2, 1, 2, 3, True, name="additive_oscillator")
+    om = O.Model(1000, 2, 1, 2, True, 3, _f, g)
+    p = [1.0, 0.5, 0.2]
+    prob = S.SDDEProblem(um.f, um.g, [1.0, 0.0], S.AffineHistory((1.0, 0.0), (0.1, 0.0)), (0.0, 3.0), p, constant_lags=(0.7,))
+    sv = O.expand_saveat(0.5, 0.0, 3.0)[0]
+    osch = O.build_schedule(0.0, 3.0, 0.02, [0.7], O.ALG_SOSRA, saveat_times=sv)
+    nz = cases.increments(osch, 4, 300)
+    sim = S.solve(S.EnsembleProblem(prob), S.SOSRA(), S.EnsembleB200(device=0), trajectories=300, noise_increments=nz, dt=0.02,
+                  saveat=0.5, adaptive=False)
+    ref, _ = O.solve_ensemble(om, p, [1.0, 0.0], [1.0, 0.0], [0.1, 0.0], [0.7], osch, O.ALG_SOSRA, nz)
+    assert cases.scaled_err(sim.out, ref) < 1e-12
