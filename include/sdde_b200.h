@@ -299,6 +299,10 @@ SDDE_API int sdde_b200_philox_normals(sdde_ctx *ctx, uint64_t seed, int64_t traj
                              int64_t n_steps, int32_t n_noise, double *out_host /* [n_steps][n_noise][n_traj] */);
 /* Host copy of the normal generator's lookup table (layout: csrc/sdde_rng_tables.cuh); needs no device.
  * out may be NULL to query *n_entries (double2 entries; out needs 2 * n_entries doubles). */
+/* The Roessler SRA tableau the library uses for alg = SDDE_ALG_SRA1 / SRA3 / SOSRA, in the layout of sdde_desc.sra_tableau
+ * (out holds 5 s + 2 s^2 <= 33 doubles): lets the caller's side compare it with its own StochasticDiffEq constructSRA1 /
+ * constructSRA3 / constructSOSRA before trusting a solve ([EXT] coefficients restated from memory, julia/replay_fixtures.jl). */
+SDDE_API int sdde_b200_sra_tableau(int32_t alg, double *out, int32_t *stages);
 SDDE_API int sdde_b200_rng_table(double *out, int64_t cap_doubles, int64_t *n_entries);
 SDDE_API int sdde_b200_dfma_peak(sdde_ctx *ctx, double *tflops);       /* measured FP64 FMA throughput of this GPU */
 SDDE_API int sdde_b200_hbm_peak(sdde_ctx *ctx, double *gbs);           /* measured device copy bandwidth (read+write) */

@@ -77,7 +77,7 @@ class SddeTiming(C.Structure):
 EXPORTS = [
     "sdde_b200_version", "sdde_b200_device_count", "sdde_b200_last_error", "sdde_b200_create", "sdde_b200_destroy",
     "sdde_b200_set_option", "sdde_b200_schedule", "sdde_b200_schedule_free", "sdde_b200_solve", "sdde_b200_solve_multi",
-    "sdde_b200_merge_moments", "sdde_b200_compile_model", "sdde_b200_philox_normals", "sdde_b200_dfma_peak",
+    "sdde_b200_merge_moments", "sdde_b200_compile_model", "sdde_b200_philox_normals", "sdde_b200_sra_tableau", "sdde_b200_dfma_peak",
     "sdde_b200_hbm_peak", "sdde_b200_alloc_pinned", "sdde_b200_free_pinned", "sdde_b200_quantiles",
     "sdde_b200_qsel_ranks", "sdde_b200_qsel_begin", "sdde_b200_qsel_local", "sdde_b200_qsel_apply", "sdde_b200_qsel_nan",
     "sdde_b200_qsel_end", "sdde_b200_moments", "sdde_b200_rng_table",
@@ -131,6 +131,7 @@ def lib():
     L.sdde_b200_solve_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(SddeDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sdde_b200_merge_moments.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.sdde_b200_compile_model.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32)]
+    L.sdde_b200_sra_tableau.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_int32)]
     L.sdde_b200_philox_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
     L.sdde_b200_quantiles.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p, _dp]

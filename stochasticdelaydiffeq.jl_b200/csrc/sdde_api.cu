@@ -617,6 +617,25 @@ void sdde_b200_schedule_free(sdde_schedule *s) {
     memset(s, 0, sizeof(*s));
 }
 
+int sdde_b200_sra_tableau(int32_t alg, double *out, int32_t *stages) {
+    if (!out || !stages) return fail(SDDE_ERR_BAD_DESC, "NULL output");
+    if (alg != SDDE_ALG_SRA1 && alg != SDDE_ALG_SRA3 && alg != SDDE_ALG_SOSRA) return fail(SDDE_ERR_BAD_DESC, "not a built-in SRA algorithm");
+    sdde::SraHost t;
+    const std::string err = sdde::sra_resolve(alg, nullptr, 0, t);
+    if (!err.empty()) return fail(SDDE_ERR_BAD_DESC, "%s", err.c_str());
+    const int s = t.s;
+    double *p = out;
+    for (int i = 0; i < s; ++i) *p++ = t.c0[i];
+    for (int i = 0; i < s; ++i) *p++ = t.c1[i];
+    for (int i = 0; i < s; ++i) for (int j = 0; j < s; ++j) *p++ = t.A0[i][j];
+    for (int i = 0; i < s; ++i) for (int j = 0; j < s; ++j) *p++ = t.B0[i][j];
+    for (int i = 0; i < s; ++i) *p++ = t.alpha[i];
+    for (int i = 0; i < s; ++i) *p++ = t.beta1[i];
+    for (int i = 0; i < s; ++i) *p++ = t.beta2[i];
+    *stages = s;
+    return SDDE_OK;
+}
+
 int sdde_b200_merge_moments(double *a, const double *b, int64_t n) {
     if (!a || !b || n < 0) return fail(SDDE_ERR_BAD_DESC, "bad arguments");
     for (int64_t i = 0; i < n; ++i) {

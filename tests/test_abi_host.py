@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "sdde_b200.h")).read()
     declared = sorted(set(re.findall(r"SDDE_API[^;(]*?\b(sdde_b200_\w+)\s*\(", hdr)))
-    assert declared == sorted(capi.EXPORTS) and len(declared) == 26
+    assert declared == sorted(capi.EXPORTS) and len(declared) == 27
     L = capi.lib()
     for name in declared:
         assert hasattr(L, name), name
@@ -379,6 +379,17 @@ def test_version_and_struct_guard_fields():
     assert L.sdde_b200_set_option(None, b"wave_traj", 1) == -1      # NULL context is rejected, not dereferenced
     d = capi.SddeDesc()
     assert hasattr(d, "out_pitch") and hasattr(d, "n_save_idxs") and len(d.save_idxs) == 8
+
+
+def test_builtin_sra_tableaus_equal_the_oracles():
+    """The coefficients the library integrates with (SRA1 / SRA3 / SOSRA) are bitwise the oracle's, whose tableaus are
+    checked against the order conditions in tests/test_oracle.py."""
+    from sdde_b200 import _capi as capi
+    for alg, tab in O.SRA_TABLEAUS.items():
+        out, st = np.zeros(33), C.c_int32(0)
+        capi.check(capi.lib().sdde_b200_sra_tableau(alg, capi.np_ptr(out), C.byref(st)))
+        flat = tab.flat()
+        assert st.value == tab.stages and np.array_equal(out[:flat.size], flat), alg
 
 
 def test_randomised_sra_schedules_equal_oracle_bitwise():
