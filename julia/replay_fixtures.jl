@@ -32,12 +32,14 @@ function algorithm(name, opt)
     name == "RKMil" && return RKMil(interpretation = Symbol(opt))
     name == "EulerHeun" && return EulerHeun()
     startswith(name, "WangLi3SMil_") && return getfield(StochasticDiffEq, Symbol(name))()
+    name in ("SRA1", "SRA3", "SOSRA") && return getfield(StochasticDiffEq, Symbol(name))()
     error("unknown algorithm $name")
 end
 
 function model(name, lags)
     name == "mackey_glass" && return B200Models.mackey_glass(lags[1]), nothing
     name == "linear1" && return B200Models.linear1(lags[1]), nothing
+    name == "hayes" && return B200Models.hayes(), nothing
     name == "linsys_4_2_2" && return B200Models.linsys(4, (lags[1], lags[2]), 2), zeros(4, 2)
     error("unknown model $name")
 end
@@ -48,6 +50,8 @@ for (name, fx) in sort(collect(filter(kv -> kv[2] isa Dict, man)); by = first)
     t = readf64(joinpath(dir, name * "_t.bin"), nn)
     W = readf64(joinpath(dir, name * "_W.bin"), nn, nc, n_traj)
     U = readf64(joinpath(dir, name * "_dense.bin"), nn, ns, n_traj)
+    has_z = get(fx, "has_z", 0) == 1                    # SRA methods: second Brownian path, NoiseGrid(t, W, Z)
+    Z = has_z ? readf64(joinpath(dir, name * "_Z.bin"), nn, nc, n_traj) : nothing
     (f, g), nrp = model(fx["model"], fx["lags"])
     alg = algorithm(fx["alg"], fx["alg_option"])
     scalar = ns == 1
@@ -57,7 +61,8 @@ for (name, fx) in sort(collect(filter(kv -> kv[2] isa Dict, man)); by = first)
     err = 0.0; terr = 0.0; nmis = 0
     for i in 1:n_traj
         Wi = scalar && nc == 1 ? W[:, 1, i] : [W[n, :, i] for n in 1:nn]
-        noise = NoiseGrid(t, Wi)
+        Zi = !has_z ? nothing : (scalar && nc == 1 ? Z[:, 1, i] : [Z[n, :, i] for n in 1:nn])
+        noise = has_z ? NoiseGrid(t, Wi, Zi) : NoiseGrid(t, Wi)
         kw = nrp === nothing ? (;) : (; noise_rate_prototype = nrp)
         prob = SDDEProblem(f, g, u0, h, (fx["tspan"][1], fx["tspan"][2]), Tuple(fx["p"]); constant_lags = Tuple(fx["lags"]),
                            order_discontinuity_t0 = fx["order_discontinuity_t0"], noise = noise, kw...)

@@ -238,7 +238,8 @@ def test_export_for_julia_kit_is_consistent(tmp_path):
                    capture_output=True)
     man = open(tmp_path / "manifest.toml").read()
     names = re.findall(r"^\[(\w+)\]", man, re.M)
-    assert {"c2_em", "c3_rkmil_o0", "c3_rkmil_o2", "c4_em", "c2_euler_heun"} <= set(names)
+    assert {"c2_em", "c3_rkmil_o0", "c3_rkmil_o2", "c4_em", "c2_euler_heun", "sra1_hayes", "sra3_hayes", "sosra_hayes"} <= set(names)
+    assert os.path.getsize(tmp_path / "sosra_hayes_Z.bin") == os.path.getsize(tmp_path / "sosra_hayes_W.bin")
     g = np.load(os.path.join(root, "tests", "golden", "golden_v1.npz"))
     for name in names:
         nn = int(re.search(r"\[%s\].*?n_nodes = (\d+)" % name, man, re.S).group(1))
@@ -256,7 +257,7 @@ def test_export_for_julia_kit_is_consistent(tmp_path):
             # (not bit-equal: the kit feeds W = cumsum(dW) and the increments are re-derived from it, as the reference does)
             assert np.allclose(U[:, :, idx].transpose(2, 1, 0), g[name + "_out"], rtol=1e-10, atol=0)
     jl = open(os.path.join(root, "julia", "replay_fixtures.jl")).read()
-    for key in ("n_nodes", "n_state", "n_chan", "alg_option", "order_discontinuity_t0", "_dense.bin", "_W.bin", "_t.bin"):
+    for key in ("n_nodes", "n_state", "n_chan", "has_z", "alg_option", "order_discontinuity_t0", "_dense.bin", "_W.bin", "_Z.bin", "_t.bin"):
         assert key in jl and (key.startswith("_") or key in man)
 
 
