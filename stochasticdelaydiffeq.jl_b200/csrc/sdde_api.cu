@@ -570,8 +570,8 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "nccl")) c->opt_nccl = value;
     else if (!strcmp(key, "jit_linsys")) c->opt_jit_linsys = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
-    else if (!strcmp(key, "zero_copy")) c->opt_zero_copy = value != 0;
-    else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); c->mem_key.clear(); }   // next solve replays the schedule and re-uploads its tables
+    else if (!strcmp(key, "zero_copy")) { c->opt_zero_copy = value < 0 ? -1 : (value != 0); c->zc_key.clear(); }   // -1 = auto (default)
+    else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); }   // next solve replays the schedule and re-uploads its tables
     else if (!strcmp(key, "lean")) { c->opt_lean = value; c->table_key.clear(); }   // 0: general body only, 1: all lean bodies, 2: without the consecutive-interpolation body (A/B)
     else if (!strcmp(key, "balance")) c->opt_balance = value != 0;
     else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
@@ -756,8 +756,12 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     const int64_t per_block = (int64_t)K.block * K.tpt / K.lanes;
     size_t free_b = 0, total_b = 0;
     {
-        std::string mkey = skey;
-        const int64_t mk[] = {NT, (int64_t)d->out_mem, (int64_t)d->want_paths, (int64_t)d->want_moments, (int64_t)d->noise_mode, (int64_t)NS};
+        // the memory plan depends on the problem's SIZES only (not on the schedule's contents): cudaMemGetInfo stalls for
+        // up to ~16 ms while copy engines are busy (measured), so it is asked again only when the sizes change
+        std::string mkey;
+        const int64_t mk[] = {NT, (int64_t)d->out_mem, (int64_t)d->want_paths, (int64_t)d->want_moments, (int64_t)d->noise_mode, (int64_t)NS,
+                              (int64_t)S.ring_slots, rows, N, (int64_t)K.n_param, (int64_t)d->n_noise_t, (int64_t)(d->u0_stride != 0),
+                              (int64_t)(d->param_stride != 0), (int64_t)d->noise_mem};
         mkey.append((const char *)mk, sizeof(mk));
         if (mkey != c->mem_key || c->mem_free_cached == 0) {
             CU_CHECK(cudaMemGetInfo(&free_b, &total_b));
@@ -772,12 +776,22 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     // Host output in page-locked (mapped) memory and no moment pass over it: the kernel's own 128-bit stores cross PCIe,
     // no staging buffers, no copy engine, no first-wave latency (C2: 77 ms instead of 81 ms per 10^6-path solve).
     double *out_mapped = nullptr;
-    if (d->want_paths && d->out_mem == SDDE_MEM_HOST && !d->want_moments && c->opt_zero_copy && c->opt_wave_traj <= 0 && rows > 0) {
+    int zc_trial = -1;             // auto mode on a large output: which arm this solve runs (0 staged, 1 zero-copy), timed below
+    if (d->want_paths && d->out_mem == SDDE_MEM_HOST && !d->want_moments && c->opt_zero_copy != 0 && c->opt_wave_traj <= 0 && rows > 0) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             out_mapped = (double *)at.devicePointer;
         else
             cudaGetLastError();
+        if (out_mapped && c->opt_zero_copy < 0 && (double)rows * (double)NT * 8.0 >= 64.0 * 1048576.0) {
+            // auto: the first large solve of a problem runs staged, the second zero-copy, later ones the faster of the two
+            std::string zkey = skey;
+            const int64_t zk[] = {NT, rows, (int64_t)d->noise_mode, (int64_t)d->model_id};
+            zkey.append((const char *)zk, sizeof(zk));
+            if (zkey != c->zc_key) { c->zc_key = zkey; c->zc_n[0] = c->zc_n[1] = 0; }
+            zc_trial = c->zc_n[0] == 0 ? 0 : (c->zc_n[1] == 0 ? 1 : (c->zc_ms[1] < c->zc_ms[0] ? 1 : 0));
+            if (zc_trial == 0) out_mapped = nullptr;
+        }
     }
     const bool zero_copy = out_mapped != nullptr;
     if (zero_copy && tm) strncat(tm->kernel_name, " -> mapped host out", sizeof(tm->kernel_name) - strlen(tm->kernel_name) - 1);
@@ -1073,6 +1087,15 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
                     (long long)wave_cnt[i / per], t[0], t[1], t[2], t[3]);
         }
         for (cudaEvent_t e : dbg_ev) cudaEventDestroy(e);
+    }
+    if (zc_trial >= 0 && !first_kernel) {
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, c->ev_k0, c->ev_k1) == cudaSuccess) {
+            if (zc_trial == 0 && cudaEventElapsedTime(&b, c->ev_k0, c->ev_c1) == cudaSuccess) a = std::max(a, b);
+            c->zc_ms[zc_trial] = c->zc_n[zc_trial] ? std::min<double>(c->zc_ms[zc_trial], a) : a;
+            ++c->zc_n[zc_trial];
+        }
+        cudaGetLastError();
     }
     if (status) memcpy(status, c->h_status.p, (size_t)NT);
     if (d->want_moments && rows > 0 && !c->keep_moments_on_device) {

@@ -79,7 +79,14 @@ struct sdde_ctx {
     int64_t opt_chunk_steps = 128;
     int64_t opt_balance = 1;       // spread a wave's last, partial round of CTAs over all SMs (0: full CTAs only)
     int64_t opt_lean = 1;          // mark uniform batches for the lean body of run_batch (0: general body everywhere; A/B and tests)
-    int64_t opt_zero_copy = 1;     // page-locked host `out`: the step kernel stores the saved paths straight into it over PCIe
+    int64_t opt_zero_copy = -1;    // page-locked host `out`: 1 = the step kernel stores the saved paths straight into it over PCIe,
+                                   // 0 = staged in HBM and copied by the copy engines wave by wave, -1 = auto: small outputs
+                                   // zero-copy; large ones try staged, then zero-copy, and keep the faster (device-timed) --
+                                   // which one wins depends on the host (SM posted writes reach 45-50 GB/s, copy engines
+                                   // 52-57 GB/s on the measured boxes) and on how many GPUs share it
+    std::string zc_key;            // auto mode: problem the two trial timings belong to
+    double zc_ms[2] = {0.0, 0.0};  // [0] staged, [1] zero-copy: device time from the first kernel to the last byte in host memory
+    int zc_n[2] = {0, 0};
     int64_t opt_ramp_start = (int64_t)1 << 16;   // trajectories of the first wave when paths leave over PCIe (host output)
     int64_t opt_mem_limit = 0;     // bytes the workspaces may use (0 = 80 % of the free device memory)
     sdde::UserModels user;

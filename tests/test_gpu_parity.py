@@ -175,7 +175,7 @@ def test_page_locked_host_output_is_written_by_the_kernel_itself():
     try:
         c = S.solve(prob, S.EM(), S.EnsembleB200(device=0), out=S.pinned_empty((n_save, 1, n)), **kw)
     finally:
-        ctx.set_option("zero_copy", 1)
+        ctx.set_option("zero_copy", -1)
     assert "mapped host out" in a.timing["kernel_name"]
     assert "mapped host out" not in b.timing["kernel_name"] and "mapped host out" not in c.timing["kernel_name"]
     assert a.timing["d2h_bytes"] >= n_save * n * 8 and c.timing["d2h_bytes"] >= n_save * n * 8
@@ -784,3 +784,20 @@ def test_sra_noise_grid_with_z_and_in_kernel_philox():
                 **case.solve_kwargs())
     with pytest.raises(S.SddeError, match="additive"):
         S.solve(S.EnsembleProblem(cases.c2(T=5.0).problem()), S.SRA1(), S.EnsembleB200(device=0), trajectories=64, dt=0.05, adaptive=False)
+
+
+def test_large_host_output_picks_the_faster_of_staged_and_zero_copy():
+    """Default (zero_copy = -1, auto): a large page-locked host output (>= 64 MB) runs staged on the first solve of a problem,
+    zero-copy on the second and the faster of the two (device-timed) from then on; the three are bit-identical."""
+    case = cases.c1(T=10.0, saveat=0.1)
+    n = 120_000                                               # 101 rows x 120 000 x 8 B = 97 MB
+    ctx = S.get_context(0)
+    ctx.set_option("zero_copy", -1)                           # also forgets earlier trials
+    prob = S.EnsembleProblem(case.problem())
+    out = S.pinned_empty((101, 1, n))
+    sims, how = [], []
+    for i in range(4):
+        sim = S.solve(prob, S.EM(), S.EnsembleB200(device=0), out=out, trajectories=n, seed=3, **case.solve_kwargs())
+        sims.append(sim.out.copy()); how.append("mapped host out" in sim.timing["kernel_name"])
+    assert how[0] is False and how[1] is True and how[2] == how[3]
+    assert all(np.array_equal(sims[0], s) for s in sims[1:])
