@@ -15,6 +15,14 @@ for case in (cases.c1(T=3.0), cases.c2(T=40.0), cases.c3(T=40.0), cases.c3(order
              cases.hayes(T=2.0, alg=9), cases.c2(T=25.0, alg=12)):
     sim = run(case)
     print(case.name, "ok", float(np.asarray(sim.out)[-1].mean()), flush=True)
+# SRA family: four lookup sets per step, two increments per channel (in-kernel Philox and supplied W, Z grids)
+import sdde_b200 as _S
+hp = cases.hayes(T=2.0, dt=0.05)
+hp.p = np.array([0.33, -4.0, -2.0, 10.0, 0.0, 0.6, 0.1]); hp.lags = [0.33]
+for alg in (_S.SRA1(), _S.SRA3(), _S.SOSRA()):
+    sim = S.solve(S.EnsembleProblem(hp.problem()), alg, S.EnsembleB200(device=0), trajectories=777, seed=3, moments=True, dt=0.05,
+                  saveat=0.25, adaptive=False)
+    print("sra", alg.name, "ok", float(np.asarray(sim.out)[-1].mean()), flush=True)
 # supplied increments, per-trajectory parameters, several waves, device output, quantiles
 case = cases.c1(T=2.0)
 dW = cases.increments(case, 300)
