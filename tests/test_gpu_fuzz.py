@@ -140,3 +140,57 @@ def test_random_configuration_philox_paths_do_not_depend_on_the_launch_geometry(
     what = (c.name, c.alg, c.lags, c.dt, c.tspan, n, base.timing["kernel_name"], other.timing["waves"])
     assert np.array_equal(base.out, other.out.cpu().numpy(), equal_nan=True), what
     assert np.array_equal(base.status, other.status), what
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_random_sra_configuration_matches_oracle(seed):
+    """The SRA family on random additive problems: Hayes with / without the delayed term in g, the scalar additive model, lags
+    on and off the step grid and equal to dt, saveat forms, per-trajectory parameters, forced waves, chunk sizes, increments or
+    NoiseGrid(t, W, Z) -- per path against the oracle (1e-12)."""
+    rng = np.random.default_rng(13000 + seed)
+    alg = int(rng.choice([13, 14, 15]))
+    dt = float(rng.choice([0.01, 0.02, 0.05, 2.0 ** -5, 0.013]))
+    T = float(rng.choice([1.5, 3.0]))
+    if rng.integers(0, 3) < 2:
+        lag = float(rng.choice([1.0, 0.33, 0.5, dt, 2.5 * dt]))
+        c = cases.hayes(T=T, dt=dt, beta=0.0).with_(alg=alg, lags=[lag], order0=int(rng.choice([0, 0, 1, 3])))
+        c.p = np.array([lag, -4.0, -2.0, 10.0, 0.0, float(rng.choice([0.0, 0.6])), 0.1])
+    else:
+        c = cases.scalar_add(T=T).with_(dt=dt, alg=alg, order0=int(rng.choice([0, 1])))
+    if c.dt > min(c.lags):
+        c = c.with_(dt=min(c.lags) / 2)
+    form = rng.choice(["number", "list", "everystep"])
+    if form == "number":
+        c = c.with_(saveat=float(rng.choice([0.1, 0.25])))
+    elif form == "list":
+        c = c.with_(saveat=sorted(set(float(np.round(x, 3)) for x in rng.uniform(0.0, T, size=3))))
+    else:
+        c = c.with_(saveat=None)
+    n = int(rng.choice([97, 256, 1000]))
+    sch = c.oracle_schedule()
+    nz = cases.increments(sch, 2, n, key=777 + seed)
+    ptraj = bool(rng.integers(0, 2))
+    pb = np.repeat(np.asarray(c.p, float)[:, None], n, axis=1) * (1.0 + 0.05 * rng.random((len(c.p), n))) if ptraj else None
+    if ptraj and c.name == "hayes":
+        pb[0] = c.p[0]                                       # the lag is a schedule quantity, not a per-trajectory one
+        pb[4] = 0.0
+    noise = {}
+    dWo = nz
+    if rng.integers(0, 2):
+        noise["noise_increments"] = nz
+    else:
+        noise["noise_grid"] = np.concatenate([np.zeros((1, 2, n)), np.cumsum(nz, axis=0)], axis=0)
+        dWo = O.noise_grid_increments(noise["noise_grid"])
+    ref, st = O.solve_ensemble(c.omodel, pb if ptraj else c.p, c.u0, c.h0, c.h1, c.lags, sch, alg, dWo)
+    ctx = S.get_context(0)
+    ctx.set_option("chunk_steps", int(rng.choice([128, 8, 24])))
+    try:
+        sim = S.solve(S.EnsembleProblem(c.problem(), p_batch=pb), cases.ALG_MAP[alg],
+                      S.EnsembleB200(device=0, wave_traj=int(rng.choice([0, 128])) or None), trajectories=n, dt=c.dt, saveat=c.saveat,
+                      adaptive=False, **noise)
+    finally:
+        ctx.set_option("chunk_steps", 128)
+    what = (c.name, alg, c.lags, c.dt, T, c.order0, form, n, ptraj, list(noise)[0])
+    assert np.array_equal(sim.t, sch.save_t), what
+    assert cases.scaled_err(sim.out, ref) < TOL, what
+    assert np.array_equal(sim.status, st), what

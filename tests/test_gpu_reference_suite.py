@@ -32,6 +32,26 @@ def test_prob_sol_smoke(alg, kw, p):
     assert np.all(np.isfinite(sol.u)) and np.all(sol.u[-1] != 0.0)   # @test sol.u[end] != zeros(1)
 
 
+@pytest.mark.parametrize("alg", [S.WangLi3SMil(v) for v in "ABCDEF"])
+def test_prob_sol_smoke_wangli(alg):
+    # test/test_prob_sol.jl:50-61 (multiplicative problem)
+    prob = S.SDDEProblem(S.hayes.f, S.hayes.g, [1.0], lambda pp, t: np.ones(1) + t, (0.0, 0.1), PMUL, constant_lags=(PMUL[0],))
+    sol = S.solve(prob, alg, dt=0.01, seed=1234)
+    assert sol.retcode == "Success" and len(sol.t) == 11 and np.all(np.isfinite(sol.u)) and np.all(sol.u[-1] != 0.0)
+
+
+@pytest.mark.parametrize("alg", [S.SRA1(), S.SRA3(), S.SOSRA()])
+def test_prob_sol_smoke_additive_sra(alg):
+    # test/test_prob_sol.jl:72-87 "Additive problems": prob.p .= padd; solve(prob, SRA1(), dt = 0.01) ... (adaptively there,
+    # fixed-step here)
+    prob = S.SDDEProblem(S.hayes.f, S.hayes.g, [1.0], lambda pp, t: np.ones(1) + t, (0.0, 0.1), PADD, constant_lags=(PADD[0],))
+    sol = S.solve(prob, alg, dt=0.01, seed=1234, adaptive=False)
+    assert sol.retcode == "Success" and len(sol.t) == 11 and sol.t[-1] == 0.1
+    assert np.all(np.isfinite(sol.u)) and np.all(sol.u[-1] != 0.0)
+    with pytest.raises(NotImplementedError, match="adaptive"):
+        S.solve(prob, alg, dt=0.01)
+
+
 def test_nondiagonal_sparse_noise_runs():
     # test/nondiagonal_sparse_noise.jl:45-70 (fixed-step EM instead of adaptive LambaEM + callback)
     case = cases.sir(T=20.0, dt=0.02)
