@@ -42,6 +42,35 @@ __device__ __forceinline__ double div_pos(double n, double d) {
     return n * y;
 }
 
+// n / d for a denominator that is a positive NORMAL number well inside the exponent range (here: a conserved population
+// N = S + I + R): reciprocal seed, cubic refinement (|1 - d y| ~ 2^-60), quotient, Markstein residual correction -- the
+// IEEE quotient up to rare last-bit cases (<= 0.5 ulp + 2^-8 ulp), without the operator's special-case checks and
+// branches (11 BRA + 5.7 BSSY/BSYNC per SIR step in profiles/r2h_sir_summary.txt).  d = 0 / inf / NaN give NaN: the
+// trajectory is flagged Unstable exactly as with the IEEE operator's inf / NaN.
+__device__ __forceinline__ double div_normal(double n, double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    y = fma(y, fma(e, e, e), y);
+    const double q = n * y;
+    const double r = fma(-d, q, n);
+    return fma(r, y, q);
+}
+
+// sqrt(max(0, x)) as test/nondiagonal_sparse_noise.jl:33 writes it: zero for x <= 0 (and NaN, like fmax(0, NaN)), else
+// MUFU.RSQ64H seed, one cubic step and a residual correction (the IEEE root up to rare last-bit cases); arguments below
+// 1e-300 count as zero (error < 1e-150).  No special-case branches.
+__device__ __forceinline__ double sqrt_clamped(double x) {
+    const double xs = fmax(x, 1e-300);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    const double r0 = xs * y;
+    const double e = fma(-r0, y, 1.0);
+    double r = fma(r0 * e, fma(e, 0.375, 0.5), r0);
+    r = fma(fma(-r, r, xs), 0.5 * y, r);
+    return x > 1e-300 ? r : 0.0;
+}
+
 // du = (a u + b u(t-tau)) dt + s u dW              BASELINE.json configs[0], configs[4]
 struct ModelLinear1 {
     static constexpr int NS = 1, NL = 1, NW = 1, NP = 3;
@@ -139,9 +168,17 @@ struct ModelSIR {
     template <class P> __device__ __forceinline__ static void rates(double &infection, double &recovery, const double *u,
                                                                     const double (*ul)[NS], const P &p) {
         const double N = (u[0] + u[1]) + u[2];
+#ifdef SDDE_SIR_IEEE
         infection = ((p[0] * p[1]) * u[1]) / N * u[0];
+#else
+        infection = div_normal((p[0] * p[1]) * u[1], N) * u[0];       // N = S + I + R is conserved by drift and noise columns
+#endif
         const double Nd = (ul[0][0] + ul[0][1]) + ul[0][2];
+#ifdef SDDE_SIR_IEEE
         recovery = ((p[0] * p[1]) * ul[0][1]) / Nd * ul[0][0];
+#else
+        recovery = div_normal((p[0] * p[1]) * ul[0][1], Nd) * ul[0][0];
+#endif
     }
     template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
         double inf, rec;
@@ -151,7 +188,11 @@ struct ModelSIR {
     template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*ul)[NS], const P &p, double) {
         double inf, rec;
         rates(inf, rec, u, ul, p);
+#ifdef SDDE_SIR_IEEE
         const double si = sqrt(fmax(0.0, inf)), sr = sqrt(fmax(0.0, rec));
+#else
+        const double si = sqrt_clamped(inf), sr = sqrt_clamped(rec);
+#endif
         gv[0] = -si; gv[1] = 0.0;
         gv[2] = si;  gv[3] = -sr;
         gv[4] = 0.0; gv[5] = sr;
