@@ -97,6 +97,9 @@ def _julia_range(a: float, s: float, b: float) -> np.ndarray:
     return np.array([float(fa + k * fs) for k in range(ln)], dtype=np.float64)
 
 
+_saveat_cache: dict = {}
+
+
 def expand_saveat(saveat, t0: float, tf: float):
     """-> (saveat times pushed to the heap, save_start default, save_end default); /root/reference/src/solve.jl:661-677:
     a number s pushes ``(t0+s):s:tf`` when ``(t0:s:tf)[end] == tf``, else ``(t0+s):s:(tf-s)``."""
@@ -106,9 +109,12 @@ def expand_saveat(saveat, t0: float, tf: float):
         s = float(saveat)
         if s <= 0:
             raise ValueError("saveat must be positive")
-        full = _julia_range(t0, s, tf)
-        sv = _julia_range(t0 + s, s, tf) if full.size and full[-1] == tf else _julia_range(t0 + s, s, tf - s)
-        return np.asarray(sv, dtype=np.float64), True, True
+        key = (s, float(t0), float(tf))
+        if _saveat_cache.get("key") != key:          # repeated solves of one problem: the exact-rational range costs ~0.5 ms
+            full = _julia_range(t0, s, tf)
+            sv = _julia_range(t0 + s, s, tf) if full.size and full[-1] == tf else _julia_range(t0 + s, s, tf - s)
+            _saveat_cache.update(key=key, sv=np.asarray(sv, dtype=np.float64))
+        return _saveat_cache["sv"].copy(), True, True
     arr = np.asarray(list(saveat), dtype=np.float64)
     if arr.size == 0:
         return np.zeros(0), True, True
