@@ -166,7 +166,11 @@ template <class M> struct Tune {
     // (they need the registers more than the occupancy: measured, profiles/README.md)
     static constexpr bool WIDE = (M::NS >= SDDE_TUNE_MULTI_MIN_NS && TPT > 1);
     static constexpr int BLOCK = WIDE ? SDDE_BLOCK_MULTI : SDDE_BLOCK_SCALAR;
+#ifdef SDDE_MINB_SCALAR
+    static constexpr int MINB = WIDE ? 1 : SDDE_MINB_SCALAR;       // A/B builds: few warps with many registers each
+#else
     static constexpr int MINB = WIDE ? 1 : (512 / SDDE_BLOCK_SCALAR > 0 ? 512 / SDDE_BLOCK_SCALAR : 1);
+#endif
 };
 
 // occupancy target per (model, algorithm): the model's, unless a measured exception is specialised next to the model
