@@ -18,7 +18,7 @@ module SDDEB200
 
 using SciMLBase, StochasticDiffEq, StochasticDelayDiffEq
 
-export EnsembleB200, B200Models, FinalState, SaveIdxs, MomentsReduction, compile_model, pinned_array, b200_quantiles, b200_moments
+export EnsembleB200, B200Models, FinalState, SaveIdxs, MomentsReduction, compile_model, pinned_array, b200_quantiles, b200_moments, check_sra_tableaus
 
 const libsdde = get(ENV, "LIBSDDE_B200", "libsdde_b200.so")
 
@@ -324,6 +324,26 @@ function sra_flat(tab)                       # RosslerSRA stores A0', B0' (colum
     s <= 3 || error("at most 3 SRA stages on this path")
     return Float64[tab.c₀; tab.c₁; vec(tab.A₀); vec(tab.B₀); tab.α; tab.β₁; tab.β₂], Int32(s)
 end
+"""
+    check_sra_tableaus() -> Bool
+
+Compares the Roessler tableaus the library integrates with (restated from memory on the CUDA side) with this session's
+StochasticDiffEq `constructSRA1 / constructSRA3 / constructSOSRA`, entry by entry; run it once before trusting an SRA solve.
+"""
+function check_sra_tableaus(; atol = 0.0)
+    ok = true
+    for (id, name, tab) in ((Int32(13), "SRA1", StochasticDiffEq.constructSRA1()), (Int32(14), "SRA3", StochasticDiffEq.constructSRA3()),
+                            (Int32(15), "SOSRA", StochasticDiffEq.constructSOSRA()))
+        mine = zeros(Float64, 33); st = Ref{Int32}(0)
+        check(ccall((:sdde_b200_sra_tableau, libsdde), Cint, (Int32, Ptr{Float64}, Ref{Int32}), id, mine, st))
+        ref, s = sra_flat(tab)
+        same = st[] == s && all(abs.(mine[1:length(ref)] .- ref) .<= atol)
+        same || @warn "tableau of $name differs from StochasticDiffEq's" library = mine[1:length(ref)] reference = ref
+        ok &= same
+    end
+    return ok
+end
+
 const B200Alg = Union{EM, RKMil, RKMilCommute, EulerHeun, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D, WangLi3SMil_E, WangLi3SMil_F,
                       SRA, SRA1, SRA2, SRA3, SOSRA, SOSRA2}
 
