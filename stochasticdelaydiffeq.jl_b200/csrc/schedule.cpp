@@ -32,7 +32,13 @@ using DiscHeap = std::priority_queue<Disc, std::vector<Disc>, DiscLater>;
 std::string build_schedule(const ScheduleInput &in, Schedule &S) {
     const double t0 = in.t0, tf = in.tf, dt = in.dt;
     if (!(tf > t0)) return "tspan must satisfy tf > t0 (only tdir=+1 is on this path)";
+    if (!std::isfinite(t0) || !std::isfinite(tf)) return "tspan must be finite";
     if (!(dt >= 0.0) || !std::isfinite(dt)) return "dt must be finite and >= 0";
+    // fail before replaying a hopeless schedule (the reference would step for hours; maxiters there is 1e5 by default)
+    if (dt > 0.0 && (tf - t0) / dt > (double)in.max_steps) return "schedule exceeds the maximum number of steps";
+    for (double x : in.tstops) if (std::isnan(x)) return "tstops must not be NaN";
+    for (double x : in.saveat) if (std::isnan(x)) return "saveat must not be NaN";
+    for (double x : in.disc_t) if (std::isnan(x)) return "d_discontinuities must not be NaN";
     if (dt == 0.0 && in.tstops.empty())  // src/solve.jl:121-123
         return "Fixed timestep methods require a choice of dt or choosing the tstops";
     for (double lag : in.lags)

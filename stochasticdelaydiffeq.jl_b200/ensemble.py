@@ -107,8 +107,10 @@ def expand_saveat(saveat, t0: float, tf: float):
         return np.zeros(0), True, True
     if np.isscalar(saveat):
         s = float(saveat)
-        if s <= 0:
-            raise ValueError("saveat must be positive")
+        if not (s > 0) or not math.isfinite(s):
+            raise ValueError("saveat must be positive and finite")
+        if not (math.isfinite(t0) and math.isfinite(tf)) or (tf - t0) / s > 2.0e8:
+            raise ValueError("saveat: more than 2e8 save points (or an infinite time span)")
         key = (s, float(t0), float(tf))
         if _saveat_cache.get("key") != key:          # repeated solves of one problem: the exact-rational range costs ~0.5 ms
             full = _julia_range(t0, s, tf)
@@ -118,6 +120,8 @@ def expand_saveat(saveat, t0: float, tf: float):
     arr = np.asarray(list(saveat), dtype=np.float64)
     if arr.size == 0:
         return np.zeros(0), True, True
+    if np.any(np.isnan(arr)):
+        raise ValueError("saveat must not contain NaN")
     return np.sort(arr[(arr > t0) & (arr < tf)]), bool(np.any(arr == t0)), bool(np.any(arr == tf))
 
 

@@ -622,3 +622,21 @@ def test_schedule_structural_invariants_on_random_problems():
         k = s.save_step >= 0
         assert np.all(s.save_t[k] <= s.t[s.save_step[k] + 1]) and np.all(s.save_t[k] >= s.t[s.save_step[k]])
         assert np.all((s.save_theta >= 0) & (s.save_theta <= 1))
+
+
+def test_hopeless_or_non_finite_schedules_fail_fast():
+    """A step count beyond the limit, an infinite span, NaN stops / save times are refused in milliseconds instead of being
+    replayed (the reference would step until maxiters)."""
+    import time
+    def sched(**kw):
+        prob = S.SDDEProblem(S.linear1.f, S.linear1.g, 1.0, 1.0, kw.pop("tspan", (0.0, 10.0)), (-1.0, 0.5, 0.2), constant_lags=(1.0,))
+        return S.schedule(prob, S.EM(), **{"dt": 0.01, **kw})
+    t0 = time.perf_counter()
+    for kw, exc, pat in (({"dt": 1e-9}, S.SddeError, "maximum number of steps"), ({"dt": 1e-300}, S.SddeError, "maximum number of steps"),
+                         ({"tspan": (0.0, float("inf"))}, S.SddeError, "finite"), ({"tstops": (float("nan"),)}, S.SddeError, "NaN"),
+                         ({"saveat": 1e-9}, ValueError, "save points"), ({"saveat": float("nan")}, ValueError, "positive"),
+                         ({"saveat": [float("nan"), 1.0]}, ValueError, "NaN"), ({"dt": float("nan")}, S.SddeError, "dt must be finite")):
+        with pytest.raises(exc, match=pat):
+            sched(**kw)
+    assert time.perf_counter() - t0 < 2.0
+    assert len(sched(tspan=(1e300, 2e300), dt=1e299).t) == 11 and len(sched(tstops=(5.0, 5.0, 5.0 + 1e-15)).t) == 1004
