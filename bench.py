@@ -188,6 +188,21 @@ def config_block(S, torch, dist, local, world, barrier_sync, peak_gbs):
          lin, S.EM(), dict(dt=0.01, saveat=1.0, moments=True, paths=False), 100_000_000, {}, 16.0, 1),
         ("C2 strong: the headline workload with 10^6 paths IN TOTAL", mg(TAU, T_END), S.EM(), dict(dt=DT, saveat=1.0), M, {}, 16.0, 1),
     ]
+    # the other fixed-step solvers of SURVEY.md section 8(f) rank 3 on the reference's own test problems (test/test_prob_sol.jl
+    # Hayes equation, lag 1, dt = 0.01, t in [0, 10]; test/nondiagonal_sparse_noise.jl SIR), 10^6 paths per GPU
+    hay = lambda p: S.SDDEProblem(S.hayes.f, S.hayes.g, 1.0, S.AffineHistory((1.0,), (1.0,)), (0.0, 10.0), p, constant_lags=(1.0,))
+    pmul, padd = (1.0, -4.0, -2.0, 10.0, -1.3, -1.2, 1.1), (1.0, -4.0, -2.0, 10.0, 0.0, 0.6, 0.1)
+    sir = S.SDDEProblem(S.sir.f, S.sir.g, [990.0, 10.0, 0.0], S.AffineHistory((1000.0, 0.0, 0.0), (0.0, 0.0, 0.0)), (0.0, 20.0),
+                        (0.05, 10.0, 4.0), lags=(4.0,))
+    runs += [
+        ("A1 Hayes EulerHeun dt=0.01 T=10 saveat=0.1", hay(pmul), S.EulerHeun(), dict(dt=0.01, saveat=0.1), M * world, {}, 16.0, 1),
+        ("A2 Hayes WangLi3SMil_A dt=0.01 T=10 saveat=0.1", hay(pmul), S.WangLi3SMil_A(), dict(dt=0.01, saveat=0.1), M * world, {}, 16.0, 1),
+        ("A3 additive Hayes SRA1 (fixed step) dt=0.01 T=10 saveat=0.1", hay(padd), S.SRA1(), dict(dt=0.01, saveat=0.1, adaptive=False),
+         M * world, {}, 16.0, 1),
+        ("A4 additive Hayes SOSRA (fixed step) dt=0.01 T=10 saveat=0.1", hay(padd), S.SOSRA(), dict(dt=0.01, saveat=0.1, adaptive=False),
+         M * world, {}, 16.0, 1),
+        ("A5 delayed SIR, 3 states, 3x2 sparse noise, EM dt=0.02 T=20 saveat=1.0", sir, S.EM(), dict(dt=0.02, saveat=1.0), M * world, {}, 48.0, 3),
+    ]
     out = []
     for name, prob, alg, kw, n_total, eakw, ring_bytes, n_state in runs:
         ea = S.EnsembleB200(device=local, distributed=world > 1, output="device", **eakw)
