@@ -46,7 +46,10 @@ __host__ __device__ constexpr int alg_noise_mult(int alg) { return alg == K_ALG_
 #ifndef SDDE_SRA_BATCH
 #define SDDE_SRA_BATCH 2   // two steps per batch: the Philox words of the next batch are produced one batch ahead and the lanes are compile-time (12.1 -> 10.3 ms on the additive Hayes problem, 10^6 x 1004 steps)
 #endif
-__host__ __device__ constexpr int alg_batch(int alg, int b) { return alg_stages(alg) >= 3 ? (b >= SDDE_SRA_BATCH ? SDDE_SRA_BATCH : 1) : ((alg_stages(alg) > 1 && b > 1) ? b / 2 : b); }
+#ifndef SDDE_EH_BATCH_DIV
+#define SDDE_EH_BATCH_DIV 1   // EulerHeun keeps the full batch depth: compile-time Philox lanes, words one batch ahead (4.82 -> 4.23 ms on Hayes, 10^6 x 1001 steps; 2 = halve it)
+#endif
+__host__ __device__ constexpr int alg_batch(int alg, int b) { return alg_stages(alg) >= 3 ? (b >= SDDE_SRA_BATCH ? SDDE_SRA_BATCH : 1) : ((alg_stages(alg) > 1 && b > 1) ? b / SDDE_EH_BATCH_DIV : b); }
 
 #define SDDE_K_MAX_STATE 8
 #define SDDE_K_MAX_PARAM 128
