@@ -801,3 +801,25 @@ def test_large_host_output_picks_the_faster_of_staged_and_zero_copy():
         sims.append(sim.out.copy()); how.append("mapped host out" in sim.timing["kernel_name"])
     assert how[0] is False and how[1] is True and how[2] == how[3]
     assert all(np.array_equal(sims[0], s) for s in sims[1:])
+
+
+def test_golden_v2_fixtures_on_gpu():
+    """The committed round-2 vectors (tests/golden/golden_v2.npz: EM(false), RKMil Stratonovich, EulerHeun, RKMilCommute on a noise
+    matrix, WangLi3SMil_A / _F, SRA1 / SRA3 / SOSRA) against the device, 1e-12."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v2.npz"))
+    mgc = lambda tau, alg: cases.c2(T=30.0, tau=tau, alg=alg)
+    hay = lambda p, lag, dt, alg: cases.hayes(T=3.0, dt=dt, saveat=0.25).with_(alg=alg, lags=[lag], p=np.array(p))
+    pmul, padd = [1.0, -4.0, -2.0, 10.0, -1.3, -1.2, 1.1], [0.33, -4.0, -2.0, 10.0, 0.0, 0.6, 0.1]
+    table = {"mg_em_nosplit": mgc(17.0, 1), "mg_rkmil_strat": mgc(17.02, 3), "mg_euler_heun": mgc(17.0, 4),
+             "hayes_wangli_a": hay(pmul, 1.0, 2.0 ** -6, 7), "hayes_wangli_f": hay(pmul, 1.0, 2.0 ** -6, 12),
+             "hayes_sra1": hay(padd, 0.33, 0.05, 13), "hayes_sra3": hay(padd, 0.33, 0.05, 14), "hayes_sosra": hay(padd, 0.33, 0.05, 15),
+             "c4_rkmil_commute": cases.c4(T=4.0).with_(alg=5)}
+    for name, case in table.items():
+        xi = g[name + "_xi"]
+        sch = case.oracle_schedule()
+        assert np.array_equal(sch.save_t, g[name + "_save_t"]), name
+        sim = S.solve(S.EnsembleProblem(case.problem()), cases.ALG_MAP[case.alg], S.EnsembleB200(device=0), trajectories=xi.shape[2],
+                      noise_increments=xi * sch.sqdt[:, None, None], **case.solve_kwargs())
+        assert np.array_equal(sim.t, g[name + "_save_t"]), name
+        assert cases.scaled_err(sim.out, g[name + "_out"]) < TOL, name
