@@ -222,7 +222,7 @@ SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value)
                                                                                     paths leave over PCIe; later waves grow x1.5; default 2^16, measured best on C2),
                                                                                     "nccl", "jit_linsys" (0/1), "zero_copy" (1: page-locked host `out` is written by the step kernel itself
                                                                                     over PCIe; 0: staged in HBM and copied wave by wave; -1 (default): small outputs zero-copy, outputs
-                                                                                    >= 64 MB try both on the first two solves of a problem and keep the faster) */
+                                                                                    >= 64 MB try both on the first two solves of their size class (power of two of the output bytes) and keep the faster) */
 
 /* Host only: builds the step/lookup/save schedule for a descriptor (no GPU needed). */
 SDDE_API int sdde_b200_schedule(const sdde_desc *d, sdde_schedule *out);

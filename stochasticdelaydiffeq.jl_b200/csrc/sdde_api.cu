@@ -570,7 +570,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "nccl")) c->opt_nccl = value;
     else if (!strcmp(key, "jit_linsys")) c->opt_jit_linsys = value;
     else if (!strcmp(key, "mem_limit")) { c->opt_mem_limit = value; c->mem_key.clear(); }
-    else if (!strcmp(key, "zero_copy")) { c->opt_zero_copy = value < 0 ? -1 : (value != 0); c->zc_key.clear(); }   // -1 = auto (default)
+    else if (!strcmp(key, "zero_copy")) { c->opt_zero_copy = value < 0 ? -1 : (value != 0); for (auto &z : c->zc) z = sdde_ctx::ZcTrial(); }   // -1 = auto (default)
     else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); }   // next solve replays the schedule and re-uploads its tables
     else if (!strcmp(key, "lean")) { c->opt_lean = value; c->table_key.clear(); }   // 0: general body only, 1: all lean bodies, 2: without the consecutive-interpolation body (A/B)
     else if (!strcmp(key, "balance")) c->opt_balance = value != 0;
@@ -776,6 +776,7 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     // Host output in page-locked (mapped) memory and no moment pass over it: the kernel's own 128-bit stores cross PCIe,
     // no staging buffers, no copy engine, no first-wave latency (C2: 77 ms instead of 81 ms per 10^6-path solve).
     double *out_mapped = nullptr;
+    int zc_class = 0;
     int zc_trial = -1;             // auto mode on a large output: which arm this solve runs (0 staged, 1 zero-copy), timed below
     if (d->want_paths && d->out_mem == SDDE_MEM_HOST && !d->want_moments && c->opt_zero_copy != 0 && c->opt_wave_traj <= 0 && rows > 0) {
         cudaPointerAttributes at;
@@ -784,12 +785,11 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
         else
             cudaGetLastError();
         if (out_mapped && c->opt_zero_copy < 0 && (double)rows * (double)NT * 8.0 >= 64.0 * 1048576.0) {
-            // auto: the first large solve of a problem runs staged, the second zero-copy, later ones the faster of the two
-            std::string zkey = skey;
-            const int64_t zk[] = {NT, rows, (int64_t)d->noise_mode, (int64_t)d->model_id};
-            zkey.append((const char *)zk, sizeof(zk));
-            if (zkey != c->zc_key) { c->zc_key = zkey; c->zc_n[0] = c->zc_n[1] = 0; }
-            zc_trial = c->zc_n[0] == 0 ? 0 : (c->zc_n[1] == 0 ? 1 : (c->zc_ms[1] < c->zc_ms[0] ? 1 : 0));
+            // auto: the first large solve of a size class runs staged, the second zero-copy, later ones the faster of the two
+            zc_class = 0;
+            for (double b = (double)rows * (double)NT * 8.0; b >= 2.0 && zc_class < 63; b *= 0.5) ++zc_class;
+            const sdde_ctx::ZcTrial &z = c->zc[zc_class];
+            zc_trial = z.n[0] == 0 ? 0 : (z.n[1] == 0 ? 1 : (z.ms_per_gb[1] < z.ms_per_gb[0] ? 1 : 0));
             if (zc_trial == 0) out_mapped = nullptr;
         }
     }
@@ -1092,8 +1092,10 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
         float a = 0.f, b = 0.f;
         if (cudaEventElapsedTime(&a, c->ev_k0, c->ev_k1) == cudaSuccess) {
             if (zc_trial == 0 && cudaEventElapsedTime(&b, c->ev_k0, c->ev_c1) == cudaSuccess) a = std::max(a, b);
-            c->zc_ms[zc_trial] = c->zc_n[zc_trial] ? std::min<double>(c->zc_ms[zc_trial], a) : a;
-            ++c->zc_n[zc_trial];
+            sdde_ctx::ZcTrial &z = c->zc[zc_class];
+            const double per_gb = (double)a / ((double)rows * (double)NT * 8.0e-9);
+            z.ms_per_gb[zc_trial] = z.n[zc_trial] ? std::min(z.ms_per_gb[zc_trial], per_gb) : per_gb;
+            ++z.n[zc_trial];
         }
         cudaGetLastError();
     }

@@ -84,9 +84,9 @@ struct sdde_ctx {
                                    // zero-copy; large ones try staged, then zero-copy, and keep the faster (device-timed) --
                                    // which one wins depends on the host (SM posted writes reach 45-50 GB/s, copy engines
                                    // 52-57 GB/s on the measured boxes) and on how many GPUs share it
-    std::string zc_key;            // auto mode: problem the two trial timings belong to
-    double zc_ms[2] = {0.0, 0.0};  // [0] staged, [1] zero-copy: device time from the first kernel to the last byte in host memory
-    int zc_n[2] = {0, 0};
+    struct ZcTrial { double ms_per_gb[2] = {0.0, 0.0}; int n[2] = {0, 0}; };   // [0] staged, [1] zero-copy: device time from the
+    ZcTrial zc[64];                // first kernel to the last byte in host memory, per GB; one entry per power-of-two class of
+                                   // output bytes (which arm wins is a property of the host and of the size, not of the model)
     int64_t opt_ramp_start = (int64_t)1 << 16;   // trajectories of the first wave when paths leave over PCIe (host output)
     int64_t opt_mem_limit = 0;     // bytes the workspaces may use (0 = 80 % of the free device memory)
     sdde::UserModels user;

@@ -787,7 +787,7 @@ def test_sra_noise_grid_with_z_and_in_kernel_philox():
 
 
 def test_large_host_output_picks_the_faster_of_staged_and_zero_copy():
-    """Default (zero_copy = -1, auto): a large page-locked host output (>= 64 MB) runs staged on the first solve of a problem,
+    """Default (zero_copy = -1, auto): a large page-locked host output (>= 64 MB) runs staged on the first solve of its size class,
     zero-copy on the second and the faster of the two (device-timed) from then on; the three are bit-identical."""
     case = cases.c1(T=10.0, saveat=0.1)
     n = 120_000                                               # 101 rows x 120 000 x 8 B = 97 MB
