@@ -324,6 +324,24 @@ class RODESolution:
     def __getitem__(self, k):
         return self.u[k]
 
+    def __call__(self, t):
+        """``sol(t)``: the saved time series interpolated linearly ([EXT] the reference's ``sde_interpolant`` on a solution saved
+        without dense output), no extrapolation.  ``t`` may be a scalar or an array of times."""
+        v = self._e.at(t)[..., self._i]
+        if hasattr(v, "cpu"):
+            v = v.cpu().numpy()
+        return v[..., 0] if self._e.scalar_state else v
+
+
+def _bracket(ts, t):
+    """-> (k, theta): t lies in [ts[k], ts[k+1]] with weight theta on the upper point; an exact hit gives theta = 0."""
+    if not (ts[0] <= t <= ts[-1]):
+        raise ValueError(f"t = {t} is outside the saved time span [{ts[0]}, {ts[-1]}] (solutions do not extrapolate)")
+    k = int(np.searchsorted(ts, t, side="right")) - 1
+    if ts[k] == t or k == len(ts) - 1:
+        return min(k, len(ts) - 1), 0.0
+    return k, float((t - ts[k]) / (ts[k + 1] - ts[k]))
+
 
 class EnsembleSolution:
     """What the ensemble solve returns: dense ``out[n_save, n_state, trajectories]`` (time-major, trajectory
@@ -358,6 +376,23 @@ class EnsembleSolution:
     @property
     def u(self):
         return _LazyList(self)
+
+    def at(self, t):
+        """All trajectories at time(s) ``t``: ``[n_state, trajectories]`` for a scalar t, ``[len(t), n_state, trajectories]`` for
+        an array -- linear interpolation between the saved points (what ``sol(t)`` does per trajectory in the reference, here
+        for the whole ensemble at once, on the device when the paths live there)."""
+        if self.out is None:
+            raise ValueError("paths were not requested (want_paths=False)")
+        if np.ndim(t) > 0:
+            rows = [self.at(float(x)) for x in np.asarray(t, dtype=np.float64).ravel()]
+            if hasattr(rows[0], "data_ptr"):
+                import torch
+                return torch.stack(rows)
+            return np.stack(rows)
+        k, th = _bracket(np.asarray(self.t), float(t))
+        if th == 0.0:
+            return self.out[k]
+        return (1.0 - th) * self.out[k] + th * self.out[k + 1]
 
     @property
     def retcodes(self):
@@ -394,11 +429,16 @@ def timeseries_steps_mean(sim):
 
 
 def timepoint_meanvar(sim, t):
+    """[EXT] EnsembleAnalysis.timepoint_meanvar(sim, t): mean and variance over the ensemble at time t -- from the moment
+    triples when t is a saved point, else from the linearly interpolated paths (``sim.at(t)``, this rank's trajectories)."""
     k = int(np.argmin(np.abs(sim.t - t)))
-    if sim.t[k] != t:
-        raise ValueError(f"t={t} is not a saved time point")
-    mean, var = timeseries_steps_meanvar(sim)
-    return mean[k], var[k]
+    if sim.t[k] == t and sim.moments is not None:
+        mean, var = timeseries_steps_meanvar(sim)
+        return mean[k], var[k]
+    x = sim.at(t)
+    if hasattr(x, "cpu"):
+        return x.mean(dim=-1).cpu().numpy(), x.var(dim=-1, unbiased=True).cpu().numpy()
+    return x.mean(axis=-1), x.var(axis=-1, ddof=1)
 
 
 def timeseries_steps_quantile(sim: EnsembleSolution, q, *, median=False, device=None, local=False):

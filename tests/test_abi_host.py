@@ -640,3 +640,24 @@ def test_hopeless_or_non_finite_schedules_fail_fast():
             sched(**kw)
     assert time.perf_counter() - t0 < 2.0
     assert len(sched(tspan=(1e300, 2e300), dt=1e299).t) == 11 and len(sched(tstops=(5.0, 5.0, 5.0 + 1e-15)).t) == 1004
+
+
+def test_solution_interpolation_and_timepoint_statistics():
+    """``sol(t)`` / ``sim.at(t)``: linear interpolation between the saved points (the reference's sde_interpolant on a saved
+    series), exact at saved points, no extrapolation; ``timepoint_meanvar`` at a time between saves uses it."""
+    import torch
+    t = np.array([0.0, 1.0, 2.0, 4.0])
+    out = np.arange(4 * 2 * 3, dtype=float).reshape(4, 2, 3) ** 2
+    for o in (out, torch.from_numpy(out)):
+        e = S.EnsembleSolution(t, o, np.zeros(3, np.uint8), None, False, 0.0, {})
+        assert np.array_equal(np.asarray(e.at(2.0)), out[2])
+        assert np.allclose(np.asarray(e.at(3.0)), 0.5 * out[2] + 0.5 * out[3])
+        assert np.allclose(e[1](0.25), 0.75 * out[0, :, 1] + 0.25 * out[1, :, 1])
+        assert np.asarray(e.at([0.5, 4.0])).shape == (2, 2, 3) and e[2]([0.5, 4.0]).shape == (2, 2)
+        m, v = S.timepoint_meanvar(e, 3.0)
+        x = 0.5 * out[2] + 0.5 * out[3]
+        assert np.allclose(m, x.mean(axis=1)) and np.allclose(v, x.var(axis=1, ddof=1))
+        with pytest.raises(ValueError, match="extrapolate"):
+            e.at(4.5)
+    es = S.EnsembleSolution(t, out[:, :1, :], None, None, True, 0.0, {})
+    assert np.isscalar(float(es[0](1.5))) and float(es[0](1.5)) == 0.5 * out[1, 0, 0] + 0.5 * out[2, 0, 0]
