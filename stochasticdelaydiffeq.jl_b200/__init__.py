@@ -9,7 +9,9 @@ from . import _capi
 from ._capi import SddeError, get_context, lib
 from .ensemble import (EnsembleB200, EnsembleSolution, EnsembleSummary, Schedule, expand_saveat, merge_moments, pinned_empty, schedule, shard_range,
                        solve, timepoint_meanvar, timeseries_steps_mean, timeseries_steps_meanvar, timeseries_steps_median,
-                       timeseries_steps_quantile)
+                       timeseries_steps_quantile, get_timestep, get_timepoint, timestep_meanvar, timestep_mean, timestep_quantile,
+                       timestep_median, timepoint_mean, timepoint_quantile, timepoint_median, timeseries_point_meanvar,
+                       timeseries_point_mean, timeseries_point_quantile, timeseries_point_median)
 from .problem import (EM, EulerHeun, AffineHistory, ConstantHistory, EnsembleProblem, FinalState, Model, MomentsReduction, RKMil, RKMilCommute,
                       SaveIdxs, SDDEProblem, SOSRA, SRA, SRA1, SRA3, UserModel, WangLi3SMil, WangLi3SMil_A, WangLi3SMil_B, WangLi3SMil_C, WangLi3SMil_D,
                       WangLi3SMil_E, WangLi3SMil_F, hayes,
@@ -21,5 +23,6 @@ __all__ = [
     "expand_saveat", "merge_moments", "pinned_empty", "shard_range", "timeseries_steps_meanvar", "timeseries_steps_mean",
     "timepoint_meanvar", "timeseries_steps_quantile", "timeseries_steps_median", "EnsembleSummary", "AffineHistory", "ConstantHistory", "Model", "UserModel", "linear1", "hayes", "mackey_glass",
     "sir", "scalar_add", "linsys", "linsys_params", "SddeError", "get_context", "lib",
+    "get_timestep", "get_timepoint", "timestep_meanvar", "timestep_mean", "timestep_quantile", "timestep_median", "timepoint_mean", "timepoint_quantile", "timepoint_median", "timeseries_point_meanvar", "timeseries_point_mean", "timeseries_point_quantile", "timeseries_point_median",
 ]
 __version__ = "0.1.0"

@@ -519,6 +519,74 @@ def _quantiles_across_ranks(ctx, dev, ptr, on_dev, n_rows, n_local, n_total, pro
     capi.check(L.sdde_b200_qsel_end(ctx.handle, capi.np_ptr(res).value))
 
 
+# ---- [EXT] SciMLBase.EnsembleAnalysis: the per-time-step / per-time-point forms (same names and argument order) ----
+def _rows(sim, rows):
+    """A solution holding only ``rows`` ([k, n_state, trajectories]) of ``sim`` (same sharding information)."""
+    return EnsembleSolution(np.arange(rows.shape[0], dtype=np.float64), rows, None, None, sim.scalar_state, 0.0, {},
+                            traj_offset=sim.traj_offset, n_total=sim.n_total)
+
+
+def get_timestep(sim, i):
+    """All trajectories at saved point i: ``[n_state, trajectories]``."""
+    return sim.out[i]
+
+
+def get_timepoint(sim, t):
+    """All trajectories at time t (linear interpolation between saved points): ``[n_state, trajectories]``."""
+    return sim.at(t)
+
+
+def timestep_meanvar(sim, i):
+    if sim.moments is not None:
+        mean, var = timeseries_steps_meanvar(sim)
+        return mean[i], var[i]
+    x = sim.out[i]
+    if hasattr(x, "cpu"):
+        return x.mean(dim=-1).cpu().numpy(), x.var(dim=-1, unbiased=True).cpu().numpy()
+    return x.mean(axis=-1), x.var(axis=-1, ddof=1)
+
+
+def timestep_mean(sim, i):
+    return timestep_meanvar(sim, i)[0]
+
+
+def timestep_quantile(sim, q, i, **kw):
+    return timeseries_steps_quantile(_rows(sim, sim.out[i:i + 1]), q, **kw)[0]
+
+
+def timestep_median(sim, i, **kw):
+    return timeseries_steps_quantile(_rows(sim, sim.out[i:i + 1]), None, median=True, **kw)[0, :, -1]
+
+
+def timepoint_mean(sim, t):
+    return timepoint_meanvar(sim, t)[0]
+
+
+def timepoint_quantile(sim, q, t, **kw):
+    return timeseries_steps_quantile(_rows(sim, sim.at(t)[None]), q, **kw)[0]
+
+
+def timepoint_median(sim, t, **kw):
+    return timeseries_steps_quantile(_rows(sim, sim.at(t)[None]), None, median=True, **kw)[0, :, -1]
+
+
+def timeseries_point_meanvar(sim, ts):
+    mv = [timepoint_meanvar(sim, float(t)) for t in ts]
+    return np.stack([m for m, _ in mv]), np.stack([v for _, v in mv])
+
+
+def timeseries_point_mean(sim, ts):
+    return timeseries_point_meanvar(sim, ts)[0]
+
+
+def timeseries_point_quantile(sim, q, ts, **kw):
+    return timeseries_steps_quantile(_rows(sim, sim.at(np.asarray(ts, dtype=np.float64))), q, **kw)
+
+
+def timeseries_point_median(sim, ts, **kw):
+    return timeseries_steps_quantile(_rows(sim, sim.at(np.asarray(ts, dtype=np.float64))), None, median=True, **kw)[..., -1]
+
+
 def timeseries_steps_median(sim: EnsembleSolution):
     return timeseries_steps_quantile(sim, None, median=True)[..., 0]
 

@@ -106,3 +106,31 @@ def test_summary_of_a_solution_solved_without_moments():
         paths = sim.out.cpu().numpy() if output == "device" else sim.out
         assert np.allclose(summ.u, paths.mean(axis=2), rtol=1e-12) and np.allclose(summ.v, paths.var(axis=2, ddof=1), rtol=1e-9)
         assert sim.moments is not None and np.all(sim.moments[..., 0] == 30_001)
+
+
+def test_ensemble_analysis_per_step_and_per_point_forms():
+    """[EXT] EnsembleAnalysis timestep_* / timepoint_* / timeseries_point_*: same names and argument order; order statistics are
+    Statistics.quantile's (= numpy 'linear'), time points between saves use the linearly interpolated paths."""
+    case = cases.c1(T=4.0, saveat=0.5)
+    for output in ("host", "device"):
+        sim = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output=output), trajectories=4001, seed=17,
+                      moments=True, **case.solve_kwargs())
+        out = sim.out.cpu().numpy() if hasattr(sim.out, "cpu") else sim.out
+        i, t = 3, 1.7                                        # saved point 3 (t = 1.5); t = 1.7 lies between saves 3 and 4
+        th = (t - 1.5) / 0.5
+        xt = (1.0 - th) * out[3] + th * out[4]
+        assert np.array_equal(np.asarray(S.get_timestep(sim, i).cpu() if hasattr(sim.out, "cpu") else S.get_timestep(sim, i)), out[i])
+        m, v = S.timestep_meanvar(sim, i)
+        assert np.allclose(m, out[i].mean(axis=1), rtol=1e-12) and np.allclose(v, out[i].var(axis=1, ddof=1), rtol=1e-9)
+        assert np.allclose(S.timestep_quantile(sim, [0.1, 0.9], i), np.quantile(out[i], [0.1, 0.9], axis=1).T, rtol=1e-14)
+        assert np.allclose(S.timestep_median(sim, i), np.median(out[i], axis=1), rtol=1e-14)
+        m, v = S.timepoint_meanvar(sim, t)
+        assert np.allclose(m, xt.mean(axis=1), rtol=1e-12) and np.allclose(v, xt.var(axis=1, ddof=1), rtol=1e-9)
+        assert np.allclose(S.timepoint_quantile(sim, 0.25, t), np.quantile(xt, 0.25, axis=1), rtol=1e-13)
+        assert np.allclose(S.timepoint_median(sim, t), np.median(xt, axis=1), rtol=1e-13)
+        ms, vs = S.timeseries_point_meanvar(sim, [0.0, 1.7, 4.0])
+        assert ms.shape == (3, 1) and np.allclose(ms[1], xt.mean(axis=1), rtol=1e-12) and np.allclose(ms[2], out[-1].mean(axis=1), rtol=1e-12)
+        q = S.timeseries_point_quantile(sim, [0.05, 0.95], [0.25, 1.7])
+        assert q.shape == (2, 1, 2) and np.allclose(q[1, 0], np.quantile(xt[0], [0.05, 0.95]), rtol=1e-13)
+        assert np.allclose(S.timeseries_point_median(sim, [1.7])[0], np.median(xt, axis=1), rtol=1e-13)
+        assert np.allclose(sim[5](t), xt[0, 5], rtol=1e-15)
