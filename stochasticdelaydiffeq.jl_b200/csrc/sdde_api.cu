@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) noise_regrid_kernel(const double *__restr
     const int c = (int)(row % nc);
     const double *lo = src + ((long long)g.lo * nc + c) * spitch + soff, *hi = src + ((long long)g.hi * nc + c) * spitch + soff;
     for (long long tr = (long long)blockIdx.y * 256 + threadIdx.x; tr < nt; tr += (long long)gridDim.y * 256)
-        dst[row * dpitch + tr] = g.lo == g.hi ? hi[tr] : (1.0 - g.theta) * lo[tr] + g.theta * hi[tr];
+        dst[row * dpitch + tr] = g.lo == g.hi ? hi[tr] : fma(g.theta, hi[tr], (1.0 - g.theta) * lo[tr]);
 }
 
 }  // namespace sdde

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK_COOP) sdde_coop_kernel(const __grid
                 const double th = r.lk[l].theta;
                 const double lo = *reinterpret_cast<const double *>(ringb + r.lk[l].off_lo);
                 const double hi = *reinterpret_cast<const double *>(ringb + r.lk[l].off_hi);
-                const double mine = (r.ring_mask & (1 << l)) ? ((1.0 - th) * lo + th * hi) : (hc0 + hc1 * th);
+                const double mine = (r.ring_mask & (1 << l)) ? fma(th, hi, (1.0 - th) * lo) : (hc0 + hc1 * th);
 #pragma unroll
                 for (int s = 0; s < NS; ++s) ul[l][s] = __shfl_sync(0xffffffffu, mine, s, LPT);
             }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(SDDE_BLOCK_COOP) sdde_coop_kernel(const __grid
             *reinterpret_cast<double *>(ringb + r.off_store) = u;
             for (int s = 0; s < r.nsave; ++s) {
                 const SaveRec sr = a.saves[ks];
-                const double v = sr.exact ? u : ((1.0 - sr.theta) * uold + sr.theta * u);
+                const double v = sr.exact ? u : fma(sr.theta, u, (1.0 - sr.theta) * uold);
                 bad = bad || !finite_d(v);
                 if (a.out && live && a.save_row[j] >= 0) a.out[((long long)ks * a.n_saved + a.save_row[j]) * a.out_pitch + a.out_off + tr] = v;
                 ++ks;

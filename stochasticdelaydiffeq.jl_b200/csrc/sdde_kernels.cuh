@@ -457,19 +457,21 @@ __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)
         M::g(g1, u, ul, p, t);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            double noise = g1[i * NW] * dw[M::DIAG ? i : 0];
+            // roundings pinned (the reference forms noise = g .* dW first, then muladd(f, dt, uprev) + noise): every batch body
+            // of every instantiation rounds alike
+            double noise = __dmul_rn(g1[i * NW], dw[M::DIAG ? i : 0]);
 #pragma unroll
-            for (int j = 1; j < NW; ++j) noise = noise + g1[i * NW + j] * dw[j];
-            tmp[i] = (u[i] + f1[i] * dt) + noise;
+            for (int j = 1; j < NW; ++j) noise = fma(g1[i * NW + j], dw[j], noise);
+            tmp[i] = __dadd_rn(fma(f1[i], dt, u[i]), noise);
         }
         M::f(f2, tmp, ul2, p, t + dt);
         M::g(g2, tmp, ul2, p, t + dt);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            double noise2 = (0.5 * (g1[i * NW] + g2[i * NW])) * dw[M::DIAG ? i : 0];
+            double noise2 = __dmul_rn(0.5 * (g1[i * NW] + g2[i * NW]), dw[M::DIAG ? i : 0]);
 #pragma unroll
-            for (int j = 1; j < NW; ++j) noise2 = noise2 + (0.5 * (g1[i * NW + j] + g2[i * NW + j])) * dw[j];
-            u[i] = (u[i] + (dt * 0.5) * (f1[i] + f2[i])) + noise2;
+            for (int j = 1; j < NW; ++j) noise2 = fma(0.5 * (g1[i * NW + j] + g2[i * NW + j]), dw[j], noise2);
+            u[i] = __dadd_rn(fma(dt * 0.5, f1[i] + f2[i], u[i]), noise2);
         }
         return;
     }
@@ -495,7 +497,7 @@ __device__ __forceinline__ void sde_step(double (&u)[M::NS], const double (&uls)
             M::g(gt, Kj, ul, p, t);
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
-                const double Jkj = (ALG == K_ALG_RKMILC_ITO && k == j) ? (0.5 * (dw[k] * dw[j]) - 0.5 * fabs(dt)) : 0.5 * (dw[k] * dw[j]);
+                const double Jkj = (ALG == K_ALG_RKMILC_ITO && k == j) ? fma(0.5, dw[k] * dw[j], -0.5 * fabs(dt)) : 0.5 * (dw[k] * dw[j]);
 #pragma unroll
                 for (int i = 0; i < NS; ++i) mil[i] = mil[i] + ((gt[i * NW + k] - L[i * NW + k]) * isq) * Jkj;
             }
@@ -785,7 +787,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
 #pragma unroll
                 for (int j = 0; j < NS; ++j)
 #pragma unroll
-                    for (int tt = 0; tt < TPT; ++tt) ul[tt][l / NL][l % NL][j] = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
+                    for (int tt = 0; tt < TPT; ++tt) ul[tt][l / NL][l % NL][j] = fma(th, xhi[k][l][j][tt], omt * xlo[k][l][j][tt]);   // explicit: every body rounds alike
             } else {
                 const double th = r.lk[l].theta;
                 const bool ring = (r.ring_mask & (1 << l)) != 0;
@@ -795,7 +797,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                     const double hv = a.hist_c0[j] + a.hist_c1[j] * th;
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt) {
-                        const double iv = omt * xlo[k][l][j][tt] + th * xhi[k][l][j][tt];
+                        const double iv = fma(th, xhi[k][l][j][tt], omt * xlo[k][l][j][tt]);
                         ul[tt][l / NL][l % NL][j] = ring ? iv : hv;
                     }
                 }
@@ -861,7 +863,7 @@ __device__ __forceinline__ void run_batch(const KArgs &a, TrajState<M, TPT, PTRA
                     double v[TPT];
 #pragma unroll
                     for (int tt = 0; tt < TPT; ++tt) {
-                        v[tt] = sr.exact ? useq[k + 1][tt][j] : ((1.0 - sr.theta) * useq[k][tt][j] + sr.theta * useq[k + 1][tt][j]);
+                        v[tt] = sr.exact ? useq[k + 1][tt][j] : fma(sr.theta, useq[k + 1][tt][j], (1.0 - sr.theta) * useq[k][tt][j]);
                         st.bad[tt] = st.bad[tt] || !finite_d(v[tt]);
                     }
                     if (a.out && a.save_row[j] >= 0) {

@@ -20,12 +20,14 @@ __device__ __forceinline__ double ipow(double x, int n) {
         const double x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
         return x2 * x8;
     }
+    // __dmul_rn: the products are never contracted into a following add (e.g. 1 + x^n), whatever shape the compiler gives
+    // this loop in a particular kernel instantiation -- every batch body then rounds alike
     double result = 1.0, base = x;
     bool first = true;
     while (n > 0) {
-        if (n & 1) { result = first ? base : result * base; first = false; }
+        if (n & 1) { result = first ? base : __dmul_rn(result, base); first = false; }
         n >>= 1;
-        if (n) base = base * base;
+        if (n) base = __dmul_rn(base, base);
     }
     return result;
 }
@@ -76,7 +78,7 @@ struct ModelLinear1 {
     static constexpr int NS = 1, NL = 1, NW = 1, NP = 3;
     static constexpr bool DIAG = true;
     template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
-        du[0] = p[0] * u[0] + p[1] * ul[0][0];
+        du[0] = fma(p[1], ul[0][0], p[0] * u[0]);      // explicit contraction: every batch body of the kernel rounds alike
     }
     template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*)[NS], const P &p, double) {
         gv[0] = p[2] * u[0];
@@ -88,10 +90,10 @@ struct ModelHayes {
     static constexpr int NS = 1, NL = 1, NW = 1, NP = 7;
     static constexpr bool DIAG = true;
     template <class P> __device__ __forceinline__ static void f(double *du, const double *u, const double (*ul)[NS], const P &p, double) {
-        du[0] = (p[1] * u[0] + p[2] * ul[0][0]) + p[3];
+        du[0] = fma(p[2], ul[0][0], p[1] * u[0]) + p[3];
     }
     template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*ul)[NS], const P &p, double) {
-        gv[0] = (p[4] * u[0] + p[5] * ul[0][0]) + p[6];
+        gv[0] = fma(p[5], ul[0][0], p[4] * u[0]) + p[6];
     }
 };
 
@@ -105,7 +107,7 @@ struct ModelMackeyGlassT {
         const double x = ul[0][0];
         const double xn = ipow(x, NEXP > 0 ? NEXP : (int)p[2]);
         // 1 + x^n >= 1 whenever n is even or x >= 0: branch-free division; otherwise the IEEE operator
-        if (NEXP > 0 && (NEXP % 2) == 0) du[0] = div_pos(p[0] * x, 1.0 + xn) - p[1] * u[0];
+        if (NEXP > 0 && (NEXP % 2) == 0) du[0] = fma(-p[1], u[0], div_pos(p[0] * x, 1.0 + xn));   // explicit contraction
         else du[0] = (p[0] * x) / (1.0 + xn) - p[1] * u[0];
     }
     template <class P> __device__ __forceinline__ static void g(double *gv, const double *u, const double (*)[NS], const P &p, double) {
