@@ -134,3 +134,37 @@ def test_ensemble_analysis_per_step_and_per_point_forms():
         assert q.shape == (2, 1, 2) and np.allclose(q[1, 0], np.quantile(xt[0], [0.05, 0.95]), rtol=1e-13)
         assert np.allclose(S.timeseries_point_median(sim, [1.7])[0], np.median(xt, axis=1), rtol=1e-13)
         assert np.allclose(sim[5](t), xt[0, 5], rtol=1e-15)
+
+
+import os as _os
+_Q0, _QN = ([int(x) for x in _os.environ["SDDE_FUZZ_SEEDS"].split(":")] if _os.environ.get("SDDE_FUZZ_SEEDS") else [0, 8])
+
+
+@pytest.mark.parametrize("seed", list(range(_Q0, _Q0 + _QN)))
+def test_random_rows_quantiles_equal_sorted_selection(seed):
+    """Randomised: row counts, lengths, value distributions (ties, few distinct values, one binade, wide range, signed zeros,
+    infinities), probabilities and residency -- bit-exact against the sort-based oracle (SDDE_FUZZ_SEEDS widens the sweep)."""
+    rng = np.random.default_rng(31000 + seed)
+    n = int(rng.choice([1, 2, 5, 63, 64, 65, 257, 1000, 4096, 4097, 50_001, 200_003]))
+    n_rows = int(rng.integers(1, 9))
+    rows = np.empty((n_rows, n))
+    for r in range(n_rows):
+        kind = rng.integers(0, 8)
+        if kind == 0: v = rng.standard_normal(n)
+        elif kind == 1: v = 1.0 + rng.random(n) * 2.0 ** -int(rng.integers(1, 50))
+        elif kind == 2: v = rng.integers(-3, 4, size=n).astype(float)
+        elif kind == 3: v = np.exp(rng.uniform(-700, 700, size=n)) * rng.choice([-1.0, 1.0], size=n)
+        elif kind == 4: v = np.full(n, float(rng.standard_normal()))
+        elif kind == 5: v = np.round(rng.standard_normal(n), int(rng.integers(0, 3)))
+        elif kind == 6: v = np.where(rng.random(n) < 0.5, 0.0, -0.0)
+        else: v = rng.standard_normal(n) * 10.0 ** float(rng.integers(-300, 300))
+        if rng.random() < 0.2 and n > 3:
+            v[rng.integers(0, n, size=max(1, n // 50))] = rng.choice([np.inf, -np.inf])
+        rows[r] = v
+    k = int(rng.integers(1, 6))
+    probs = sorted(set(float(x) for x in rng.choice([0.0, 0.01, 0.05, 0.1, 0.25, 1 / 3, 0.5, 0.75, 0.9, 0.95, 0.99, 1.0], size=k, replace=False)))
+    median = bool(rng.integers(0, 2))
+    got = _device_quantiles(rows, probs, median, bool(rng.integers(0, 2)))
+    ref = O.ensemble_quantiles(rows, probs, want_median=median)
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), (seed, n, n_rows, probs, median)
