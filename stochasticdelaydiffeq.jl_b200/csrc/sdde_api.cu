@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
 
 #include "rng_table.hpp"
 #include "sra_tableau.hpp"
@@ -549,6 +551,9 @@ void sdde_b200_destroy(sdde_ctx *c) {
     c->ring.release(); c->out[0].release(); c->out[1].release(); c->steps.release(); c->saves.release();
     c->noise.release(); c->u0.release(); c->ptraj.release(); c->status.release(); c->mom.release();
     c->h_status.release(); c->h_mom.release(); c->h_count.release(); c->gather.release();
+    c->bounce[0].release(); c->bounce[1].release();
+    for (cudaEvent_t &e : c->ev_bounce) { if (e) cudaEventDestroy(e); e = nullptr; }
+    c->pool.reset();
     c->noise_src.release(); c->noise_nodes.release(); c->mom_part.release();
     sdde_qsel_free(c->qsel); c->qsel = nullptr;
     c->qs_rows.release(); c->qs_hist.release(); c->qs_paths.release(); c->qs_cand.release();
@@ -574,6 +579,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); }   // next solve replays the schedule and re-uploads its tables
     else if (!strcmp(key, "lean")) { c->opt_lean = value; c->table_key.clear(); }   // 0: general body only, 1: all lean bodies, 2: without the consecutive-interpolation body (A/B)
     else if (!strcmp(key, "balance")) c->opt_balance = value != 0;
+    else if (!strcmp(key, "host_threads")) { if (value < 0 || value > 256) return fail(SDDE_ERR_BAD_DESC, "host_threads out of range"); c->opt_host_threads = value; c->pool.reset(); }
     else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
     else return fail(SDDE_ERR_BAD_DESC, "unknown option '%s'", key);
@@ -936,6 +942,67 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     CU_CHECK(cudaEventRecord(c->ev_c0, c->copy_out));
     bool first_kernel = true;
 
+    // Host output in PAGEABLE memory (what a caller gets who did not allocate page-locked memory): a cudaMemcpy2DAsync into it is
+    // staged by the driver on one thread and, for a fresh allocation, takes the first-touch page faults there too (835 ms for
+    // the 4 GB of C2 against 78 ms into page-locked memory).  Here each wave's tile leaves in 64 MB chunks into two page-locked
+    // bounce buffers; while chunk k+1 crosses PCIe the host threads scatter chunk k into the caller's rows.
+    bool pageable_out = false;
+    if (d->want_paths && !out_dev && rows > 0 && (double)rows * (double)NT * 8.0 >= 32.0 * 1048576.0 && c->opt_host_threads != 1) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess) pageable_out = at.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    const size_t kBounce = (size_t)64 << 20;
+    if (pageable_out) {
+        CU_CHECK(c->bounce[0].reserve(kBounce));
+        CU_CHECK(c->bounce[1].reserve(kBounce));
+        for (cudaEvent_t &e : c->ev_bounce) if (!e) CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (!c->pool) {
+            const int hw = (int)std::thread::hardware_concurrency();
+            const int nthr = c->opt_host_threads > 0 ? (int)c->opt_host_threads : std::max(2, std::min(16, hw > 0 ? hw : 8));
+            c->pool.reset(new sdde::HostPool(nthr - 1));
+        }
+    }
+    // wave w's staging tile (rows x nt doubles, row pitch `pitch`) -> out[:, off : off + nt], blocking the calling thread; the GPU
+    // meanwhile runs the next wave's kernel, which was enqueued before this call
+    auto drain_pageable = [&](const double *tile, int64_t off, int64_t nt, int buf) -> int {
+        CU_CHECK(cudaStreamWaitEvent(c->copy_out, c->ev_kdone[buf], 0));
+        const int64_t row_bytes = nt * 8;
+        const int64_t rpc = std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)kBounce / row_bytes));   // rows per chunk
+        const int64_t n_seg = (row_bytes + kBounce - 1) / (int64_t)kBounce;                                 // a row longer than a buffer is cut
+        const int64_t seg_elems = (nt + n_seg - 1) / n_seg;
+        struct Chunk { int64_t r0, nr, e0, ne; };
+        std::vector<Chunk> chunks;
+        for (int64_t r0 = 0; r0 < rows; r0 += rpc)
+            for (int64_t sg = 0; sg < n_seg; ++sg) {
+                const int64_t e0 = sg * seg_elems, ne = std::min(seg_elems, nt - e0);
+                if (ne > 0) chunks.push_back(Chunk{r0, std::min(rpc, rows - r0), e0, ne});
+            }
+        auto issue = [&](size_t k) -> cudaError_t {
+            const Chunk &ch = chunks[k];
+            cudaError_t e = cudaMemcpy2DAsync(c->bounce[k & 1].p, (size_t)ch.ne * 8, tile + ch.r0 * pitch + ch.e0, (size_t)pitch * 8, (size_t)ch.ne * 8,
+                                              (size_t)ch.nr, cudaMemcpyDeviceToHost, c->copy_out);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev_bounce[k & 1], c->copy_out);
+            return e;
+        };
+        if (!chunks.empty()) CU_CHECK(issue(0));
+        for (size_t k = 0; k < chunks.size(); ++k) {
+            if (k + 1 < chunks.size()) CU_CHECK(issue(k + 1));            // the other buffer: its previous contents were scattered at k - 1
+            CU_CHECK(cudaEventSynchronize(c->ev_bounce[k & 1]));
+            const Chunk ch = chunks[k];
+            const double *src = (const double *)c->bounce[k & 1].p;
+            const int64_t piece = (int64_t)1 << 17;                        // 1 MB pieces: enough tasks for every thread, whole pages
+            const int64_t ppr = (ch.ne + piece - 1) / piece;
+            std::function<void(int64_t)> fn = [&](int64_t task) {
+                const int64_t r = task / ppr, p0 = (task % ppr) * piece, pn = std::min(piece, ch.ne - p0);
+                memcpy(out + (ch.r0 + r) * OP + off + ch.e0 + p0, src + r * ch.ne + p0, (size_t)pn * 8);
+            };
+            c->pool->parallel_for(ch.nr * ppr, fn);
+        }
+        return SDDE_OK;
+    };
+    int pending_w = -1;                              // pageable path: wave whose tile still has to be drained
+
     std::vector<cudaEvent_t> dbg_ev;                 // SDDE_DEBUG_TIMING: per wave (kernel start, kernel end, copy start, copy end)
     auto dbg_mark = [&](cudaStream_t s) { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); dbg_ev.push_back(e); } };
     for (int w = 0; w < n_waves; ++w) {
@@ -1033,7 +1100,16 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
         CU_CHECK(cudaEventRecord(c->ev_kdone[buf], c->compute));
         dbg_mark(c->compute);
         // outputs of this wave
-        if (d->want_paths && !out_dev && rows > 0) {
+        if (d->want_paths && !out_dev && rows > 0 && pageable_out) {
+            // this wave's kernel is enqueued: drain the PREVIOUS wave's tile on the host while it runs
+            if (pending_w >= 0) {
+                rc = drain_pageable((const double *)c->out[(n_waves > 1) ? (pending_w & 1) : 0].p, wave_off[(size_t)pending_w],
+                                    wave_cnt[(size_t)pending_w], pending_w & 1);
+                if (rc) return rc;
+            }
+            pending_w = w;
+            d2h += nt * 8 * rows;
+        } else if (d->want_paths && !out_dev && rows > 0) {
             CU_CHECK(cudaStreamWaitEvent(c->copy_out, c->ev_kdone[buf], 0));
             dbg_mark(c->copy_out);
             CU_CHECK(cudaMemcpy2DAsync(out + off, OP * 8, A.out, pitch * 8, nt * 8, rows, cudaMemcpyDeviceToHost, c->copy_out));
@@ -1041,6 +1117,11 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
             dbg_mark(c->copy_out);
             d2h += nt * 8 * rows;
         }
+    }
+    if (pending_w >= 0) {
+        rc = drain_pageable((const double *)c->out[(n_waves > 1) ? (pending_w & 1) : 0].p, wave_off[(size_t)pending_w], wave_cnt[(size_t)pending_w],
+                            pending_w & 1);
+        if (rc) return rc;
     }
     CU_CHECK(cudaEventRecord(c->ev_k1, c->compute));
     // Status bytes leave in ONE copy after the last wave: a small D2H per wave on the compute stream would queue behind the
@@ -1079,7 +1160,7 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     lap("copy streams synced");
     CU_CHECK(cudaGetLastError());
     if (dbg && !dbg_ev.empty()) {
-        const int per = (d->want_paths && !out_dev && rows > 0) ? 4 : 2;
+        const int per = (d->want_paths && !out_dev && rows > 0 && !pageable_out) ? 4 : 2;
         for (size_t i = 0; i + per <= dbg_ev.size(); i += per) {
             float t[4] = {0, 0, 0, 0};
             for (int j = 0; j < per; ++j) cudaEventElapsedTime(&t[j], dbg_ev[0], dbg_ev[i + j]);

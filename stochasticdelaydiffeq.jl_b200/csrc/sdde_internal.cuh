@@ -25,6 +25,10 @@ const std::string &sdde_last_error_string();
                              __FILE__, __LINE__);                                                             \
     } while (0)
 
+#include <memory>
+
+#include "host_pool.hpp"
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -66,6 +70,10 @@ struct sdde_ctx {
     DevBuf mom_part;                 // per-slice moment triples of one wave (moments_kernel -> merge_moments_kernel)
     DevBuf noise_src, noise_nodes;   // supplied NoiseGrid on its own grid: staged W rows and the node table (plan_noise_grid)
     PinnedBuf h_status, h_mom, h_count;
+    PinnedBuf bounce[2];           // pageable host output: page-locked landing buffers of the D2H chunks (2 x 64 MB, on first use)
+    cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
+    std::unique_ptr<sdde::HostPool> pool;   // host threads that scatter the bounce buffers into the caller's pageable array
+    int64_t opt_host_threads = 0;  // 0 = min(16, hardware threads)
     DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
     struct sdde_qsel *qsel = nullptr;   // the active order-statistics selection (sdde_summary_api.cu), freed by sdde_qsel_free
     DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)

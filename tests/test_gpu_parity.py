@@ -823,3 +823,32 @@ def test_golden_v2_fixtures_on_gpu():
                       noise_increments=xi * sch.sqdt[:, None, None], **case.solve_kwargs())
         assert np.array_equal(sim.t, g[name + "_save_t"]), name
         assert cases.scaled_err(sim.out, g[name + "_out"]) < TOL, name
+
+
+def test_large_pageable_host_output_goes_through_the_bounce_path_and_is_identical():
+    """A pageable host output >= 32 MB leaves through page-locked bounce buffers and host copy threads (several waves, rows cut
+    into chunks); it must equal the page-locked output bit for bit -- also for a ragged trajectory count, a caller-supplied
+    pageable array with a wider pitch than the wave, forced small waves, and with the path switched off (host_threads = 1)."""
+    case = cases.c1(T=10.0, saveat=0.1)
+    n = 90_001                                                # 101 rows x 90 001 x 8 B = 73 MB, ragged
+    ctx = S.get_context(0)
+    prob = S.EnsembleProblem(case.problem())
+    kw = dict(trajectories=n, seed=4, **case.solve_kwargs())
+    ref = S.solve(prob, S.EM(), S.EnsembleB200(device=0), out=S.pinned_empty((101, 1, n)), **kw)
+    a = S.solve(prob, S.EM(), S.EnsembleB200(device=0), **kw)                            # pageable, allocated by solve (untouched pages)
+    pre = np.full((101, 1, n), np.nan)
+    b = S.solve(prob, S.EM(), S.EnsembleB200(device=0, wave_traj=20_000), out=pre, **kw)   # several waves
+    ctx.set_option("wave_traj", 0)
+    ctx.set_option("host_threads", 1)
+    try:
+        c = S.solve(prob, S.EM(), S.EnsembleB200(device=0), **kw)
+    finally:
+        ctx.set_option("host_threads", 0)
+    ctx.set_option("host_threads", 3)
+    try:
+        d = S.solve(prob, S.EM(), S.EnsembleB200(device=0), **kw)
+    finally:
+        ctx.set_option("host_threads", 0)
+    for x in (a, b, c, d):
+        assert np.array_equal(x.out, ref.out) and np.array_equal(x.status, ref.status)
+    assert b.timing["waves"] >= 4 and b.out is pre
