@@ -529,6 +529,20 @@ def main():
         one_pass(0, ea_dev, out_dev, False)
         e2e.update(pcie_ceiling(torch, dist, local, world, out_dev, out_host, barrier_sync))
         del out_host
+        if not args.no_extras:
+            # the same solve when the caller passes NO page-locked buffer (a plain numpy result, fresh pageable pages each time):
+            # bounce buffers + host copy threads inside the library; reported beside the page-locked figure above, not instead of it
+            barrier_sync()
+            tp = time.perf_counter()
+            for i in range(2):
+                simp = S.solve(eprob, S.EM(), ea_host, dt=DT, saveat=1.0, trajectories=n_total, seed=0xB2000001 + i)
+                checksum = float(simp.out[-1, 0, :8].sum())
+                del simp
+            barrier_sync()
+            elp = torch.tensor([time.perf_counter() - tp], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(elp, op=dist.ReduceOp.MAX)
+            e2e["pageable_result_ms_per_step"] = float(elp[0]) / 2 * 1e3
 
     if rank != 0:
         if world > 1:
