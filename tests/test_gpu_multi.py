@@ -156,3 +156,19 @@ def test_order_statistics_across_two_ranks_sharing_one_gpu():
     host): shard ranges, per-rank histograms, the agreed bin decisions, the distributed solve + merged moments -- every leg
     but the NCCL transport itself runs on a 1-GPU box."""
     _run_two_ranks("gloo")
+
+
+def test_two_contexts_large_pageable_output_through_the_bounce_path():
+    """sdde_b200_solve_multi into ONE large pageable host array: each context (own bounce buffers, own host copy threads, its own
+    host thread inside the library) scatters its column range concurrently; equal to the single-context result."""
+    from sdde_b200 import _capi as capi
+    ca, cb = capi.Context(0), capi.Context(0)
+    try:
+        case = cases.c1(T=10.0, saveat=0.1)
+        n = 130_001                                           # 101 rows x 65 000 x 8 B = 52 MB per context
+        kw = dict(trajectories=n, seed=78, **case.solve_kwargs())
+        a = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(device=0, output="device"), **kw)
+        b = S.solve(S.EnsembleProblem(case.problem()), S.EM(), S.EnsembleB200(devices=(ca, cb)), **kw)
+        assert np.array_equal(a.out.cpu().numpy(), b.out) and np.array_equal(a.status, b.status)
+    finally:
+        ca.close(); cb.close()
