@@ -201,3 +201,44 @@ def test_random_sra_configuration_matches_oracle(seed):
     assert np.array_equal(sim.t, sch.save_t), what
     assert cases.scaled_err(sim.out, ref) < TOL, what
     assert np.array_equal(sim.status, st), what
+
+
+@pytest.mark.parametrize("seed", _seeds(8))
+def test_random_noise_grid_on_its_own_time_grid(seed):
+    """NoiseGrid(t, W[, Z]) on a random grid unrelated to the steps (random spacing, some shared nodes, the last node possibly a
+    few ulps off tf), random model / algorithm (incl. SRA with its Z path) / waves / residency: W is interpolated on the device
+    exactly as the oracle restates DiffEqNoiseProcess's rule."""
+    rng = np.random.default_rng(17000 + seed)
+    sra = rng.integers(0, 4) == 0
+    if sra:
+        alg = int(rng.choice([13, 14, 15]))
+        c = cases.hayes(T=float(rng.choice([1.5, 3.0])), dt=float(rng.choice([0.02, 0.05])), beta=0.0).with_(alg=alg, lags=[0.33])
+        c.p = np.array([0.33, -4.0, -2.0, 10.0, 0.0, 0.6, 0.1])
+        c = c.with_(saveat=0.25)
+    else:
+        c = _random_case(rng)
+        if c.alg >= 5 and c.name != "C4":
+            c = c.with_(alg=int(rng.choice([0, 2])))
+    n = int(rng.choice([65, 300, 1000]))
+    sch = c.oracle_schedule()
+    t0, tf = c.tspan
+    nch = c.model.n_chan * (2 if c.alg in (13, 14, 15) else 1)
+    m = int(rng.integers(5, 400))
+    ts = np.sort(rng.uniform(t0, tf, size=m))
+    ts = np.unique(np.concatenate([[t0], ts, sch.t[rng.integers(0, sch.t.size, size=3)], [tf * (1 + float(rng.choice([0.0, 3e-16]))) if tf != 0 else tf]]))
+    Wg = np.cumsum(np.sqrt(np.diff(ts, prepend=ts[0]))[:, None, None] * rng.standard_normal((ts.size, nch, n)), axis=0)
+    Wn = O.noise_grid_on_nodes(ts, Wg, sch.t)
+    ref, st = O.solve_ensemble(c.omodel, c.p, c.u0, c.h0, c.h1, c.lags, sch, c.alg, O.noise_grid_increments(Wn))
+    W_in = Wg
+    if rng.integers(0, 2):
+        import torch
+        W_in = torch.from_numpy(Wg).cuda()
+    kw = dict(dt=c.dt, saveat=c.saveat)
+    if c.alg in (2, 3, 5, 6, 13, 14, 15):
+        kw["adaptive"] = False
+    sim = S.solve(S.EnsembleProblem(c.problem()), cases.ALG_MAP[c.alg], S.EnsembleB200(device=0, wave_traj=int(rng.choice([0, 128])) or None),
+                  trajectories=n, noise_grid=(ts, W_in), **kw)
+    S.get_context(0).set_option("wave_traj", 0)
+    ok = np.isfinite(ref).all(axis=(0, 1))
+    what = (c.name, c.alg, c.lags, c.dt, c.tspan, m, n)
+    assert ok.any() and cases.scaled_err(sim.out[:, :, ok], ref[:, :, ok]) < TOL, what
