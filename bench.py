@@ -120,7 +120,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_total": n_all, "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(steps, warmup, sample_paths=None):
+def cpu_reference_run(steps, warmup, sample_paths=None, rng="ziggurat"):
     """The reference's per-trajectory algorithm (C++ restatement) on all host cores; returns (value, info, ms per pass)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
@@ -131,15 +131,17 @@ def cpu_reference_run(steps, warmup, sample_paths=None):
     times, n_steps = [], 0
     for i in range(warmup + steps):
         _, _, el, n_steps = c_oracle.solve(O.MODEL_MACKEY_GLASS, O.ALG_EM_SPLIT, 1, 1, 1, list(P_MG), [1.2], [1.2], [0.0], [TAU],
-                                           0.0, T_END, DT, sv, 501, n_traj=n, seed=0xB2000001 + i, n_threads=cores)
+                                           0.0, T_END, DT, sv, 501, n_traj=n, seed=0xB2000001 + i, n_threads=cores, rng=rng)
         if i >= warmup:
             times.append(el)
     total = sum(times)
     value = n * n_steps * len(times) / total
     info = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "rng": "Philox4x32-10 + libm Box-Muller (log, sqrt, sin, cos per pair) -- NOT the reference's Xoroshiro128+ / ziggurat "
-                   "randn, which is several times cheaper per normal; the restatement also omits Julia's per-trajectory __init, "
-                   "deepcopy and dynamic dispatch",
+            "rng": ("xoroshiro128+ + 128-layer ziggurat (the cost class of the reference's Xoroshiro128Plus + randn; timing only, "
+                    "oracle/sdde_oracle.cpp); the restatement omits Julia's per-trajectory __init, deepcopy and dynamic dispatch, so "
+                    "it is expected to be faster than the Julia reference per core") if rng == "ziggurat" else
+                   ("Philox4x32-10 + libm Box-Muller (log, sqrt, sin, cos per pair): the generator the parity tests share with the "
+                    "device, several times dearer per normal than the reference's ziggurat"),
             "sample": f"{n} of the 10^6 trajectories x {n_steps} steps per pass, {len(times)} passes, C++ restatement of the "
                       f"reference's per-trajectory loop (oracle/sdde_oracle.cpp: growing history + binary search), std::thread "
                       f"static chunks over {cores} cores; not the Julia reference (Julia is not in the image)"}
@@ -587,6 +589,9 @@ def main():
     if not args.no_cpu_baseline:
         # about 10-15 s of CPU work: 15 000 trajectories per core x 10 000 steps in one pass
         _, cpu_baseline, _ = cpu_reference_run(1, 0, sample_paths=(os.cpu_count() or 1) * 15000)
+        # the same port with the generator the parity tests use (Philox + libm Box-Muller), on a third of the sample
+        v_bm, _, _ = cpu_reference_run(1, 0, sample_paths=(os.cpu_count() or 1) * 5000, rng="philox")
+        cpu_baseline["value_with_philox_box_muller"] = v_bm
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

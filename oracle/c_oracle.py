@@ -49,7 +49,7 @@ def lib():
 
 def solve(model_id, alg, n_state, n_lag, n_noise, params, u0, h0, h1, lags, t0, tf, dt, saveat_times, n_save, *,
           save_start=True, save_end=True, save_everystep=False, order0=0, declared=True, n_traj=1, traj_offset=0,
-          seed=0, dW=None, noise_grid=None, n_threads=1, d_discontinuities=(), tableau=None):
+          seed=0, dW=None, noise_grid=None, n_threads=1, d_discontinuities=(), tableau=None, rng="philox"):
     """-> (out[n_save, n_state, n_traj], status[n_traj], elapsed seconds, steps)."""
     d = Desc()
     d.struct_size = C.sizeof(Desc)
@@ -88,6 +88,8 @@ def solve(model_id, alg, n_state, n_lag, n_noise, params, u0, h0, h1, lags, t0, 
     elif noise_grid is not None:
         nz = np.ascontiguousarray(noise_grid, dtype=np.float64); d.noise_mode = 2; nrows = nz.shape[0]
     d.noise = nz.ctypes.data if nz is not None else None
+    if nz is None and rng == "ziggurat":        # timing only: xoroshiro128+ + ziggurat, the cost class of the reference's randn
+        d.noise_mode = 100
     out = np.full((n_save, n_state, n_traj), np.nan)
     status = np.zeros(n_traj, dtype=np.uint8)
     el, steps = C.c_double(0), C.c_int64(0)

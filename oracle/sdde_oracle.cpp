@@ -65,6 +65,48 @@ inline void normal_quad(uint64_t gid, uint64_t call, uint64_t seed, double z[4])
     box_muller_pair(w[2], w[3], z[2], z[3]);
 }
 
+// ---- TIMING ONLY: a normal generator of the reference's cost class (noise_mode = SDDE_ORACLE_NOISE_ZIGGURAT) ----
+// The reference draws its increments with Xoroshiro128Plus + Julia's randn (a 256-layer ziggurat on 52 random bits), /root/
+// reference/src/solve.jl:313-336; the Philox + libm Box-Muller above is several times dearer per normal.  bench.py's CPU legs
+// report the port's throughput with BOTH.  Doornik's ZIGNOR layout (128 layers, r = 3.442619855899, v = 9.91256303526217e-3),
+// stream = xoroshiro128+ seeded per trajectory by splitmix64(seed, trajectory id).  Not used by any parity test.
+#define SDDE_ORACLE_NOISE_ZIGGURAT 100
+struct Zig {
+    double x[129], ratio[128];
+    Zig() {
+        const double r = 3.442619855899, v = 9.91256303526217e-3;
+        double f = std::exp(-0.5 * r * r);
+        x[0] = v / f; x[1] = r; x[128] = 0.0;
+        for (int i = 2; i < 128; ++i) { x[i] = std::sqrt(-2.0 * std::log(v / x[i - 1] + f)); f = std::exp(-0.5 * x[i] * x[i]); }
+        for (int i = 0; i < 128; ++i) ratio[i] = x[i + 1] / x[i];
+    }
+};
+static const Zig g_zig;
+struct Xoro {
+    uint64_t s0, s1;
+    static uint64_t splitmix(uint64_t &z) { z += 0x9E3779B97F4A7C15ull; uint64_t r = z; r = (r ^ (r >> 30)) * 0xBF58476D1CE4E5B9ull; r = (r ^ (r >> 27)) * 0x94D049BB133111EBull; return r ^ (r >> 31); }
+    Xoro(uint64_t seed, uint64_t id) { uint64_t z = seed ^ (id * 0xD1342543DE82EF95ull); s0 = splitmix(z); s1 = splitmix(z); if (!(s0 | s1)) s1 = 1; }
+    inline uint64_t next() { const uint64_t a = s0; uint64_t b = s1; const uint64_t r = a + b; b ^= a; s0 = ((a << 24) | (a >> 40)) ^ b ^ (b << 16); s1 = (b << 37) | (b >> 27); return r; }
+    inline double u01() { return (double)(next() >> 11) * 0x1.0p-53; }
+};
+inline double zig_normal(Xoro &g) {
+    for (;;) {
+        const uint64_t w = g.next();
+        const int i = (int)(w & 127);
+        const double u = 2.0 * ((double)(w >> 11) * 0x1.0p-53) - 1.0;
+        if (std::fabs(u) < g_zig.ratio[i]) return u * g_zig.x[i];
+        if (i == 0) {                                   // tail beyond r
+            const double r = 3.442619855899;
+            double xx, yy;
+            do { xx = std::log(1.0 - g.u01()) / r; yy = std::log(1.0 - g.u01()); } while (-2.0 * yy < xx * xx);
+            return u < 0 ? xx - r : r - xx;
+        }
+        const double xv = u * g_zig.x[i];
+        const double f0 = std::exp(-0.5 * (g_zig.x[i] * g_zig.x[i] - xv * xv)), f1 = std::exp(-0.5 * (g_zig.x[i + 1] * g_zig.x[i + 1] - xv * xv));
+        if (f1 + g.u01() * (f0 - f1) < 1.0) return xv;
+    }
+}
+
 inline double ipow(double x, int n) {   // same multiplication order as oracle/sdde_oracle.py::ipow
     double result = 1.0, base = x;
     bool first = true;
@@ -233,6 +275,7 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
 
     int64_t n = 0;
     double zc[4] = {0, 0, 0, 0}; uint64_t zcall = ~0ull;
+    Xoro xoro(d->seed, (uint64_t)(d->traj_offset + traj));
     double curW[2 * SDDE_MAX_NOISE] = {0};
     if (d->noise_mode == SDDE_NOISE_SUPPLIED_GRID) for (int c = 0; c < nc; ++c) curW[c] = dW[(int64_t)c * NT + traj];
     double du[SDDE_MAX_STATE], K[SDDE_MAX_STATE], gv[SDDE_MAX_STATE * SDDE_MAX_NOISE], g2[SDDE_MAX_STATE], ut[SDDE_MAX_STATE], dw[2 * SDDE_MAX_NOISE];
@@ -244,7 +287,9 @@ int64_t solve_one(const sdde_desc *d, const Model &M, int64_t traj, const double
             const double sq = std::sqrt(std::fabs(dtn));
             for (int j = 0; j < ns; ++j) uprev[j] = u[j];
             for (int c = 0; c < nc; ++c) {
-                if (d->noise_mode == SDDE_NOISE_PHILOX) {
+                if (d->noise_mode == SDDE_ORACLE_NOISE_ZIGGURAT) {
+                    dw[c] = sq * zig_normal(xoro);
+                } else if (d->noise_mode == SDDE_NOISE_PHILOX) {
                     const uint64_t q = (uint64_t)n * nc + c, call = q >> 2;
                     if (call != zcall) { normal_quad((uint64_t)(d->traj_offset + traj), call, d->seed, zc); zcall = call; }
                     dw[c] = sq * zc[q & 3];
