@@ -221,7 +221,8 @@ SDDE_API int sdde_b200_set_option(sdde_ctx *ctx, const char *key, int64_t value)
                                                                                     shared-memory refill, 1..1024), "ramp_start" (trajectories of the first wave when the
                                                                                     paths leave over PCIe; later waves grow x1.5; default 2^16, measured best on C2),
                                                                                     "host_threads" (host threads that copy a PAGEABLE host output out of the
-                                                                                    page-locked bounce buffers; 0 = min(16, hardware threads), 1 = plain cudaMemcpy2DAsync),
+                                                                                    page-locked bounce buffers; 0 = min(16, hardware threads), 1 = plain cudaMemcpy2DAsync), "bounce_min_mb" (smallest pageable
+                                                                                    output that takes that path, default 32; 0 = always, used by the tests),
                                                                                     "nccl", "jit_linsys" (0/1), "zero_copy" (1: page-locked host `out` is written by the step kernel itself
                                                                                     over PCIe; 0: staged in HBM and copied wave by wave; -1 (default): small outputs zero-copy, outputs
                                                                                     >= 64 MB try both on the first two solves of their size class (power of two of the output bytes) and keep the faster) */

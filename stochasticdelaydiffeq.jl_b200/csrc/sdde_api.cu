@@ -579,6 +579,7 @@ int sdde_b200_set_option(sdde_ctx *c, const char *key, int64_t value) {
     else if (!strcmp(key, "drop_caches")) { c->sched_key.clear(); c->table_key.clear(); }   // next solve replays the schedule and re-uploads its tables
     else if (!strcmp(key, "lean")) { c->opt_lean = value; c->table_key.clear(); }   // 0: general body only, 1: all lean bodies, 2: without the consecutive-interpolation body (A/B)
     else if (!strcmp(key, "balance")) c->opt_balance = value != 0;
+    else if (!strcmp(key, "bounce_min_mb")) { if (value < 0) return fail(SDDE_ERR_BAD_DESC, "bounce_min_mb out of range"); c->opt_bounce_min_mb = value; }
     else if (!strcmp(key, "host_threads")) { if (value < 0 || value > 256) return fail(SDDE_ERR_BAD_DESC, "host_threads out of range"); c->opt_host_threads = value; c->pool.reset(); }
     else if (!strcmp(key, "ramp_start")) { if (value < 256 || value > ((int64_t)1 << 22)) return fail(SDDE_ERR_BAD_DESC, "ramp_start out of range"); c->opt_ramp_start = value; }
     else if (!strcmp(key, "chunk_steps")) { if (value < 1 || value > 1024) return fail(SDDE_ERR_BAD_DESC, "chunk_steps out of range"); c->opt_chunk_steps = value; }
@@ -947,7 +948,7 @@ static int solve_once(sdde_ctx *c, const sdde_desc *d, double *out, double *mome
     // the 4 GB of C2 against 78 ms into page-locked memory).  Here each wave's tile leaves in 64 MB chunks into two page-locked
     // bounce buffers; while chunk k+1 crosses PCIe the host threads scatter chunk k into the caller's rows.
     bool pageable_out = false;
-    if (d->want_paths && !out_dev && rows > 0 && (double)rows * (double)NT * 8.0 >= 32.0 * 1048576.0 && c->opt_host_threads != 1) {
+    if (d->want_paths && !out_dev && rows > 0 && (double)rows * (double)NT * 8.0 >= (double)c->opt_bounce_min_mb * 1048576.0 && c->opt_host_threads != 1) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, out) == cudaSuccess) pageable_out = at.type == cudaMemoryTypeUnregistered;
         else cudaGetLastError();

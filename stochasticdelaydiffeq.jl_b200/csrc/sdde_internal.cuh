@@ -74,6 +74,7 @@ struct sdde_ctx {
     cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
     std::unique_ptr<sdde::HostPool> pool;   // host threads that scatter the bounce buffers into the caller's pageable array
     int64_t opt_host_threads = 0;  // 0 = min(16, hardware threads)
+    int64_t opt_bounce_min_mb = 32; // pageable outputs below this size take the plain cudaMemcpy2DAsync (0: always bounce -- tests)
     DevBuf qs_rows, qs_hist, qs_paths, qs_cand;   // order-statistics workspaces (sdde_b200_quantiles)
     struct sdde_qsel *qsel = nullptr;   // the active order-statistics selection (sdde_summary_api.cu), freed by sdde_qsel_free
     DevBuf gather;                 // [n_gpu][rows][3] moment triples received over NCCL (sdde_b200_solve_multi)
