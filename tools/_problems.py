@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sdde_b200 as S  # noqa: E402
 
 ALG_MAP = {0: S.EM(True), 1: S.EM(False), 2: S.RKMil("Ito"), 3: S.RKMil("Stratonovich"), 4: S.EulerHeun(),
-           5: S.RKMilCommute("Ito"), 6: S.RKMilCommute("Stratonovich"), **{7 + i: S.WangLi3SMil("ABCDEF"[i]) for i in range(6)}}
+           5: S.RKMilCommute("Ito"), 6: S.RKMilCommute("Stratonovich"), **{7 + i: S.WangLi3SMil("ABCDEF"[i]) for i in range(6)},
+           13: S.SRA1(), 14: S.SRA3(), 15: S.SOSRA()}
 
 
 class Case:
@@ -28,7 +29,7 @@ class Case:
 
     def solve_kwargs(self):
         kw = dict(dt=self.dt, saveat=self.saveat)
-        if self.alg in (2, 3, 5, 6):
+        if self.alg in (2, 3, 5, 6, 13, 14, 15):
             kw["adaptive"] = False
         return kw
 
