@@ -452,7 +452,7 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::B200Alg, 
     end
     idxs = save_idxs === nothing ? Int32[] : Int32[i - 1 for i in save_idxs]          # 0-based on the C side
     n_saved = isempty(idxs) ? Int(m.n_state) : length(idxs)
-    nz = noise_increments === nothing ? Float64[] : noise_increments        # Array{Float64,3}(n_traj, n_chan, n_steps) == C [n][c][traj]
+    nz = noise_increments === nothing ? Float64[] : noise_increments        # Array{Float64,3}(n_traj, n_chan, n_steps) == C [n][c][traj]; SRA family: 2 n_chan channels, dW rows first, then dZ
     d = SddeDesc(; struct_size = sizeof(SddeDesc), model_id = m.id, alg = alg_id(alg), n_state = m.n_state,
         n_noise = m.n_noise, n_lag = m.n_lag, n_param = m.n_param,
         order_discontinuity_t0 = prob.order_discontinuity_t0, constant_lags_declared = isempty(prob.constant_lags) ? 0 : 1,
